@@ -1,0 +1,134 @@
+/*
+ * qumcmc_b200.h -- C-ABI of libqumcmc_b200.so, the B200-native (sm_100a) replacement for the
+ * quantum-proposal hot path of pafloxy/quMCMC.
+ *
+ * The reference has no FFI of its own: its seam is the Python API that sits on top of the qulacs
+ * pybind11 module.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - basis index idx = int(bitstring, 2); qubit q = bit q of idx; spin j (string position j from
+ *     the left) is bit n-1-j; s_j = +1 for '1'.
+ *   - All pointers named *_dev are device pointers on the model's device; *_host are host pointers.
+ *     The caller owns every buffer.  The library owns only the handle and its scratch.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls taking device
+ *     buffers are asynchronous on that stream; *_host variants synchronise before returning.
+ *   - Return value: 0 ok; QMC_ERR_* (<0) otherwise, message via qmc_last_error() (thread-local).
+ *     There is no CPU fallback: unsupported configurations return QMC_ERR_UNSUPPORTED.
+ *   - One host thread per handle at a time.
+ *
+ * RNG stream contract (Philox4x32-10; identical in oracle/qmc_oracle.c)
+ *   key = (seed lo32, seed hi32); counter = (chain lo32, chain hi32, hop, slot)
+ *   slot 0: w0,w1 -> u_gamma (53 bit), w2 -> t = 2 + floor(w2*10/2^32), w3 -> u_group = w3/2^32
+ *   slot 1: w0,w1 -> u_measure, w2,w3 -> u_accept        u53(a,b) = ((a>>5)*2^26 + (b>>6)) / 2^53
+ *   initial state (when s0 is NULL): hop = 0xFFFFFFFF, slot 0: (w1<<32 | w0) & (2^n - 1)
+ *   gamma = g_lo + (g_hi-g_lo)*u_gamma;  r = max(1, floor(t/delta_time)).
+ *   `chain` is the GLOBAL chain id, so results do not depend on how chains are sharded over GPUs.
+ */
+#ifndef QUMCMC_B200_H
+#define QUMCMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QMC_OK 0
+#define QMC_ERR_BADARG (-1)
+#define QMC_ERR_CUDA (-2)
+#define QMC_ERR_NCCL (-3)
+#define QMC_ERR_UNSUPPORTED (-4)
+
+#define QMC_DTYPE_F32 0 /* complex64 statevector  */
+#define QMC_DTYPE_F64 1 /* complex128 statevector */
+
+#define QMC_MAX_SPINS 34       /* single-GPU statevector limit (2^34 complex64 = 128 GiB) */
+#define QMC_SMEM_MAX_SPINS_F32 13 /* whole statevector in shared memory, one CTA per chain */
+#define QMC_SMEM_MAX_SPINS_F64 12
+
+typedef struct qmc_model qmc_model;
+
+int qmc_version(void);
+const char *qmc_last_error(void);
+
+/* IsingEnergyFunction.__init__ (qumcmc/energy_models.py:22-52).  J, circJ: n*n row-major host
+ * arrays; h, circh: n.  circJ/circh NULL = J/h.  alpha is model.alpha (:41-47), computed by the
+ * caller.  Uploads the model and precomputes the phase table D(idx) of fn_qckt_problem_half
+ * (qumcmc/quantum_mcmc_routines.py:54-91) when n > the shared-memory limits. */
+int qmc_model_create(qmc_model **out, int n, const double *J_host, const double *h_host,
+                     const double *circJ_host, const double *circh_host, double alpha, int device);
+int qmc_model_destroy(qmc_model *m);
+
+/* Mixer.get_mixer_circuit (qumcmc/mixers.py:8-18, 34-52, 89-105, 124-130, 149-151) as data:
+ * group g owns terms [group_offsets[g], group_offsets[g+1]); term k = X-string over the qubits
+ * set in masks[k], evolved by exp(-i * gamma * weights[k] * delta_time * X_mask).
+ * group_prob NULL (or n_groups == 1): one coherent mixer (GenericMixer / CustomMixer /
+ * CoherentMixerSum, weights = normalised w_m).  Otherwise IncoherentMixerSum: one group per
+ * proposal with probability group_prob[g].  All host pointers. */
+int qmc_mixer_set(qmc_model *m, int n_groups, const int *group_offsets, const uint64_t *masks,
+                  const double *weights, const double *group_prob);
+
+/* IsingEnergyFunction.get_energy (qumcmc/energy_models.py:124-144), batched:
+ * E = 0.5 * s.(J s) + h.s in fixed row-major sequential fp64 order (bit-exact vs the oracle). */
+int qmc_energies(qmc_model *m, const uint64_t *idx_dev, int64_t count, double *E_dev, void *stream);
+int qmc_energies_host(qmc_model *m, const uint64_t *idx_host, int64_t count, double *E_host);
+
+/* Exact_Sampling.get_boltzmann_distribution / run_exact_sampling
+ * (qumcmc/energy_models.py:218-275, 277-297): all 2^n energies, log Z by a grid-wide
+ * logsumexp, p = exp(-beta*E - logZ).  energies/probs nullable (index order). logZ: 1 double. */
+int qmc_exact_sampling(qmc_model *m, double beta, double *logZ_dev, double *energies_dev,
+                       double *probs_dev, void *stream);
+int qmc_exact_sampling_host(qmc_model *m, double beta, double *logZ_host, double *energies_host,
+                            double *probs_host);
+
+/* Test hook: |<s'|U|s>|^2 for all s' with U = M (P M)^{r-1}, the circuit of
+ * run_qmcmc_quantum_ckt (qumcmc/quantum_mcmc_routines.py:110-152) for fixed gamma and r and
+ * mixer group `group`.  probs_dev: 2^n float (F32) or double (F64), index order.
+ * amps_dev (nullable): 2^n interleaved complex of the same precision. */
+int qmc_transition_probs(qmc_model *m, uint64_t s, double gamma, int r, double delta_time, int group,
+                         int dtype, void *probs_dev, void *amps_dev, void *stream);
+
+/* Test hook: one proposal per chain with explicit draws; replaces run_qmcmc_quantum_ckt
+ * (:110-156) incl. QuantumState.sampling(1) (:153).  u_dev = measurement uniforms in [0,1);
+ * group_dev nullable (0). */
+int qmc_propose(qmc_model *m, int64_t n_chains, const uint64_t *s_in_dev, const double *gamma_dev,
+                const int *r_dev, const double *u_dev, const int *group_dev, double delta_time,
+                int dtype, uint64_t *s_out_dev, void *stream);
+
+/* quantum_enhanced_mcmc (qumcmc/quantum_mcmc_routines.py:159-227) for n_chains independent
+ * chains x n_hops hops: per hop draw (gamma, t, group), propose, get_energy, test_accept
+ * (qumcmc/classical_mcmc_routines.py:28-41), record.  s0_dev NULL = Philox initial states.
+ * chain_id0 = global id of chain 0 of this call; hop0 = index of the first hop (resume).
+ * Outputs (all nullable except final_state_dev): proposals_dev/accepted_dev [n_chains*n_hops]
+ * row-major (chain, hop) = the MCMCState fields (qumcmc/basic_utils.py:54-57);
+ * final_state_dev [n_chains] = current state after the last hop; acc_count_dev [n_chains];
+ * hamming_hist_dev [n_chains*(n+1)] = proposal Hamming distances w.r.t. the current state. */
+int qmc_run_chains(qmc_model *m, int64_t n_chains, int64_t n_hops, const uint64_t *s0_dev,
+                   uint64_t chain_id0, uint32_t hop0, double temperature, double gamma_lo,
+                   double gamma_hi, double delta_time, uint64_t seed, int dtype,
+                   uint64_t *proposals_dev, uint8_t *accepted_dev, uint64_t *final_state_dev,
+                   int64_t *acc_count_dev, int64_t *hamming_hist_dev, void *stream);
+/* Same with host buffers (copies inside): the reference-facing call. */
+int qmc_run_chains_host(qmc_model *m, int64_t n_chains, int64_t n_hops, const uint64_t *s0_host,
+                        uint64_t chain_id0, uint32_t hop0, double temperature, double gamma_lo,
+                        double gamma_hi, double delta_time, uint64_t seed, int dtype,
+                        uint64_t *proposals_host, uint8_t *accepted_host,
+                        uint64_t *final_state_host, int64_t *acc_count_host,
+                        int64_t *hamming_hist_host);
+
+/* Introspection for benchmarks/tests. */
+int qmc_model_num_spins(const qmc_model *m);
+/* Number of kernels this library has launched on behalf of handle m since creation. */
+int64_t qmc_model_launch_count(const qmc_model *m);
+/* Events around the dominant sweep kernel: accumulated device ms and launches since reset
+ * (timing is recorded only while enabled; off by default). */
+int qmc_profile_enable(qmc_model *m, int on);
+int qmc_profile_read(qmc_model *m, double *sweep_ms, int64_t *sweep_launches,
+                     double *algorithmic_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUMCMC_B200_H */

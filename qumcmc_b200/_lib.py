@@ -1,0 +1,110 @@
+"""ctypes binding of ``csrc/libqumcmc_b200.so`` (C-ABI in ``include/qumcmc_b200.h``).
+
+There is no CPU fallback: if the shared library is missing or cannot be loaded, every entry point of
+the hot path raises.  Build it with ``python -c "import __graft_entry__ as g; g.build()"`` or
+``make -C qumcmc_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libqumcmc_b200.so")
+
+QMC_OK = 0
+QMC_ERR_BADARG = -1
+QMC_ERR_CUDA = -2
+QMC_ERR_NCCL = -3
+QMC_ERR_UNSUPPORTED = -4
+DTYPE_F32 = 0
+DTYPE_F64 = 1
+SMEM_MAX_SPINS_F32 = 13
+SMEM_MAX_SPINS_F64 = 12
+MAX_SPINS = 34
+
+# every symbol include/qumcmc_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "qmc_version", "qmc_last_error", "qmc_model_create", "qmc_model_destroy", "qmc_mixer_set",
+    "qmc_energies", "qmc_energies_host", "qmc_exact_sampling", "qmc_exact_sampling_host",
+    "qmc_transition_probs", "qmc_propose", "qmc_run_chains", "qmc_run_chains_host",
+    "qmc_model_num_spins", "qmc_model_launch_count", "qmc_profile_enable", "qmc_profile_read",
+]
+
+
+class QmcError(RuntimeError):
+    """Non-zero return code from libqumcmc_b200."""
+
+
+class QmcUnsupported(QmcError, NotImplementedError):
+    """QMC_ERR_UNSUPPORTED: the configuration has no CUDA path (and there is no CPU fallback)."""
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA extension for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC, "-j4"], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0:
+        raise RuntimeError("building libqumcmc_b200.so failed")
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise QmcError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built "
+            "(run __graft_entry__.build() or `make -C qumcmc_b200/csrc`). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, dp, u64p, i64p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p  # raw addresses (host or device)
+    L.qmc_version.restype = C.c_int
+    L.qmc_last_error.restype = C.c_char_p
+    L.qmc_model_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, dp, dp, dp, dp, C.c_double, C.c_int]
+    L.qmc_model_destroy.argtypes = [C.c_void_p]
+    L.qmc_mixer_set.argtypes = [C.c_void_p, C.c_int, vp, vp, vp, vp]
+    L.qmc_energies.argtypes = [C.c_void_p, u64p, C.c_int64, dp, vp]
+    L.qmc_energies_host.argtypes = [C.c_void_p, u64p, C.c_int64, dp]
+    L.qmc_exact_sampling.argtypes = [C.c_void_p, C.c_double, dp, dp, dp, vp]
+    L.qmc_exact_sampling_host.argtypes = [C.c_void_p, C.c_double, dp, dp, dp]
+    L.qmc_transition_probs.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_int, C.c_double, C.c_int,
+                                       C.c_int, vp, vp, vp]
+    L.qmc_propose.argtypes = [C.c_void_p, C.c_int64, u64p, dp, vp, dp, vp, C.c_double, C.c_int, u64p, vp]
+    L.qmc_run_chains.argtypes = [C.c_void_p, C.c_int64, C.c_int64, u64p, C.c_uint64, C.c_uint32, C.c_double,
+                                 C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int, u64p, vp, u64p,
+                                 i64p, i64p, vp]
+    L.qmc_run_chains_host.argtypes = [C.c_void_p, C.c_int64, C.c_int64, u64p, C.c_uint64, C.c_uint32,
+                                      C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int,
+                                      u64p, vp, u64p, i64p, i64p]
+    L.qmc_model_num_spins.argtypes = [C.c_void_p]
+    L.qmc_model_launch_count.argtypes = [C.c_void_p]
+    L.qmc_model_launch_count.restype = C.c_int64
+    L.qmc_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.qmc_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("qmc_last_error", "qmc_model_launch_count"):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc == QMC_OK:
+        return
+    msg = lib().qmc_last_error()
+    text = msg.decode(errors="replace") if msg else ""
+    if rc == QMC_ERR_UNSUPPORTED:
+        raise QmcUnsupported(f"libqumcmc_b200: unsupported ({text})")
+    if rc == QMC_ERR_BADARG:
+        raise ValueError(f"libqumcmc_b200: bad argument ({text})")
+    raise QmcError(f"libqumcmc_b200: error {rc} ({text})")

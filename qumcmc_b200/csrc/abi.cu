@@ -1,0 +1,125 @@
+// abi.cu -- extern "C" entry points of the proposal path; dispatch between the shared-memory
+// kernel (small n) and the HBM sweep kernels (large n).  See include/qumcmc_b200.h.
+#include "common.cuh"
+
+static bool use_small_path(const qmc_model *m, int dtype) {
+    const int lim = dtype == QMC_DTYPE_F64 ? QMC_SMEM_MAX_SPINS_F64 : QMC_SMEM_MAX_SPINS_F32;
+    if (m->n > lim) return false;
+    const size_t esz = dtype == QMC_DTYPE_F64 ? 16 : 8;
+    const size_t smem = (2 * ((size_t)1 << m->n) + (size_t)m->max_terms_in_group) * esz;
+    return smem <= 227 * 1024;
+}
+
+static int dispatch(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, const uint64_t *s_in,
+                    uint64_t chain_id0, uint32_t hop0, double temperature, double g_lo, double g_hi, double dt,
+                    uint64_t seed, int dtype, const double *gamma_arr, const int *r_arr, const double *u_arr,
+                    const int *group_arr, uint64_t *proposals, uint8_t *accepted, uint64_t *final_state,
+                    int64_t *acc_count, int64_t *hamming_hist, void *probs_out, void *amps_out, void *stream) {
+    QMC_REQUIRE(m, QMC_ERR_BADARG, "null model handle");
+    QMC_REQUIRE(dtype == QMC_DTYPE_F32 || dtype == QMC_DTYPE_F64, QMC_ERR_BADARG, "dtype must be QMC_DTYPE_F32/F64");
+    QMC_REQUIRE(n_chains >= 0 && n_hops >= 0, QMC_ERR_BADARG, "negative chain or hop count");
+    QMC_REQUIRE(dt > 0.0, QMC_ERR_BADARG, "delta_time must be positive");
+    QMC_CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (use_small_path(m, dtype))
+        return qmc_small_run(m, mode, n_chains, n_hops, s_in, chain_id0, hop0, temperature, g_lo, g_hi, dt, seed,
+                             dtype, gamma_arr, r_arr, u_arr, group_arr, proposals, accepted, final_state,
+                             acc_count, hamming_hist, probs_out, amps_out, st);
+    return qmc_sweep_run(m, mode, n_chains, n_hops, s_in, chain_id0, hop0, temperature, g_lo, g_hi, dt, seed, dtype,
+                         gamma_arr, r_arr, u_arr, group_arr, proposals, accepted, final_state, acc_count,
+                         hamming_hist, probs_out, amps_out, st);
+}
+
+// single-element device staging for the transition_probs hook
+struct ProbeArgs {
+    uint64_t s;
+    double gamma;
+    int r;
+    int group;
+};
+
+extern "C" int qmc_transition_probs(qmc_model *m, uint64_t s, double gamma, int r, double delta_time, int group,
+                                    int dtype, void *probs_dev, void *amps_dev, void *stream) {
+    QMC_REQUIRE(m && (probs_dev || amps_dev), QMC_ERR_BADARG, "qmc_transition_probs: null argument");
+    QMC_REQUIRE(m->n >= 64 || s < (1ULL << m->n), QMC_ERR_BADARG, "qmc_transition_probs: state out of range");
+    QMC_REQUIRE(group >= 0 && group < m->n_groups, QMC_ERR_BADARG, "qmc_transition_probs: group %d of %d", group, m->n_groups);
+    QMC_REQUIRE(r >= 0, QMC_ERR_BADARG, "qmc_transition_probs: negative r");
+    QMC_CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ProbeArgs h = {s, gamma, r, group};
+    ProbeArgs *d = nullptr;
+    QMC_CUDA_TRY(cudaMallocAsync(&d, sizeof(ProbeArgs), st));
+    QMC_CUDA_TRY(cudaMemcpyAsync(d, &h, sizeof(ProbeArgs), cudaMemcpyHostToDevice, st));
+    QMC_CUDA_TRY(cudaStreamSynchronize(st));  // h is a stack object
+    int rc = dispatch(m, QMC_MODE_PROBS, 1, 1, &d->s, 0, 0, 1.0, gamma, gamma, delta_time, 0, dtype, &d->gamma, &d->r,
+                      nullptr, &d->group, nullptr, nullptr, nullptr, nullptr, nullptr, probs_dev, amps_dev, stream);
+    cudaFreeAsync(d, st);
+    return rc;
+}
+
+extern "C" int qmc_propose(qmc_model *m, int64_t n_chains, const uint64_t *s_in_dev, const double *gamma_dev,
+                           const int *r_dev, const double *u_dev, const int *group_dev, double delta_time, int dtype,
+                           uint64_t *s_out_dev, void *stream) {
+    QMC_REQUIRE(m && (n_chains == 0 || (s_in_dev && gamma_dev && r_dev && u_dev && s_out_dev)), QMC_ERR_BADARG,
+                "qmc_propose: null argument");
+    return dispatch(m, QMC_MODE_PROPOSE, n_chains, 1, s_in_dev, 0, 0, 1.0, 0.0, 0.0, delta_time, 0, dtype, gamma_dev,
+                    r_dev, u_dev, group_dev, s_out_dev, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int qmc_run_chains(qmc_model *m, int64_t n_chains, int64_t n_hops, const uint64_t *s0_dev,
+                              uint64_t chain_id0, uint32_t hop0, double temperature, double gamma_lo, double gamma_hi,
+                              double delta_time, uint64_t seed, int dtype, uint64_t *proposals_dev,
+                              uint8_t *accepted_dev, uint64_t *final_state_dev, int64_t *acc_count_dev,
+                              int64_t *hamming_hist_dev, void *stream) {
+    QMC_REQUIRE(m && final_state_dev, QMC_ERR_BADARG, "qmc_run_chains: final_state_dev is required");
+    QMC_REQUIRE(temperature > 0.0, QMC_ERR_BADARG, "qmc_run_chains: temperature must be positive");
+    return dispatch(m, QMC_MODE_CHAIN, n_chains, n_hops, s0_dev, chain_id0, hop0, temperature, gamma_lo, gamma_hi,
+                    delta_time, seed, dtype, nullptr, nullptr, nullptr, nullptr, proposals_dev, accepted_dev,
+                    final_state_dev, acc_count_dev, hamming_hist_dev, nullptr, nullptr, stream);
+}
+
+extern "C" int qmc_run_chains_host(qmc_model *m, int64_t n_chains, int64_t n_hops, const uint64_t *s0_host,
+                                   uint64_t chain_id0, uint32_t hop0, double temperature, double gamma_lo,
+                                   double gamma_hi, double delta_time, uint64_t seed, int dtype,
+                                   uint64_t *proposals_host, uint8_t *accepted_host, uint64_t *final_state_host,
+                                   int64_t *acc_count_host, int64_t *hamming_hist_host) {
+    QMC_REQUIRE(m && final_state_host, QMC_ERR_BADARG, "qmc_run_chains_host: final_state_host is required");
+    QMC_REQUIRE(n_chains >= 0 && n_hops >= 0, QMC_ERR_BADARG, "negative chain or hop count");
+    if (n_chains == 0) return QMC_OK;
+    QMC_CUDA_TRY(cudaSetDevice(m->device));
+    const size_t CH = (size_t)n_chains * (size_t)n_hops;
+    const size_t hb = (size_t)n_chains * (size_t)(m->n + 1);
+    uint64_t *d_s0 = nullptr, *d_prop = nullptr, *d_fin = nullptr;
+    uint8_t *d_acc = nullptr;
+    int64_t *d_cnt = nullptr, *d_hist = nullptr;
+    cudaError_t e = cudaSuccess;
+    int rc = QMC_OK;
+    auto A = [&](void **p, size_t bytes) {
+        if (e == cudaSuccess && bytes) e = cudaMalloc(p, bytes);
+    };
+    if (s0_host) A((void **)&d_s0, sizeof(uint64_t) * n_chains);
+    if (proposals_host) A((void **)&d_prop, sizeof(uint64_t) * CH);
+    if (accepted_host) A((void **)&d_acc, CH);
+    A((void **)&d_fin, sizeof(uint64_t) * n_chains);
+    if (acc_count_host) A((void **)&d_cnt, sizeof(int64_t) * n_chains);
+    if (hamming_hist_host) A((void **)&d_hist, sizeof(int64_t) * hb);
+    if (e == cudaSuccess && d_s0) e = cudaMemcpy(d_s0, s0_host, sizeof(uint64_t) * n_chains, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        rc = qmc_run_chains(m, n_chains, n_hops, d_s0, chain_id0, hop0, temperature, gamma_lo, gamma_hi, delta_time,
+                            seed, dtype, d_prop, d_acc, d_fin, d_cnt, d_hist, nullptr);
+    if (e == cudaSuccess && rc == QMC_OK) e = cudaDeviceSynchronize();
+    auto D2H = [&](void *dst, const void *src, size_t bytes) {
+        if (e == cudaSuccess && rc == QMC_OK && dst && src && bytes) e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+    };
+    D2H(proposals_host, d_prop, sizeof(uint64_t) * CH);
+    D2H(accepted_host, d_acc, CH);
+    D2H(final_state_host, d_fin, sizeof(uint64_t) * n_chains);
+    D2H(acc_count_host, d_cnt, sizeof(int64_t) * n_chains);
+    D2H(hamming_hist_host, d_hist, sizeof(int64_t) * hb);
+    cudaFree(d_s0); cudaFree(d_prop); cudaFree(d_acc); cudaFree(d_fin); cudaFree(d_cnt); cudaFree(d_hist);
+    if (e != cudaSuccess) {
+        qmc_set_error("qmc_run_chains_host: %s", cudaGetErrorString(e));
+        return QMC_ERR_CUDA;
+    }
+    return rc;
+}

@@ -1,0 +1,445 @@
+// model.cu -- model handle, phase/energy tables, batched energies (K4 energy part) and the
+// exact Boltzmann enumerator with a grid-wide logsumexp (K5).
+//
+// Reference behaviour restated here:
+//   IsingEnergyFunction.get_energy            qumcmc/energy_models.py:124-144
+//   fn_qckt_problem_half (phase exponent D)   qumcmc/quantum_mcmc_routines.py:54-91
+//   Exact_Sampling.get_boltzmann_distribution qumcmc/energy_models.py:218-275
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local std::string g_last_error;
+
+void qmc_set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+extern "C" const char *qmc_last_error(void) { return g_last_error.c_str(); }
+extern "C" int qmc_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+#define QMC_MAXN 40
+
+// E(idx[k]) for arbitrary index lists.  J/h staged in shared memory; one thread per state.
+__global__ void __launch_bounds__(256) energies_kernel(int n, const double *__restrict__ J,
+                                                       const double *__restrict__ h,
+                                                       const uint64_t *__restrict__ idx, int64_t count,
+                                                       double *__restrict__ out) {
+    extern __shared__ double sm[];
+    double *sJ = sm, *sh = sm + n * n;
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) sJ[i] = J[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = h[i];
+    __syncthreads();
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < count;
+         k += (int64_t)gridDim.x * blockDim.x)
+        out[k] = qmc_energy_dev(n, sJ, sh, idx[k]);
+}
+
+// Phase exponent D(idx) = sum_{j<k} J_jk z_j z_k + sum_j h_j z_j, z = -s, same loop order as the
+// oracle (orc_phase_D) so the table is bit-identical.
+__global__ void __launch_bounds__(256) phase_table_kernel(int n, const double *__restrict__ J,
+                                                          const double *__restrict__ h,
+                                                          double *__restrict__ D) {
+    extern __shared__ double sm[];
+    double *sJ = sm, *sh = sm + n * n;
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) sJ[i] = J[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = h[i];
+    __syncthreads();
+    const int64_t N = 1LL << n;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < N;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        double d = 0.0;
+        for (int j = 0; j < n - 1; ++j) {
+            const double zj = ((idx >> (n - 1 - j)) & 1LL) ? -1.0 : 1.0;
+            for (int k = j + 1; k < n; ++k) {
+                const double zk = ((idx >> (n - 1 - k)) & 1LL) ? -1.0 : 1.0;
+                d = __dadd_rn(d, __dmul_rn(__dmul_rn(sJ[j * n + k], zj), zk));
+            }
+        }
+        for (int j = 0; j < n; ++j) {
+            const double zj = ((idx >> (n - 1 - j)) & 1LL) ? -1.0 : 1.0;
+            d = __dadd_rn(d, __dmul_rn(sh[j], zj));
+        }
+        D[idx] = d;
+    }
+}
+
+// K5: enumerate all 2^n states; per-thread online logsumexp of x = -beta*E, block tree-reduce in a
+// fixed order, one (max, sumexp) partial per block.
+struct LseState {
+    double m, s;
+};
+__device__ __forceinline__ LseState lse_merge(LseState a, LseState b) {
+    if (b.m == -INFINITY) return a;
+    if (a.m == -INFINITY) return b;
+    LseState o;
+    if (a.m >= b.m) {
+        o.m = a.m;
+        o.s = a.s + b.s * exp(b.m - a.m);
+    } else {
+        o.m = b.m;
+        o.s = b.s + a.s * exp(a.m - b.m);
+    }
+    return o;
+}
+
+__global__ void __launch_bounds__(256) exact_enumerate_kernel(int n, const double *__restrict__ J,
+                                                              const double *__restrict__ h, double beta,
+                                                              double *__restrict__ energies,
+                                                              LseState *__restrict__ partials) {
+    extern __shared__ double sm[];
+    double *sJ = sm, *sh = sm + n * n;
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) sJ[i] = J[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = h[i];
+    __syncthreads();
+    const int64_t N = 1LL << n;
+    LseState acc = {-INFINITY, 0.0};
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < N;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const double e = qmc_energy_dev(n, sJ, sh, (uint64_t)idx);
+        if (energies) energies[idx] = e;
+        const double x = -beta * e;
+        if (x > acc.m) {
+            acc.s = acc.s * exp(acc.m - x) + 1.0;  // exp(-inf)=0 on the first element
+            acc.m = x;
+        } else {
+            acc.s += exp(x - acc.m);
+        }
+    }
+    // block reduce (fixed pairing order => deterministic)
+    __shared__ LseState red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] = lse_merge(red[threadIdx.x], red[threadIdx.x + off]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(256) exact_finalize_kernel(const LseState *__restrict__ partials, int nparts,
+                                                             double *__restrict__ logZ) {
+    __shared__ LseState red[256];
+    LseState acc = {-INFINITY, 0.0};
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) acc = lse_merge(acc, partials[i]);
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] = lse_merge(red[threadIdx.x], red[threadIdx.x + off]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) logZ[0] = red[0].m + log(red[0].s);
+}
+
+// p = exp(-beta*E - logZ); E read back if materialised, recomputed otherwise.
+__global__ void __launch_bounds__(256) exact_probs_kernel(int n, const double *__restrict__ J,
+                                                          const double *__restrict__ h, double beta,
+                                                          const double *__restrict__ energies,
+                                                          const double *__restrict__ logZ,
+                                                          double *__restrict__ probs) {
+    extern __shared__ double sm[];
+    double *sJ = sm, *sh = sm + n * n;
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) sJ[i] = J[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = h[i];
+    __syncthreads();
+    const int64_t N = 1LL << n;
+    const double lz = logZ[0];
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < N;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const double e = energies ? energies[idx] : qmc_energy_dev(n, sJ, sh, (uint64_t)idx);
+        probs[idx] = exp(-beta * e - lz);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int grid_for(int64_t items, int block, int sms = 148, int per_sm = 8) {
+    int64_t g = (items + block - 1) / block;
+    const int64_t cap = (int64_t)sms * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+int qmc_launch_energies(qmc_model *m, const uint64_t *idx_dev, int64_t count, double *E_dev, cudaStream_t st) {
+    if (count == 0) return QMC_OK;
+    const size_t smem = sizeof(double) * (size_t)(m->n * m->n + m->n);
+    energies_kernel<<<grid_for(count, 256), 256, smem, st>>>(m->n, m->dJ, m->dh, idx_dev, count, E_dev);
+    m->launches++;
+    QMC_CUDA_TRY(cudaGetLastError());
+    return QMC_OK;
+}
+
+extern "C" int qmc_model_create(qmc_model **out, int n, const double *J, const double *h, const double *circJ,
+                                const double *circh, double alpha, int device) {
+    QMC_REQUIRE(out && J && h, QMC_ERR_BADARG, "qmc_model_create: null argument");
+    QMC_REQUIRE(n >= 1 && n <= QMC_MAX_SPINS, QMC_ERR_UNSUPPORTED,
+                "qmc_model_create: n=%d outside [1,%d] (single-GPU statevector limit)", n, QMC_MAX_SPINS);
+    int ndev = 0;
+    QMC_CUDA_TRY(cudaGetDeviceCount(&ndev));
+    QMC_REQUIRE(device >= 0 && device < ndev, QMC_ERR_BADARG, "qmc_model_create: device %d of %d", device, ndev);
+    QMC_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    QMC_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    QMC_REQUIRE(prop.major == 10, QMC_ERR_UNSUPPORTED,
+                "libqumcmc_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+
+    qmc_model *m = new qmc_model();
+    m->n = n;
+    m->device = device;
+    m->alpha = alpha;
+    m->host_J.assign(J, J + (size_t)n * n);
+    m->host_h.assign(h, h + n);
+    m->host_cJ.assign(circJ ? circJ : J, (circJ ? circJ : J) + (size_t)n * n);
+    m->host_ch.assign(circh ? circh : h, (circh ? circh : h) + n);
+    // skip rule of fn_qckt_problem_half (:64-67): mean|h| <= 1e-3 and mean|J| <= 1e-3
+    double mh = 0.0, mJ = 0.0;
+    for (int i = 0; i < n; ++i) mh += fabs(m->host_ch[i]);
+    for (int i = 0; i < n * n; ++i) mJ += fabs(m->host_cJ[i]);
+    mh /= (double)n;
+    mJ /= (double)n * (double)n;
+    m->phase_active = !(mh <= 1e-3 && mJ <= 1e-3);
+
+    double *dcJ = nullptr, *dch = nullptr;
+    auto fail = [&](int code) {
+        cudaFree(dcJ);
+        cudaFree(dch);
+        qmc_model_destroy(m);
+        return code;
+    };
+#define TRY_OR_FAIL(expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            qmc_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));   \
+            return fail(QMC_ERR_CUDA);                                                             \
+        }                                                                                          \
+    } while (0)
+    const size_t bJ = sizeof(double) * (size_t)n * n, bh = sizeof(double) * (size_t)n;
+    TRY_OR_FAIL(cudaMalloc(&m->dJ, bJ));
+    TRY_OR_FAIL(cudaMalloc(&m->dh, bh));
+    TRY_OR_FAIL(cudaMalloc(&dcJ, bJ));
+    TRY_OR_FAIL(cudaMalloc(&dch, bh));
+    TRY_OR_FAIL(cudaMemcpy(m->dJ, m->host_J.data(), bJ, cudaMemcpyHostToDevice));
+    TRY_OR_FAIL(cudaMemcpy(m->dh, m->host_h.data(), bh, cudaMemcpyHostToDevice));
+    TRY_OR_FAIL(cudaMemcpy(dcJ, m->host_cJ.data(), bJ, cudaMemcpyHostToDevice));
+    TRY_OR_FAIL(cudaMemcpy(dch, m->host_ch.data(), bh, cudaMemcpyHostToDevice));
+    const size_t smem = sizeof(double) * (size_t)(n * n + n);
+    if (n <= 26) {  // 2^26 doubles = 512 MiB; larger n evaluates D on the fly
+        const int64_t N = 1LL << n;
+        TRY_OR_FAIL(cudaMalloc(&m->dD, sizeof(double) * (size_t)N));
+        phase_table_kernel<<<grid_for(N, 256), 256, smem>>>(n, dcJ, dch, m->dD);
+        m->launches++;
+        TRY_OR_FAIL(cudaGetLastError());
+    }
+    if (n <= QMC_SMEM_MAX_SPINS_F32) {
+        const int64_t N = 1LL << n;
+        TRY_OR_FAIL(cudaMalloc(&m->dE, sizeof(double) * (size_t)N));
+        LseState *dummy = nullptr;
+        TRY_OR_FAIL(cudaMalloc(&dummy, sizeof(LseState) * 1184));
+        exact_enumerate_kernel<<<grid_for(N, 256), 256, smem>>>(n, m->dJ, m->dh, 0.0, m->dE, dummy);
+        m->launches++;
+        TRY_OR_FAIL(cudaGetLastError());
+        TRY_OR_FAIL(cudaDeviceSynchronize());
+        cudaFree(dummy);
+    }
+    TRY_OR_FAIL(cudaDeviceSynchronize());
+    cudaFree(dcJ);
+    cudaFree(dch);
+    dcJ = dch = nullptr;
+#undef TRY_OR_FAIL
+    // default mixer: GenericMixer.OneBodyMixer(n) (README-era default)
+    std::vector<int> off = {0, n};
+    std::vector<uint64_t> masks(n);
+    std::vector<double> w(n, 1.0);
+    for (int q = 0; q < n; ++q) masks[q] = 1ULL << q;
+    int rc = qmc_mixer_set(m, 1, off.data(), masks.data(), w.data(), nullptr);
+    if (rc != QMC_OK) {
+        qmc_model_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return QMC_OK;
+}
+
+extern "C" int qmc_model_destroy(qmc_model *m) {
+    if (!m) return QMC_OK;
+    cudaSetDevice(m->device);
+    qmc_sweep_free(m);
+    cudaFree(m->dJ);
+    cudaFree(m->dh);
+    cudaFree(m->dD);
+    cudaFree(m->dE);
+    cudaFree(m->d_group_off);
+    cudaFree(m->d_masks);
+    cudaFree(m->d_weights);
+    cudaFree(m->d_group_cum);
+    delete m;
+    return QMC_OK;
+}
+
+extern "C" int qmc_mixer_set(qmc_model *m, int n_groups, const int *group_offsets, const uint64_t *masks,
+                             const double *weights, const double *group_prob) {
+    QMC_REQUIRE(m && group_offsets && masks && weights, QMC_ERR_BADARG, "qmc_mixer_set: null argument");
+    QMC_REQUIRE(n_groups >= 1 && n_groups <= 64, QMC_ERR_BADARG, "qmc_mixer_set: n_groups=%d", n_groups);
+    QMC_REQUIRE(group_offsets[0] == 0, QMC_ERR_BADARG, "qmc_mixer_set: group_offsets[0] must be 0");
+    const int nt = group_offsets[n_groups];
+    int max_terms = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        const int c = group_offsets[g + 1] - group_offsets[g];
+        QMC_REQUIRE(c >= 1, QMC_ERR_BADARG, "qmc_mixer_set: group %d is empty", g);
+        if (c > max_terms) max_terms = c;
+    }
+    const uint64_t full = (m->n >= 64) ? ~0ULL : ((1ULL << m->n) - 1ULL);
+    bool one_body = true;
+    for (int k = 0; k < nt; ++k) {
+        QMC_REQUIRE(masks[k] != 0 && (masks[k] & ~full) == 0, QMC_ERR_BADARG,
+                    "qmc_mixer_set: term %d has an empty mask or a qubit >= n", k);
+        if (__builtin_popcountll(masks[k]) != 1) one_body = false;
+    }
+    if (one_body) {  // each qubit at most once per group
+        for (int g = 0; g < n_groups && one_body; ++g) {
+            uint64_t seen = 0;
+            for (int k = group_offsets[g]; k < group_offsets[g + 1]; ++k) {
+                if (seen & masks[k]) one_body = false;
+                seen |= masks[k];
+            }
+        }
+    }
+    QMC_CUDA_TRY(cudaSetDevice(m->device));
+    m->n_groups = n_groups;
+    m->group_off.assign(group_offsets, group_offsets + n_groups + 1);
+    m->masks.assign(masks, masks + nt);
+    m->weights.assign(weights, weights + nt);
+    m->group_cum.assign(n_groups, 1.0);
+    if (group_prob && n_groups > 1) {
+        double tot = 0.0;
+        for (int g = 0; g < n_groups; ++g) {
+            QMC_REQUIRE(group_prob[g] >= 0.0, QMC_ERR_BADARG, "qmc_mixer_set: negative probability");
+            tot += group_prob[g];
+        }
+        QMC_REQUIRE(tot > 0.0, QMC_ERR_BADARG, "qmc_mixer_set: probabilities sum to zero");
+        double c = 0.0;
+        for (int g = 0; g < n_groups; ++g) {
+            c += group_prob[g] / tot;
+            m->group_cum[g] = c;
+        }
+        m->group_cum[n_groups - 1] = 1.0;
+    } else {
+        QMC_REQUIRE(n_groups == 1, QMC_ERR_BADARG,
+                    "qmc_mixer_set: %d groups need group_prob (coherent sums are one group)", n_groups);
+    }
+    m->max_terms_in_group = max_terms;
+    m->all_one_body = one_body;
+    cudaFree(m->d_group_off);
+    cudaFree(m->d_masks);
+    cudaFree(m->d_weights);
+    cudaFree(m->d_group_cum);
+    m->d_group_off = nullptr; m->d_masks = nullptr; m->d_weights = nullptr; m->d_group_cum = nullptr;
+    QMC_CUDA_TRY(cudaMalloc(&m->d_group_off, sizeof(int) * (n_groups + 1)));
+    QMC_CUDA_TRY(cudaMalloc(&m->d_masks, sizeof(uint64_t) * nt));
+    QMC_CUDA_TRY(cudaMalloc(&m->d_weights, sizeof(double) * nt));
+    QMC_CUDA_TRY(cudaMalloc(&m->d_group_cum, sizeof(double) * n_groups));
+    QMC_CUDA_TRY(cudaMemcpy(m->d_group_off, m->group_off.data(), sizeof(int) * (n_groups + 1), cudaMemcpyHostToDevice));
+    QMC_CUDA_TRY(cudaMemcpy(m->d_masks, m->masks.data(), sizeof(uint64_t) * nt, cudaMemcpyHostToDevice));
+    QMC_CUDA_TRY(cudaMemcpy(m->d_weights, m->weights.data(), sizeof(double) * nt, cudaMemcpyHostToDevice));
+    QMC_CUDA_TRY(cudaMemcpy(m->d_group_cum, m->group_cum.data(), sizeof(double) * n_groups, cudaMemcpyHostToDevice));
+    return QMC_OK;
+}
+
+extern "C" int qmc_energies(qmc_model *m, const uint64_t *idx_dev, int64_t count, double *E_dev, void *stream) {
+    QMC_REQUIRE(m && (count == 0 || (idx_dev && E_dev)) && count >= 0, QMC_ERR_BADARG, "qmc_energies: bad argument");
+    QMC_CUDA_TRY(cudaSetDevice(m->device));
+    return qmc_launch_energies(m, idx_dev, count, E_dev, (cudaStream_t)stream);
+}
+
+extern "C" int qmc_energies_host(qmc_model *m, const uint64_t *idx_host, int64_t count, double *E_host) {
+    QMC_REQUIRE(m && (count == 0 || (idx_host && E_host)) && count >= 0, QMC_ERR_BADARG, "qmc_energies_host: bad argument");
+    if (count == 0) return QMC_OK;
+    QMC_CUDA_TRY(cudaSetDevice(m->device));
+    uint64_t *di = nullptr;
+    double *de = nullptr;
+    QMC_CUDA_TRY(cudaMalloc(&di, sizeof(uint64_t) * count));
+    cudaError_t e = cudaMalloc(&de, sizeof(double) * count);
+    int rc = QMC_OK;
+    if (e != cudaSuccess) { cudaFree(di); qmc_set_error("cudaMalloc: %s", cudaGetErrorString(e)); return QMC_ERR_CUDA; }
+    e = cudaMemcpy(di, idx_host, sizeof(uint64_t) * count, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) rc = qmc_launch_energies(m, di, count, de, 0);
+    if (e == cudaSuccess && rc == QMC_OK) e = cudaMemcpy(E_host, de, sizeof(double) * count, cudaMemcpyDeviceToHost);
+    cudaFree(di);
+    cudaFree(de);
+    if (e != cudaSuccess) { qmc_set_error("qmc_energies_host: %s", cudaGetErrorString(e)); return QMC_ERR_CUDA; }
+    return rc;
+}
+
+extern "C" int qmc_exact_sampling(qmc_model *m, double beta, double *logZ_dev, double *energies_dev,
+                                  double *probs_dev, void *stream) {
+    QMC_REQUIRE(m && logZ_dev, QMC_ERR_BADARG, "qmc_exact_sampling: null argument");
+    QMC_CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = m->n;
+    const int64_t N = 1LL << n;
+    const size_t smem = sizeof(double) * (size_t)(n * n + n);
+    const int grid = grid_for(N, 256);
+    LseState *partials = nullptr;
+    QMC_CUDA_TRY(cudaMallocAsync(&partials, sizeof(LseState) * grid, st));
+    exact_enumerate_kernel<<<grid, 256, smem, st>>>(n, m->dJ, m->dh, beta, energies_dev, partials);
+    exact_finalize_kernel<<<1, 256, 0, st>>>(partials, grid, logZ_dev);
+    m->launches += 2;
+    if (probs_dev) {
+        exact_probs_kernel<<<grid, 256, smem, st>>>(n, m->dJ, m->dh, beta, energies_dev, logZ_dev, probs_dev);
+        m->launches++;
+    }
+    QMC_CUDA_TRY(cudaGetLastError());
+    QMC_CUDA_TRY(cudaFreeAsync(partials, st));
+    return QMC_OK;
+}
+
+extern "C" int qmc_exact_sampling_host(qmc_model *m, double beta, double *logZ_host, double *energies_host,
+                                       double *probs_host) {
+    QMC_REQUIRE(m && logZ_host, QMC_ERR_BADARG, "qmc_exact_sampling_host: null argument");
+    QMC_CUDA_TRY(cudaSetDevice(m->device));
+    const int64_t N = 1LL << m->n;
+    double *dl = nullptr, *de = nullptr, *dp = nullptr;
+    int rc = QMC_OK;
+    cudaError_t e = cudaMalloc(&dl, sizeof(double));
+    if (e == cudaSuccess && energies_host) e = cudaMalloc(&de, sizeof(double) * N);
+    if (e == cudaSuccess && probs_host) e = cudaMalloc(&dp, sizeof(double) * N);
+    if (e == cudaSuccess) rc = qmc_exact_sampling(m, beta, dl, de, dp, nullptr);
+    if (e == cudaSuccess && rc == QMC_OK) e = cudaMemcpy(logZ_host, dl, sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rc == QMC_OK && de) e = cudaMemcpy(energies_host, de, sizeof(double) * N, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rc == QMC_OK && dp) e = cudaMemcpy(probs_host, dp, sizeof(double) * N, cudaMemcpyDeviceToHost);
+    cudaFree(dl);
+    cudaFree(de);
+    cudaFree(dp);
+    if (e != cudaSuccess) { qmc_set_error("qmc_exact_sampling_host: %s", cudaGetErrorString(e)); return QMC_ERR_CUDA; }
+    return rc;
+}
+
+extern "C" int qmc_model_num_spins(const qmc_model *m) { return m ? m->n : -1; }
+extern "C" int64_t qmc_model_launch_count(const qmc_model *m) { return m ? m->launches : -1; }
+extern "C" int qmc_profile_enable(qmc_model *m, int on) {
+    QMC_REQUIRE(m, QMC_ERR_BADARG, "qmc_profile_enable: null handle");
+    m->profile = on;
+    m->prof_ms = 0.0;
+    m->prof_launches = 0;
+    m->prof_bytes = 0.0;
+    return QMC_OK;
+}
+extern "C" int qmc_profile_read(qmc_model *m, double *sweep_ms, int64_t *sweep_launches, double *algorithmic_bytes) {
+    QMC_REQUIRE(m, QMC_ERR_BADARG, "qmc_profile_read: null handle");
+    if (sweep_ms) *sweep_ms = m->prof_ms;
+    if (sweep_launches) *sweep_launches = m->prof_launches;
+    if (algorithmic_bytes) *algorithmic_bytes = m->prof_bytes;
+    return QMC_OK;
+}

@@ -1,0 +1,305 @@
+// small_n.cu -- shared-memory-resident proposal path: the whole 2^n statevector of one chain lives
+// in the shared memory of one CTA, which stays resident over all hops of that chain
+// (n <= 13 complex64, n <= 12 complex128).  Thousands of chains = thousands of CTAs.
+//
+// Per hop (quantum_enhanced_mcmc, qumcmc/quantum_mcmc_routines.py:201-225):
+//   draws  -> gamma, t -> r, mixer group, u_measure, u_accept         (Philox, common.cuh)
+//   K1     -> phase table exp(+i c D(idx)), c = (1-gamma) alpha dt    (fn_qckt_problem_half :54-91)
+//   K2     -> U = M (P M)^{r-1}: X-string butterflies + pointwise phase (trotter :95-106, mixers.py)
+//   K3     -> block prefix-sum of |a|^2 + inverse CDF                 (QuantumState.sampling :153)
+//   K4     -> energy lookup + Metropolis accept                       (test_accept, classical_mcmc_routines.py:28-41)
+#include <math.h>
+
+#include "common.cuh"
+
+struct SmallParams {
+    int n, mode, phase_active, n_groups, max_terms;
+    int64_t n_hops;
+    uint64_t chain_id0, seed;
+    uint32_t hop0;
+    double temperature, g_lo, g_hi, dt, alpha;
+    const double *D, *E;
+    const int *group_off;
+    const uint64_t *masks;
+    const double *weights, *group_cum;
+    const uint64_t *s_in;
+    const double *gamma_arr;
+    const int *r_arr;
+    const double *u_arr;
+    const int *group_arr;
+    uint64_t *proposals;
+    uint8_t *accepted;
+    uint64_t *final_state;
+    int64_t *acc_count, *hamming_hist;
+    void *probs_out, *amps_out;
+};
+
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+
+// exp(i x) with the argument formed and range-reduced in fp64, evaluated in T
+__device__ __forceinline__ float2 phase_factor(double x, float) {
+    double t = x * 0.31830988618379067154;  // x / pi
+    t -= 2.0 * rint(0.5 * t);               // t in [-1, 1]
+    float s, c;
+    sincospif((float)t, &s, &c);
+    return make_float2(c, s);
+}
+__device__ __forceinline__ double2 phase_factor(double x, double) {
+    double s, c;
+    sincos(x, &s, &c);
+    return make_double2(c, s);
+}
+
+constexpr int SMALL_NT = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(SMALL_NT) smem_chain_kernel(const SmallParams p) {
+    using T2 = typename Vec2<T>::type;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int n = p.n;
+    const int N = 1 << n;
+    T2 *st = reinterpret_cast<T2 *>(smraw);
+    T2 *ph = st + N;
+    T2 *cs = ph + N;
+    __shared__ double s_incl[SMALL_NT];
+    __shared__ double s_warp[SMALL_NT / 32];
+    __shared__ unsigned long long s_sel;
+    __shared__ int s_hist[QMC_MAX_SPINS + 2];
+
+    const int tid = threadIdx.x;
+    const int NT = blockDim.x;
+    const int64_t chain = blockIdx.x;
+    const uint64_t gchain = p.chain_id0 + (uint64_t)chain;
+
+    uint64_t cur;
+    if (p.mode == QMC_MODE_CHAIN)
+        cur = p.s_in ? p.s_in[chain] : qmc_initial_state(p.seed, gchain, n);
+    else
+        cur = p.s_in[chain];
+    double e_cur = (p.mode == QMC_MODE_CHAIN) ? p.E[cur] : 0.0;
+    long long n_acc = 0;
+    for (int i = tid; i < n + 1; i += NT) s_hist[i] = 0;
+
+    const int64_t hops = (p.mode == QMC_MODE_CHAIN) ? p.n_hops : 1;
+    for (int64_t hop = 0; hop < hops; ++hop) {
+        // ---- draws (every thread computes the same values; no broadcast needed)
+        double gamma, u_meas, u_acc = 0.0;
+        int r, grp;
+        if (p.mode == QMC_MODE_CHAIN) {
+            const HopDraws d = qmc_hop_draws(p.seed, gchain, p.hop0 + (uint32_t)hop);
+            gamma = p.g_lo + (p.g_hi - p.g_lo) * d.u_gamma;
+            r = qmc_trotter_steps(d.t, p.dt);
+            grp = qmc_pick_group(p.n_groups, p.group_cum, d.u_group);
+            u_meas = d.u_meas;
+            u_acc = d.u_acc;
+        } else {
+            gamma = p.gamma_arr[chain];
+            r = p.r_arr[chain] < 1 ? 1 : p.r_arr[chain];
+            grp = p.group_arr ? p.group_arr[chain] : 0;
+            u_meas = p.u_arr ? p.u_arr[chain] : 0.0;
+        }
+        const int t0 = p.group_off[grp], t1 = p.group_off[grp + 1];
+        const int nterms = t1 - t0;
+
+        // ---- per-term rotation constants: exp(-i gamma w dt X_S) -> (cos, sin)
+        for (int k = tid; k < nterms; k += NT) {
+            double s, c;
+            sincos(gamma * p.weights[t0 + k] * p.dt, &s, &c);
+            T2 v;
+            v.x = (T)c;
+            v.y = (T)s;
+            cs[k] = v;
+        }
+        // ---- K1: phase table for this proposal (same c for all r-1 layers)
+        const bool phase = p.phase_active && r > 1;
+        if (phase) {
+            const double c = (1.0 - gamma) * p.alpha * p.dt;
+            for (int i = tid; i < N; i += NT) ph[i] = phase_factor(c * p.D[i], T(0));
+        }
+        // ---- |s>
+        for (int i = tid; i < N; i += NT) {
+            T2 z;
+            z.x = (i == (int)cur) ? T(1) : T(0);
+            z.y = T(0);
+            st[i] = z;
+        }
+        __syncthreads();
+
+        // ---- K2: M (P M)^{r-1}
+        for (int layer = 0; layer < r; ++layer) {
+            if (layer > 0 && phase) {
+                for (int i = tid; i < N; i += NT) {
+                    const T2 a = st[i], f = ph[i];
+                    T2 o;
+                    o.x = a.x * f.x - a.y * f.y;
+                    o.y = a.x * f.y + a.y * f.x;
+                    st[i] = o;
+                }
+                __syncthreads();
+            }
+            for (int k = 0; k < nterms; ++k) {
+                const uint64_t mask = p.masks[t0 + k];
+                const int tb = 63 - __clzll((long long)mask);
+                const int lowmask = (1 << tb) - 1;
+                const T c = cs[k].x, s = cs[k].y;
+                for (int q = tid; q < (N >> 1); q += NT) {
+                    const int i = ((q >> tb) << (tb + 1)) | (q & lowmask);
+                    const int j = i ^ (int)mask;
+                    const T2 a = st[i], b = st[j];
+                    T2 oa, ob;
+                    oa.x = c * a.x + s * b.y;
+                    oa.y = c * a.y - s * b.x;
+                    ob.x = c * b.x + s * a.y;
+                    ob.y = c * b.y - s * a.x;
+                    st[i] = oa;
+                    st[j] = ob;
+                }
+                __syncthreads();
+            }
+        }
+
+        if (p.mode == QMC_MODE_PROBS) {
+            T *po = reinterpret_cast<T *>(p.probs_out);
+            T2 *ao = reinterpret_cast<T2 *>(p.amps_out);
+            for (int i = tid; i < N; i += NT) {
+                const T2 a = st[i];
+                if (po) po[i] = a.x * a.x + a.y * a.y;
+                if (ao) ao[i] = a;
+            }
+            return;
+        }
+
+        // ---- K3: measurement. contiguous chunk per thread, fp64 accumulation, block scan
+        const int chunk = (N + NT - 1) / NT;
+        const int i0 = tid * chunk;
+        const int i1 = min(N, i0 + chunk);
+        double local = 0.0;
+        for (int i = i0; i < i1; ++i) {
+            const T2 a = st[i];
+            local += (double)(a.x * a.x + a.y * a.y);
+        }
+        double incl = local;
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        double base = 0.0;
+        for (int w = 0; w < warp; ++w) base += s_warp[w];
+        incl += base;
+        s_incl[tid] = incl;
+        __syncthreads();
+        const double total = s_incl[NT - 1];
+        const double target = u_meas * total;
+        const double lo = tid == 0 ? 0.0 : s_incl[tid - 1];
+        const double hi = incl;
+        const bool last_active = (i1 == N) && (i0 < N);
+        if (i0 < N && target >= lo && (target < hi || last_active)) {
+            double c = lo;
+            int sel = i1 - 1;
+            for (int i = i0; i < i1; ++i) {
+                const T2 a = st[i];
+                c += (double)(a.x * a.x + a.y * a.y);
+                if (target < c) {
+                    sel = i;
+                    break;
+                }
+            }
+            s_sel = (unsigned long long)sel;
+        }
+        __syncthreads();
+        const uint64_t sp = s_sel;
+
+        if (p.mode == QMC_MODE_PROPOSE) {
+            if (tid == 0) p.proposals[chain] = sp;
+            return;
+        }
+
+        // ---- K4: Metropolis accept (all threads evaluate identically)
+        const double e_sp = p.E[sp];
+        const bool acc = qmc_accept_dev(e_cur, e_sp, p.temperature, u_acc);
+        if (tid == 0) {
+            if (p.proposals) p.proposals[chain * p.n_hops + hop] = sp;
+            if (p.accepted) p.accepted[chain * p.n_hops + hop] = (uint8_t)acc;
+            s_hist[__popcll(cur ^ sp)] += 1;
+        }
+        if (acc) {
+            cur = sp;
+            e_cur = e_sp;
+            ++n_acc;
+        }
+        __syncthreads();  // st / s_sel reuse in the next hop
+    }
+
+    if (tid == 0) {
+        if (p.final_state) p.final_state[chain] = cur;
+        if (p.acc_count) p.acc_count[chain] = n_acc;
+    }
+    __syncthreads();
+    if (p.hamming_hist)
+        for (int i = tid; i < n + 1; i += NT) p.hamming_hist[chain * (n + 1) + i] = s_hist[i];
+}
+
+int qmc_small_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, const uint64_t *s_in,
+                  uint64_t chain_id0, uint32_t hop0, double temperature, double g_lo, double g_hi, double dt,
+                  uint64_t seed, int dtype, const double *gamma_arr, const int *r_arr, const double *u_arr,
+                  const int *group_arr, uint64_t *proposals, uint8_t *accepted, uint64_t *final_state,
+                  int64_t *acc_count, int64_t *hamming_hist, void *probs_out, void *amps_out, cudaStream_t st) {
+    SmallParams p;
+    p.n = m->n;
+    p.mode = mode;
+    p.phase_active = m->phase_active;
+    p.n_groups = m->n_groups;
+    p.max_terms = m->max_terms_in_group;
+    p.n_hops = n_hops;
+    p.chain_id0 = chain_id0;
+    p.seed = seed;
+    p.hop0 = hop0;
+    p.temperature = temperature;
+    p.g_lo = g_lo;
+    p.g_hi = g_hi;
+    p.dt = dt;
+    p.alpha = m->alpha;
+    p.D = m->dD;
+    p.E = m->dE;
+    p.group_off = m->d_group_off;
+    p.masks = m->d_masks;
+    p.weights = m->d_weights;
+    p.group_cum = m->d_group_cum;
+    p.s_in = s_in;
+    p.gamma_arr = gamma_arr;
+    p.r_arr = r_arr;
+    p.u_arr = u_arr;
+    p.group_arr = group_arr;
+    p.proposals = proposals;
+    p.accepted = accepted;
+    p.final_state = final_state;
+    p.acc_count = acc_count;
+    p.hamming_hist = hamming_hist;
+    p.probs_out = probs_out;
+    p.amps_out = amps_out;
+
+    const size_t N = (size_t)1 << m->n;
+    const size_t esz = dtype == QMC_DTYPE_F64 ? sizeof(double2) : sizeof(float2);
+    const size_t smem = (2 * N + (size_t)m->max_terms_in_group) * esz;
+    QMC_REQUIRE(smem <= 227 * 1024, QMC_ERR_UNSUPPORTED,
+                "shared-memory path: n=%d with %d mixer terms needs %zu B of shared memory (> 227 KiB)", m->n,
+                m->max_terms_in_group, smem);
+    QMC_REQUIRE(n_chains <= 0x7fffffffLL, QMC_ERR_BADARG, "too many chains for one launch");
+    if (n_chains == 0) return QMC_OK;
+    if (dtype == QMC_DTYPE_F64) {
+        QMC_CUDA_TRY(cudaFuncSetAttribute(smem_chain_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_chain_kernel<double><<<(unsigned)n_chains, SMALL_NT, smem, st>>>(p);
+    } else {
+        QMC_CUDA_TRY(cudaFuncSetAttribute(smem_chain_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_chain_kernel<float><<<(unsigned)n_chains, SMALL_NT, smem, st>>>(p);
+    }
+    m->launches++;
+    QMC_CUDA_TRY(cudaGetLastError());
+    return QMC_OK;
+}

@@ -1,0 +1,221 @@
+"""Pins the CPU oracle against the reference's own recorded outputs: notebook known-answers
+(tests/golden/known_answers.json) and recorded chains (tests/golden/chain_stats.json)."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import np_oracle as npo
+from tests import models
+
+KA = models.golden("known_answers.json")
+CS = models.golden("chain_stats.json")
+
+
+def test_qulacs_rotation_sign_vector():
+    # exp(+i*angle/2*(X0+X1)), angle = 1, on ket '10': a mixer term has angle -2*gamma*w*dt
+    exp = np.array([complex(re, im) for re, im in KA["qulacs_rotation_sign"]["amplitudes_re_im"]])
+    for gatewise in (True, False):
+        a = oracle.evolve(np.zeros((2, 2)), np.zeros(2), 1.0, -0.5, 1.0, 1, [1, 2], [1.0, 1.0], int("10", 2), gatewise)
+        assert np.allclose(a, exp, atol=1e-15)
+
+
+def test_bas3_bars_and_stripes_known_answers():
+    J, h, _ = models.bas3("both")
+    ka = KA["bas3_bars_stripes"]
+    assert oracle.alpha(J, h) == ka["alpha"]
+    assert oracle.energy(J, h, int(ka["state"], 2)) == ka["energy"]
+    _, _, P = oracle.exact_boltzmann(J, h, 1.0)
+    assert int((P > 0.01).sum()) == ka["n_states_gt_0.01_beta1"]
+    assert npo.entropy_ref(P) == pytest.approx(ka["entropy_beta_1.0"], abs=1e-12)
+    _, _, P = oracle.exact_boltzmann(J, h, 1.5)
+    assert npo.entropy_ref(P) == pytest.approx(ka["entropy_beta_1.5"], abs=1e-12)
+
+
+def test_bas3_bars_only_and_scaled():
+    J, h, _ = models.bas3("bars")
+    ka = KA["bas3_bars_only"]
+    assert oracle.alpha(J, h) == pytest.approx(ka["alpha"], rel=1e-15)
+    assert oracle.energy(J, h, int(ka["state"], 2)) == ka["energy"]
+    _, _, P = oracle.exact_boltzmann(J, h, 1.5)
+    assert int((P > 0.01).sum()) == ka["n_states_gt_0.01"]
+    assert npo.entropy_ref(P) == pytest.approx(ka["entropy_beta_1.5"], abs=1e-12)
+    J5, h5, data = models.bas3("both", scale=5.0)
+    ka5 = KA["bas3_times5"]
+    assert oracle.alpha(J5, h5) == pytest.approx(ka5["alpha"], rel=1e-15)
+    assert all(oracle.energy(J5, h5, int(s, 2)) == ka5["energy_data_states"] for s in data)
+    _, _, P = oracle.exact_boltzmann(J5, h5, 1.0)
+    assert npo.entropy_ref(P) == pytest.approx(ka5["entropy_beta_1.0"], abs=1e-12)
+
+
+def test_cardinality_and_random_models():
+    J, h, _ = models.cardinality_model(4, 2)
+    ka = KA["cardinality_4_2"]
+    assert oracle.alpha(J, h) == pytest.approx(ka["alpha"], rel=1e-15)
+    _, _, P = oracle.exact_boltzmann(J, h, 1.0)
+    assert npo.entropy_ref(P) == pytest.approx(ka["entropy_beta_1.0"], abs=1e-12)
+    J, h = models.recipe_b(10, 4)
+    kb = KA["recipe_b_n10_seed4"]
+    _, _, P = oracle.exact_boltzmann(J, h, 1.0)
+    assert int((P > 0.01).sum()) == kb["n_states_gt_0.01"]
+    assert npo.entropy_ref(P) == pytest.approx(kb["entropy_beta_1.0"], abs=1e-12)
+    kr = KA["random_ising_model_n5"]
+    for seed, cnt in zip(kr["seeds"], kr["n_states_gt_0.01"]):
+        J, h = models.packaged_random_model(5, seed)
+        _, _, P = oracle.exact_boltzmann(J, h, kr["beta"])
+        assert int((P > 0.01).sum()) == cnt
+        assert npo.entropy_ref(P) is None  # quirk Q7: no p <= 1e-5 is ever reached
+
+
+def test_rough_check_alpha():
+    np.random.seed(6)
+    n = 4
+    J = np.random.randn(n, n)
+    J = 0.5 * (J + J.transpose())
+    J = J - np.diag(np.diag(J))
+    h = np.random.randn(n)
+    # the notebook's exact recipe is not recoverable to the digit; alpha is pinned by formula instead
+    a = np.sqrt(n) / np.sqrt(sum(J[i][j] ** 2 for i in range(n) for j in range(i)) + sum(h ** 2))
+    assert oracle.alpha(J, h) == pytest.approx(a, rel=1e-15)
+
+
+def test_energy_matches_numpy_formula():
+    """Oracle = fixed sequential order; numpy = BLAS order. Equal to a few ulp, exact on integer models."""
+    rng = np.random.default_rng(0)
+    for n in (5, 9, 10, 16, 20):
+        J, h = models.packaged_random_model(n, 100 + n)
+        scale = np.abs(J).sum() + np.abs(h).sum()
+        for _ in range(200):
+            idx = int(rng.integers(0, 1 << n))
+            s = np.array([1 if (idx >> (n - 1 - j)) & 1 else -1 for j in range(n)])
+            e_np = 0.5 * np.dot(s.transpose(), J.dot(s)) + np.dot(h.transpose(), s)
+            assert abs(e_np - oracle.energy(J, h, idx)) <= 8 * np.finfo(float).eps * scale
+    J, h, _ = models.bas3("both")
+    for idx in range(512):
+        s = np.array([1 if (idx >> (8 - j)) & 1 else -1 for j in range(9)])
+        assert 0.5 * np.dot(s, J.dot(s)) + np.dot(h, s) == oracle.energy(J, h, idx)
+
+
+def test_phase_exponent_is_energy_of_complement():
+    """Quirk Q1: D(idx) = E(~idx) because the phase layer's h-term carries z = -s."""
+    J, h = models.recipe_b(8, 1)
+    for idx in range(0, 256, 7):
+        assert oracle.phase_D(J, h, idx) == pytest.approx(oracle.energy(J, h, (~idx) & 255), abs=1e-12)
+
+
+@pytest.mark.parametrize("n,terms", [(5, "one"), (6, "two"), (9, "bas")])
+def test_gatewise_equals_fused(n, terms):
+    J, h = models.recipe_b(n, 3)
+    if terms == "one":
+        masks, w = models.one_body(n)
+    elif terms == "two":
+        masks = [(1 << a) | (1 << b) for a in range(n) for b in range(a + 1, n)]
+        w = [1.0] * len(masks)
+    else:
+        masks = [1 << q for q in range(9)] + [0b111, 0b111000, 0b111000000]
+        w = [0.75] * 9 + [0.25] * 3
+    al = oracle.alpha(J, h)
+    for r in (1, 2, 5, 13):
+        a = oracle.evolve(J, h, al, 0.42, 0.8, r, masks, w, 3, gatewise=True)
+        b = oracle.evolve(J, h, al, 0.42, 0.8, r, masks, w, 3, gatewise=False)
+        assert np.abs(a - b).max() < 1e-13
+        assert abs(np.vdot(a, a).real - 1.0) < 1e-12
+
+
+def test_proposal_matrix_is_symmetric_and_stochastic():
+    J, h = models.recipe_b(5, 2)
+    masks, w = models.one_body(5)
+    U = npo.dense_unitary(J, h, oracle.alpha(J, h), 0.37, 0.8, 6, masks, w)
+    assert np.abs(U - U.T).max() < 1e-13          # U^T = U  =>  Q(s->s') = Q(s'->s)
+    assert np.abs(U.conj().T @ U - np.eye(32)).max() < 1e-12
+
+
+def test_trotter_converges_to_exact_unitary_path():
+    """quantum_mcmc_routines_exact.py: U = expm(-iHt). With the Trotter path's labelling
+    (reverse_labels=False) and dt -> 0 the first-order Trotter circuit converges to it."""
+    n = 4
+    J, h = models.recipe_b(n, 5)
+    al = oracle.alpha(J, h)
+    gamma, t = 0.45, 2
+    terms = npo.contiguous_x_mixer_terms(n, 1)
+    Uex = npo.exact_path_unitary(J, h, al, gamma, t, terms, reverse_labels=False, round_decimals=None)
+    errs = []
+    for dt in (0.02, 0.01):
+        r = int(round(t / dt))
+        masks, w = models.one_body(n)
+        a = oracle.evolve(J, h, al, gamma, dt, r, masks, w, 5, gatewise=False)
+        errs.append(np.abs(np.abs(a) ** 2 - np.abs(Uex[:, 5]) ** 2).max())
+    assert errs[1] < errs[0] < 2e-2 and errs[1] < 0.6 * errs[0]
+    # quirk Q10: the reference's exact path labels qubit i = spin i (reversed w.r.t. the strings)
+    Urev = npo.exact_path_unitary(J, h, al, gamma, t, terms, reverse_labels=True, round_decimals=6)
+    perm = [int(f"{k:0{n}b}"[::-1], 2) for k in range(1 << n)]
+    assert np.abs(np.abs(Urev[np.ix_(perm, perm)]) ** 2 - np.abs(Uex) ** 2).max() < 1e-5
+
+
+def test_philox_known_answer_and_draw_ranges():
+    # Random123 known-answer test for philox4x32-10 with counter/key = 0 and the pi digits
+    assert oracle.philox(0, 0, 0, 0).tolist() == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    w = oracle.philox(0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF)
+    assert w.tolist() == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    ts = set()
+    for hop in range(400):
+        ug, t, ugrp, um, ua = oracle.hop_draws(7, 3, hop)
+        assert 0 <= ug < 1 and 0 <= ugrp < 1 and 0 <= um < 1 and 0 <= ua < 1
+        ts.add(t)
+    assert ts == set(range(2, 12))
+    assert {oracle.trotter_steps(t, 0.8) for t in range(2, 12)} == {2, 3, 5, 6, 7, 8, 10, 11, 12, 13}  # quirk Q3
+
+
+def test_sampler_and_accept_semantics():
+    a = np.sqrt(np.array([0.1, 0.2, 0.3, 0.4])).astype(complex)
+    assert [oracle.sample_index(a, u) for u in (0.0, 0.0999, 0.1001, 0.2999, 0.3001, 0.5999, 0.6001, 0.9999)] == \
+        [0, 0, 1, 1, 2, 2, 3, 3]
+    assert oracle.test_accept(1.0, 0.0, 1.0, 0.999999)       # downhill always
+    assert oracle.test_accept(0.0, 1.0, 1.0, 0.36) and not oracle.test_accept(0.0, 1.0, 1.0, 0.37)  # e^-1 = 0.3679
+    assert oracle.test_accept(0.0, -1e6, 1e-3, 0.5)          # exp overflow -> inf -> min(1, inf) = 1
+
+
+def test_chain_fixture_bas_one_body_gamma_half():
+    """BAS 3x3, beta = 1.5, OneBodyMixer, gamma = 0.5: closed-form stationary acceptance and
+    proposal-Hamming distribution from the oracle's Q vs the reference's 5 recorded chains."""
+    J, h, _ = models.bas3("both")
+    masks, w = models.one_body(9)
+    Q = npo.proposal_matrix(J, h, masks, w, 0.5)
+    acc, ham = npo.stationary_chain_stats(J, h, Q, beta=1.5)
+    fx = CS["bas"]["BAS_new_code_final_plots_wt1.pkl"]
+    sem = max(fx["acceptance_std"], 0.004) / np.sqrt(fx["n_chains"])
+    assert abs(acc - fx["acceptance_mean"]) < 3 * sem + 0.004
+    assert np.abs(ham - np.array(fx["hamming_mean"])).max() < 0.01
+
+
+@pytest.mark.parametrize("fname,kind", [
+    ("BAS_new_code_final_plots_wt1_75_bars_info_symm_25_gamma_std.pkl", "coh_bars"),
+    ("BAS_new_code_final_plots_wt1_75_bars_info_symm_25_gamma_std_incoherent.pkl", "inc_bars"),
+])
+def test_chain_fixture_bas_mixer_sums(fname, kind):
+    """testing.py:56-73 mixers: CoherentMixerSum / IncoherentMixerSum (0.75 one-body, 0.25 bars)."""
+    J, h, _ = models.bas3("both")
+    one, w1 = models.one_body(9)
+    bars = [0b111, 0b111000, 0b111000000]
+    if kind == "coh_bars":
+        Q = npo.proposal_matrix(J, h, one + bars, [0.75] * 9 + [0.25] * 3, 0.5)
+    else:
+        Q = 0.75 * npo.proposal_matrix(J, h, one, w1, 0.5) + 0.25 * npo.proposal_matrix(J, h, bars, [1.0] * 3, 0.5)
+    acc, ham = npo.stationary_chain_stats(J, h, Q, beta=1.5)
+    fx = CS["bas"][fname]
+    assert abs(acc - fx["acceptance_mean"]) < 0.012
+    assert np.abs(ham - np.array(fx["hamming_mean"])).max() < 0.012
+
+
+@pytest.mark.parametrize("key", ["n8_seed1", "n8_seed2"])
+def test_chain_fixture_gamma_variation(key):
+    """gamma_variation/*.pkl: Recipe-B models, beta 1.5, single-X mixer, gamma ~ U(range)."""
+    fx = CS["gamma_variation"][key]
+    n, seed = fx["num_spins"], fx["seed"]
+    J, h = models.recipe_b(n, seed)
+    masks, w = models.one_body(n)
+    for rng_key, st in fx["ranges"].items():
+        lo, hi = eval(rng_key.split("=")[1])
+        Q = npo.proposal_matrix(J, h, masks, w, (lo, hi), n_gamma_nodes=6)
+        acc, _ = npo.stationary_chain_stats(J, h, Q, beta=1.5)
+        # one autocorrelated 10 000-hop chain: allow 0.03 absolute
+        assert abs(acc - st["acceptance"]) < 0.03, (rng_key, acc, st["acceptance"])
