@@ -160,17 +160,6 @@ __global__ void __launch_bounds__(SMALL_NT) smem_chain_kernel(const SmallParams 
             }
         }
 
-        if (p.mode == QMC_MODE_PROBS) {
-            T *po = reinterpret_cast<T *>(p.probs_out);
-            T2 *ao = reinterpret_cast<T2 *>(p.amps_out);
-            for (int i = tid; i < N; i += NT) {
-                const T2 a = st[i];
-                if (po) po[i] = a.x * a.x + a.y * a.y;
-                if (ao) ao[i] = a;
-            }
-            return;
-        }
-
         // ---- K3: measurement. contiguous chunk per thread, fp64 accumulation, block scan
         const int chunk = (N + NT - 1) / NT;
         const int i0 = tid * chunk;
@@ -196,6 +185,23 @@ __global__ void __launch_bounds__(SMALL_NT) smem_chain_kernel(const SmallParams 
         __syncthreads();
         const double total = s_incl[NT - 1];
         const double target = u_meas * total;
+        if (p.mode == QMC_MODE_PROBS) {
+            // normalised output: fp32 rotation constants drift the norm by ~1e-7 per gate
+            T *po = reinterpret_cast<T *>(p.probs_out);
+            T2 *ao = reinterpret_cast<T2 *>(p.amps_out);
+            const T inv = (T)(1.0 / total), inva = (T)(1.0 / sqrt(total));
+            for (int i = tid; i < N; i += NT) {
+                const T2 a = st[i];
+                if (po) po[i] = (a.x * a.x + a.y * a.y) * inv;
+                if (ao) {
+                    T2 o;
+                    o.x = a.x * inva;
+                    o.y = a.y * inva;
+                    ao[i] = o;
+                }
+            }
+            return;
+        }
         const double lo = tid == 0 ? 0.0 : s_incl[tid - 1];
         const double hi = incl;
         const bool last_active = (i1 == N) && (i0 < N);

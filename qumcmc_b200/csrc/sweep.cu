@@ -1,10 +1,891 @@
-// sweep.cu -- HBM-resident statevector path (n above the shared-memory limits). Placeholder.
+// sweep.cu -- HBM-resident statevector path for 14 <= n <= 20 (complex64), many chains in flight.
+//
+// The reference pays one memory pass per *gate* (n(n-1)/2 + n diagonal gates + n X rotations per
+// Trotter layer: qumcmc/quantum_mcmc_routines.py:54-106).  Here one proposal U = M (P M)^{r-1}
+// costs r sweeps over the 2^n amplitudes:
+//   * K1: all ZZ/Z gates of a layer collapse into the pointwise phase exp(+i c D(idx)); D comes from
+//     a fixed-point table (int32, resolution < 1e-7) and the phase is formed in integer turns
+//     (wrap-around = mod 2pi for free) before MUFU sin/cos.
+//   * K2: the one-body mixer factorises over qubits, M = M_lo M_hi (bits 0..11 | bits 12..n-1).
+//     Sweeps alternate between a LO tile (2^13 contiguous amplitudes) and a HI tile
+//     (bits [0,Lc) u [12,n)); sweep k applies the second half of layer k and, after the phase, the
+//     first half of layer k+1:   LO: M_lo(k) P M_lo(k+1)    HI: M_hi(k) P M_hi(k+1).
+//     The first sweep starts from the analytic product state M|s> (write-only) and the last sweep
+//     (always LO) is read-only: it emits sums of |a|^2 over 64-amplitude segments.
+//     Butterflies are in "tan form" a' = a - i tan(theta) b (2 FFMA per amplitude per qubit); the
+//     prod cos(theta) scale of each layer is folded into the phase factor.
+//     Each thread owns 64 amplitudes (6 qubits) in registers; the other qubits of the tile are
+//     reached by one register<->shared-memory transposition (XOR-swizzled, conflict-free).
+//   * K3: segment sums -> block scan -> inverse CDF; the selected tile is recomputed from the
+//     last written state (64 KiB) to resolve the index inside the segment.
+//   * K4: energies in the oracle's fixed fp64 order + Metropolis accept with Philox uniforms.
+//
+// Layout in HBM: state[chain][2^n] interleaved complex64 (8 B/amplitude), index order.
+#include <math.h>
+
+#include <algorithm>
+
 #include "common.cuh"
-struct SweepWorkspace { int dummy; };
-void qmc_sweep_free(qmc_model *m) { delete m->sweep; m->sweep = nullptr; }
-int qmc_sweep_run(qmc_model *m, int, int64_t, int64_t, const uint64_t *, uint64_t, uint32_t, double, double, double,
-                  double, uint64_t, int, const double *, const int *, const double *, const int *, uint64_t *,
-                  uint8_t *, uint64_t *, int64_t *, int64_t *, void *, void *, cudaStream_t) {
-    qmc_set_error("HBM sweep path not built yet (n=%d)", m->n);
+
+namespace {
+
+constexpr int TILE_BITS = 13;
+constexpr int TILE = 1 << TILE_BITS;
+constexpr int NT = 128;       // threads per CTA; 64 amplitudes per thread
+constexpr int LO_BITS = 12;   // qubits butterflied by the LO sweep
+constexpr int SEG = 64;       // amplitudes per measurement segment (= one thread's registers)
+
+struct ChainParams {
+    unsigned long long cur;
+    double e_cur;
+    double u_meas, u_acc;
+    long long n_acc;
+    int r;       // mixer layers of this proposal (>= 1)
+    int group;
+    int cfx;     // round(c/(2 pi) * 2^m), c = (1-gamma) alpha dt
+    int shift;   // k_fx + m - 32
+    float scale; // prod_q cos(theta_q)
+    int active;  // phase layer present
+    float tq[QMC_MAX_SPINS];  // tan(theta_q), theta_q = gamma w_q dt
+};
+
+struct SweepArgs {
+    int n;
+    float2 *state;            // [chains][2^n]
+    ChainParams *params;      // [chains]
+    const int *dfx_nat;       // D fixed point, index order
+    const int *dfx_lo;        // D fixed point, permuted for the LO B-layout: [tile][c 16][thread 128][4]
+    float *segsum;            // [chains][2^n / 64]
+    float *probs_out;         // PROBS mode: unnormalised |a|^2 (index order) or null
+    float2 *amps_out;
+};
+
+// ------------------------------------------------------------------------------------------
+// register-level pieces
+// ------------------------------------------------------------------------------------------
+// a' = a - i t b ; b' = b - i t a   on register bit `b`, for the bits set in ACTIVE
+template <int ACTIVE>
+__device__ __forceinline__ void bfly6(float2 (&v)[64], const float (&t)[6]) {
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        if (!((ACTIVE >> b) & 1)) continue;
+        const float tb = t[b];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            if (j & (1 << b)) continue;
+            const float2 a = v[j], c = v[j | (1 << b)];
+            v[j].x = fmaf(tb, c.y, a.x);
+            v[j].y = fmaf(-tb, c.x, a.y);
+            v[j | (1 << b)].x = fmaf(tb, a.y, c.x);
+            v[j | (1 << b)].y = fmaf(-tb, a.x, c.y);
+        }
+    }
+}
+
+// phase factor scale * exp(2 pi i * turns), turns = frac(D * c/(2 pi)) in 32-bit fixed point
+__device__ __forceinline__ float2 phase_from_fx(int dfx, int cfx, int shift, float scale) {
+    const long long p = (long long)dfx * (long long)cfx;
+    const int t32 = (int)(unsigned int)(p >> shift);  // wraps mod 1 turn
+    const float ang = (float)t32 * 1.4629180792671596e-09f;  // 2 pi / 2^32
+    float s, c;
+    __sincosf(ang, &s, &c);
+    return make_float2(c * scale, s * scale);
+}
+
+__device__ __forceinline__ void apply_phase(float2 &a, const float2 f) {
+    const float x = a.x * f.x - a.y * f.y;
+    const float y = a.x * f.y + a.y * f.x;
+    a.x = x;
+    a.y = y;
+}
+
+// amplitude of M|s0> at index idx (tan form incl. the layer scale):
+//   scale * prod_{q in idx^s0} (-i t_q)
+__device__ __forceinline__ float2 product_state_amp(float mag, int d) {
+    switch (d & 3) {
+        case 0: return make_float2(mag, 0.f);
+        case 1: return make_float2(0.f, -mag);
+        case 2: return make_float2(-mag, 0.f);
+        default: return make_float2(0.f, mag);
+    }
+}
+
+__device__ __forceinline__ int lo_swz(int local) { return local ^ (((local >> 6) & 7) << 1); }
+
+// ------------------------------------------------------------------------------------------
+// LO tile: 2^13 contiguous amplitudes, qubits 0..11 butterflied.
+//   A layout: regs = local bits 6..11; lane = bits 0..4; warp = bits (5, 12)   (coalesced HBM access)
+//   B layout: regs = local bits 0..5 (64 contiguous amplitudes); thread = bits 6..12
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lo_base_a(int tid) {
+    const int lane = tid & 31, w = tid >> 5;
+    return lane | ((w & 1) << 5) | ((w >> 1) << 12);
+}
+
+__device__ __forceinline__ void lo_load_a(float2 (&v)[64], const float2 *__restrict__ tile, int tid) {
+    const float2 *p = tile + lo_base_a(tid);
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = p[j << 6];
+}
+__device__ __forceinline__ void lo_store_a(const float2 (&v)[64], float2 *__restrict__ tile, int tid) {
+    float2 *p = tile + lo_base_a(tid);
+#pragma unroll
+    for (int j = 0; j < 64; ++j) p[j << 6] = v[j];
+}
+__device__ __forceinline__ void lo_a_to_smem(const float2 (&v)[64], float2 *sm, int tid) {
+    const int base = lo_base_a(tid);
+#pragma unroll
+    for (int j = 0; j < 64; ++j) sm[lo_swz(base | (j << 6))] = v[j];
+}
+__device__ __forceinline__ void lo_smem_to_a(float2 (&v)[64], const float2 *sm, int tid) {
+    const int base = lo_base_a(tid);
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = sm[lo_swz(base | (j << 6))];
+}
+__device__ __forceinline__ void lo_b_to_smem(const float2 (&v)[64], float2 *sm, int tid) {
+#pragma unroll
+    for (int j = 0; j < 64; j += 2) {
+        float4 x = make_float4(v[j].x, v[j].y, v[j + 1].x, v[j + 1].y);
+        *reinterpret_cast<float4 *>(&sm[lo_swz((tid << 6) | j)]) = x;
+    }
+}
+__device__ __forceinline__ void lo_smem_to_b(float2 (&v)[64], const float2 *sm, int tid) {
+#pragma unroll
+    for (int j = 0; j < 64; j += 2) {
+        const float4 x = *reinterpret_cast<const float4 *>(&sm[lo_swz((tid << 6) | j)]);
+        v[j] = make_float2(x.x, x.y);
+        v[j + 1] = make_float2(x.z, x.w);
+    }
+}
+
+__device__ __forceinline__ void load_tq(float (&t)[6], const float *tq, int q0) {
+#pragma unroll
+    for (int b = 0; b < 6; ++b) t[b] = tq[q0 + b];
+}
+
+// phase for the B layout: thread's 64 consecutive indices; permuted table => LDG.128 coalesced
+__device__ __forceinline__ void lo_phase_b(float2 (&v)[64], const int *__restrict__ dfx_lo, int64_t tile, int tid,
+                                           const ChainParams &cp) {
+    const int4 *p = reinterpret_cast<const int4 *>(dfx_lo) + (tile * 16) * NT + tid;
+    if (cp.active) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const int4 d = __ldg(p + c * NT);
+            apply_phase(v[4 * c + 0], phase_from_fx(d.x, cp.cfx, cp.shift, cp.scale));
+            apply_phase(v[4 * c + 1], phase_from_fx(d.y, cp.cfx, cp.shift, cp.scale));
+            apply_phase(v[4 * c + 2], phase_from_fx(d.z, cp.cfx, cp.shift, cp.scale));
+            apply_phase(v[4 * c + 3], phase_from_fx(d.w, cp.cfx, cp.shift, cp.scale));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            v[j].x *= cp.scale;
+            v[j].y *= cp.scale;
+        }
+    }
+}
+
+// M|s0> restricted to this thread's 64 amplitudes; reg bit b <-> global qubit qpos[b]
+template <typename QP>
+__device__ __forceinline__ void init_product(float2 (&v)[64], uint64_t base_idx, int n, const ChainParams &cp, QP qpos) {
+    // fixed part: all qubits outside the register bits
+    uint64_t regmask = 0;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) regmask |= 1ULL << qpos(b);
+    const uint64_t diff = (base_idx ^ cp.cur) & ~regmask;
+    float mag0 = cp.scale;
+    for (int q = 0; q < n; ++q)
+        if ((diff >> q) & 1ULL) mag0 *= cp.tq[q];
+    const int d0 = __popcll(diff);
+    float f[6];
+    int sbit[6];
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        f[b] = cp.tq[qpos(b)];
+        sbit[b] = (int)((cp.cur >> qpos(b)) & 1ULL);
+    }
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        float mag = mag0;
+        int d = d0;
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            const int differs = ((j >> b) & 1) ^ sbit[b];
+            mag *= differs ? f[b] : 1.0f;
+            d += differs;
+        }
+        v[j] = product_state_amp(mag, d);
+    }
+}
+
+struct LoQ0 { __device__ __forceinline__ int operator()(int b) const { return b; } };       // B layout: bits 0..5
+
+// Final LO computation for (chain, tile): leaves the final amplitudes of the tile in B layout.
+// Used by the last sweep (segment sums) and by the sampler (recompute of the selected tile).
+__device__ __forceinline__ void lo_final_tile(float2 (&v)[64], float2 *sm, const float2 *__restrict__ state_chain,
+                                              int64_t tile, int tid, int n, const ChainParams &cp) {
+    float t[6];
+    if (cp.r == 1) {
+        init_product(v, ((uint64_t)tile << TILE_BITS) | ((uint64_t)tid << 6), n, cp, LoQ0());
+        return;
+    }
+    lo_load_a(v, state_chain + (tile << TILE_BITS), tid);
+    load_tq(t, cp.tq, 6);
+    bfly6<63>(v, t);
+    lo_a_to_smem(v, sm, tid);
+    __syncthreads();
+    lo_smem_to_b(v, sm, tid);
+    load_tq(t, cp.tq, 0);
+    bfly6<63>(v, t);
+}
+
+// ------------------------------------------------------------------------------------------
+// HI tile for W = n - 12 X-qubits: local bits [0,Lc) <-> global [0,Lc), local [Lc,13) <-> global [12,n)
+//   A' layout: regs = local 7..12; lane = local 0..4; warp = local (5, 6)
+//   B' layout (W > 6 only): regs = local 5..10; lane = local 0..4; warp = local (11, 12)
+// Both layouts keep lanes on the 32 lowest amplitudes => coalesced HBM access and conflict-free smem.
+// ------------------------------------------------------------------------------------------
+template <int W>
+struct HiGeom {
+    static constexpr int Lc = TILE_BITS - W;
+    __host__ __device__ static constexpr int gpos(int i) { return i < Lc ? i : 12 + (i - Lc); }
+    __host__ __device__ static constexpr int64_t off_a(int j) {  // regs = local 7..12
+        int64_t o = 0;
+        for (int b = 0; b < 6; ++b)
+            if ((j >> b) & 1) o |= (int64_t)1 << gpos(7 + b);
+        return o;
+    }
+    __host__ __device__ static constexpr int64_t off_b(int j) {  // regs = local 5..10
+        int64_t o = 0;
+        for (int b = 0; b < 6; ++b)
+            if ((j >> b) & 1) o |= (int64_t)1 << gpos(5 + b);
+        return o;
+    }
+    static constexpr int active_a = W >= 6 ? 63 : (63 & ~((1 << (6 - W)) - 1));
+    static constexpr int active_b = W == 8 ? 3 : (W == 7 ? 2 : 0);
+    static constexpr bool two_rounds = W > 6;
+};
+
+template <int W> struct HiQA { __device__ __forceinline__ int operator()(int b) const { return HiGeom<W>::gpos(7 + b); } };
+template <int W> struct HiQB { __device__ __forceinline__ int operator()(int b) const { return HiGeom<W>::gpos(5 + b); } };
+
+template <int W>
+__device__ __forceinline__ int64_t hi_base_a(int tid, int64_t tile) {
+    using G = HiGeom<W>;
+    const int lane = tid & 31, w = tid >> 5;
+    return (int64_t)lane | ((int64_t)(w & 1) << G::gpos(5)) | ((int64_t)(w >> 1) << G::gpos(6)) | (tile << G::Lc);
+}
+template <int W>
+__device__ __forceinline__ int64_t hi_base_b(int tid, int64_t tile) {
+    using G = HiGeom<W>;
+    const int lane = tid & 31, w = tid >> 5;
+    return (int64_t)lane | ((int64_t)(w & 1) << G::gpos(11)) | ((int64_t)(w >> 1) << G::gpos(12)) | (tile << G::Lc);
+}
+__device__ __forceinline__ int hi_loc_a(int tid, int j) { return (tid & 31) | ((tid >> 5) << 5) | (j << 7); }
+__device__ __forceinline__ int hi_loc_b(int tid, int j) { return (tid & 31) | (j << 5) | ((tid >> 5) << 11); }
+
+template <int W, bool BLAYOUT>
+__device__ __forceinline__ void hi_phase(float2 (&v)[64], const int *__restrict__ dfx, int64_t base, const ChainParams &cp) {
+    using G = HiGeom<W>;
+    if (cp.active) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            const int d = __ldg(dfx + base + (BLAYOUT ? G::off_b(j) : G::off_a(j)));
+            apply_phase(v[j], phase_from_fx(d, cp.cfx, cp.shift, cp.scale));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            v[j].x *= cp.scale;
+            v[j].y *= cp.scale;
+        }
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void hi_tq_a(float (&t)[6], const float *tq) {
+#pragma unroll
+    for (int b = 0; b < 6; ++b) t[b] = tq[HiGeom<W>::gpos(7 + b)];
+}
+template <int W>
+__device__ __forceinline__ void hi_tq_b(float (&t)[6], const float *tq) {
+#pragma unroll
+    for (int b = 0; b < 6; ++b) t[b] = tq[HiGeom<W>::gpos(5 + b)];
+}
+
+// ------------------------------------------------------------------------------------------
+// the sweep kernel: grid = (tiles, chains); step k = 1..r_max
+// ------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(NT, 3) sweep_kernel(const SweepArgs a, const int step) {
+    using G = HiGeom<W>;
+    extern __shared__ __align__(16) float2 sm[];
+    __shared__ ChainParams cp_s;
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t chain = blockIdx.y;
+    {
+        const int r = a.params[chain].r;
+        if (step > r) return;  // this chain's proposal needs fewer sweeps
+    }
+    // stage the chain's parameters in shared memory (broadcast reads afterwards)
+    {
+        const int *src = reinterpret_cast<const int *>(a.params + chain);
+        int *dst = reinterpret_cast<int *>(&cp_s);
+        for (int i = tid; i < (int)(sizeof(ChainParams) / 4); i += NT) dst[i] = src[i];
+    }
+    __syncthreads();
+    const ChainParams &cp = cp_s;
+    const int n = a.n;
+    const int r = cp.r;
+    const bool first = (step == 1), last = (step == r);
+    const bool lo = ((r - step) & 1) == 0;
+    float2 *state = a.state + ((int64_t)chain << n);
+    float2 v[64];
+    float t[6];
+
+    if (lo) {
+        if (last) {
+            lo_final_tile(v, sm, state, tile, tid, n, cp);
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) s += v[j].x * v[j].x + v[j].y * v[j].y;
+            a.segsum[(chain << (n - 6)) + tile * NT + tid] = s;
+            if (a.probs_out) {
+                float *po = a.probs_out + ((int64_t)chain << n) + (tile << TILE_BITS) + (tid << 6);
+#pragma unroll
+                for (int j = 0; j < 64; ++j) po[j] = v[j].x * v[j].x + v[j].y * v[j].y;
+            }
+            if (a.amps_out) {
+                float2 *ao = a.amps_out + ((int64_t)chain << n) + (tile << TILE_BITS) + (tid << 6);
+#pragma unroll
+                for (int j = 0; j < 64; ++j) ao[j] = v[j];
+            }
+            return;
+        }
+        if (first) {
+            init_product(v, ((uint64_t)tile << TILE_BITS) | ((uint64_t)tid << 6), n, cp, LoQ0());
+        } else {
+            lo_load_a(v, state + (tile << TILE_BITS), tid);
+            load_tq(t, cp.tq, 6);
+            bfly6<63>(v, t);
+            lo_a_to_smem(v, sm, tid);
+            __syncthreads();
+            lo_smem_to_b(v, sm, tid);
+            load_tq(t, cp.tq, 0);
+            bfly6<63>(v, t);
+            __syncthreads();  // everyone has read the A->B transposition before smem is rewritten
+        }
+        lo_phase_b(v, a.dfx_lo, tile, tid, cp);
+        load_tq(t, cp.tq, 0);
+        bfly6<63>(v, t);
+        lo_b_to_smem(v, sm, tid);
+        __syncthreads();
+        lo_smem_to_a(v, sm, tid);
+        load_tq(t, cp.tq, 6);
+        bfly6<63>(v, t);
+        lo_store_a(v, state + (tile << TILE_BITS), tid);
+    } else {
+        // HI sweep (never the last one)
+        const int64_t base_a = hi_base_a<W>(tid, tile);
+        if (G::two_rounds) {
+            const int64_t base_b = hi_base_b<W>(tid, tile);
+            if (first) {
+                init_product(v, (uint64_t)base_b, n, cp, HiQB<W>());
+            } else {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] = state[base_a + G::off_a(j)];
+                hi_tq_a<W>(t, cp.tq);
+                bfly6<G::active_a>(v, t);
+#pragma unroll
+                for (int j = 0; j < 64; ++j) sm[hi_loc_a(tid, j)] = v[j];
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] = sm[hi_loc_b(tid, j)];
+                hi_tq_b<W>(t, cp.tq);
+                bfly6<G::active_b>(v, t);
+                __syncthreads();
+            }
+            hi_phase<W, true>(v, a.dfx_nat, base_b, cp);
+            hi_tq_b<W>(t, cp.tq);
+            bfly6<G::active_b>(v, t);
+#pragma unroll
+            for (int j = 0; j < 64; ++j) sm[hi_loc_b(tid, j)] = v[j];
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = sm[hi_loc_a(tid, j)];
+            hi_tq_a<W>(t, cp.tq);
+            bfly6<G::active_a>(v, t);
+#pragma unroll
+            for (int j = 0; j < 64; ++j) state[base_a + G::off_a(j)] = v[j];
+        } else {
+            hi_tq_a<W>(t, cp.tq);
+            if (first) {
+                init_product(v, (uint64_t)base_a, n, cp, HiQA<W>());
+            } else {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] = state[base_a + G::off_a(j)];
+                bfly6<G::active_a>(v, t);
+            }
+            hi_phase<W, false>(v, a.dfx_nat, base_a, cp);
+            bfly6<G::active_a>(v, t);
+#pragma unroll
+            for (int j = 0; j < 64; ++j) state[base_a + G::off_a(j)] = v[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-hop bookkeeping kernels
+// ------------------------------------------------------------------------------------------
+struct HopArgs {
+    int n, mode, n_groups, phase_active, k_fx;
+    int64_t n_chains, n_hops, hop;
+    uint64_t chain_id0, seed;
+    uint32_t hop0;
+    double temperature, g_lo, g_hi, dt, alpha;
+    const double *J, *h;
+    const int *group_off;
+    const uint64_t *masks;
+    const double *weights, *group_cum;
+    const uint64_t *s_in;
+    const double *gamma_arr;
+    const int *r_arr;
+    const double *u_arr;
+    const int *group_arr;
+    uint64_t *proposals;
+    uint8_t *accepted;
+    uint64_t *final_state;
+    int64_t *acc_count, *hamming_hist;
+    int *hist;  // [chains][n+1] running histogram
+};
+
+__device__ void fill_proposal_params(ChainParams &cp, const HopArgs &h, double gamma, int r, int grp) {
+    cp.r = r < 1 ? 1 : r;
+    cp.group = grp;
+    for (int q = 0; q < QMC_MAX_SPINS; ++q) cp.tq[q] = 0.f;
+    double scale = 1.0;
+    for (int k = h.group_off[grp]; k < h.group_off[grp + 1]; ++k) {
+        const int q = __ffsll((long long)h.masks[k]) - 1;
+        double s, c;
+        sincos(gamma * h.weights[k] * h.dt, &s, &c);
+        cp.tq[q] = (float)(s / c);
+        scale *= c;
+    }
+    cp.scale = (float)scale;
+    const double cprime = (1.0 - gamma) * h.alpha * h.dt * 0.15915494309189533577;  // c / (2 pi)
+    cp.active = h.phase_active && cp.r > 1 && cprime != 0.0;
+    int m = 0;
+    if (cp.active) {
+        m = (int)floor(log2(2147483647.0 / fabs(cprime)));
+        if (m > 40) m = 40;
+        if (m < 0) m = 0;
+    }
+    cp.cfx = cp.active ? (int)rint(ldexp(cprime, m)) : 0;
+    cp.shift = h.k_fx + m - 32;
+}
+
+__global__ void chains_init_kernel(const HopArgs h, ChainParams *params) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= h.n_chains) return;
+    ChainParams &cp = params[c];
+    uint64_t cur;
+    if (h.mode == QMC_MODE_CHAIN)
+        cur = h.s_in ? h.s_in[c] : qmc_initial_state(h.seed, h.chain_id0 + (uint64_t)c, h.n);
+    else
+        cur = h.s_in[c];
+    cp.cur = cur;
+    cp.e_cur = (h.mode == QMC_MODE_CHAIN) ? qmc_energy_dev(h.n, h.J, h.h, cur) : 0.0;
+    cp.n_acc = 0;
+    for (int i = 0; i <= h.n; ++i) h.hist[c * (h.n + 1) + i] = 0;
+}
+
+__global__ void hop_prepare_kernel(const HopArgs h, ChainParams *params) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= h.n_chains) return;
+    ChainParams &cp = params[c];
+    if (h.mode == QMC_MODE_CHAIN) {
+        const HopDraws d = qmc_hop_draws(h.seed, h.chain_id0 + (uint64_t)c, h.hop0 + (uint32_t)h.hop);
+        const double gamma = h.g_lo + (h.g_hi - h.g_lo) * d.u_gamma;
+        cp.u_meas = d.u_meas;
+        cp.u_acc = d.u_acc;
+        fill_proposal_params(cp, h, gamma, qmc_trotter_steps(d.t, h.dt), qmc_pick_group(h.n_groups, h.group_cum, d.u_group));
+    } else {
+        cp.u_meas = h.u_arr ? h.u_arr[c] : 0.0;
+        cp.u_acc = 0.0;
+        fill_proposal_params(cp, h, h.gamma_arr[c], h.r_arr[c], h.group_arr ? h.group_arr[c] : 0);
+    }
+}
+
+// K3 + K4: one CTA per chain
+__global__ void __launch_bounds__(NT) sample_accept_kernel(const SweepArgs a, const HopArgs h) {
+    extern __shared__ __align__(16) float2 sm[];
+    __shared__ ChainParams cp_s;
+    __shared__ double s_incl[NT];
+    __shared__ double s_warp[NT / 32];
+    __shared__ long long s_seg;
+    __shared__ double s_rem;
+    __shared__ unsigned long long s_sel;
+    const int tid = threadIdx.x;
+    const int64_t chain = blockIdx.x;
+    const int n = a.n;
+    {
+        const int *src = reinterpret_cast<const int *>(a.params + chain);
+        int *dst = reinterpret_cast<int *>(&cp_s);
+        for (int i = tid; i < (int)(sizeof(ChainParams) / 4); i += NT) dst[i] = src[i];
+    }
+    __syncthreads();
+    const ChainParams &cp = cp_s;
+    const int64_t nseg = 1LL << (n - 6);
+    const int64_t per = nseg / NT;  // >= 2 for n >= 14
+    const float *seg = a.segsum + (chain << (n - 6));
+    double local = 0.0;
+    for (int64_t i = 0; i < per; ++i) local += (double)seg[tid * per + i];
+    double incl = local;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double x = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += x;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    double base = 0.0;
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    incl += base;
+    s_incl[tid] = incl;
+    __syncthreads();
+    const double total = s_incl[NT - 1];
+    const double target = cp.u_meas * total;
+    const double lo = tid == 0 ? 0.0 : s_incl[tid - 1];
+    if (target >= lo && (target < incl || tid == NT - 1)) {
+        double c = lo;  // cumulative sum before segment i
+        int64_t sel = -1;
+        double before = 0.0;
+        for (int64_t i = 0; i < per; ++i) {
+            const double x = (double)seg[tid * per + i];
+            if (target < c + x) {
+                sel = tid * per + i;
+                before = c;
+                break;
+            }
+            c += x;
+        }
+        if (sel < 0) {  // rounding tail: last segment of this thread
+            sel = tid * per + per - 1;
+            before = c - (double)seg[sel];
+        }
+        s_seg = sel;
+        s_rem = target - before;
+    }
+    __syncthreads();
+    const int64_t sg = s_seg;
+    const int64_t tile = sg / NT;
+    const int owner = (int)(sg % NT);
+    float2 v[64];
+    lo_final_tile(v, sm, a.state + ((int64_t)chain << n), tile, tid, n, cp);
+    if (tid == owner) {
+        const double rem = s_rem;
+        double c = 0.0;
+        int selj = 63;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            c += (double)(v[j].x * v[j].x + v[j].y * v[j].y);
+            if (selj == 63 && rem < c) selj = j;
+        }
+        s_sel = ((unsigned long long)tile << TILE_BITS) | ((unsigned long long)owner << 6) | (unsigned long long)selj;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint64_t sp = s_sel;
+        ChainParams &out = a.params[chain];
+        if (h.mode == QMC_MODE_PROPOSE) {
+            h.proposals[chain] = sp;
+        } else {
+            const double e_sp = qmc_energy_dev(n, h.J, h.h, sp);
+            const bool acc = qmc_accept_dev(cp.e_cur, e_sp, h.temperature, cp.u_acc);
+            if (h.proposals) h.proposals[chain * h.n_hops + h.hop] = sp;
+            if (h.accepted) h.accepted[chain * h.n_hops + h.hop] = (uint8_t)acc;
+            h.hist[chain * (n + 1) + __popcll(cp.cur ^ sp)] += 1;
+            if (acc) {
+                out.cur = sp;
+                out.e_cur = e_sp;
+                out.n_acc = cp.n_acc + 1;
+            }
+        }
+    }
+}
+
+__global__ void chains_finish_kernel(const HopArgs h, const ChainParams *params) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= h.n_chains) return;
+    if (h.final_state) h.final_state[c] = params[c].cur;
+    if (h.acc_count) h.acc_count[c] = params[c].n_acc;
+    if (h.hamming_hist)
+        for (int i = 0; i <= h.n; ++i) h.hamming_hist[c * (h.n + 1) + i] = h.hist[c * (h.n + 1) + i];
+}
+
+// PROBS mode: divide by the total norm (tan-form butterflies are unnormalised only by rounding)
+__global__ void probs_normalize_kernel(int n, const float *segsum, float *probs, float2 *amps) {
+    __shared__ double red[256];
+    const int64_t nseg = 1LL << (n - 6);
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < nseg; i += blockDim.x) s += (double)segsum[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    const double total = red[0];
+    const float inv = (float)(1.0 / total), inva = (float)(1.0 / sqrt(total));
+    const int64_t N = 1LL << n;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        if (probs) probs[i] *= inv;
+        if (amps) {
+            amps[i].x *= inva;
+            amps[i].y *= inva;
+        }
+    }
+}
+
+// D -> fixed point tables
+__global__ void dfx_tables_kernel(int n, const double *__restrict__ D, double scale, int *__restrict__ nat,
+                                  int *__restrict__ lo) {
+    const int64_t N = 1LL << n;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < N; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)rint(D[idx] * scale);
+        nat[idx] = v;
+        // LO B-layout: idx = tile*8192 + thread*64 + c*4 + e  ->  [tile][c][thread][e]
+        const int64_t tile = idx >> TILE_BITS;
+        const int thread = (int)(idx >> 6) & 127, c = (int)(idx >> 2) & 15, e = (int)idx & 3;
+        lo[((tile * 16 + c) * NT + thread) * 4 + e] = v;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct SweepWorkspace {
+    int64_t cap_chains = 0;
+    float2 *state = nullptr;
+    ChainParams *params = nullptr;
+    float *segsum = nullptr;
+    int *hist = nullptr;
+    int *dfx_nat = nullptr, *dfx_lo = nullptr;
+    int k_fx = 0;
+    std::vector<cudaEvent_t> ev;
+};
+
+void qmc_sweep_free(qmc_model *m) {
+    SweepWorkspace *w = m->sweep;
+    if (!w) return;
+    cudaFree(w->state);
+    cudaFree(w->params);
+    cudaFree(w->segsum);
+    cudaFree(w->hist);
+    cudaFree(w->dfx_nat);
+    cudaFree(w->dfx_lo);
+    for (auto e : w->ev) cudaEventDestroy(e);
+    delete w;
+    m->sweep = nullptr;
+}
+
+static int ensure_workspace(qmc_model *m, int64_t chains, cudaStream_t st) {
+    if (!m->sweep) m->sweep = new SweepWorkspace();
+    SweepWorkspace *w = m->sweep;
+    const int n = m->n;
+    const int64_t N = 1LL << n;
+    if (!w->dfx_nat) {
+        double dmax = 0.0;
+        for (int j = 0; j < n; ++j) {
+            dmax += fabs(m->host_ch[j]);
+            for (int k = j + 1; k < n; ++k) dmax += fabs(m->host_cJ[(size_t)j * n + k]);
+        }
+        if (dmax < 1e-300) dmax = 1.0;
+        w->k_fx = (int)floor(log2(2147483647.0 / (dmax * 1.0000001)));
+        if (w->k_fx > 30) w->k_fx = 30;
+        QMC_CUDA_TRY(cudaMalloc(&w->dfx_nat, sizeof(int) * (size_t)N));
+        QMC_CUDA_TRY(cudaMalloc(&w->dfx_lo, sizeof(int) * (size_t)N));
+        dfx_tables_kernel<<<148 * 8, 256, 0, st>>>(n, m->dD, ldexp(1.0, w->k_fx), w->dfx_nat, w->dfx_lo);
+        m->launches++;
+        QMC_CUDA_TRY(cudaGetLastError());
+    }
+    if (chains > w->cap_chains) {
+        QMC_CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(w->state); cudaFree(w->params); cudaFree(w->segsum); cudaFree(w->hist);
+        w->state = nullptr; w->params = nullptr; w->segsum = nullptr; w->hist = nullptr;
+        w->cap_chains = 0;
+        QMC_CUDA_TRY(cudaMalloc(&w->state, sizeof(float2) * (size_t)N * chains));
+        QMC_CUDA_TRY(cudaMalloc(&w->params, sizeof(ChainParams) * chains));
+        QMC_CUDA_TRY(cudaMalloc(&w->segsum, sizeof(float) * (size_t)(N >> 6) * chains));
+        QMC_CUDA_TRY(cudaMalloc(&w->hist, sizeof(int) * (size_t)(n + 1) * chains));
+        w->cap_chains = chains;
+    }
+    return QMC_OK;
+}
+
+template <int W>
+static int launch_sweep(const SweepArgs &a, int step, int64_t tiles, int64_t chains, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        QMC_CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 8));
+        attr_set = true;
+    }
+    sweep_kernel<W><<<dim3((unsigned)tiles, (unsigned)chains), NT, TILE * 8, st>>>(a, step);
+    return QMC_OK;
+}
+
+static int launch_sweep_n(int n, const SweepArgs &a, int step, int64_t tiles, int64_t chains, cudaStream_t st) {
+    switch (n - LO_BITS) {
+        case 2: return launch_sweep<2>(a, step, tiles, chains, st);
+        case 3: return launch_sweep<3>(a, step, tiles, chains, st);
+        case 4: return launch_sweep<4>(a, step, tiles, chains, st);
+        case 5: return launch_sweep<5>(a, step, tiles, chains, st);
+        case 6: return launch_sweep<6>(a, step, tiles, chains, st);
+        case 7: return launch_sweep<7>(a, step, tiles, chains, st);
+        case 8: return launch_sweep<8>(a, step, tiles, chains, st);
+    }
+    qmc_set_error("sweep path: n=%d outside [14, 20]", n);
     return QMC_ERR_UNSUPPORTED;
+}
+
+int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, const uint64_t *s_in, uint64_t chain_id0,
+                  uint32_t hop0, double temperature, double g_lo, double g_hi, double dt, uint64_t seed, int dtype,
+                  const double *gamma_arr, const int *r_arr, const double *u_arr, const int *group_arr,
+                  uint64_t *proposals, uint8_t *accepted, uint64_t *final_state, int64_t *acc_count,
+                  int64_t *hamming_hist, void *probs_out, void *amps_out, cudaStream_t st) {
+    const int n = m->n;
+    QMC_REQUIRE(dtype == QMC_DTYPE_F32, QMC_ERR_UNSUPPORTED,
+                "complex128 statevectors are supported on the shared-memory path only (n <= %d); n=%d needs dtype fp32",
+                QMC_SMEM_MAX_SPINS_F64, n);
+    QMC_REQUIRE(n >= 14 && n <= 20, QMC_ERR_UNSUPPORTED, "HBM sweep path covers 14 <= n <= 20 in this build (n=%d)", n);
+    QMC_REQUIRE(m->all_one_body, QMC_ERR_UNSUPPORTED,
+                "n=%d > %d: only one-body X mixers have an HBM sweep path (k-body/custom mixers: shared-memory path)", n,
+                QMC_SMEM_MAX_SPINS_F32);
+    if (n_chains == 0) return QMC_OK;
+    static bool smem_attr = false;
+    if (!smem_attr) {
+        QMC_CUDA_TRY(cudaFuncSetAttribute(sample_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 8));
+        smem_attr = true;
+    }
+    const int64_t N = 1LL << n;
+    const int64_t tiles = N >> TILE_BITS;
+    // chains per batch: bounded by free memory (state dominates)
+    size_t free_b = 0, total_b = 0;
+    QMC_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const size_t per_chain = sizeof(float2) * (size_t)N + sizeof(float) * (size_t)(N >> 6) + sizeof(ChainParams) + 256;
+    SweepWorkspace *w0 = m->sweep;
+    const size_t have = w0 ? (size_t)w0->cap_chains * per_chain : 0;
+    int64_t cap = (int64_t)(((double)(free_b + have) * 0.85) / (double)per_chain);
+    if (cap > 65535) cap = 65535;  // gridDim.y
+    QMC_REQUIRE(cap >= 1, QMC_ERR_CUDA, "not enough device memory for one 2^%d statevector", n);
+    const int64_t batch = std::min<int64_t>(cap, n_chains);
+    int rc = ensure_workspace(m, batch, st);
+    if (rc != QMC_OK) return rc;
+    SweepWorkspace *w = m->sweep;
+
+    const int r_cap = qmc_trotter_steps(11, dt);
+    int r_max = r_cap;
+    std::vector<int> r_host;
+    if (mode != QMC_MODE_CHAIN) {
+        r_host.resize(n_chains);
+        QMC_CUDA_TRY(cudaMemcpyAsync(r_host.data(), r_arr, sizeof(int) * n_chains, cudaMemcpyDeviceToHost, st));
+        QMC_CUDA_TRY(cudaStreamSynchronize(st));
+        r_max = 1;
+        for (int64_t c = 0; c < n_chains; ++c) r_max = std::max(r_max, r_host[c]);
+    }
+
+    for (int64_t c0 = 0; c0 < n_chains; c0 += batch) {
+        const int64_t nc = std::min<int64_t>(batch, n_chains - c0);
+        HopArgs h;
+        h.n = n; h.mode = mode; h.n_groups = m->n_groups; h.phase_active = m->phase_active; h.k_fx = w->k_fx;
+        h.n_chains = nc; h.n_hops = n_hops; h.hop = 0;
+        h.chain_id0 = chain_id0 + (uint64_t)c0; h.seed = seed; h.hop0 = hop0;
+        h.temperature = temperature; h.g_lo = g_lo; h.g_hi = g_hi; h.dt = dt; h.alpha = m->alpha;
+        h.J = m->dJ; h.h = m->dh;
+        h.group_off = m->d_group_off; h.masks = m->d_masks; h.weights = m->d_weights; h.group_cum = m->d_group_cum;
+        h.s_in = s_in ? s_in + c0 : nullptr;
+        h.gamma_arr = gamma_arr ? gamma_arr + c0 : nullptr;
+        h.r_arr = r_arr ? r_arr + c0 : nullptr;
+        h.u_arr = u_arr ? u_arr + c0 : nullptr;
+        h.group_arr = group_arr ? group_arr + c0 : nullptr;
+        h.proposals = proposals ? proposals + (mode == QMC_MODE_CHAIN ? c0 * n_hops : c0) : nullptr;
+        h.accepted = accepted ? accepted + c0 * n_hops : nullptr;
+        h.final_state = final_state ? final_state + c0 : nullptr;
+        h.acc_count = acc_count ? acc_count + c0 : nullptr;
+        h.hamming_hist = hamming_hist ? hamming_hist + c0 * (n + 1) : nullptr;
+        h.hist = w->hist;
+        SweepArgs a;
+        a.n = n; a.state = w->state; a.params = w->params; a.dfx_nat = w->dfx_nat; a.dfx_lo = w->dfx_lo;
+        a.segsum = w->segsum;
+        a.probs_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float *>(probs_out) : nullptr;
+        a.amps_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float2 *>(amps_out) : nullptr;
+        // PROBS with amps only: still need a probs-free normalisation; handled by the normalise kernel
+
+        const int gb = (int)((nc + 127) / 128);
+        chains_init_kernel<<<gb, 128, 0, st>>>(h, w->params);
+        m->launches++;
+        const int64_t hops = mode == QMC_MODE_CHAIN ? n_hops : 1;
+        for (int64_t hop = 0; hop < hops; ++hop) {
+            h.hop = hop;
+            hop_prepare_kernel<<<gb, 128, 0, st>>>(h, w->params);
+            m->launches++;
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (m->profile) {
+                QMC_CUDA_TRY(cudaEventCreate(&e0));
+                QMC_CUDA_TRY(cudaEventCreate(&e1));
+                QMC_CUDA_TRY(cudaEventRecord(e0, st));
+            }
+            for (int step = 1; step <= r_max; ++step) {
+                rc = launch_sweep_n(n, a, step, tiles, nc, st);
+                if (rc != QMC_OK) return rc;
+                m->launches++;
+            }
+            if (m->profile) {
+                QMC_CUDA_TRY(cudaEventRecord(e1, st));
+                w->ev.push_back(e0);
+                w->ev.push_back(e1);
+                // algorithmic bytes of this hop: 2 * 2^n * 8 B * r per chain
+                double sum_r = 0.0;
+                for (int64_t c = 0; c < nc; ++c) {
+                    if (mode == QMC_MODE_CHAIN) {
+                        const HopDraws d = qmc_hop_draws(seed, h.chain_id0 + (uint64_t)c, hop0 + (uint32_t)hop);
+                        sum_r += qmc_trotter_steps(d.t, dt);
+                    } else {
+                        sum_r += std::max(1, r_host[c0 + c]);
+                    }
+                }
+                m->prof_bytes += 2.0 * (double)N * 8.0 * sum_r;
+                m->prof_launches += r_max;
+            }
+            if (mode == QMC_MODE_PROBS) {
+                probs_normalize_kernel<<<148 * 4, 256, 0, st>>>(n, w->segsum, a.probs_out, a.amps_out);
+                m->launches++;
+            } else {
+                sample_accept_kernel<<<(unsigned)nc, NT, TILE * 8, st>>>(a, h);
+                m->launches++;
+            }
+            QMC_CUDA_TRY(cudaGetLastError());
+        }
+        if (mode == QMC_MODE_CHAIN) {
+            chains_finish_kernel<<<gb, 128, 0, st>>>(h, w->params);
+            m->launches++;
+        }
+        QMC_CUDA_TRY(cudaGetLastError());
+        if (m->profile) {
+            QMC_CUDA_TRY(cudaStreamSynchronize(st));
+            for (size_t i = 0; i + 1 < w->ev.size(); i += 2) {
+                float ms = 0.f;
+                QMC_CUDA_TRY(cudaEventElapsedTime(&ms, w->ev[i], w->ev[i + 1]));
+                m->prof_ms += ms;
+                cudaEventDestroy(w->ev[i]);
+                cudaEventDestroy(w->ev[i + 1]);
+            }
+            w->ev.clear();
+        }
+    }
+    return QMC_OK;
 }

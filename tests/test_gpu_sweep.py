@@ -1,0 +1,167 @@
+"""GPU parity for the HBM sweep path (14 <= n <= 20, complex64): transition probabilities,
+measurement indices and chain bookkeeping vs the CPU oracle; full-size properties at n = 20."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import np_oracle as npo
+from tests import models
+
+pytestmark = pytest.mark.gpu
+
+
+def _api():
+    import qumcmc_b200 as q
+    return q
+
+
+def _setup(n, seed=3):
+    q = _api()
+    J, h = models.packaged_random_model(n, seed)
+    m = q.IsingEnergyFunction(J, h)
+    mx = q.GenericMixer.OneBodyMixer(n)
+    masks, w = models.one_body(n)
+    return q, J, h, m, mx, masks, w
+
+
+@pytest.mark.parametrize("n", [14, 15, 16, 17, 18, 19, 20])
+def test_sweep_transition_probabilities(n):
+    """Every tile geometry (W = n-12 = 2..8), LO-first (odd r) and HI-first (even r) schedules."""
+    q, J, h, m, mx, masks, w = _setup(n)
+    al = oracle.alpha(J, h)
+    rng = np.random.default_rng(n)
+    rs = (1, 2, 3, 6, 13) if n <= 18 else (2, 3, 8)
+    for r in rs:
+        s = int(rng.integers(0, 1 << n))
+        gamma = float(rng.uniform(0.25, 0.6))
+        p, a = q.transition_probabilities(m, mx, s, gamma, r, dtype="fp32", return_amplitudes=True)
+        ref = oracle.evolve(J, h, al, gamma, 0.8, r, masks, w, s, gatewise=False)
+        pref = np.abs(ref) ** 2
+        assert abs(p.sum() - 1.0) < 1e-5
+        assert np.abs(p - pref).max() < 1e-6, (n, r)                      # north-star tolerance (fp32)
+        assert np.linalg.norm(a - ref) < 2e-5, (n, r, np.linalg.norm(a - ref))  # relative L2 (|ref| = 1)
+
+
+def test_sweep_gamma_extremes_and_skip_rule():
+    q, J, h, m, mx, masks, w = _setup(15, seed=8)
+    al = oracle.alpha(J, h)
+    for gamma in (0.01, 0.95):
+        p = q.transition_probabilities(m, mx, 77, gamma, 7, dtype="fp32")
+        ref = oracle.transition_probs(J, h, al, gamma, 0.8, 7, masks, w, 77, gatewise=False)
+        assert np.abs(p - ref).max() < 1e-6
+    n = 14
+    Jz = np.full((n, n), 4e-4); np.fill_diagonal(Jz, 0.0)
+    hz = np.full(n, 4e-4)
+    mz = q.IsingEnergyFunction(Jz, hz)
+    mk, wk = models.one_body(n)
+    p = q.transition_probabilities(mz, q.GenericMixer.OneBodyMixer(n), 5, 0.3, 6, dtype="fp32")
+    ref = oracle.transition_probs(Jz, hz, oracle.alpha(Jz, hz), 0.3, 0.8, 6, mk, wk, 5, gatewise=False)
+    assert np.abs(p - ref).max() < 1e-6
+
+
+@pytest.mark.parametrize("n,C", [(14, 96), (16, 64), (20, 24)])
+def test_sweep_propose_indices(n, C):
+    """qmc_propose with explicit (s, gamma, r, u): the sampled index equals the oracle's sequential
+    inverse CDF except where u sits within fp32 rounding of a CDF boundary."""
+    import torch
+    from qumcmc_b200 import _lib
+    q, J, h, m, mx, masks, w = _setup(n, seed=5)
+    dm = m.device_model(0)
+    dm.set_mixer(mx)
+    rng = np.random.default_rng(n)
+    s_in = rng.integers(0, 1 << n, size=C).astype(np.int64)
+    gam = rng.uniform(0.25, 0.6, size=C)
+    rr = rng.choice([1, 2, 3, 5, 6, 7, 8, 10, 11, 12, 13], size=C).astype(np.int32)
+    uu = rng.uniform(0, 1, size=C)
+    dev = torch.device("cuda", 0)
+    t = lambda x: torch.from_numpy(x).to(dev)
+    d_s, d_g, d_r, d_u = t(s_in), t(gam), t(rr), t(uu)
+    out = torch.empty(C, dtype=torch.int64, device=dev)
+    _lib.check(_lib.lib().qmc_propose(dm.handle, C, d_s.data_ptr(), d_g.data_ptr(), d_r.data_ptr(), d_u.data_ptr(),
+                                      None, 0.8, _lib.DTYPE_F32, out.data_ptr(), None))
+    got = out.cpu().numpy()
+    al = oracle.alpha(J, h)
+    near = 0
+    for c in range(C):
+        st = oracle.evolve(J, h, al, gam[c], 0.8, int(rr[c]), masks, w, int(s_in[c]), gatewise=False)
+        exp = oracle.sample_index(st, uu[c])
+        if exp != got[c]:
+            cdf = np.cumsum(np.abs(st) ** 2)
+            # the fp32 CDF may be off by ~1e-6: the device index must be a neighbour in CDF terms
+            lo = cdf[got[c] - 1] if got[c] > 0 else 0.0
+            assert lo - 5e-6 <= uu[c] <= cdf[got[c]] + 5e-6, (c, exp, int(got[c]))
+            near += 1
+    assert near <= max(2, C // 3)
+
+
+def test_sweep_chain_bookkeeping_exact():
+    """K4 is independent of the statevector numerics: given the device's proposals, the accept
+    flags, acceptance counts, final states and Hamming histograms must equal the oracle's
+    Metropolis rule with the same Philox uniforms, bit for bit."""
+    q, J, h, m, mx, masks, w = _setup(14, seed=9)
+    C, H, seed, beta = 48, 40, 99, 1.0
+    b = q.quantum_enhanced_mcmc(H, m, mx, (0.25, 0.6), temperature=1 / beta, n_chains=C, seed=seed, dtype="fp32",
+                                chain_id0=5)
+    for c in range(C):
+        cur = oracle.initial_state(seed, 5 + c, 14)
+        assert int(b.initial[c]) == cur
+        e_cur = oracle.energy(J, h, cur)
+        nacc = 0
+        hist = np.zeros(15, dtype=np.int64)
+        for hop in range(H):
+            _, _, _, _, ua = oracle.hop_draws(seed, 5 + c, hop)
+            sp = int(b.proposals[c, hop])
+            e_sp = oracle.energy(J, h, sp)
+            acc = oracle.test_accept(e_cur, e_sp, 1 / beta, ua)
+            assert bool(b.accepted[c, hop]) == acc
+            hist[bin(cur ^ sp).count("1")] += 1
+            if acc:
+                cur, e_cur = sp, e_sp
+                nacc += 1
+        assert int(b.final_state[c]) == cur and int(b.acc_count[c]) == nacc
+        assert np.array_equal(b.hamming_hist[c], hist)
+
+
+def test_sweep_chain_statistics_vs_oracle_chains():
+    """Acceptance rate and proposal-Hamming distribution at n = 14 vs oracle chains (same model,
+    different random streams are fine: compare distributions)."""
+    q, J, h, m, mx, masks, w = _setup(14, seed=4)
+    beta = 1.0
+    b = q.quantum_enhanced_mcmc(60, m, mx, (0.25, 0.6), temperature=1 / beta, n_chains=256, seed=7, dtype="fp32")
+    acc_gpu = b.acceptance_rate()
+    ham_gpu = b.hamming_hist.sum(axis=0) / b.hamming_hist.sum()
+    accs, hams = [], np.zeros(15)
+    for c in range(24):
+        s0 = oracle.initial_state(7, c, 14)
+        props, acc = oracle.run_chain(J, h, masks, w, s0, 60, 1 / beta, (0.25, 0.6), 0.8, 7, chain_id=c)
+        accs.append(acc.mean())
+        mc = npo.markov_chain_from(s0, props, acc)
+        hams += np.bincount([bin(int(x) ^ int(y)).count("1") for x, y in zip(mc[:-1], props)], minlength=15)
+    assert abs(acc_gpu - np.mean(accs)) < 0.03
+    assert np.abs(ham_gpu - hams / hams.sum()).max() < 0.03
+
+
+def test_sweep_full_size_properties_n20():
+    """BASELINE config C3 shape (n = 20): norm conservation through 13 layers, symmetry
+    Q(s->s') = Q(s'->s) (U^T = U), and chain-sharding invariance of the Philox streams."""
+    q, J, h, m, mx, masks, w = _setup(20, seed=1)
+    s, sp = 123456, 654321
+    p1 = q.transition_probabilities(m, mx, s, 0.4, 13, dtype="fp32")
+    p2 = q.transition_probabilities(m, mx, sp, 0.4, 13, dtype="fp32")
+    assert abs(p1.sum() - 1.0) < 1e-5
+    assert abs(p1[sp] - p2[s]) < 1e-9 + 1e-4 * p1[sp]
+    full = q.quantum_enhanced_mcmc(3, m, mx, (0.25, 0.6), temperature=1.0, n_chains=8, seed=5, dtype="fp32")
+    half = q.quantum_enhanced_mcmc(3, m, mx, (0.25, 0.6), temperature=1.0, n_chains=4, seed=5, dtype="fp32", chain_id0=4)
+    assert np.array_equal(full.proposals[4:], half.proposals)
+    assert np.array_equal(full.accepted[4:], half.accepted)
+
+
+def test_unsupported_configurations_fail_loudly():
+    q = _api()
+    from qumcmc_b200 import _lib
+    J, h = models.packaged_random_model(16, 2)
+    m = q.IsingEnergyFunction(J, h)
+    with pytest.raises(_lib.QmcUnsupported):   # no k-body sweep path, and no CPU fallback
+        q.transition_probabilities(m, q.GenericMixer.TwoBodyMixer(16), 0, 0.3, 2, dtype="fp32")
+    with pytest.raises(_lib.QmcUnsupported):
+        q.transition_probabilities(m, q.GenericMixer.OneBodyMixer(16), 0, 0.3, 2, dtype="fp64")
