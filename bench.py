@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- quantum proposals/sec on BASELINE config C3: n = 20 random Ising
+(random_ising_model(20, seed=1), qumcmc/energy_models.py:419-446), one-body X mixer,
+gamma ~ U(0.25, 0.6), delta_t = 0.8, t ~ U{2..11}, beta = 1, 4096 independent chains per GPU.
+
+A "step" = one hop of every chain (4096 proposals per GPU): Philox draws, U = M (P M)^{r-1} on a
+2^20 complex64 statevector per chain, one measurement, get_energy, Metropolis accept.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   # CPU arm (gate-at-a-time)
+
+For N > 1 launch under torchrun (one rank per GPU); chains are sharded, no collective in the hop
+loop, one gather of acceptance counts / Hamming histograms at the end (inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_SPINS = 20
+MODEL_SEED = 1
+BETA = 1.0
+GAMMA = (0.25, 0.6)
+DELTA_T = 0.8
+PHILOX_SEED = 0x5EED
+METRIC = "quantum proposals/sec (n=20 Ising, 4096 chains)"
+UNIT = "proposals/s"
+
+
+def workload_config(chains_per_gpu, n_gpus, extra=None):
+    cfg = {
+        "workload": "C3: random_ising_model(20, seed=1), OneBodyMixer, gamma~U(0.25,0.6), dt=0.8, t~U{2..11}, beta=1.0",
+        "n_spins": N_SPINS, "chains_per_gpu": chains_per_gpu, "chains_total": chains_per_gpu * n_gpus,
+        "step": "one hop of every chain", "statevector": "complex64, 8 MiB per chain",
+        "l2_policy": "working set (chains x 8 MiB = %.1f GiB per GPU) >> 126 MB L2; no flush needed"
+                     % (chains_per_gpu * 8 / 1024),
+        "parallelism": "chain-sharded x%d, no collective in the hop loop" % n_gpus,
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (one pass over the complex128 state per gate) restated in
+# oracle/qmc_oracle.c, OpenMP over the host cores.  qulacs is not installable in this image.
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_rate(hops, warm=0):
+    import oracle
+    from qumcmc_b200.energy_models import random_ising_model
+    from qumcmc_b200.mixers import GenericMixer
+
+    model = random_ising_model(N_SPINS, MODEL_SEED)
+    _, masks, w, _ = GenericMixer.OneBodyMixer(N_SPINS).lower()
+    s0 = oracle.initial_state(PHILOX_SEED, 0, N_SPINS)
+    if warm:
+        oracle.run_chain(model.J, model.h, masks, w, s0, warm, 1 / BETA, GAMMA, DELTA_T, PHILOX_SEED, chain_id=0,
+                         gatewise=True)
+    t0 = time.perf_counter()
+    oracle.run_chain(model.J, model.h, masks, w, s0, hops, 1 / BETA, GAMMA, DELTA_T, PHILOX_SEED, chain_id=0,
+                     hop0=warm, gatewise=True)
+    dt = time.perf_counter() - t0
+    return hops / dt, dt, oracle.num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    rate, dt, threads = cpu_reference_rate(args.steps, warm=args.warmup)
+    sample = "1 chain x %d hops (+%d warm-up), gate-at-a-time complex128 (n(n-1)/2+n diagonal + n X gates per layer)" % (
+        args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": workload_config(args.chains, args.gpus, {"reference_step": "one hop of one chain on the host CPU"}),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "note": "oracle/qmc_oracle.c restatement of the qulacs circuit; qulacs itself is not installable here"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+
+    from qumcmc_b200 import _device, _lib
+    from qumcmc_b200.distributed import gather_statistics
+    from qumcmc_b200.energy_models import random_ising_model
+    from qumcmc_b200.mixers import GenericMixer
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    L = _lib.lib()
+    model = random_ising_model(N_SPINS, MODEL_SEED)
+    mixer = GenericMixer.OneBodyMixer(N_SPINS)
+    dm = model.device_model(local_rank)
+    dm.set_mixer(mixer)
+    C, K, W = args.chains, args.steps, args.warmup
+    chain_id0 = rank * C
+    dev = torch.device("cuda", local_rank)
+    stream = _device.current_stream_ptr(local_rank)
+    n1 = N_SPINS + 1
+
+    Hbuf = max(K, W, 1)
+    props_buf = torch.empty(C * Hbuf, dtype=torch.int64, device=dev)
+    acc_buf = torch.empty(C * Hbuf, dtype=torch.uint8, device=dev)
+    fin = torch.empty(C, dtype=torch.int64, device=dev)
+    cnt = torch.empty(C, dtype=torch.int64, device=dev)
+    hist = torch.empty((C, n1), dtype=torch.int64, device=dev)
+
+    def run_dev(n_hops, s0, hop0):
+        _lib.check(L.qmc_run_chains(dm.handle, C, n_hops, None if s0 is None else s0.data_ptr(), chain_id0, hop0,
+                                    1.0 / BETA, GAMMA[0], GAMMA[1], DELTA_T, PHILOX_SEED, _lib.DTYPE_F32,
+                                    props_buf.data_ptr(), acc_buf.data_ptr(), fin.data_ptr(), cnt.data_ptr(),
+                                    hist.data_ptr(), stream))
+
+    # ---- warm-up (allocates the statevector workspace and phase tables)
+    run_dev(max(W, 1), None, 0)
+    torch.cuda.synchronize()
+    s0 = fin.clone()
+
+    # ---- timed region: K steps, inputs resident in HBM
+    _lib.check(L.qmc_profile_enable(dm.handle, 1))
+    launches0 = dm.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    run_dev(K, s0, W)
+    g_acc = g_hist = None
+    if dist is not None:  # the one exchange of the chain-parallel path: statistics gather
+        g_acc, g_hist = gather_statistics(cnt.cpu().numpy(), hist.cpu().numpy(), C * world)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop() if sampler else None
+    launches = dm.launch_count() - launches0
+    sweep_ms, sweep_launches, alg_bytes = (torch.zeros(1, dtype=torch.float64).numpy(), np.zeros(1, dtype=np.int64),
+                                           np.zeros(1, dtype=np.float64))
+    import ctypes as Ct
+    c_ms, c_ln, c_by = Ct.c_double(), Ct.c_int64(), Ct.c_double()
+    _lib.check(L.qmc_profile_read(dm.handle, Ct.byref(c_ms), Ct.byref(c_ln), Ct.byref(c_by)))
+    _lib.check(L.qmc_profile_enable(dm.handle, 0))
+    value = world * C * K / (ms * 1e-3)
+    acc_rate = float(cnt.sum().item()) / (C * K)
+
+    # ---- end to end through the host-buffer C-ABI: every step copies its inputs H2D and results D2H
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+    h_s0 = pin(C, torch.int64)
+    h_s0.copy_(s0)
+    h_prop, h_acc = pin(C, torch.int64), pin(C, torch.uint8)
+    h_fin, h_cnt, h_hist = pin(C, torch.int64), pin(C, torch.int64), pin((C, n1), torch.int64)
+    Ke = min(K, args.e2e_steps)
+
+    def step_host(hop0):
+        _lib.check(L.qmc_run_chains_host(dm.handle, C, 1, h_s0.data_ptr(), chain_id0, hop0, 1.0 / BETA, GAMMA[0],
+                                         GAMMA[1], DELTA_T, PHILOX_SEED, _lib.DTYPE_F32, h_prop.data_ptr(),
+                                         h_acc.data_ptr(), h_fin.data_ptr(), h_cnt.data_ptr(), h_hist.data_ptr()))
+        h_s0.copy_(h_fin)
+
+    step_host(W)  # warm
+    h_s0.copy_(s0)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(Ke):
+        step_host(W + k)
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * C * Ke / t_e2e
+    # same hops through both entry points must give the same chain (device-resident vs host buffers)
+    e2e_consistent = bool(torch.equal(h_prop.to(dev), props_buf[: C * K].view(C, K)[:, Ke - 1])) if Ke >= 1 else None
+    bi = C * 8
+    bo = C * (8 + 1 + 8 + 8 + n1 * 8)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    achieved = (c_by.value / 1e9) / (c_ms.value * 1e-3) if c_ms.value > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "hbm", "kernel": "sweep_kernel<8> (fused phase + butterfly sweep)", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": None if achieved is None else achieved / peak, "traffic": traffic,
+        "peak_source": peak_src, "sweep_ms_per_step": c_ms.value / max(1, K),
+        "algorithmic_bytes_per_step": c_by.value / max(1, K), "launches_per_step": c_ln.value / max(1, K),
+        "share_of_step": c_ms.value / ms if ms > 0 else None,
+        "definition": "B_alg = 2 * 2^n * 8 B * r per proposal (SURVEY 8d); achieved = sum B_alg / device time of the sweep launches (CUDA events)",
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, dt, threads = cpu_reference_rate(args.cpu_hops)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "1 chain x %d hops of the same workload, gate-at-a-time complex128 (reference cost structure), %.1f s"
+                         % (args.cpu_hops, dt),
+               "published_context": "authors' qulacs runs: ~500 proposals/s at n=10, ~52 at n=12 (BASELINE.md); none at n=20"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / max(1, K), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "c64 (fp32 arithmetic; energies/accept fp64)", "data": "synthetic",
+        "config": workload_config(C, world, {"acceptance_rate": acc_rate}),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
+                "steps": Ke, "api": "qmc_run_chains_host (one hop per call, pinned host buffers)",
+                "matches_device_resident_run": e2e_consistent},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    if g_acc is not None:
+        line["config"]["gathered_chains"] = int(len(g_acc))
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=4096, help="chains per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-hops", type=int, default=12)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()
