@@ -314,124 +314,166 @@ __device__ __forceinline__ void hi_tq_b(float (&t)[6], const float *tq) {
 }
 
 // ------------------------------------------------------------------------------------------
-// the sweep kernel: grid = (tiles, chains); step k = 1..r_max
+// sweep kernels: grid = (tiles, chains of one role); chain = order[list_off + blockIdx.y].
+// One kernel per role so that every CTA of a launch runs the same straight-line code
+// (small instruction footprint) and no CTA exits early:
+//   LO_FIRST  r odd >= 3, step 1   : M|s> analytic, P, M_lo(2)                  (write-only)
+//   LO_MID    1 < step < r         : M_lo(k) P M_lo(k+1)                         (read + write)
+//   LO_FINAL  step == r            : M_lo(r), |a|^2 segment sums                 (read-only)
+//   HI_FIRST  r even, step 1       : M|s> analytic, P, M_hi(2)                   (write-only)
+//   HI_MID                         : M_hi(k) P M_hi(k+1)                         (read + write)
 // ------------------------------------------------------------------------------------------
-template <int W>
-__global__ void __launch_bounds__(NT, 3) sweep_kernel(const SweepArgs a, const int step) {
+__device__ __forceinline__ void stage_params(ChainParams &dst_s, const ChainParams *src_g, int tid) {
+    const int *src = reinterpret_cast<const int *>(src_g);
+    int *dst = reinterpret_cast<int *>(&dst_s);
+    for (int i = tid; i < (int)(sizeof(ChainParams) / 4); i += NT) dst[i] = src[i];
+    __syncthreads();
+}
+
+enum { LO_FIRST = 0, LO_MID = 1, LO_FINAL = 2 };
+
+template <int ROLE>
+__global__ void __launch_bounds__(NT, 3) lo_sweep_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off) {
+    extern __shared__ __align__(16) float2 sm[];
+    __shared__ ChainParams cp_s;
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t chain = order[list_off + blockIdx.y];
+    stage_params(cp_s, a.params + chain, tid);
+    const ChainParams &cp = cp_s;
+    const int n = a.n;
+    float2 *state = a.state + (chain << n);
+    float2 v[64];
+    float t[6];
+    if (ROLE == LO_FINAL) {
+        lo_final_tile(v, sm, state, tile, tid, n, cp);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) s += v[j].x * v[j].x + v[j].y * v[j].y;
+        a.segsum[(chain << (n - 6)) + tile * NT + tid] = s;
+        if (a.probs_out) {
+            float *po = a.probs_out + (chain << n) + (tile << TILE_BITS) + (tid << 6);
+#pragma unroll
+            for (int j = 0; j < 64; ++j) po[j] = v[j].x * v[j].x + v[j].y * v[j].y;
+        }
+        if (a.amps_out) {
+            float2 *ao = a.amps_out + (chain << n) + (tile << TILE_BITS) + (tid << 6);
+#pragma unroll
+            for (int j = 0; j < 64; ++j) ao[j] = v[j];
+        }
+        return;
+    }
+    if (ROLE == LO_FIRST) {
+        init_product(v, ((uint64_t)tile << TILE_BITS) | ((uint64_t)tid << 6), n, cp, LoQ0());
+    } else {
+        lo_load_a(v, state + (tile << TILE_BITS), tid);
+        load_tq(t, cp.tq, 6);
+        bfly6<63>(v, t);
+        lo_a_to_smem(v, sm, tid);
+        __syncthreads();
+        lo_smem_to_b(v, sm, tid);
+        load_tq(t, cp.tq, 0);
+        bfly6<63>(v, t);
+        __syncthreads();  // everyone has read the A->B transposition before smem is rewritten
+    }
+    lo_phase_b(v, a.dfx_lo, tile, tid, cp);
+    load_tq(t, cp.tq, 0);
+    bfly6<63>(v, t);
+    lo_b_to_smem(v, sm, tid);
+    __syncthreads();
+    lo_smem_to_a(v, sm, tid);
+    load_tq(t, cp.tq, 6);
+    bfly6<63>(v, t);
+    lo_store_a(v, state + (tile << TILE_BITS), tid);
+}
+
+template <int W, bool FIRST>
+__global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off) {
     using G = HiGeom<W>;
     extern __shared__ __align__(16) float2 sm[];
     __shared__ ChainParams cp_s;
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
-    const int64_t chain = blockIdx.y;
-    {
-        const int r = a.params[chain].r;
-        if (step > r) return;  // this chain's proposal needs fewer sweeps
-    }
-    // stage the chain's parameters in shared memory (broadcast reads afterwards)
-    {
-        const int *src = reinterpret_cast<const int *>(a.params + chain);
-        int *dst = reinterpret_cast<int *>(&cp_s);
-        for (int i = tid; i < (int)(sizeof(ChainParams) / 4); i += NT) dst[i] = src[i];
-    }
-    __syncthreads();
+    const int64_t chain = order[list_off + blockIdx.y];
+    stage_params(cp_s, a.params + chain, tid);
     const ChainParams &cp = cp_s;
     const int n = a.n;
-    const int r = cp.r;
-    const bool first = (step == 1), last = (step == r);
-    const bool lo = ((r - step) & 1) == 0;
-    float2 *state = a.state + ((int64_t)chain << n);
+    float2 *state = a.state + (chain << n);
     float2 v[64];
     float t[6];
-
-    if (lo) {
-        if (last) {
-            lo_final_tile(v, sm, state, tile, tid, n, cp);
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) s += v[j].x * v[j].x + v[j].y * v[j].y;
-            a.segsum[(chain << (n - 6)) + tile * NT + tid] = s;
-            if (a.probs_out) {
-                float *po = a.probs_out + ((int64_t)chain << n) + (tile << TILE_BITS) + (tid << 6);
-#pragma unroll
-                for (int j = 0; j < 64; ++j) po[j] = v[j].x * v[j].x + v[j].y * v[j].y;
-            }
-            if (a.amps_out) {
-                float2 *ao = a.amps_out + ((int64_t)chain << n) + (tile << TILE_BITS) + (tid << 6);
-#pragma unroll
-                for (int j = 0; j < 64; ++j) ao[j] = v[j];
-            }
-            return;
-        }
-        if (first) {
-            init_product(v, ((uint64_t)tile << TILE_BITS) | ((uint64_t)tid << 6), n, cp, LoQ0());
+    const int64_t base_a = hi_base_a<W>(tid, tile);
+    if (G::two_rounds) {
+        const int64_t base_b = hi_base_b<W>(tid, tile);
+        if (FIRST) {
+            init_product(v, (uint64_t)base_b, n, cp, HiQB<W>());
         } else {
-            lo_load_a(v, state + (tile << TILE_BITS), tid);
-            load_tq(t, cp.tq, 6);
-            bfly6<63>(v, t);
-            lo_a_to_smem(v, sm, tid);
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = state[base_a + G::off_a(j)];
+            hi_tq_a<W>(t, cp.tq);
+            bfly6<G::active_a>(v, t);
+#pragma unroll
+            for (int j = 0; j < 64; ++j) sm[hi_loc_a(tid, j)] = v[j];
             __syncthreads();
-            lo_smem_to_b(v, sm, tid);
-            load_tq(t, cp.tq, 0);
-            bfly6<63>(v, t);
-            __syncthreads();  // everyone has read the A->B transposition before smem is rewritten
-        }
-        lo_phase_b(v, a.dfx_lo, tile, tid, cp);
-        load_tq(t, cp.tq, 0);
-        bfly6<63>(v, t);
-        lo_b_to_smem(v, sm, tid);
-        __syncthreads();
-        lo_smem_to_a(v, sm, tid);
-        load_tq(t, cp.tq, 6);
-        bfly6<63>(v, t);
-        lo_store_a(v, state + (tile << TILE_BITS), tid);
-    } else {
-        // HI sweep (never the last one)
-        const int64_t base_a = hi_base_a<W>(tid, tile);
-        if (G::two_rounds) {
-            const int64_t base_b = hi_base_b<W>(tid, tile);
-            if (first) {
-                init_product(v, (uint64_t)base_b, n, cp, HiQB<W>());
-            } else {
 #pragma unroll
-                for (int j = 0; j < 64; ++j) v[j] = state[base_a + G::off_a(j)];
-                hi_tq_a<W>(t, cp.tq);
-                bfly6<G::active_a>(v, t);
-#pragma unroll
-                for (int j = 0; j < 64; ++j) sm[hi_loc_a(tid, j)] = v[j];
-                __syncthreads();
-#pragma unroll
-                for (int j = 0; j < 64; ++j) v[j] = sm[hi_loc_b(tid, j)];
-                hi_tq_b<W>(t, cp.tq);
-                bfly6<G::active_b>(v, t);
-                __syncthreads();
-            }
-            hi_phase<W, true>(v, a.dfx_nat, base_b, cp);
+            for (int j = 0; j < 64; ++j) v[j] = sm[hi_loc_b(tid, j)];
             hi_tq_b<W>(t, cp.tq);
             bfly6<G::active_b>(v, t);
-#pragma unroll
-            for (int j = 0; j < 64; ++j) sm[hi_loc_b(tid, j)] = v[j];
             __syncthreads();
-#pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = sm[hi_loc_a(tid, j)];
-            hi_tq_a<W>(t, cp.tq);
-            bfly6<G::active_a>(v, t);
-#pragma unroll
-            for (int j = 0; j < 64; ++j) state[base_a + G::off_a(j)] = v[j];
-        } else {
-            hi_tq_a<W>(t, cp.tq);
-            if (first) {
-                init_product(v, (uint64_t)base_a, n, cp, HiQA<W>());
-            } else {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) v[j] = state[base_a + G::off_a(j)];
-                bfly6<G::active_a>(v, t);
-            }
-            hi_phase<W, false>(v, a.dfx_nat, base_a, cp);
-            bfly6<G::active_a>(v, t);
-#pragma unroll
-            for (int j = 0; j < 64; ++j) state[base_a + G::off_a(j)] = v[j];
         }
+        hi_phase<W, true>(v, a.dfx_nat, base_b, cp);
+        hi_tq_b<W>(t, cp.tq);
+        bfly6<G::active_b>(v, t);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) sm[hi_loc_b(tid, j)] = v[j];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] = sm[hi_loc_a(tid, j)];
+        hi_tq_a<W>(t, cp.tq);
+        bfly6<G::active_a>(v, t);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) state[base_a + G::off_a(j)] = v[j];
+    } else {
+        hi_tq_a<W>(t, cp.tq);
+        if (FIRST) {
+            init_product(v, (uint64_t)base_a, n, cp, HiQA<W>());
+        } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = state[base_a + G::off_a(j)];
+            bfly6<G::active_a>(v, t);
+        }
+        hi_phase<W, false>(v, a.dfx_nat, base_a, cp);
+        bfly6<G::active_a>(v, t);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) state[base_a + G::off_a(j)] = v[j];
+    }
+}
+
+// Device-side schedule: order[] = chains with odd r sorted by r descending, then chains with even r
+// sorted by r descending.  The host replays the same Philox draws to know the class sizes.
+constexpr int SCHED_RMAX = 2047;
+__global__ void __launch_bounds__(1024) schedule_kernel(const ChainParams *__restrict__ params, int64_t n_chains,
+                                                        int r_cap, int *__restrict__ order) {
+    __shared__ int hist[SCHED_RMAX + 1];
+    __shared__ int start[SCHED_RMAX + 1];
+    for (int i = threadIdx.x; i <= r_cap; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int64_t c = threadIdx.x; c < n_chains; c += blockDim.x) atomicAdd(&hist[params[c].r], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int pos = 0;
+        for (int parity = 1; parity >= 0; --parity)
+            for (int r = r_cap; r >= 1; --r)
+                if ((r & 1) == parity) {
+                    start[r] = pos;
+                    pos += hist[r];
+                }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= r_cap; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int64_t c = threadIdx.x; c < n_chains; c += blockDim.x) {
+        const int r = params[c].r;
+        order[start[r] + atomicAdd(&hist[r], 1)] = (int)c;
     }
 }
 
@@ -674,6 +716,7 @@ struct SweepWorkspace {
     ChainParams *params = nullptr;
     float *segsum = nullptr;
     int *hist = nullptr;
+    int *order = nullptr;
     int *dfx_nat = nullptr, *dfx_lo = nullptr;
     int k_fx = 0;
     std::vector<cudaEvent_t> ev;
@@ -686,6 +729,7 @@ void qmc_sweep_free(qmc_model *m) {
     cudaFree(w->params);
     cudaFree(w->segsum);
     cudaFree(w->hist);
+    cudaFree(w->order);
     cudaFree(w->dfx_nat);
     cudaFree(w->dfx_lo);
     for (auto e : w->ev) cudaEventDestroy(e);
@@ -715,38 +759,56 @@ static int ensure_workspace(qmc_model *m, int64_t chains, cudaStream_t st) {
     }
     if (chains > w->cap_chains) {
         QMC_CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(w->state); cudaFree(w->params); cudaFree(w->segsum); cudaFree(w->hist);
-        w->state = nullptr; w->params = nullptr; w->segsum = nullptr; w->hist = nullptr;
+        cudaFree(w->state); cudaFree(w->params); cudaFree(w->segsum); cudaFree(w->hist); cudaFree(w->order);
+        w->state = nullptr; w->params = nullptr; w->segsum = nullptr; w->hist = nullptr; w->order = nullptr;
         w->cap_chains = 0;
         QMC_CUDA_TRY(cudaMalloc(&w->state, sizeof(float2) * (size_t)N * chains));
         QMC_CUDA_TRY(cudaMalloc(&w->params, sizeof(ChainParams) * chains));
         QMC_CUDA_TRY(cudaMalloc(&w->segsum, sizeof(float) * (size_t)(N >> 6) * chains));
         QMC_CUDA_TRY(cudaMalloc(&w->hist, sizeof(int) * (size_t)(n + 1) * chains));
+        QMC_CUDA_TRY(cudaMalloc(&w->order, sizeof(int) * (size_t)chains));
         w->cap_chains = chains;
     }
     return QMC_OK;
 }
 
-template <int W>
-static int launch_sweep(const SweepArgs &a, int step, int64_t tiles, int64_t chains, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        QMC_CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 8));
-        attr_set = true;
+template <typename K>
+static int set_smem_once(K kernel, bool &done) {
+    if (!done) {
+        QMC_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 8));
+        done = true;
     }
-    sweep_kernel<W><<<dim3((unsigned)tiles, (unsigned)chains), NT, TILE * 8, st>>>(a, step);
     return QMC_OK;
 }
 
-static int launch_sweep_n(int n, const SweepArgs &a, int step, int64_t tiles, int64_t chains, cudaStream_t st) {
+template <int ROLE>
+static int launch_lo(const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
+    static bool done = false;
+    int rc = set_smem_once(lo_sweep_kernel<ROLE>, done);
+    if (rc != QMC_OK) return rc;
+    lo_sweep_kernel<ROLE><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off);
+    return QMC_OK;
+}
+
+template <int W, bool FIRST>
+static int launch_hi_w(const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
+    static bool done = false;
+    int rc = set_smem_once(hi_sweep_kernel<W, FIRST>, done);
+    if (rc != QMC_OK) return rc;
+    hi_sweep_kernel<W, FIRST><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off);
+    return QMC_OK;
+}
+
+template <bool FIRST>
+static int launch_hi(int n, const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
     switch (n - LO_BITS) {
-        case 2: return launch_sweep<2>(a, step, tiles, chains, st);
-        case 3: return launch_sweep<3>(a, step, tiles, chains, st);
-        case 4: return launch_sweep<4>(a, step, tiles, chains, st);
-        case 5: return launch_sweep<5>(a, step, tiles, chains, st);
-        case 6: return launch_sweep<6>(a, step, tiles, chains, st);
-        case 7: return launch_sweep<7>(a, step, tiles, chains, st);
-        case 8: return launch_sweep<8>(a, step, tiles, chains, st);
+        case 2: return launch_hi_w<2, FIRST>(a, order, off, tiles, count, st);
+        case 3: return launch_hi_w<3, FIRST>(a, order, off, tiles, count, st);
+        case 4: return launch_hi_w<4, FIRST>(a, order, off, tiles, count, st);
+        case 5: return launch_hi_w<5, FIRST>(a, order, off, tiles, count, st);
+        case 6: return launch_hi_w<6, FIRST>(a, order, off, tiles, count, st);
+        case 7: return launch_hi_w<7, FIRST>(a, order, off, tiles, count, st);
+        case 8: return launch_hi_w<8, FIRST>(a, order, off, tiles, count, st);
     }
     qmc_set_error("sweep path: n=%d outside [14, 20]", n);
     return QMC_ERR_UNSUPPORTED;
@@ -798,6 +860,8 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         for (int64_t c = 0; c < n_chains; ++c) r_max = std::max(r_max, r_host[c]);
     }
 
+    QMC_REQUIRE(r_max <= SCHED_RMAX, QMC_ERR_UNSUPPORTED, "delta_time=%g gives up to %d Trotter layers (> %d)", dt, r_max, SCHED_RMAX);
+    std::vector<int> rhist(r_max + 2, 0);
     for (int64_t c0 = 0; c0 < n_chains; c0 += batch) {
         const int64_t nc = std::min<int64_t>(batch, n_chains - c0);
         HopArgs h;
@@ -832,34 +896,65 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         for (int64_t hop = 0; hop < hops; ++hop) {
             h.hop = hop;
             hop_prepare_kernel<<<gb, 128, 0, st>>>(h, w->params);
-            m->launches++;
+            schedule_kernel<<<1, 1024, 0, st>>>(w->params, nc, r_max, w->order);
+            m->launches += 2;
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (m->profile) {
                 QMC_CUDA_TRY(cudaEventCreate(&e0));
                 QMC_CUDA_TRY(cudaEventCreate(&e1));
                 QMC_CUDA_TRY(cudaEventRecord(e0, st));
             }
-            for (int step = 1; step <= r_max; ++step) {
-                rc = launch_sweep_n(n, a, step, tiles, nc, st);
-                if (rc != QMC_OK) return rc;
-                m->launches++;
+            // host replica of the draws: class sizes of the device-side schedule
+            std::fill(rhist.begin(), rhist.end(), 0);
+            double sum_r = 0.0;
+            for (int64_t c = 0; c < nc; ++c) {
+                int r;
+                if (mode == QMC_MODE_CHAIN) {
+                    const HopDraws d = qmc_hop_draws(seed, h.chain_id0 + (uint64_t)c, hop0 + (uint32_t)hop);
+                    r = qmc_trotter_steps(d.t, dt);
+                } else {
+                    r = std::max(1, r_host[c0 + c]);
+                }
+                rhist[r]++;
+                sum_r += r;
             }
+            int base[2] = {0, 0};  // start of the odd-r / even-r class in order[]
+            for (int r = 1; r <= r_max; r += 2) base[1] += rhist[r];  // even class starts after all odd-r chains
+            int launched = 0;
+            for (int step = 1; step <= r_max; ++step) {
+                const int p = step & 1;                 // chains with r == step (mod 2) sweep LO at this step
+                const int lo_base = p ? base[0] : base[1];
+                const int hi_base = p ? base[1] : base[0];
+                int lo_gt = 0, hi_gt = 0;
+                for (int r = step + 2; r <= r_max; r += 2) lo_gt += rhist[r];
+                for (int r = step + 1; r <= r_max; r += 2) hi_gt += rhist[r];
+                const int lo_eq = rhist[step];
+                if (lo_gt > 0) {
+                    rc = step == 1 ? launch_lo<LO_FIRST>(a, w->order, lo_base, tiles, lo_gt, st)
+                                   : launch_lo<LO_MID>(a, w->order, lo_base, tiles, lo_gt, st);
+                    if (rc != QMC_OK) return rc;
+                    ++launched;
+                }
+                if (lo_eq > 0) {
+                    rc = launch_lo<LO_FINAL>(a, w->order, lo_base + lo_gt, tiles, lo_eq, st);
+                    if (rc != QMC_OK) return rc;
+                    ++launched;
+                }
+                if (hi_gt > 0) {
+                    rc = step == 1 ? launch_hi<true>(n, a, w->order, hi_base, tiles, hi_gt, st)
+                                   : launch_hi<false>(n, a, w->order, hi_base, tiles, hi_gt, st);
+                    if (rc != QMC_OK) return rc;
+                    ++launched;
+                }
+            }
+            m->launches += launched;
             if (m->profile) {
                 QMC_CUDA_TRY(cudaEventRecord(e1, st));
                 w->ev.push_back(e0);
                 w->ev.push_back(e1);
                 // algorithmic bytes of this hop: 2 * 2^n * 8 B * r per chain
-                double sum_r = 0.0;
-                for (int64_t c = 0; c < nc; ++c) {
-                    if (mode == QMC_MODE_CHAIN) {
-                        const HopDraws d = qmc_hop_draws(seed, h.chain_id0 + (uint64_t)c, hop0 + (uint32_t)hop);
-                        sum_r += qmc_trotter_steps(d.t, dt);
-                    } else {
-                        sum_r += std::max(1, r_host[c0 + c]);
-                    }
-                }
                 m->prof_bytes += 2.0 * (double)N * 8.0 * sum_r;
-                m->prof_launches += r_max;
+                m->prof_launches += launched;
             }
             if (mode == QMC_MODE_PROBS) {
                 probs_normalize_kernel<<<148 * 4, 256, 0, st>>>(n, w->segsum, a.probs_out, a.amps_out);
