@@ -31,7 +31,7 @@ void qmc_set_error(const char *fmt, ...);
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 -- stream contract in include/qumcmc_b200.h, mirrored in oracle/qmc_oracle.c
+// Philox4x32-10 -- stream contract in include/qumcmc_b200.h, mirrored by the CPU checker under oracle/
 // ---------------------------------------------------------------------------------------------
 struct Philox4 {
     uint32_t w[4];
