@@ -104,6 +104,7 @@ def cpu_reference_rate(hops, warm=0):
     from qumcmc_b200.energy_models import random_ising_model
     from qumcmc_b200.mixers import GenericMixer
 
+    oracle.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1
     model = random_ising_model(N_SPINS, MODEL_SEED)
     _, masks, w, _ = GenericMixer.OneBodyMixer(N_SPINS).lower()
     s0 = oracle.initial_state(PHILOX_SEED, 0, N_SPINS)
@@ -166,6 +167,9 @@ def run_ours(args, rank, local_rank, world):
 
     L = _lib.lib()
     model = random_ising_model(N_SPINS, MODEL_SEED)
+    if args.model_scale != 1.0:
+        from qumcmc_b200.energy_models import IsingEnergyFunction
+        model = IsingEnergyFunction(model.J * args.model_scale, model.h * args.model_scale)
     mixer = GenericMixer.OneBodyMixer(N_SPINS)
     dm = model.device_model(local_rank)
     dm.set_mixer(mixer)
@@ -311,6 +315,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-hops", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model-scale", type=float, default=1.0, help="diagnostics only: scales J,h (1e-6 disables the phase layer)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

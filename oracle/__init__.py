@@ -73,6 +73,8 @@ def lib() -> C.CDLL:
         L.orc_run_chain.restype = C.c_int64
         L.orc_exact_boltzmann.argtypes = [C.c_int, dp, dp, C.c_double, dp, dp]
         L.orc_exact_boltzmann.restype = C.c_double
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_set_num_threads.restype = None
         L.orc_num_threads.argtypes = []
         L.orc_num_threads.restype = C.c_int
         _lib = L
@@ -221,6 +223,11 @@ def exact_boltzmann(J, h, beta: float, want_probs: bool = True):
     P = np.empty(1 << n, dtype=np.float64) if want_probs else None
     logZ = lib().orc_exact_boltzmann(n, _dp(J), _dp(h), float(beta), _dp(E), None if P is None else _dp(P))
     return float(logZ), E, P
+
+
+def set_num_threads(t: int) -> None:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm may use all host cores."""
+    lib().orc_set_num_threads(int(t))
 
 
 def num_threads() -> int:

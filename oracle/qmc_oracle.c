@@ -419,6 +419,14 @@ ORC_API double orc_exact_boltzmann(int n, const double *J, const double *h, doub
     return logZ;
 }
 
+ORC_API void orc_set_num_threads(int t) {
+#ifdef _OPENMP
+    if (t > 0) omp_set_num_threads(t);
+#else
+    (void)t;
+#endif
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -23,6 +23,9 @@
 // Layout in HBM: state[chain][2^n] interleaved complex64 (8 B/amplitude), index order.
 #include <math.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -47,14 +50,17 @@ struct ChainParams {
     float scale; // prod_q cos(theta_q)
     int active;  // phase layer present
     float tq[QMC_MAX_SPINS];  // tan(theta_q), theta_q = gamma w_q dt
+    float2 tpair[QMC_MAX_SPINS][2];  // [q][0] = (t, -t), [q][1] = (-t, t): packed FFMA2 multipliers
 };
 
 struct SweepArgs {
     int n;
     float2 *state;            // [chains][2^n]
     ChainParams *params;      // [chains]
-    const int *dfx_nat;       // D fixed point, index order
-    const int *dfx_lo;        // D fixed point, permuted for the LO B-layout: [tile][c 16][thread 128][4]
+    // on-the-fly phase exponent: D_fx(idx) = A + sum_b z_b F_b + R(j) per register layout;
+    // af_*[tile*128 + thread] = {A, F0, F1, F2}, {F3, F4, F5, -}; dr_*[i] = Gray-order increments of R
+    const int4 *af_lo, *af_hia, *af_hib;
+    int dr_lo[64], dr_hia[64], dr_hib[64];
     float *segsum;            // [chains][2^n / 64]
     float *probs_out;         // PROBS mode: unnormalised |a|^2 (index order) or null
     float2 *amps_out;
@@ -63,24 +69,55 @@ struct SweepArgs {
 // ------------------------------------------------------------------------------------------
 // register-level pieces
 // ------------------------------------------------------------------------------------------
-// a' = a - i t b ; b' = b - i t a   on register bit `b`, for the bits set in ACTIVE
-template <int ACTIVE>
-__device__ __forceinline__ void bfly6(float2 (&v)[64], const float (&t)[6]) {
+// Amplitudes live in registers as opaque 64-bit pairs so that the packed FP32 FMA of sm_100
+// (fma.rn.f32x2 -> SASS FFMA2) consumes them without repacking.
+typedef unsigned long long A64;
+__device__ __forceinline__ A64 pk(float x, float y) {
+    A64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ float2 upk(A64 r) {
+    float2 o;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+    return o;
+}
+__device__ __forceinline__ A64 fma2(A64 a, A64 b, A64 c) {
+    A64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float norm2(A64 a) {
+    const float2 f = upk(a);
+    return f.x * f.x + f.y * f.y;
+}
+
+// Storage convention of the sweep path: amplitude idx is held as (re, im) when popcount(idx) is even and
+// as (im, re) when it is odd -- in registers, shared memory and HBM alike.  Butterfly partners always
+// differ in parity, so a' = a - i t b ; b' = b - i t a becomes two packed FFMA2 (fma.rn.f32x2, sm_100):
+//   even' = even + (t, -t) * odd_stored      odd_stored' = odd_stored + (-t, t) * even
+// `tpar` = parity of the thread's base index (all index bits outside the 6 register bits).
+// reg bit b <-> qubit qpos(b); multiplier pairs are fetched per stage as opaque 64-bit values
+// ([q][0] = (t,-t), [q][1] = (-t,t); a thread of odd base parity uses them crosswise).
+template <int ACTIVE, typename QP>
+__device__ __forceinline__ void bfly6(A64 (&v)[64], const ChainParams &cp, QP qpos, const int tpar) {
 #pragma unroll
     for (int b = 0; b < 6; ++b) {
         if (!((ACTIVE >> b) & 1)) continue;
-        const float tb = t[b];
+        const A64 *p = reinterpret_cast<const A64 *>(&cp.tpair[qpos(b)][0]);
+        const A64 TA = p[tpar], TB = p[tpar ^ 1];
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
             if (j & (1 << b)) continue;
-            const float2 a = v[j], c = v[j | (1 << b)];
-            v[j].x = fmaf(tb, c.y, a.x);
-            v[j].y = fmaf(-tb, c.x, a.y);
-            v[j | (1 << b)].x = fmaf(tb, a.y, c.x);
-            v[j | (1 << b)].y = fmaf(-tb, a.x, c.y);
+            const bool odd = (__builtin_popcount(j) & 1) != 0;  // folds: j is a compile-time constant
+            const A64 u = v[j], w = v[j | (1 << b)];
+            v[j] = fma2(odd ? TB : TA, w, u);
+            v[j | (1 << b)] = fma2(odd ? TA : TB, u, w);
         }
     }
 }
+
+__device__ __forceinline__ int parity64(unsigned long long x) { return __popcll(x) & 1; }
 
 // phase factor scale * exp(2 pi i * turns), turns = frac(D * c/(2 pi)) in 32-bit fixed point
 __device__ __forceinline__ float2 phase_from_fx(int dfx, int cfx, int shift, float scale) {
@@ -92,11 +129,13 @@ __device__ __forceinline__ float2 phase_from_fx(int dfx, int cfx, int shift, flo
     return make_float2(c * scale, s * scale);
 }
 
-__device__ __forceinline__ void apply_phase(float2 &a, const float2 f) {
-    const float x = a.x * f.x - a.y * f.y;
-    const float y = a.x * f.y + a.y * f.x;
-    a.x = x;
-    a.y = y;
+__device__ __forceinline__ void apply_phase(A64 &a, const float2 f) {
+    const float2 v = upk(a);
+    a = pk(v.x * f.x - v.y * f.y, v.x * f.y + v.y * f.x);
+}
+__device__ __forceinline__ void apply_scale(A64 &a, const float g) {
+    const float2 v = upk(a);
+    a = pk(v.x * g, v.y * g);
 }
 
 // amplitude of M|s0> at index idx (tan form incl. the layer scale):
@@ -122,72 +161,92 @@ __device__ __forceinline__ int lo_base_a(int tid) {
     return lane | ((w & 1) << 5) | ((w >> 1) << 12);
 }
 
-__device__ __forceinline__ void lo_load_a(float2 (&v)[64], const float2 *__restrict__ tile, int tid) {
-    const float2 *p = tile + lo_base_a(tid);
+__device__ __forceinline__ void lo_load_a(A64 (&v)[64], const float2 *__restrict__ tile, int tid) {
+    const A64 *p = reinterpret_cast<const A64 *>(tile) + lo_base_a(tid);
 #pragma unroll
     for (int j = 0; j < 64; ++j) v[j] = p[j << 6];
 }
-__device__ __forceinline__ void lo_store_a(const float2 (&v)[64], float2 *__restrict__ tile, int tid) {
-    float2 *p = tile + lo_base_a(tid);
+__device__ __forceinline__ void lo_store_a(const A64 (&v)[64], float2 *__restrict__ tile, int tid) {
+    A64 *p = reinterpret_cast<A64 *>(tile) + lo_base_a(tid);
 #pragma unroll
     for (int j = 0; j < 64; ++j) p[j << 6] = v[j];
 }
-__device__ __forceinline__ void lo_a_to_smem(const float2 (&v)[64], float2 *sm, int tid) {
+__device__ __forceinline__ void lo_a_to_smem(const A64 (&v)[64], float2 *sm_, int tid) {
+    A64 *sm = reinterpret_cast<A64 *>(sm_);
     const int base = lo_base_a(tid);
 #pragma unroll
     for (int j = 0; j < 64; ++j) sm[lo_swz(base | (j << 6))] = v[j];
 }
-__device__ __forceinline__ void lo_smem_to_a(float2 (&v)[64], const float2 *sm, int tid) {
+__device__ __forceinline__ void lo_smem_to_a(A64 (&v)[64], const float2 *sm_, int tid) {
+    const A64 *sm = reinterpret_cast<const A64 *>(sm_);
     const int base = lo_base_a(tid);
 #pragma unroll
     for (int j = 0; j < 64; ++j) v[j] = sm[lo_swz(base | (j << 6))];
 }
-__device__ __forceinline__ void lo_b_to_smem(const float2 (&v)[64], float2 *sm, int tid) {
+__device__ __forceinline__ void lo_b_to_smem(const A64 (&v)[64], float2 *sm_, int tid) {
+    A64 *sm = reinterpret_cast<A64 *>(sm_);
 #pragma unroll
-    for (int j = 0; j < 64; j += 2) {
-        float4 x = make_float4(v[j].x, v[j].y, v[j + 1].x, v[j + 1].y);
-        *reinterpret_cast<float4 *>(&sm[lo_swz((tid << 6) | j)]) = x;
-    }
+    for (int j = 0; j < 64; j += 2)
+        *reinterpret_cast<ulonglong2 *>(&sm[lo_swz((tid << 6) | j)]) = make_ulonglong2(v[j], v[j + 1]);
 }
-__device__ __forceinline__ void lo_smem_to_b(float2 (&v)[64], const float2 *sm, int tid) {
+__device__ __forceinline__ void lo_smem_to_b(A64 (&v)[64], const float2 *sm_, int tid) {
+    const A64 *sm = reinterpret_cast<const A64 *>(sm_);
 #pragma unroll
     for (int j = 0; j < 64; j += 2) {
-        const float4 x = *reinterpret_cast<const float4 *>(&sm[lo_swz((tid << 6) | j)]);
-        v[j] = make_float2(x.x, x.y);
-        v[j + 1] = make_float2(x.z, x.w);
+        const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(&sm[lo_swz((tid << 6) | j)]);
+        v[j] = x.x;
+        v[j + 1] = x.y;
     }
 }
 
-__device__ __forceinline__ void load_tq(float (&t)[6], const float *tq, int q0) {
-#pragma unroll
-    for (int b = 0; b < 6; ++b) t[b] = tq[q0 + b];
+// K1, evaluated without a table lookup in the inner loop.  For a thread whose 6 register bits sit
+// at qubits p_0..p_5 and whose other index bits are fixed:
+//     D(idx) = A + sum_b z_b F_b + R(j),   z_b = +1 / -1 for register bit b clear / set,
+// A, F_b (fixed-point int32, exact fp64 values rounded once) come from two 16-byte loads issued at
+// the top of the kernel; R(j) couples the register qubits among themselves and enters as a
+// compile-time-indexed constant-bank operand.  The 64 amplitudes are visited in Gray-code order so
+// that one IADD3 updates D per amplitude.  Odd-parity amplitudes are stored swapped, for which
+// multiplying by exp(i phi) is the same formula with phi -> -phi: the rate cfx carries the sign.
+struct PhaseAF {
+    int4 a0, a1;
+};
+__device__ __forceinline__ PhaseAF load_af(const int4 *__restrict__ af, int64_t f) {
+    PhaseAF r;
+    r.a0 = __ldg(af + 2 * f);
+    r.a1 = __ldg(af + 2 * f + 1);
+    return r;
 }
-
-// phase for the B layout: thread's 64 consecutive indices; permuted table => LDG.128 coalesced
-__device__ __forceinline__ void lo_phase_b(float2 (&v)[64], const int *__restrict__ dfx_lo, int64_t tile, int tid,
-                                           const ChainParams &cp) {
-    const int4 *p = reinterpret_cast<const int4 *>(dfx_lo) + (tile * 16) * NT + tid;
+__device__ __forceinline__ void phase_gray(A64 (&v)[64], const PhaseAF af, const int (&dr)[64], const ChainParams &cp,
+                                           const int tpar) {
     if (cp.active) {
+        const int ce = tpar ? -cp.cfx : cp.cfx, co = -ce;  // rate for locally even / odd register index
+        const int F[6] = {af.a0.y, af.a0.z, af.a0.w, af.a1.x, af.a1.y, af.a1.z};
+        int F2[6];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            const int4 d = __ldg(p + c * NT);
-            apply_phase(v[4 * c + 0], phase_from_fx(d.x, cp.cfx, cp.shift, cp.scale));
-            apply_phase(v[4 * c + 1], phase_from_fx(d.y, cp.cfx, cp.shift, cp.scale));
-            apply_phase(v[4 * c + 2], phase_from_fx(d.z, cp.cfx, cp.shift, cp.scale));
-            apply_phase(v[4 * c + 3], phase_from_fx(d.w, cp.cfx, cp.shift, cp.scale));
+        for (int b = 0; b < 6; ++b) F2[b] = 2 * F[b];
+        int d = af.a0.x + F[0] + F[1] + F[2] + F[3] + F[4] + F[5] + dr[0];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            const int j = i ^ (i >> 1);
+            const bool odd = (__builtin_popcount(j) & 1) != 0;
+            apply_phase(v[j], phase_from_fx(d, odd ? co : ce, cp.shift, cp.scale));
+            if (i < 63) {
+                const int i1 = i + 1;
+                const int b = (i1 & 1) ? 0 : (i1 & 2) ? 1 : (i1 & 4) ? 2 : (i1 & 8) ? 3 : (i1 & 16) ? 4 : 5;
+                const int jn = (i + 1) ^ ((i + 1) >> 1);
+                d = ((jn >> b) & 1) ? d - F2[b] + dr[i + 1] : d + F2[b] + dr[i + 1];
+            }
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            v[j].x *= cp.scale;
-            v[j].y *= cp.scale;
-        }
+        for (int j = 0; j < 64; ++j) apply_scale(v[j], cp.scale);
     }
 }
 
 // M|s0> restricted to this thread's 64 amplitudes; reg bit b <-> global qubit qpos[b]
 template <typename QP>
-__device__ __forceinline__ void init_product(float2 (&v)[64], uint64_t base_idx, int n, const ChainParams &cp, QP qpos) {
+__device__ __forceinline__ void init_product(A64 (&v)[64], uint64_t base_idx, int n, const ChainParams &cp, QP qpos) {
+    const int tpar = parity64(base_idx);
     // fixed part: all qubits outside the register bits
     uint64_t regmask = 0;
 #pragma unroll
@@ -214,29 +273,29 @@ __device__ __forceinline__ void init_product(float2 (&v)[64], uint64_t base_idx,
             mag *= differs ? f[b] : 1.0f;
             d += differs;
         }
-        v[j] = product_state_amp(mag, d);
+        const float2 amp = product_state_amp(mag, d);
+        const bool odd = ((__builtin_popcount(j) & 1) ^ tpar) != 0;
+        v[j] = odd ? pk(amp.y, amp.x) : pk(amp.x, amp.y);
     }
 }
 
 struct LoQ0 { __device__ __forceinline__ int operator()(int b) const { return b; } };       // B layout: bits 0..5
+struct LoQ6 { __device__ __forceinline__ int operator()(int b) const { return 6 + b; } };   // A layout: bits 6..11
 
 // Final LO computation for (chain, tile): leaves the final amplitudes of the tile in B layout.
 // Used by the last sweep (segment sums) and by the sampler (recompute of the selected tile).
-__device__ __forceinline__ void lo_final_tile(float2 (&v)[64], float2 *sm, const float2 *__restrict__ state_chain,
+__device__ __forceinline__ void lo_final_tile(A64 (&v)[64], float2 *sm, const float2 *__restrict__ state_chain,
                                               int64_t tile, int tid, int n, const ChainParams &cp) {
-    float t[6];
     if (cp.r == 1) {
         init_product(v, ((uint64_t)tile << TILE_BITS) | ((uint64_t)tid << 6), n, cp, LoQ0());
         return;
     }
     lo_load_a(v, state_chain + (tile << TILE_BITS), tid);
-    load_tq(t, cp.tq, 6);
-    bfly6<63>(v, t);
+    bfly6<63>(v, cp, LoQ6(), parity64(((unsigned long long)tile << TILE_BITS) | (unsigned)lo_base_a(tid)));
     lo_a_to_smem(v, sm, tid);
     __syncthreads();
     lo_smem_to_b(v, sm, tid);
-    load_tq(t, cp.tq, 0);
-    bfly6<63>(v, t);
+    bfly6<63>(v, cp, LoQ0(), parity64(((unsigned long long)tile << TILE_BITS) | ((unsigned)tid << 6)));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -284,35 +343,6 @@ __device__ __forceinline__ int64_t hi_base_b(int tid, int64_t tile) {
 __device__ __forceinline__ int hi_loc_a(int tid, int j) { return (tid & 31) | ((tid >> 5) << 5) | (j << 7); }
 __device__ __forceinline__ int hi_loc_b(int tid, int j) { return (tid & 31) | (j << 5) | ((tid >> 5) << 11); }
 
-template <int W, bool BLAYOUT>
-__device__ __forceinline__ void hi_phase(float2 (&v)[64], const int *__restrict__ dfx, int64_t base, const ChainParams &cp) {
-    using G = HiGeom<W>;
-    if (cp.active) {
-#pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            const int d = __ldg(dfx + base + (BLAYOUT ? G::off_b(j) : G::off_a(j)));
-            apply_phase(v[j], phase_from_fx(d, cp.cfx, cp.shift, cp.scale));
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            v[j].x *= cp.scale;
-            v[j].y *= cp.scale;
-        }
-    }
-}
-
-template <int W>
-__device__ __forceinline__ void hi_tq_a(float (&t)[6], const float *tq) {
-#pragma unroll
-    for (int b = 0; b < 6; ++b) t[b] = tq[HiGeom<W>::gpos(7 + b)];
-}
-template <int W>
-__device__ __forceinline__ void hi_tq_b(float (&t)[6], const float *tq) {
-#pragma unroll
-    for (int b = 0; b < 6; ++b) t[b] = tq[HiGeom<W>::gpos(5 + b)];
-}
-
 // ------------------------------------------------------------------------------------------
 // sweep kernels: grid = (tiles, chains of one role); chain = order[list_off + blockIdx.y].
 // One kernel per role so that every CTA of a launch runs the same straight-line code
@@ -343,47 +373,49 @@ __global__ void __launch_bounds__(NT, 3) lo_sweep_kernel(const SweepArgs a, cons
     const ChainParams &cp = cp_s;
     const int n = a.n;
     float2 *state = a.state + (chain << n);
-    float2 v[64];
-    float t[6];
+    A64 v[64];
     if (ROLE == LO_FINAL) {
         lo_final_tile(v, sm, state, tile, tid, n, cp);
         float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) s += v[j].x * v[j].x + v[j].y * v[j].y;
+        for (int j = 0; j < 64; ++j) s += norm2(v[j]);
         a.segsum[(chain << (n - 6)) + tile * NT + tid] = s;
         if (a.probs_out) {
             float *po = a.probs_out + (chain << n) + (tile << TILE_BITS) + (tid << 6);
 #pragma unroll
-            for (int j = 0; j < 64; ++j) po[j] = v[j].x * v[j].x + v[j].y * v[j].y;
+            for (int j = 0; j < 64; ++j) po[j] = norm2(v[j]);
         }
         if (a.amps_out) {
             float2 *ao = a.amps_out + (chain << n) + (tile << TILE_BITS) + (tid << 6);
 #pragma unroll
-            for (int j = 0; j < 64; ++j) ao[j] = v[j];
+            for (int j = 0; j < 64; ++j) {
+                const bool odd = ((__builtin_popcount(j) & 1) ^ parity64(((unsigned long long)tile << TILE_BITS) | ((unsigned)tid << 6))) != 0;
+                const float2 f = upk(v[j]);
+                ao[j] = odd ? make_float2(f.y, f.x) : f;
+            }
         }
         return;
     }
+    const int par_a = parity64(((unsigned long long)tile << TILE_BITS) | (unsigned)lo_base_a(tid));
+    const int par_b = parity64(((unsigned long long)tile << TILE_BITS) | ((unsigned)tid << 6));
+    const PhaseAF af = load_af(a.af_lo, tile * NT + tid);  // issued before the amplitude loads
     if (ROLE == LO_FIRST) {
         init_product(v, ((uint64_t)tile << TILE_BITS) | ((uint64_t)tid << 6), n, cp, LoQ0());
     } else {
         lo_load_a(v, state + (tile << TILE_BITS), tid);
-        load_tq(t, cp.tq, 6);
-        bfly6<63>(v, t);
+        bfly6<63>(v, cp, LoQ6(), par_a);
         lo_a_to_smem(v, sm, tid);
         __syncthreads();
         lo_smem_to_b(v, sm, tid);
-        load_tq(t, cp.tq, 0);
-        bfly6<63>(v, t);
+        bfly6<63>(v, cp, LoQ0(), par_b);
         __syncthreads();  // everyone has read the A->B transposition before smem is rewritten
     }
-    lo_phase_b(v, a.dfx_lo, tile, tid, cp);
-    load_tq(t, cp.tq, 0);
-    bfly6<63>(v, t);
+    phase_gray(v, af, a.dr_lo, cp, par_b);
+    bfly6<63>(v, cp, LoQ0(), par_b);
     lo_b_to_smem(v, sm, tid);
     __syncthreads();
     lo_smem_to_a(v, sm, tid);
-    load_tq(t, cp.tq, 6);
-    bfly6<63>(v, t);
+    bfly6<63>(v, cp, LoQ6(), par_a);
     lo_store_a(v, state + (tile << TILE_BITS), tid);
 }
 
@@ -399,52 +431,230 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
     const ChainParams &cp = cp_s;
     const int n = a.n;
     float2 *state = a.state + (chain << n);
-    float2 v[64];
-    float t[6];
+    A64 v[64];
     const int64_t base_a = hi_base_a<W>(tid, tile);
+    const PhaseAF af = load_af(G::two_rounds ? a.af_hib : a.af_hia, tile * NT + tid);
     if (G::two_rounds) {
         const int64_t base_b = hi_base_b<W>(tid, tile);
         if (FIRST) {
             init_product(v, (uint64_t)base_b, n, cp, HiQB<W>());
         } else {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = state[base_a + G::off_a(j)];
-            hi_tq_a<W>(t, cp.tq);
-            bfly6<G::active_a>(v, t);
+            for (int j = 0; j < 64; ++j) v[j] = reinterpret_cast<const A64 *>(state)[base_a + G::off_a(j)];
+            bfly6<G::active_a>(v, cp, HiQA<W>(), parity64((unsigned long long)base_a));
 #pragma unroll
-            for (int j = 0; j < 64; ++j) sm[hi_loc_a(tid, j)] = v[j];
+            for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(sm)[hi_loc_a(tid, j)] = v[j];
             __syncthreads();
 #pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = sm[hi_loc_b(tid, j)];
-            hi_tq_b<W>(t, cp.tq);
-            bfly6<G::active_b>(v, t);
+            for (int j = 0; j < 64; ++j) v[j] = reinterpret_cast<const A64 *>(sm)[hi_loc_b(tid, j)];
+            bfly6<G::active_b>(v, cp, HiQB<W>(), parity64((unsigned long long)base_b));
             __syncthreads();
         }
-        hi_phase<W, true>(v, a.dfx_nat, base_b, cp);
-        hi_tq_b<W>(t, cp.tq);
-        bfly6<G::active_b>(v, t);
+        phase_gray(v, af, a.dr_hib, cp, parity64((unsigned long long)base_b));
+        bfly6<G::active_b>(v, cp, HiQB<W>(), parity64((unsigned long long)base_b));
 #pragma unroll
-        for (int j = 0; j < 64; ++j) sm[hi_loc_b(tid, j)] = v[j];
+        for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(sm)[hi_loc_b(tid, j)] = v[j];
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] = sm[hi_loc_a(tid, j)];
-        hi_tq_a<W>(t, cp.tq);
-        bfly6<G::active_a>(v, t);
+        for (int j = 0; j < 64; ++j) v[j] = reinterpret_cast<const A64 *>(sm)[hi_loc_a(tid, j)];
+        bfly6<G::active_a>(v, cp, HiQA<W>(), parity64((unsigned long long)base_a));
 #pragma unroll
-        for (int j = 0; j < 64; ++j) state[base_a + G::off_a(j)] = v[j];
+        for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(state)[base_a + G::off_a(j)] = v[j];
     } else {
-        hi_tq_a<W>(t, cp.tq);
         if (FIRST) {
             init_product(v, (uint64_t)base_a, n, cp, HiQA<W>());
         } else {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = state[base_a + G::off_a(j)];
-            bfly6<G::active_a>(v, t);
+            for (int j = 0; j < 64; ++j) v[j] = reinterpret_cast<const A64 *>(state)[base_a + G::off_a(j)];
+            bfly6<G::active_a>(v, cp, HiQA<W>(), parity64((unsigned long long)base_a));
         }
-        hi_phase<W, false>(v, a.dfx_nat, base_a, cp);
-        bfly6<G::active_a>(v, t);
+        phase_gray(v, af, a.dr_hia, cp, parity64((unsigned long long)base_a));
+        bfly6<G::active_a>(v, cp, HiQA<W>(), parity64((unsigned long long)base_a));
 #pragma unroll
-        for (int j = 0; j < 64; ++j) state[base_a + G::off_a(j)] = v[j];
+        for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(state)[base_a + G::off_a(j)] = v[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent, warp-specialised MID sweeps (the dominant kernels): one CTA per SM,
+//   warp 8          producer: streams tiles HBM -> shared memory with cp.async.bulk (TMA), completion on mbarriers
+//   warps 0-3, 4-7  two consumer groups of 128 threads that ping-pong over tiles: a tile lands in a
+//                   64 KiB ring slot, is pulled into registers, butterflied / phased (the slot doubles as
+//                   the transposition buffer), and is written back to HBM with coalesced STG.
+// Ring of 3 slots (192 KiB): two being computed on, one in flight, so compute never waits on HBM.
+// Work item i of CTA b = global item b + i * gridDim.x = (chain-in-list, tile); group i & 1; slot i % 3.
+// ------------------------------------------------------------------------------------------
+constexpr int PIPE_THREADS = 256;
+constexpr int RING = 3;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(NT) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct PipeShared {
+    uint64_t full[RING];
+    uint64_t empty[RING];
+    ChainParams cp[2];
+};
+
+// W = 0: LO tile (contiguous 64 KiB); W in 2..8: HI tile of n = 12 + W.
+// There is no dedicated producer warp (a 9th warp would cap the consumers at 168 registers):
+// the group that frees a ring slot (item j) issues the bulk copies of item j + 3 into it.
+template <int W>
+__global__ void __launch_bounds__(PIPE_THREADS, 1) mid_pipe_kernel(const SweepArgs a, const int *__restrict__ order,
+                                                                   const int list_off, const long long total_items) {
+    constexpr bool IS_LO = (W == 0);
+    constexpr int WW = IS_LO ? 8 : W;
+    using G = HiGeom<WW>;
+    extern __shared__ __align__(1024) unsigned char dsm[];
+    __shared__ PipeShared ps;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int n = a.n;
+    const int tile_bits = n - TILE_BITS;
+    const long long tile_mask = (1LL << tile_bits) - 1;
+    const long long first = blockIdx.x;
+    const long long n_items = first < total_items ? (total_items - first + gridDim.x - 1) / gridDim.x : 0;
+
+    // issue the HBM -> smem copies of item i (executed by one full warp; lane 0 owns the barrier handshake)
+    auto issue = [&](long long i) {
+        const int b = (int)(i % RING);
+        const long long item = first + i * gridDim.x;
+        const long long chain = order[list_off + (int)(item >> tile_bits)];
+        const long long tile = item & tile_mask;
+        float2 *dst = reinterpret_cast<float2 *>(dsm) + (size_t)b * TILE;
+        const float2 *src = a.state + (chain << n);
+        if (lane == 0) {
+            mbar_wait(&ps.empty[b], (uint32_t)(((i / RING) & 1) ^ 1));  // slot released by item i - 3
+            mbar_expect_tx(&ps.full[b], TILE * 8);
+        }
+        __syncwarp();
+        if (IS_LO) {
+            if (lane == 0) bulk_g2s(dst, src + (tile << TILE_BITS), TILE * 8, &ps.full[b]);
+        } else {
+            constexpr int ROWS = 1 << WW;
+            constexpr int ROW_AMPS = 1 << G::Lc;
+            for (int r = lane; r < ROWS; r += 32)
+                bulk_g2s(dst + r * ROW_AMPS, src + (tile << G::Lc) + ((long long)r << 12), ROW_AMPS * 8, &ps.full[b]);
+        }
+    };
+
+    if (tid == 0) {
+        for (int b = 0; b < RING; ++b) {
+            mbar_init(&ps.full[b], 1);
+            mbar_init(&ps.empty[b], NT);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0)
+        for (long long i = 0; i < RING && i < n_items; ++i) issue(i);
+
+    const int g = warp >> 2;
+    const int gt = tid & (NT - 1);
+    ChainParams &cp = ps.cp[g];
+    A64 v[64];
+    for (long long i = g; i < n_items; i += 2) {
+        const int b = (int)(i % RING);
+        const long long item = first + i * gridDim.x;
+        const long long chain = order[list_off + (int)(item >> tile_bits)];
+        const long long tile = item & tile_mask;
+        float2 *sm = reinterpret_cast<float2 *>(dsm) + (size_t)b * TILE;
+        float2 *state = a.state + (chain << n);
+        group_sync(g);  // previous item's readers of cp are done
+        {
+            const int *src = reinterpret_cast<const int *>(a.params + chain);
+            int *dst = reinterpret_cast<int *>(&cp);
+            for (int k = gt; k < (int)(sizeof(ChainParams) / 4); k += NT) dst[k] = src[k];
+        }
+        group_sync(g);
+        const PhaseAF af = load_af(IS_LO ? a.af_lo : (G::two_rounds ? a.af_hib : a.af_hia), tile * NT + gt);
+        mbar_wait(&ps.full[b], (uint32_t)((i / RING) & 1));
+        if (IS_LO) {
+            const int base = lo_base_a(gt);
+            const int par_a = parity64(((unsigned long long)tile << TILE_BITS) | (unsigned)base);
+            const int par_b = parity64(((unsigned long long)tile << TILE_BITS) | ((unsigned)gt << 6));
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = reinterpret_cast<const A64 *>(sm)[base | (j << 6)];  // linear layout as landed
+            bfly6<63>(v, cp, LoQ6(), par_a);
+            // linear -> swizzled rewrite stays inside each warp-instruction's own 32 slots: no barrier needed
+            lo_a_to_smem(v, sm, gt);
+            group_sync(g);
+            lo_smem_to_b(v, sm, gt);
+            bfly6<63>(v, cp, LoQ0(), par_b);
+            phase_gray(v, af, a.dr_lo, cp, par_b);
+            bfly6<63>(v, cp, LoQ0(), par_b);
+            lo_b_to_smem(v, sm, gt);  // same slots this thread just read
+            group_sync(g);
+            lo_smem_to_a(v, sm, gt);
+            fence_async_smem();
+            mbar_arrive(&ps.empty[b]);
+            if ((gt >> 5) == 0 && i + RING < n_items) issue(i + RING);
+            bfly6<63>(v, cp, LoQ6(), par_a);
+            lo_store_a(v, state + (tile << TILE_BITS), gt);
+        } else {
+            const long long base_a = hi_base_a<WW>(gt, tile);
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = reinterpret_cast<const A64 *>(sm)[hi_loc_a(gt, j)];
+            bfly6<G::active_a>(v, cp, HiQA<WW>(), parity64((unsigned long long)base_a));
+            if (G::two_rounds) {
+                const long long base_b = hi_base_b<WW>(gt, tile);
+#pragma unroll
+                for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(sm)[hi_loc_a(gt, j)] = v[j];
+                group_sync(g);
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] = reinterpret_cast<const A64 *>(sm)[hi_loc_b(gt, j)];
+                bfly6<G::active_b>(v, cp, HiQB<WW>(), parity64((unsigned long long)base_b));
+                phase_gray(v, af, a.dr_hib, cp, parity64((unsigned long long)base_b));
+                bfly6<G::active_b>(v, cp, HiQB<WW>(), parity64((unsigned long long)base_b));
+#pragma unroll
+                for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(sm)[hi_loc_b(gt, j)] = v[j];
+                group_sync(g);
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] = reinterpret_cast<const A64 *>(sm)[hi_loc_a(gt, j)];
+                fence_async_smem();
+                mbar_arrive(&ps.empty[b]);
+                if ((gt >> 5) == 0 && i + RING < n_items) issue(i + RING);
+                bfly6<G::active_a>(v, cp, HiQA<WW>(), parity64((unsigned long long)base_a));
+            } else {
+                fence_async_smem();
+                mbar_arrive(&ps.empty[b]);
+                if ((gt >> 5) == 0 && i + RING < n_items) issue(i + RING);
+                phase_gray(v, af, a.dr_hia, cp, parity64((unsigned long long)base_a));
+                bfly6<G::active_a>(v, cp, HiQA<WW>(), parity64((unsigned long long)base_a));
+            }
+#pragma unroll
+            for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(state)[base_a + G::off_a(j)] = v[j];
+        }
     }
 }
 
@@ -515,6 +725,10 @@ __device__ void fill_proposal_params(ChainParams &cp, const HopArgs &h, double g
         scale *= c;
     }
     cp.scale = (float)scale;
+    for (int q = 0; q < QMC_MAX_SPINS; ++q) {
+        cp.tpair[q][0] = make_float2(cp.tq[q], -cp.tq[q]);
+        cp.tpair[q][1] = make_float2(-cp.tq[q], cp.tq[q]);
+    }
     const double cprime = (1.0 - gamma) * h.alpha * h.dt * 0.15915494309189533577;  // c / (2 pi)
     cp.active = h.phase_active && cp.r > 1 && cprime != 0.0;
     int m = 0;
@@ -624,7 +838,7 @@ __global__ void __launch_bounds__(NT) sample_accept_kernel(const SweepArgs a, co
     const int64_t sg = s_seg;
     const int64_t tile = sg / NT;
     const int owner = (int)(sg % NT);
-    float2 v[64];
+    A64 v[64];
     lo_final_tile(v, sm, a.state + ((int64_t)chain << n), tile, tid, n, cp);
     if (tid == owner) {
         const double rem = s_rem;
@@ -632,7 +846,7 @@ __global__ void __launch_bounds__(NT) sample_accept_kernel(const SweepArgs a, co
         int selj = 63;
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
-            c += (double)(v[j].x * v[j].x + v[j].y * v[j].y);
+            c += (double)norm2(v[j]);
             if (selj == 63 && rem < c) selj = j;
         }
         s_sel = ((unsigned long long)tile << TILE_BITS) | ((unsigned long long)owner << 6) | (unsigned long long)selj;
@@ -691,17 +905,39 @@ __global__ void probs_normalize_kernel(int n, const float *segsum, float *probs,
     }
 }
 
-// D -> fixed point tables
-__global__ void dfx_tables_kernel(int n, const double *__restrict__ D, double scale, int *__restrict__ nat,
-                                  int *__restrict__ lo) {
-    const int64_t N = 1LL << n;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < N; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int v = (int)rint(D[idx] * scale);
-        nat[idx] = v;
-        // LO B-layout: idx = tile*8192 + thread*64 + c*4 + e  ->  [tile][c][thread][e]
-        const int64_t tile = idx >> TILE_BITS;
-        const int thread = (int)(idx >> 6) & 127, c = (int)(idx >> 2) & 15, e = (int)idx & 3;
-        lo[((tile * 16 + c) * NT + thread) * 4 + e] = v;
+// A / F_b tables of one register layout: LAYOUT 0 = LO B (regs = qubits 0..5), 1 = HI A', 2 = HI B'.
+// Jq/hq are the circuit couplings in qubit order (qubit a = spin n-1-a); values are exact fp64 sums
+// rounded once to fixed point (scale 2^k_fx).
+template <int W, int LAYOUT>
+__global__ void af_table_kernel(int n, const double *__restrict__ Jq, const double *__restrict__ hq, double scale,
+                                int4 *__restrict__ af) {
+    const int64_t total = (int64_t)1 << (n - 6);
+    for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < total; f += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t tile = f >> 7;
+        const int tid = (int)(f & 127);
+        uint64_t base;
+        int p[6];
+        for (int b = 0; b < 6; ++b) p[b] = LAYOUT == 0 ? b : (LAYOUT == 1 ? HiGeom<W>::gpos(7 + b) : HiGeom<W>::gpos(5 + b));
+        if (LAYOUT == 0) base = ((uint64_t)tile << TILE_BITS) | ((uint64_t)tid << 6);
+        else if (LAYOUT == 1) base = (uint64_t)hi_base_a<W>(tid, tile);
+        else base = (uint64_t)hi_base_b<W>(tid, tile);
+        uint64_t regmask = 0;
+        for (int b = 0; b < 6; ++b) regmask |= 1ULL << p[b];
+        double A = 0.0, F[6];
+        for (int b = 0; b < 6; ++b) F[b] = hq[p[b]];
+        for (int q = 0; q < n; ++q) {
+            if ((regmask >> q) & 1ULL) continue;
+            const double zq = ((base >> q) & 1ULL) ? -1.0 : 1.0;
+            A += hq[q] * zq;
+            for (int q2 = q + 1; q2 < n; ++q2) {
+                if ((regmask >> q2) & 1ULL) continue;
+                const double z2 = ((base >> q2) & 1ULL) ? -1.0 : 1.0;
+                A += Jq[q * n + q2] * zq * z2;
+            }
+            for (int b = 0; b < 6; ++b) F[b] += Jq[q * n + p[b]] * zq;
+        }
+        af[2 * f] = make_int4((int)rint(A * scale), (int)rint(F[0] * scale), (int)rint(F[1] * scale), (int)rint(F[2] * scale));
+        af[2 * f + 1] = make_int4((int)rint(F[3] * scale), (int)rint(F[4] * scale), (int)rint(F[5] * scale), 0);
     }
 }
 
@@ -717,7 +953,8 @@ struct SweepWorkspace {
     float *segsum = nullptr;
     int *hist = nullptr;
     int *order = nullptr;
-    int *dfx_nat = nullptr, *dfx_lo = nullptr;
+    int4 *af_lo = nullptr, *af_hia = nullptr, *af_hib = nullptr;
+    int dr_lo[64], dr_hia[64], dr_hib[64];
     int k_fx = 0;
     std::vector<cudaEvent_t> ev;
 };
@@ -730,11 +967,42 @@ void qmc_sweep_free(qmc_model *m) {
     cudaFree(w->segsum);
     cudaFree(w->hist);
     cudaFree(w->order);
-    cudaFree(w->dfx_nat);
-    cudaFree(w->dfx_lo);
+    cudaFree(w->af_lo);
+    cudaFree(w->af_hia);
+    cudaFree(w->af_hib);
     for (auto e : w->ev) cudaEventDestroy(e);
     delete w;
     m->sweep = nullptr;
+}
+
+template <int W>
+static int build_af_w(int n, const double *dJq, const double *dhq, double scale, int4 *lo, int4 *hia, int4 *hib,
+                      int (&pos)[3][6], cudaStream_t st) {
+    const int grid = (int)std::min<int64_t>(148 * 8, (((int64_t)1 << (n - 6)) + 127) / 128);
+    af_table_kernel<W, 0><<<grid, 128, 0, st>>>(n, dJq, dhq, scale, lo);
+    af_table_kernel<W, 1><<<grid, 128, 0, st>>>(n, dJq, dhq, scale, hia);
+    af_table_kernel<W, 2><<<grid, 128, 0, st>>>(n, dJq, dhq, scale, hib);
+    for (int b = 0; b < 6; ++b) {
+        pos[0][b] = b;
+        pos[1][b] = HiGeom<W>::gpos(7 + b);
+        pos[2][b] = HiGeom<W>::gpos(5 + b);
+    }
+    return QMC_OK;
+}
+
+static int build_af_tables(int n, const double *dJq, const double *dhq, double scale, int4 *lo, int4 *hia, int4 *hib,
+                           int (&pos)[3][6], cudaStream_t st) {
+    switch (n - LO_BITS) {
+        case 2: return build_af_w<2>(n, dJq, dhq, scale, lo, hia, hib, pos, st);
+        case 3: return build_af_w<3>(n, dJq, dhq, scale, lo, hia, hib, pos, st);
+        case 4: return build_af_w<4>(n, dJq, dhq, scale, lo, hia, hib, pos, st);
+        case 5: return build_af_w<5>(n, dJq, dhq, scale, lo, hia, hib, pos, st);
+        case 6: return build_af_w<6>(n, dJq, dhq, scale, lo, hia, hib, pos, st);
+        case 7: return build_af_w<7>(n, dJq, dhq, scale, lo, hia, hib, pos, st);
+        case 8: return build_af_w<8>(n, dJq, dhq, scale, lo, hia, hib, pos, st);
+    }
+    qmc_set_error("sweep path: n=%d outside [14, 20]", n);
+    return QMC_ERR_UNSUPPORTED;
 }
 
 static int ensure_workspace(qmc_model *m, int64_t chains, cudaStream_t st) {
@@ -742,20 +1010,55 @@ static int ensure_workspace(qmc_model *m, int64_t chains, cudaStream_t st) {
     SweepWorkspace *w = m->sweep;
     const int n = m->n;
     const int64_t N = 1LL << n;
-    if (!w->dfx_nat) {
+    if (!w->af_lo) {
+        // circuit couplings in qubit order: qubit a = spin n-1-a (quantum_mcmc_routines.py:75,87)
+        std::vector<double> Jq((size_t)n * n), hq(n);
         double dmax = 0.0;
-        for (int j = 0; j < n; ++j) {
-            dmax += fabs(m->host_ch[j]);
-            for (int k = j + 1; k < n; ++k) dmax += fabs(m->host_cJ[(size_t)j * n + k]);
+        for (int a = 0; a < n; ++a) {
+            hq[a] = m->host_ch[n - 1 - a];
+            dmax += fabs(hq[a]);
+            for (int b = 0; b < n; ++b) {
+                Jq[(size_t)a * n + b] = m->host_cJ[(size_t)(n - 1 - a) * n + (n - 1 - b)];
+                if (b > a) dmax += fabs(Jq[(size_t)a * n + b]);
+            }
         }
         if (dmax < 1e-300) dmax = 1.0;
-        w->k_fx = (int)floor(log2(2147483647.0 / (dmax * 1.0000001)));
+        w->k_fx = (int)floor(log2(2147483647.0 / (dmax * 1.0000001))) - 1;  // one bit of headroom for rounding
         if (w->k_fx > 30) w->k_fx = 30;
-        QMC_CUDA_TRY(cudaMalloc(&w->dfx_nat, sizeof(int) * (size_t)N));
-        QMC_CUDA_TRY(cudaMalloc(&w->dfx_lo, sizeof(int) * (size_t)N));
-        dfx_tables_kernel<<<148 * 8, 256, 0, st>>>(n, m->dD, ldexp(1.0, w->k_fx), w->dfx_nat, w->dfx_lo);
-        m->launches++;
+        const double scale = ldexp(1.0, w->k_fx);
+        double *dJq = nullptr, *dhq = nullptr;
+        QMC_CUDA_TRY(cudaMalloc(&dJq, sizeof(double) * (size_t)n * n));
+        QMC_CUDA_TRY(cudaMalloc(&dhq, sizeof(double) * (size_t)n));
+        QMC_CUDA_TRY(cudaMemcpyAsync(dJq, Jq.data(), sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, st));
+        QMC_CUDA_TRY(cudaMemcpyAsync(dhq, hq.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+        const size_t af_bytes = sizeof(int4) * 2 * (size_t)(N >> 6);
+        QMC_CUDA_TRY(cudaMalloc(&w->af_lo, af_bytes));
+        QMC_CUDA_TRY(cudaMalloc(&w->af_hia, af_bytes));
+        QMC_CUDA_TRY(cudaMalloc(&w->af_hib, af_bytes));
+        int pos[3][6];
+        int rc = build_af_tables(n, dJq, dhq, scale, w->af_lo, w->af_hia, w->af_hib, pos, st);
+        m->launches += 3;
         QMC_CUDA_TRY(cudaGetLastError());
+        QMC_CUDA_TRY(cudaStreamSynchronize(st));  // Jq/hq are stack-owned staging
+        cudaFree(dJq);
+        cudaFree(dhq);
+        if (rc != QMC_OK) return rc;
+        // R(j) = sum_{b<b'} Jq[p_b][p_b'] z_b z_b' and its Gray-order increments
+        int *drs[3] = {w->dr_lo, w->dr_hia, w->dr_hib};
+        for (int L = 0; L < 3; ++L) {
+            int R[64];
+            for (int j = 0; j < 64; ++j) {
+                double r = 0.0;
+                for (int b = 0; b < 6; ++b)
+                    for (int b2 = b + 1; b2 < 6; ++b2) {
+                        const double zb = ((j >> b) & 1) ? -1.0 : 1.0, zb2 = ((j >> b2) & 1) ? -1.0 : 1.0;
+                        r += Jq[(size_t)pos[L][b] * n + pos[L][b2]] * zb * zb2;
+                    }
+                R[j] = (int)rint(r * scale);
+            }
+            drs[L][0] = R[0];
+            for (int i = 1; i < 64; ++i) drs[L][i] = R[i ^ (i >> 1)] - R[(i - 1) ^ ((i - 1) >> 1)];
+        }
     }
     if (chains > w->cap_chains) {
         QMC_CUDA_TRY(cudaStreamSynchronize(st));
@@ -797,6 +1100,35 @@ static int launch_hi_w(const SweepArgs &a, const int *order, int off, int64_t ti
     if (rc != QMC_OK) return rc;
     hi_sweep_kernel<W, FIRST><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off);
     return QMC_OK;
+}
+
+template <int W>
+static int launch_pipe_w(const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
+    static bool done = false;
+    if (!done) {
+        QMC_CUDA_TRY(cudaFuncSetAttribute(mid_pipe_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, RING * TILE * 8));
+        done = true;
+    }
+    const long long items = (long long)tiles * count;
+    const unsigned grid = (unsigned)std::min<long long>(148, (items + 1) / 2);
+    mid_pipe_kernel<W><<<grid, PIPE_THREADS, RING * TILE * 8, st>>>(a, order, off, items);
+    return QMC_OK;
+}
+
+// W = 0 -> LO mid; otherwise HI mid for n = 12 + W
+static int launch_pipe(int w, const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
+    switch (w) {
+        case 0: return launch_pipe_w<0>(a, order, off, tiles, count, st);
+        case 2: return launch_pipe_w<2>(a, order, off, tiles, count, st);
+        case 3: return launch_pipe_w<3>(a, order, off, tiles, count, st);
+        case 4: return launch_pipe_w<4>(a, order, off, tiles, count, st);
+        case 5: return launch_pipe_w<5>(a, order, off, tiles, count, st);
+        case 6: return launch_pipe_w<6>(a, order, off, tiles, count, st);
+        case 7: return launch_pipe_w<7>(a, order, off, tiles, count, st);
+        case 8: return launch_pipe_w<8>(a, order, off, tiles, count, st);
+    }
+    qmc_set_error("sweep path: tile geometry W=%d not built", w);
+    return QMC_ERR_UNSUPPORTED;
 }
 
 template <bool FIRST>
@@ -849,6 +1181,9 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     if (rc != QMC_OK) return rc;
     SweepWorkspace *w = m->sweep;
 
+    // QUMCMC_SWEEP_PIPE=1 selects the persistent TMA-ring MID kernels (A/B parity and profiling)
+    const char *pipe_env = getenv("QUMCMC_SWEEP_PIPE");
+    const bool use_pipe = pipe_env && pipe_env[0] == '1';  // default: non-persistent MID kernels (measured faster)
     const int r_cap = qmc_trotter_steps(11, dt);
     int r_max = r_cap;
     std::vector<int> r_host;
@@ -883,7 +1218,8 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         h.hamming_hist = hamming_hist ? hamming_hist + c0 * (n + 1) : nullptr;
         h.hist = w->hist;
         SweepArgs a;
-        a.n = n; a.state = w->state; a.params = w->params; a.dfx_nat = w->dfx_nat; a.dfx_lo = w->dfx_lo;
+        a.n = n; a.state = w->state; a.params = w->params; a.af_lo = w->af_lo; a.af_hia = w->af_hia; a.af_hib = w->af_hib;
+        memcpy(a.dr_lo, w->dr_lo, sizeof(a.dr_lo)); memcpy(a.dr_hia, w->dr_hia, sizeof(a.dr_hia)); memcpy(a.dr_hib, w->dr_hib, sizeof(a.dr_hib));
         a.segsum = w->segsum;
         a.probs_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float *>(probs_out) : nullptr;
         a.amps_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float2 *>(amps_out) : nullptr;
@@ -931,7 +1267,8 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                 const int lo_eq = rhist[step];
                 if (lo_gt > 0) {
                     rc = step == 1 ? launch_lo<LO_FIRST>(a, w->order, lo_base, tiles, lo_gt, st)
-                                   : launch_lo<LO_MID>(a, w->order, lo_base, tiles, lo_gt, st);
+                         : use_pipe ? launch_pipe(0, a, w->order, lo_base, tiles, lo_gt, st)
+                                    : launch_lo<LO_MID>(a, w->order, lo_base, tiles, lo_gt, st);
                     if (rc != QMC_OK) return rc;
                     ++launched;
                 }
@@ -942,7 +1279,8 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                 }
                 if (hi_gt > 0) {
                     rc = step == 1 ? launch_hi<true>(n, a, w->order, hi_base, tiles, hi_gt, st)
-                                   : launch_hi<false>(n, a, w->order, hi_base, tiles, hi_gt, st);
+                         : use_pipe ? launch_pipe(n - LO_BITS, a, w->order, hi_base, tiles, hi_gt, st)
+                                    : launch_hi<false>(n, a, w->order, hi_base, tiles, hi_gt, st);
                     if (rc != QMC_OK) return rc;
                     ++launched;
                 }
