@@ -115,7 +115,7 @@ struct qmc_model {
     int phase_active = 1;  // fn_qckt_problem_half skip rule (:64-67)
     // device copies (fp64): J, h (energies) and circuit_J/h (phase layer)
     double *dJ = nullptr, *dh = nullptr;
-    // phase exponent D(idx), fp64, index order (all n <= 26; larger n computes on the fly)
+    // phase exponent D(idx), fp64, index order (shared-memory path only)
     double *dD = nullptr;
     // energy table E(idx) for the shared-memory path (n <= QMC_SMEM_MAX_SPINS_F32)
     double *dE = nullptr;

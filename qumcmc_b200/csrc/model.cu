@@ -235,7 +235,7 @@ extern "C" int qmc_model_create(qmc_model **out, int n, const double *J, const d
     TRY_OR_FAIL(cudaMemcpy(dcJ, m->host_cJ.data(), bJ, cudaMemcpyHostToDevice));
     TRY_OR_FAIL(cudaMemcpy(dch, m->host_ch.data(), bh, cudaMemcpyHostToDevice));
     const size_t smem = sizeof(double) * (size_t)(n * n + n);
-    if (n <= 26) {  // 2^26 doubles = 512 MiB; larger n evaluates D on the fly
+    if (n <= QMC_SMEM_MAX_SPINS_F32) {  // only the shared-memory path reads the D table; the sweep paths evaluate D on the fly
         const int64_t N = 1LL << n;
         TRY_OR_FAIL(cudaMalloc(&m->dD, sizeof(double) * (size_t)N));
         phase_table_kernel<<<grid_for(N, 256), 256, smem>>>(n, dcJ, dch, m->dD);

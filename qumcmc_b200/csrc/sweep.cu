@@ -360,7 +360,7 @@ __device__ __forceinline__ void stage_params(ChainParams &dst_s, const ChainPara
     __syncthreads();
 }
 
-enum { LO_FIRST = 0, LO_MID = 1, LO_FINAL = 2 };
+enum { LO_FIRST = 0, LO_MID = 1, LO_FINAL = 2, LO_SINGLE = 3 };  // SINGLE: M_lo only (3+ qubit groups)
 
 template <int ROLE>
 __global__ void __launch_bounds__(NT, 3) lo_sweep_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off) {
@@ -398,6 +398,19 @@ __global__ void __launch_bounds__(NT, 3) lo_sweep_kernel(const SweepArgs a, cons
     }
     const int par_a = parity64(((unsigned long long)tile << TILE_BITS) | (unsigned)lo_base_a(tid));
     const int par_b = parity64(((unsigned long long)tile << TILE_BITS) | ((unsigned)tid << 6));
+    if (ROLE == LO_SINGLE) {
+        lo_load_a(v, state + (tile << TILE_BITS), tid);
+        bfly6<63>(v, cp, LoQ6(), par_a);
+        lo_a_to_smem(v, sm, tid);
+        __syncthreads();
+        lo_smem_to_b(v, sm, tid);
+        bfly6<63>(v, cp, LoQ0(), par_b);
+        lo_b_to_smem(v, sm, tid);  // each thread rewrites exactly the slots it read
+        __syncthreads();
+        lo_smem_to_a(v, sm, tid);
+        lo_store_a(v, state + (tile << TILE_BITS), tid);
+        return;
+    }
     const PhaseAF af = load_af(a.af_lo, tile * NT + tid);  // issued before the amplitude loads
     if (ROLE == LO_FIRST) {
         init_product(v, ((uint64_t)tile << TILE_BITS) | ((uint64_t)tid << 6), n, cp, LoQ0());
@@ -408,11 +421,10 @@ __global__ void __launch_bounds__(NT, 3) lo_sweep_kernel(const SweepArgs a, cons
         __syncthreads();
         lo_smem_to_b(v, sm, tid);
         bfly6<63>(v, cp, LoQ0(), par_b);
-        __syncthreads();  // everyone has read the A->B transposition before smem is rewritten
     }
     phase_gray(v, af, a.dr_lo, cp, par_b);
     bfly6<63>(v, cp, LoQ0(), par_b);
-    lo_b_to_smem(v, sm, tid);
+    lo_b_to_smem(v, sm, tid);  // each thread rewrites exactly the slots it read: no barrier needed before
     __syncthreads();
     lo_smem_to_a(v, sm, tid);
     bfly6<63>(v, cp, LoQ6(), par_a);
@@ -658,11 +670,109 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) mid_pipe_kernel(const SweepAr
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Generic large-n path (n >= 21: three or more qubit groups).  LO group = qubits 0..11 (kernels
+// above, roles SINGLE / FINAL); the remaining qubits are covered by register-only HI6 sweeps:
+// a thread owns the 64 amplitudes over qubits [p, p+6), lanes sit on qubits 0..4, so every access is
+// a coalesced 256 B segment and no shared-memory exchange is needed.  Roles:
+//   HI6_FIRST   M|s> analytic, P, M_g(2)       HI6_MID   M_g(k) P M_g(k+1)       HI6_SINGLE   M_g(k)
+// The phase exponent fields A, F_b are evaluated per thread in fp64 from the couplings (staged in
+// shared memory) -- no table, any n.  ACT = number of active (top) register qubits of the group.
+// ------------------------------------------------------------------------------------------
+enum { HI6_FIRST = 0, HI6_MID = 1, HI6_SINGLE = 2 };
+
+struct HiP {
+    int p;
+    __device__ __forceinline__ int operator()(int b) const { return p + b; }
+};
+
+struct Hi6Args {
+    int p;          // first register qubit
+    int dr[64];     // Gray-order increments of R(j) for this group
+    const double *Jq, *hq;  // circuit couplings in qubit order
+    double fx_scale;        // 2^k_fx
+};
+
+template <int ROLE, int ACT>
+__global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, const Hi6Args g, const int *__restrict__ order,
+                                                          const int list_off) {
+    extern __shared__ __align__(16) double smd[];  // Jq[n*n], hq[n]
+    __shared__ ChainParams cp_s;
+    const int tid = threadIdx.x;
+    const int n = a.n;
+    const int64_t tile = blockIdx.x;
+    const int64_t chain = order[list_off + blockIdx.y];
+    if (ROLE != HI6_SINGLE) {
+        for (int i = tid; i < n * n; i += NT) smd[i] = g.Jq[i];
+        for (int i = tid; i < n; i += NT) smd[n * n + i] = g.hq[i];
+    }
+    stage_params(cp_s, a.params + chain, tid);  // barrier inside
+    const ChainParams &cp = cp_s;
+    const int p = g.p;
+    constexpr int ACTIVE = 63 & ~((1 << (6 - ACT)) - 1);
+    // index bits: lane 0..4, warp bits 5,6, tile-low bits 7..p-1, register bits p..p+5, tile-high bits p+6..n-1
+    const int low_bits = p - 7;
+    const int64_t base = (int64_t)(tid & 31) | ((int64_t)(tid >> 5) << 5) | ((tile & (((int64_t)1 << low_bits) - 1)) << 7) |
+                         ((tile >> low_bits) << (p + 6));
+    A64 *state = reinterpret_cast<A64 *>(a.state + (chain << n)) + base;
+    const int tpar = parity64((unsigned long long)base);
+    const int64_t stride = (int64_t)1 << p;
+    const HiP qp{p};
+    // phase exponent fields first (fp64, registers still free): A = sum_{a<b fixed} Jq z z + sum_{a fixed} hq z,
+    // F_b = hq[p+b] + sum_{a fixed} Jq[a][p+b] z_a
+    PhaseAF af;
+    af.a0 = make_int4(0, 0, 0, 0);
+    af.a1 = af.a0;
+    if (ROLE != HI6_SINGLE && cp.active) {
+        const double *Jq = smd, *hq = smd + n * n;
+        double A = 0.0, F[6];
+#pragma unroll
+        for (int b = 0; b < 6; ++b) F[b] = hq[p + b];
+        for (int q = 0; q < n; ++q) {
+            if (q >= p && q < p + 6) continue;
+            const double zq = ((base >> q) & 1) ? -1.0 : 1.0;
+            double acc = hq[q];
+            for (int q2 = q + 1; q2 < n; ++q2) {
+                if (q2 >= p && q2 < p + 6) continue;
+                acc += ((base >> q2) & 1) ? -Jq[q * n + q2] : Jq[q * n + q2];
+            }
+            A += zq * acc;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) F[b] += Jq[q * n + p + b] * zq;
+        }
+        af.a0 = make_int4((int)rint(A * g.fx_scale), (int)rint(F[0] * g.fx_scale), (int)rint(F[1] * g.fx_scale),
+                          (int)rint(F[2] * g.fx_scale));
+        af.a1 = make_int4((int)rint(F[3] * g.fx_scale), (int)rint(F[4] * g.fx_scale), (int)rint(F[5] * g.fx_scale), 0);
+    }
+    A64 v[64];
+    if (ROLE == HI6_FIRST) {
+        init_product(v, (uint64_t)base, n, cp, qp);
+    } else {
+        const A64 *src = state;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            v[j] = *src;
+            src += stride;
+        }
+        bfly6<ACTIVE>(v, cp, qp, tpar);
+    }
+    if (ROLE != HI6_SINGLE) {
+        phase_gray(v, af, g.dr, cp, tpar);
+        bfly6<ACTIVE>(v, cp, qp, tpar);
+    }
+    A64 *dst = state;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        *dst = v[j];
+        dst += stride;
+    }
+}
+
 // Device-side schedule: order[] = chains with odd r sorted by r descending, then chains with even r
 // sorted by r descending.  The host replays the same Philox draws to know the class sizes.
 constexpr int SCHED_RMAX = 2047;
 __global__ void __launch_bounds__(1024) schedule_kernel(const ChainParams *__restrict__ params, int64_t n_chains,
-                                                        int r_cap, int *__restrict__ order) {
+                                                        int r_cap, int *__restrict__ order, int by_parity) {
     __shared__ int hist[SCHED_RMAX + 1];
     __shared__ int start[SCHED_RMAX + 1];
     for (int i = threadIdx.x; i <= r_cap; i += blockDim.x) hist[i] = 0;
@@ -673,7 +783,7 @@ __global__ void __launch_bounds__(1024) schedule_kernel(const ChainParams *__res
         int pos = 0;
         for (int parity = 1; parity >= 0; --parity)
             for (int r = r_cap; r >= 1; --r)
-                if ((r & 1) == parity) {
+                if (by_parity ? (r & 1) == parity : parity == 1) {  // by_parity = 0: plain r-descending order
                     start[r] = pos;
                     pos += hist[r];
                 }
@@ -955,6 +1065,10 @@ struct SweepWorkspace {
     int *order = nullptr;
     int4 *af_lo = nullptr, *af_hia = nullptr, *af_hib = nullptr;
     int dr_lo[64], dr_hia[64], dr_hib[64];
+    bool tables_ready = false;
+    std::vector<double> Jq, hq;   // circuit couplings in qubit order (host)
+    double *dJq = nullptr, *dhq = nullptr;
+    double fx_scale = 1.0;
     int k_fx = 0;
     std::vector<cudaEvent_t> ev;
 };
@@ -970,9 +1084,27 @@ void qmc_sweep_free(qmc_model *m) {
     cudaFree(w->af_lo);
     cudaFree(w->af_hia);
     cudaFree(w->af_hib);
+    cudaFree(w->dJq);
+    cudaFree(w->dhq);
     for (auto e : w->ev) cudaEventDestroy(e);
     delete w;
     m->sweep = nullptr;
+}
+
+// R(j) = sum_{b<b'} Jq[p_b][p_b'] z_b z_b' over the 6 register qubits, as Gray-order increments
+static void gray_increments(const std::vector<double> &Jq, int n, double scale, const int (&pos)[6], int (&dr)[64]) {
+    int R[64];
+    for (int j = 0; j < 64; ++j) {
+        double r = 0.0;
+        for (int b = 0; b < 6; ++b)
+            for (int b2 = b + 1; b2 < 6; ++b2) {
+                const double zb = ((j >> b) & 1) ? -1.0 : 1.0, zb2 = ((j >> b2) & 1) ? -1.0 : 1.0;
+                r += Jq[(size_t)pos[b] * n + pos[b2]] * zb * zb2;
+            }
+        R[j] = (int)rint(r * scale);
+    }
+    dr[0] = R[0];
+    for (int i = 1; i < 64; ++i) dr[i] = R[i ^ (i >> 1)] - R[(i - 1) ^ ((i - 1) >> 1)];
 }
 
 template <int W>
@@ -1010,55 +1142,44 @@ static int ensure_workspace(qmc_model *m, int64_t chains, cudaStream_t st) {
     SweepWorkspace *w = m->sweep;
     const int n = m->n;
     const int64_t N = 1LL << n;
-    if (!w->af_lo) {
+    if (!w->tables_ready) {
         // circuit couplings in qubit order: qubit a = spin n-1-a (quantum_mcmc_routines.py:75,87)
-        std::vector<double> Jq((size_t)n * n), hq(n);
+        w->Jq.assign((size_t)n * n, 0.0);
+        w->hq.assign(n, 0.0);
         double dmax = 0.0;
         for (int a = 0; a < n; ++a) {
-            hq[a] = m->host_ch[n - 1 - a];
-            dmax += fabs(hq[a]);
+            w->hq[a] = m->host_ch[n - 1 - a];
+            dmax += fabs(w->hq[a]);
             for (int b = 0; b < n; ++b) {
-                Jq[(size_t)a * n + b] = m->host_cJ[(size_t)(n - 1 - a) * n + (n - 1 - b)];
-                if (b > a) dmax += fabs(Jq[(size_t)a * n + b]);
+                w->Jq[(size_t)a * n + b] = m->host_cJ[(size_t)(n - 1 - a) * n + (n - 1 - b)];
+                if (b > a) dmax += fabs(w->Jq[(size_t)a * n + b]);
             }
         }
         if (dmax < 1e-300) dmax = 1.0;
         w->k_fx = (int)floor(log2(2147483647.0 / (dmax * 1.0000001))) - 1;  // one bit of headroom for rounding
         if (w->k_fx > 30) w->k_fx = 30;
-        const double scale = ldexp(1.0, w->k_fx);
-        double *dJq = nullptr, *dhq = nullptr;
-        QMC_CUDA_TRY(cudaMalloc(&dJq, sizeof(double) * (size_t)n * n));
-        QMC_CUDA_TRY(cudaMalloc(&dhq, sizeof(double) * (size_t)n));
-        QMC_CUDA_TRY(cudaMemcpyAsync(dJq, Jq.data(), sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, st));
-        QMC_CUDA_TRY(cudaMemcpyAsync(dhq, hq.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
-        const size_t af_bytes = sizeof(int4) * 2 * (size_t)(N >> 6);
-        QMC_CUDA_TRY(cudaMalloc(&w->af_lo, af_bytes));
-        QMC_CUDA_TRY(cudaMalloc(&w->af_hia, af_bytes));
-        QMC_CUDA_TRY(cudaMalloc(&w->af_hib, af_bytes));
-        int pos[3][6];
-        int rc = build_af_tables(n, dJq, dhq, scale, w->af_lo, w->af_hia, w->af_hib, pos, st);
-        m->launches += 3;
-        QMC_CUDA_TRY(cudaGetLastError());
-        QMC_CUDA_TRY(cudaStreamSynchronize(st));  // Jq/hq are stack-owned staging
-        cudaFree(dJq);
-        cudaFree(dhq);
-        if (rc != QMC_OK) return rc;
-        // R(j) = sum_{b<b'} Jq[p_b][p_b'] z_b z_b' and its Gray-order increments
-        int *drs[3] = {w->dr_lo, w->dr_hia, w->dr_hib};
-        for (int L = 0; L < 3; ++L) {
-            int R[64];
-            for (int j = 0; j < 64; ++j) {
-                double r = 0.0;
-                for (int b = 0; b < 6; ++b)
-                    for (int b2 = b + 1; b2 < 6; ++b2) {
-                        const double zb = ((j >> b) & 1) ? -1.0 : 1.0, zb2 = ((j >> b2) & 1) ? -1.0 : 1.0;
-                        r += Jq[(size_t)pos[L][b] * n + pos[L][b2]] * zb * zb2;
-                    }
-                R[j] = (int)rint(r * scale);
-            }
-            drs[L][0] = R[0];
-            for (int i = 1; i < 64; ++i) drs[L][i] = R[i ^ (i >> 1)] - R[(i - 1) ^ ((i - 1) >> 1)];
+        w->fx_scale = ldexp(1.0, w->k_fx);
+        QMC_CUDA_TRY(cudaMalloc(&w->dJq, sizeof(double) * (size_t)n * n));
+        QMC_CUDA_TRY(cudaMalloc(&w->dhq, sizeof(double) * (size_t)n));
+        QMC_CUDA_TRY(cudaMemcpy(w->dJq, w->Jq.data(), sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
+        QMC_CUDA_TRY(cudaMemcpy(w->dhq, w->hq.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+        // LO layout (regs = qubits 0..5) is shared by both paths
+        const int pos_lo[6] = {0, 1, 2, 3, 4, 5};
+        gray_increments(w->Jq, n, w->fx_scale, pos_lo, w->dr_lo);
+        if (n <= 20) {
+            const size_t af_bytes = sizeof(int4) * 2 * (size_t)(N >> 6);
+            QMC_CUDA_TRY(cudaMalloc(&w->af_lo, af_bytes));
+            QMC_CUDA_TRY(cudaMalloc(&w->af_hia, af_bytes));
+            QMC_CUDA_TRY(cudaMalloc(&w->af_hib, af_bytes));
+            int pos[3][6];
+            int rc = build_af_tables(n, w->dJq, w->dhq, w->fx_scale, w->af_lo, w->af_hia, w->af_hib, pos, st);
+            if (rc != QMC_OK) return rc;
+            m->launches += 3;
+            QMC_CUDA_TRY(cudaGetLastError());
+            gray_increments(w->Jq, n, w->fx_scale, pos[1], w->dr_hia);
+            gray_increments(w->Jq, n, w->fx_scale, pos[2], w->dr_hib);
         }
+        w->tables_ready = true;
     }
     if (chains > w->cap_chains) {
         QMC_CUDA_TRY(cudaStreamSynchronize(st));
@@ -1146,6 +1267,67 @@ static int launch_hi(int n, const SweepArgs &a, const int *order, int off, int64
     return QMC_ERR_UNSUPPORTED;
 }
 
+template <int ROLE, int ACT>
+static int launch_hi6_ra(const SweepArgs &a, const Hi6Args &g, const int *order, int off, int64_t tiles, int count,
+                         cudaStream_t st) {
+    const size_t smem = ROLE == HI6_SINGLE ? 0 : sizeof(double) * (size_t)(a.n * a.n + a.n);
+    hi6_sweep_kernel<ROLE, ACT><<<dim3((unsigned)tiles, (unsigned)count), NT, smem, st>>>(a, g, order, off);
+    return QMC_OK;
+}
+template <int ROLE>
+static int launch_hi6(int act, const SweepArgs &a, const Hi6Args &g, const int *order, int off, int64_t tiles, int count,
+                      cudaStream_t st) {
+    switch (act) {
+        case 1: return launch_hi6_ra<ROLE, 1>(a, g, order, off, tiles, count, st);
+        case 2: return launch_hi6_ra<ROLE, 2>(a, g, order, off, tiles, count, st);
+        case 3: return launch_hi6_ra<ROLE, 3>(a, g, order, off, tiles, count, st);
+        case 4: return launch_hi6_ra<ROLE, 4>(a, g, order, off, tiles, count, st);
+        case 5: return launch_hi6_ra<ROLE, 5>(a, g, order, off, tiles, count, st);
+        case 6: return launch_hi6_ra<ROLE, 6>(a, g, order, off, tiles, count, st);
+    }
+    qmc_set_error("hi6 sweep: %d active qubits", act);
+    return QMC_ERR_BADARG;
+}
+
+// Sweep list of one proposal with r mixer layers on the generic path (LO group + K >= 2 HI6 groups):
+//   HI6_FIRST(g0); per middle layer: LO_SINGLE, HI6_SINGLE for the other groups, HI6_MID on the next
+//   group (which carries its M into the following layer); last layer: HI6_SINGLE..., LO_FINAL.
+static int run_generic_schedule(int n, int r, const SweepArgs &a, const std::vector<Hi6Args> &groups,
+                                const std::vector<int> &acts, const int *order, int off, int count, int64_t tiles,
+                                cudaStream_t st, int &launched) {
+    int rc = QMC_OK;
+    const int K = (int)groups.size();
+    if (r <= 1) {
+        ++launched;
+        return launch_lo<LO_FINAL>(a, order, off, tiles, count, st);
+    }
+    rc = launch_hi6<HI6_FIRST>(acts[0], a, groups[0], order, off, tiles, count, st);
+    ++launched;
+    int carried = 0;
+    for (int layer = 2; layer <= r && rc == QMC_OK; ++layer) {
+        const bool last = layer == r;
+        const int mid = (carried + 1) % K;
+        if (!last) {
+            rc = launch_lo<LO_SINGLE>(a, order, off, tiles, count, st);
+            ++launched;
+        }
+        for (int k = 0; k < K && rc == QMC_OK; ++k) {
+            if (k == carried || (!last && k == mid)) continue;
+            rc = launch_hi6<HI6_SINGLE>(acts[k], a, groups[k], order, off, tiles, count, st);
+            ++launched;
+        }
+        if (rc != QMC_OK) break;
+        if (!last) {
+            rc = launch_hi6<HI6_MID>(acts[mid], a, groups[mid], order, off, tiles, count, st);
+            carried = mid;
+        } else {
+            rc = launch_lo<LO_FINAL>(a, order, off, tiles, count, st);
+        }
+        ++launched;
+    }
+    return rc;
+}
+
 int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, const uint64_t *s_in, uint64_t chain_id0,
                   uint32_t hop0, double temperature, double g_lo, double g_hi, double dt, uint64_t seed, int dtype,
                   const double *gamma_arr, const int *r_arr, const double *u_arr, const int *group_arr,
@@ -1155,7 +1337,8 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     QMC_REQUIRE(dtype == QMC_DTYPE_F32, QMC_ERR_UNSUPPORTED,
                 "complex128 statevectors are supported on the shared-memory path only (n <= %d); n=%d needs dtype fp32",
                 QMC_SMEM_MAX_SPINS_F64, n);
-    QMC_REQUIRE(n >= 14 && n <= 20, QMC_ERR_UNSUPPORTED, "HBM sweep path covers 14 <= n <= 20 in this build (n=%d)", n);
+    QMC_REQUIRE(n >= 14 && n <= QMC_MAX_SPINS, QMC_ERR_UNSUPPORTED, "HBM sweep path covers 14 <= n <= %d (n=%d)", QMC_MAX_SPINS, n);
+    const bool generic = n > 20;  // three or more qubit groups
     QMC_REQUIRE(m->all_one_body, QMC_ERR_UNSUPPORTED,
                 "n=%d > %d: only one-body X mixers have an HBM sweep path (k-body/custom mixers: shared-memory path)", n,
                 QMC_SMEM_MAX_SPINS_F32);
@@ -1180,6 +1363,24 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     int rc = ensure_workspace(m, batch, st);
     if (rc != QMC_OK) return rc;
     SweepWorkspace *w = m->sweep;
+    std::vector<Hi6Args> groups;
+    std::vector<int> acts;
+    if (generic) {
+        const int hi_qubits = n - LO_BITS;
+        const int K = (hi_qubits + 5) / 6;
+        for (int k = 0; k < K; ++k) {
+            Hi6Args g;
+            const bool last = (k == K - 1);
+            g.p = last ? n - 6 : LO_BITS + 6 * k;
+            acts.push_back(last ? hi_qubits - 6 * (K - 1) : 6);
+            const int pos[6] = {g.p, g.p + 1, g.p + 2, g.p + 3, g.p + 4, g.p + 5};
+            gray_increments(w->Jq, n, w->fx_scale, pos, g.dr);
+            g.Jq = w->dJq;
+            g.hq = w->dhq;
+            g.fx_scale = w->fx_scale;
+            groups.push_back(g);
+        }
+    }
 
     // QUMCMC_SWEEP_PIPE=1 selects the persistent TMA-ring MID kernels (A/B parity and profiling)
     const char *pipe_env = getenv("QUMCMC_SWEEP_PIPE");
@@ -1232,7 +1433,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         for (int64_t hop = 0; hop < hops; ++hop) {
             h.hop = hop;
             hop_prepare_kernel<<<gb, 128, 0, st>>>(h, w->params);
-            schedule_kernel<<<1, 1024, 0, st>>>(w->params, nc, r_max, w->order);
+            schedule_kernel<<<1, 1024, 0, st>>>(w->params, nc, r_max, w->order, generic ? 0 : 1);
             m->launches += 2;
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (m->profile) {
@@ -1254,35 +1455,46 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                 rhist[r]++;
                 sum_r += r;
             }
-            int base[2] = {0, 0};  // start of the odd-r / even-r class in order[]
-            for (int r = 1; r <= r_max; r += 2) base[1] += rhist[r];  // even class starts after all odd-r chains
             int launched = 0;
-            for (int step = 1; step <= r_max; ++step) {
-                const int p = step & 1;                 // chains with r == step (mod 2) sweep LO at this step
-                const int lo_base = p ? base[0] : base[1];
-                const int hi_base = p ? base[1] : base[0];
-                int lo_gt = 0, hi_gt = 0;
-                for (int r = step + 2; r <= r_max; r += 2) lo_gt += rhist[r];
-                for (int r = step + 1; r <= r_max; r += 2) hi_gt += rhist[r];
-                const int lo_eq = rhist[step];
-                if (lo_gt > 0) {
-                    rc = step == 1 ? launch_lo<LO_FIRST>(a, w->order, lo_base, tiles, lo_gt, st)
-                         : use_pipe ? launch_pipe(0, a, w->order, lo_base, tiles, lo_gt, st)
-                                    : launch_lo<LO_MID>(a, w->order, lo_base, tiles, lo_gt, st);
+            if (generic) {
+                // order[] is sorted by r descending: one schedule per distinct r over its contiguous range
+                int off = 0;
+                for (int r = r_max; r >= 1; --r) {
+                    if (rhist[r] == 0) continue;
+                    rc = run_generic_schedule(n, r, a, groups, acts, w->order, off, rhist[r], tiles, st, launched);
                     if (rc != QMC_OK) return rc;
-                    ++launched;
+                    off += rhist[r];
                 }
-                if (lo_eq > 0) {
-                    rc = launch_lo<LO_FINAL>(a, w->order, lo_base + lo_gt, tiles, lo_eq, st);
-                    if (rc != QMC_OK) return rc;
-                    ++launched;
-                }
-                if (hi_gt > 0) {
-                    rc = step == 1 ? launch_hi<true>(n, a, w->order, hi_base, tiles, hi_gt, st)
-                         : use_pipe ? launch_pipe(n - LO_BITS, a, w->order, hi_base, tiles, hi_gt, st)
-                                    : launch_hi<false>(n, a, w->order, hi_base, tiles, hi_gt, st);
-                    if (rc != QMC_OK) return rc;
-                    ++launched;
+            } else {
+                int base[2] = {0, 0};  // start of the odd-r / even-r class in order[]
+                for (int r = 1; r <= r_max; r += 2) base[1] += rhist[r];  // even class starts after all odd-r chains
+                for (int step = 1; step <= r_max; ++step) {
+                    const int p = step & 1;                 // chains with r == step (mod 2) sweep LO at this step
+                    const int lo_base = p ? base[0] : base[1];
+                    const int hi_base = p ? base[1] : base[0];
+                    int lo_gt = 0, hi_gt = 0;
+                    for (int r = step + 2; r <= r_max; r += 2) lo_gt += rhist[r];
+                    for (int r = step + 1; r <= r_max; r += 2) hi_gt += rhist[r];
+                    const int lo_eq = rhist[step];
+                    if (lo_gt > 0) {
+                        rc = step == 1 ? launch_lo<LO_FIRST>(a, w->order, lo_base, tiles, lo_gt, st)
+                             : use_pipe ? launch_pipe(0, a, w->order, lo_base, tiles, lo_gt, st)
+                                        : launch_lo<LO_MID>(a, w->order, lo_base, tiles, lo_gt, st);
+                        if (rc != QMC_OK) return rc;
+                        ++launched;
+                    }
+                    if (lo_eq > 0) {
+                        rc = launch_lo<LO_FINAL>(a, w->order, lo_base + lo_gt, tiles, lo_eq, st);
+                        if (rc != QMC_OK) return rc;
+                        ++launched;
+                    }
+                    if (hi_gt > 0) {
+                        rc = step == 1 ? launch_hi<true>(n, a, w->order, hi_base, tiles, hi_gt, st)
+                             : use_pipe ? launch_pipe(n - LO_BITS, a, w->order, hi_base, tiles, hi_gt, st)
+                                        : launch_hi<false>(n, a, w->order, hi_base, tiles, hi_gt, st);
+                        if (rc != QMC_OK) return rc;
+                        ++launched;
+                    }
                 }
             }
             m->launches += launched;

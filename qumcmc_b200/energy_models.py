@@ -187,7 +187,7 @@ class Exact_Sampling(IsingEnergyFunction):
         self.beta = beta
         if verbose:
             print("Running Exact Sampling | beta : ", beta)
-        if self.num_spins > 28:  # 2^n doubles x2 on the host stops being sensible; keep log Z only
+        if self.num_spins > 26:  # 2^n doubles x2 on the host stops being sensible; keep log Z only
             self.logZ, self.energies, self.probs = self._enumerate(beta, want_arrays=False)
         else:
             self.get_boltzmann_distribution(beta=beta, save_distribution=True, return_dist=False, verbose=verbose)

@@ -165,3 +165,38 @@ def test_unsupported_configurations_fail_loudly():
         q.transition_probabilities(m, q.GenericMixer.TwoBodyMixer(16), 0, 0.3, 2, dtype="fp32")
     with pytest.raises(_lib.QmcUnsupported):
         q.transition_probabilities(m, q.GenericMixer.OneBodyMixer(16), 0, 0.3, 2, dtype="fp64")
+
+
+@pytest.mark.parametrize("n,rs", [(21, (1, 2, 3, 6)), (22, (2, 5)), (23, (3, 4)), (24, (2, 7)), (25, (3,)), (26, (4,))])
+def test_generic_path_transition_probabilities(n, rs):
+    """n >= 21: LO group + K >= 2 register-only HI6 groups (every ACT / group-count combination up to
+    n = 26), vs the oracle's fused simulator."""
+    q, J, h, m, mx, masks, w = _setup(n, seed=2)
+    al = oracle.alpha(J, h)
+    rng = np.random.default_rng(n)
+    for r in rs:
+        s = int(rng.integers(0, 1 << n))
+        gamma = float(rng.uniform(0.25, 0.6))
+        p, a = q.transition_probabilities(m, mx, s, gamma, r, dtype="fp32", return_amplitudes=True)
+        ref = oracle.evolve(J, h, al, gamma, 0.8, r, masks, w, s, gatewise=False)
+        assert abs(p.sum() - 1.0) < 1e-5
+        assert np.abs(p - np.abs(ref) ** 2).max() < 1e-6, (n, r)
+        assert np.linalg.norm(a - ref) < 3e-5, (n, r, np.linalg.norm(a - ref))
+
+
+def test_generic_path_chain_bookkeeping_n22():
+    q, J, h, m, mx, masks, w = _setup(22, seed=6)
+    C, H, seed = 6, 5, 31
+    b = q.quantum_enhanced_mcmc(H, m, mx, (0.25, 0.6), temperature=1.0, n_chains=C, seed=seed, dtype="fp32")
+    for c in range(C):
+        cur = oracle.initial_state(seed, c, 22)
+        e_cur = oracle.energy(J, h, cur)
+        for hop in range(H):
+            _, _, _, _, ua = oracle.hop_draws(seed, c, hop)
+            sp = int(b.proposals[c, hop])
+            e_sp = oracle.energy(J, h, sp)
+            acc = oracle.test_accept(e_cur, e_sp, 1.0, ua)
+            assert bool(b.accepted[c, hop]) == acc
+            if acc:
+                cur, e_cur = sp, e_sp
+        assert int(b.final_state[c]) == cur
