@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Secondary measurements on the other BASELINE.json configs (the driver's headline is bench.py):
+   C1 README 10-spin single chain x 10 000 hops (+ classical_mcmc + Exact_Sampling)
+   C2 BAS 3x3, 1024 chains x 2 000 hops, gamma ~ U(0.25, 0.6) (shared-memory path, fp32 and fp64)
+   C4 28-spin single chain (generic HBM sweep path) + Exact_Sampling log Z
+Prints one JSON line per measurement.  Usage: python benchmarks/configs.py [c1 c2 c4 exact]"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import qumcmc_b200 as q  # noqa: E402
+from tests import models  # noqa: E402
+
+
+def timed(fn, reps=1):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps, out
+
+
+def c1():
+    J, h = models.readme_model()
+    m = q.IsingEnergyFunction(J, h, name="my_model")
+    beta = 1.100209
+    np.random.seed(1)
+    q.quantum_enhanced_mcmc(n_hops=100, model=m, temperature=1 / beta)  # warm
+    for dtype in ("fp64", "fp32"):
+        dt, ch = timed(lambda: q.quantum_enhanced_mcmc(n_hops=10000, model=m, temperature=1 / beta, dtype=dtype))
+        print(json.dumps({"config": "C1 README n=10, 1 chain x 10000 hops", "dtype": dtype, "seconds": dt,
+                          "proposals_per_s": 10000 / dt, "acceptance": ch.acceptance_rate(),
+                          "reference_published": "476-550 it/s (qulacs, authors' CPU; BASELINE.md)"}))
+    dt, cl = timed(lambda: q.classical_mcmc(n_hops=10000, model=m, temperature=1 / beta))
+    print(json.dumps({"config": "C1 classical_mcmc (host loop, device energies)", "seconds": dt, "hops_per_s": 10000 / dt}))
+    dt, ex = timed(lambda: q.Exact_Sampling(m, beta))
+    print(json.dumps({"config": "C1 Exact_Sampling n=10 (incl. host arrays)", "seconds": dt, "logZ": ex.logZ}))
+
+
+def c2():
+    J, h, _ = models.bas3("both")
+    m = q.IsingEnergyFunction(J, h)
+    mx = q.GenericMixer.OneBodyMixer(9)
+    for dtype in ("fp32", "fp64"):
+        q.quantum_enhanced_mcmc(100, m, mx, (0.25, 0.6), initial_state="111000111", temperature=1 / 1.5, n_chains=1024,
+                                seed=1, dtype=dtype)
+        H = 2000
+        dt, b = timed(lambda: q.quantum_enhanced_mcmc(H, m, mx, (0.25, 0.6), initial_state="111000111",
+                                                      temperature=1 / 1.5, n_chains=1024, seed=2, dtype=dtype))
+        print(json.dumps({"config": "C2 BAS 3x3, 1024 chains x %d hops, gamma~U(0.25,0.6)" % H, "dtype": dtype,
+                          "seconds": dt, "proposals_per_s": 1024 * H / dt, "acceptance": b.acceptance_rate(),
+                          "path": "shared-memory kernel (on-chip; no HBM roofline)",
+                          "reference_published": "497-1045 it/s per chain (gamma-variation-v0.1.ipynb)"}))
+
+
+def c4():
+    n = 28
+    m = q.random_ising_model(n, 1)
+    mx = q.GenericMixer.OneBodyMixer(n)
+    q.quantum_enhanced_mcmc(1, m, mx, (0.25, 0.6), temperature=1.0, n_chains=1, seed=3, dtype="fp32")  # warm + alloc
+    H = 8
+    dt, b = timed(lambda: q.quantum_enhanced_mcmc(H, m, mx, (0.25, 0.6), temperature=1.0, n_chains=1, seed=4, dtype="fp32"))
+    # layers of these hops (host replica of the Philox draws)
+    from qumcmc_b200.rng import philox4x32
+    ts = [2 + ((int(philox4x32(4, np.array([0], dtype=np.uint64), hop, 0)[0, 2]) * 10) >> 32) for hop in range(H)]
+    rs = [max(1, int(np.floor(t / 0.8))) for t in ts]
+    alg = sum(2 * (1 << n) * 8 * r for r in rs)
+    print(json.dumps({"config": "C4 n=28 single chain x %d hops (2 GiB complex64 statevector)" % H, "seconds": dt,
+                      "proposals_per_s": H / dt, "layers": rs, "algorithmic_GB": alg / 1e9,
+                      "algorithmic_GBps": alg / 1e9 / dt, "frac_of_measured_hbm": alg / 1e9 / dt / 6547.8,
+                      "path": "generic sweeps: LO(12) + HI6 groups, ~3 passes per layer"}))
+
+
+def exact():
+    for n in (20, 24, 28):
+        m = q.random_ising_model(n, 1)
+        dm = m.device_model(0)
+        from qumcmc_b200 import _device, _lib
+        pair = torch.empty(2, dtype=torch.float64, device="cuda")
+        f = lambda: _lib.check(_lib.lib().qmc_exact_partial(dm.handle, 1.0, 0, 1 << n, pair.data_ptr(), None,
+                                                            _device.current_stream_ptr(0)))
+        f()
+        dt, _ = timed(f, reps=3)
+        mm, ss = pair.cpu().numpy()
+        print(json.dumps({"config": "Exact_Sampling log Z only, n=%d" % n, "seconds": dt, "Gstates_per_s": (1 << n) / dt / 1e9,
+                          "logZ": float(mm + np.log(ss)), "bound": "fp64 ALU (bit-exact O(n^2) energy per state), 0 HBM bytes"}))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c1", "c2", "c4", "exact"]
+    for w in which:
+        {"c1": c1, "c2": c2, "c4": c4, "exact": exact}[w]()

@@ -83,6 +83,16 @@ int qmc_exact_sampling(qmc_model *m, double beta, double *logZ_dev, double *ener
 int qmc_exact_sampling_host(qmc_model *m, double beta, double *logZ_host, double *energies_host,
                             double *probs_host);
 
+/* Sharded enumeration (exact sampler over several GPUs / index ranges): (max, sum exp(x - max)) of
+ * x = -beta*E over idx in [idx_begin, idx_begin+idx_count) -> lse_pair_dev[2]; ranks combine the
+ * pairs (an all-gather of 16 bytes per rank = the "allreduce for Z").  energies_dev nullable
+ * (idx_count doubles, range order).  qmc_exact_probs_range writes exp(-beta*E - logZ) for a range
+ * given the global logZ. */
+int qmc_exact_partial(qmc_model *m, double beta, uint64_t idx_begin, int64_t idx_count,
+                      double *lse_pair_dev, double *energies_dev, void *stream);
+int qmc_exact_probs_range(qmc_model *m, double beta, double logZ, uint64_t idx_begin, int64_t idx_count,
+                          const double *energies_dev, double *probs_dev, void *stream);
+
 /* Test hook: |<s'|U|s>|^2 for all s' with U = M (P M)^{r-1}, the circuit of
  * run_qmcmc_quantum_ckt (qumcmc/quantum_mcmc_routines.py:110-152) for fixed gamma and r and
  * mixer group `group`.  probs_dev: 2^n float (F32) or double (F64), index order.

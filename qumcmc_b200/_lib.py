@@ -30,6 +30,7 @@ MAX_SPINS = 34
 EXPORTS = [
     "qmc_version", "qmc_last_error", "qmc_model_create", "qmc_model_destroy", "qmc_mixer_set",
     "qmc_energies", "qmc_energies_host", "qmc_exact_sampling", "qmc_exact_sampling_host",
+    "qmc_exact_partial", "qmc_exact_probs_range",
     "qmc_transition_probs", "qmc_propose", "qmc_run_chains", "qmc_run_chains_host",
     "qmc_model_num_spins", "qmc_model_launch_count", "qmc_profile_enable", "qmc_profile_read",
 ]
@@ -76,6 +77,8 @@ def lib() -> C.CDLL:
     L.qmc_energies_host.argtypes = [C.c_void_p, u64p, C.c_int64, dp]
     L.qmc_exact_sampling.argtypes = [C.c_void_p, C.c_double, dp, dp, dp, vp]
     L.qmc_exact_sampling_host.argtypes = [C.c_void_p, C.c_double, dp, dp, dp]
+    L.qmc_exact_partial.argtypes = [C.c_void_p, C.c_double, C.c_uint64, C.c_int64, dp, dp, vp]
+    L.qmc_exact_probs_range.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_uint64, C.c_int64, dp, dp, vp]
     L.qmc_transition_probs.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_int, C.c_double, C.c_int,
                                        C.c_int, vp, vp, vp]
     L.qmc_propose.argtypes = [C.c_void_p, C.c_int64, u64p, dp, vp, dp, vp, C.c_double, C.c_int, u64p, vp]

@@ -94,6 +94,7 @@ __device__ __forceinline__ LseState lse_merge(LseState a, LseState b) {
 
 __global__ void __launch_bounds__(256) exact_enumerate_kernel(int n, const double *__restrict__ J,
                                                               const double *__restrict__ h, double beta,
+                                                              int64_t begin, int64_t count,
                                                               double *__restrict__ energies,
                                                               LseState *__restrict__ partials) {
     extern __shared__ double sm[];
@@ -101,12 +102,11 @@ __global__ void __launch_bounds__(256) exact_enumerate_kernel(int n, const doubl
     for (int i = threadIdx.x; i < n * n; i += blockDim.x) sJ[i] = J[i];
     for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = h[i];
     __syncthreads();
-    const int64_t N = 1LL << n;
     LseState acc = {-INFINITY, 0.0};
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < N;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const double e = qmc_energy_dev(n, sJ, sh, (uint64_t)idx);
-        if (energies) energies[idx] = e;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < count;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        const double e = qmc_energy_dev(n, sJ, sh, (uint64_t)(begin + k));
+        if (energies) energies[k] = e;
         const double x = -beta * e;
         if (x > acc.m) {
             acc.s = acc.s * exp(acc.m - x) + 1.0;  // exp(-inf)=0 on the first element
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) exact_enumerate_kernel(int n, const doubl
 }
 
 __global__ void __launch_bounds__(256) exact_finalize_kernel(const LseState *__restrict__ partials, int nparts,
-                                                             double *__restrict__ logZ) {
+                                                             double *__restrict__ logZ, double *__restrict__ pair) {
     __shared__ LseState red[256];
     LseState acc = {-INFINITY, 0.0};
     for (int i = threadIdx.x; i < nparts; i += blockDim.x) acc = lse_merge(acc, partials[i]);
@@ -137,26 +137,32 @@ __global__ void __launch_bounds__(256) exact_finalize_kernel(const LseState *__r
         if (threadIdx.x < off) red[threadIdx.x] = lse_merge(red[threadIdx.x], red[threadIdx.x + off]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) logZ[0] = red[0].m + log(red[0].s);
+    if (threadIdx.x == 0) {
+        if (logZ) logZ[0] = red[0].m + log(red[0].s);
+        if (pair) {
+            pair[0] = red[0].m;
+            pair[1] = red[0].s;
+        }
+    }
 }
 
 // p = exp(-beta*E - logZ); E read back if materialised, recomputed otherwise.
 __global__ void __launch_bounds__(256) exact_probs_kernel(int n, const double *__restrict__ J,
                                                           const double *__restrict__ h, double beta,
+                                                          int64_t begin, int64_t count,
                                                           const double *__restrict__ energies,
-                                                          const double *__restrict__ logZ,
+                                                          const double *__restrict__ logZ, double logZ_value,
                                                           double *__restrict__ probs) {
     extern __shared__ double sm[];
     double *sJ = sm, *sh = sm + n * n;
     for (int i = threadIdx.x; i < n * n; i += blockDim.x) sJ[i] = J[i];
     for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = h[i];
     __syncthreads();
-    const int64_t N = 1LL << n;
-    const double lz = logZ[0];
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < N;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const double e = energies ? energies[idx] : qmc_energy_dev(n, sJ, sh, (uint64_t)idx);
-        probs[idx] = exp(-beta * e - lz);
+    const double lz = logZ ? logZ[0] : logZ_value;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < count;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        const double e = energies ? energies[k] : qmc_energy_dev(n, sJ, sh, (uint64_t)(begin + k));
+        probs[k] = exp(-beta * e - lz);
     }
 }
 
@@ -247,7 +253,7 @@ extern "C" int qmc_model_create(qmc_model **out, int n, const double *J, const d
         TRY_OR_FAIL(cudaMalloc(&m->dE, sizeof(double) * (size_t)N));
         LseState *dummy = nullptr;
         TRY_OR_FAIL(cudaMalloc(&dummy, sizeof(LseState) * 1184));
-        exact_enumerate_kernel<<<grid_for(N, 256), 256, smem>>>(n, m->dJ, m->dh, 0.0, m->dE, dummy);
+        exact_enumerate_kernel<<<grid_for(N, 256), 256, smem>>>(n, m->dJ, m->dh, 0.0, 0, N, m->dE, dummy);
         m->launches++;
         TRY_OR_FAIL(cudaGetLastError());
         TRY_OR_FAIL(cudaDeviceSynchronize());
@@ -393,15 +399,50 @@ extern "C" int qmc_exact_sampling(qmc_model *m, double beta, double *logZ_dev, d
     const int grid = grid_for(N, 256);
     LseState *partials = nullptr;
     QMC_CUDA_TRY(cudaMallocAsync(&partials, sizeof(LseState) * grid, st));
-    exact_enumerate_kernel<<<grid, 256, smem, st>>>(n, m->dJ, m->dh, beta, energies_dev, partials);
-    exact_finalize_kernel<<<1, 256, 0, st>>>(partials, grid, logZ_dev);
+    exact_enumerate_kernel<<<grid, 256, smem, st>>>(n, m->dJ, m->dh, beta, 0, N, energies_dev, partials);
+    exact_finalize_kernel<<<1, 256, 0, st>>>(partials, grid, logZ_dev, nullptr);
     m->launches += 2;
     if (probs_dev) {
-        exact_probs_kernel<<<grid, 256, smem, st>>>(n, m->dJ, m->dh, beta, energies_dev, logZ_dev, probs_dev);
+        exact_probs_kernel<<<grid, 256, smem, st>>>(n, m->dJ, m->dh, beta, 0, N, energies_dev, logZ_dev, 0.0, probs_dev);
         m->launches++;
     }
     QMC_CUDA_TRY(cudaGetLastError());
     QMC_CUDA_TRY(cudaFreeAsync(partials, st));
+    return QMC_OK;
+}
+
+extern "C" int qmc_exact_partial(qmc_model *m, double beta, uint64_t idx_begin, int64_t idx_count, double *lse_pair_dev,
+                                 double *energies_dev, void *stream) {
+    QMC_REQUIRE(m && lse_pair_dev && idx_count >= 0, QMC_ERR_BADARG, "qmc_exact_partial: bad argument");
+    const uint64_t N = 1ULL << m->n;
+    QMC_REQUIRE(idx_begin <= N && (uint64_t)idx_count <= N - idx_begin, QMC_ERR_BADARG, "qmc_exact_partial: range outside [0, 2^n)");
+    QMC_CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = m->n;
+    const size_t smem = sizeof(double) * (size_t)(n * n + n);
+    const int grid = grid_for(idx_count, 256);
+    LseState *partials = nullptr;
+    QMC_CUDA_TRY(cudaMallocAsync(&partials, sizeof(LseState) * grid, st));
+    exact_enumerate_kernel<<<grid, 256, smem, st>>>(n, m->dJ, m->dh, beta, (int64_t)idx_begin, idx_count, energies_dev, partials);
+    exact_finalize_kernel<<<1, 256, 0, st>>>(partials, grid, nullptr, lse_pair_dev);
+    m->launches += 2;
+    QMC_CUDA_TRY(cudaGetLastError());
+    QMC_CUDA_TRY(cudaFreeAsync(partials, st));
+    return QMC_OK;
+}
+
+extern "C" int qmc_exact_probs_range(qmc_model *m, double beta, double logZ, uint64_t idx_begin, int64_t idx_count,
+                                     const double *energies_dev, double *probs_dev, void *stream) {
+    QMC_REQUIRE(m && probs_dev && idx_count >= 0, QMC_ERR_BADARG, "qmc_exact_probs_range: bad argument");
+    const uint64_t N = 1ULL << m->n;
+    QMC_REQUIRE(idx_begin <= N && (uint64_t)idx_count <= N - idx_begin, QMC_ERR_BADARG, "qmc_exact_probs_range: range outside [0, 2^n)");
+    QMC_CUDA_TRY(cudaSetDevice(m->device));
+    const int n = m->n;
+    const size_t smem = sizeof(double) * (size_t)(n * n + n);
+    exact_probs_kernel<<<grid_for(idx_count, 256), 256, smem, (cudaStream_t)stream>>>(n, m->dJ, m->dh, beta, (int64_t)idx_begin, idx_count,
+                                                                                     energies_dev, nullptr, logZ, probs_dev);
+    m->launches++;
+    QMC_CUDA_TRY(cudaGetLastError());
     return QMC_OK;
 }
 

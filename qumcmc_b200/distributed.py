@@ -58,3 +58,37 @@ def run_chains_sharded(run_local: Callable[[int, int], tuple], n_chains: int, gr
     acc, hist, payload = run_local(a, b - a)
     g_acc, g_hist = gather_statistics(np.asarray(acc), np.asarray(hist), n_chains, group)
     return g_acc, g_hist, payload
+
+
+def combine_logsumexp(pairs: np.ndarray) -> float:
+    """log sum_k s_k exp(m_k) for (m_k, s_k) partial results of disjoint index ranges."""
+    pairs = np.asarray(pairs, dtype=np.float64).reshape(-1, 2)
+    keep = pairs[:, 1] > 0
+    if not keep.any():
+        return float("-inf")
+    m = pairs[keep, 0].max()
+    return float(m + np.log(np.sum(pairs[keep, 1] * np.exp(pairs[keep, 0] - m))))
+
+
+def exact_logz_sharded(model, beta: float, device: int = 0, group=None, partial_fn=None) -> float:
+    """log Z of the Boltzmann distribution with the 2^n indices split evenly over the ranks: every rank
+    enumerates its range on its GPU (qmc_exact_partial), the (max, sumexp) pairs are all-gathered and
+    combined on every rank.  ``partial_fn(begin, count) -> (max, sumexp)`` replaces the CUDA call in the
+    CPU (gloo) tests."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    begin, end = shard_range(1 << model.num_spins, rank, world)
+    if partial_fn is None:
+        from . import _device, _lib
+        dm = model.device_model(device)
+        pair = torch.empty(2, dtype=torch.float64, device=torch.device("cuda", device))
+        _lib.check(_lib.lib().qmc_exact_partial(dm.handle, float(beta), int(begin), int(end - begin), pair.data_ptr(),
+                                                None, _device.current_stream_ptr(device)))
+        mine = pair
+    else:
+        mine = torch.tensor(partial_fn(begin, end - begin), dtype=torch.float64)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    return combine_logsumexp(np.stack([o.cpu().numpy() for o in out]))

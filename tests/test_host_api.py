@@ -205,3 +205,50 @@ def test_chain_sharding_gather_gloo_world2():
         assert acc == (ids * 3).tolist()
         assert hist == np.stack([ids * 10 + k for k in range(width)], axis=1).tolist()
     assert sorted(p[3] for p in outs) == [(0, 6), (6, 5)]
+
+
+def _gloo_logz_worker(rank, world, port, n, beta, q):
+    import torch.distributed as dist
+    from qumcmc_b200.distributed import exact_logz_sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    J, h = models.packaged_random_model(n, 5)
+
+    class M:  # only num_spins is needed when partial_fn replaces the CUDA call
+        num_spins = n
+
+    def partial(begin, count):  # oracle energies stand in for qmc_exact_partial on CPU
+        x = -beta * oracle.energies(J, h, np.arange(begin, begin + count, dtype=np.uint64))
+        m = x.max()
+        return float(m), float(np.exp(x - m).sum())
+
+    q.put((rank, exact_logz_sharded(M(), beta, partial_fn=partial)))
+    dist.destroy_process_group()
+
+
+def test_exact_logz_sharding_gloo_world2():
+    """The 'allreduce for Z' of the sharded exact sampler: per-rank (max, sumexp) pairs, all-gather, combine."""
+    import torch.multiprocessing as mp
+    n, beta, world = 10, 1.3, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 200)
+    procs = [ctx.Process(target=_gloo_logz_worker, args=(r, world, port, n, beta, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    J, h = models.packaged_random_model(n, 5)
+    logZ, _, _ = oracle.exact_boltzmann(J, h, beta, want_probs=False)
+    for _, val in outs:
+        assert val == pytest.approx(logZ, rel=1e-13)
+
+
+def test_combine_logsumexp_edge_cases():
+    from qumcmc_b200.distributed import combine_logsumexp
+    assert combine_logsumexp([[0.0, 1.0], [0.0, 1.0]]) == pytest.approx(np.log(2.0))
+    assert combine_logsumexp([[1000.0, 1.0], [-1000.0, 5.0]]) == pytest.approx(1000.0)
+    assert combine_logsumexp([[float("-inf"), 0.0], [2.0, 3.0]]) == pytest.approx(2.0 + np.log(3.0))
