@@ -44,7 +44,8 @@ extern "C" {
 #define QMC_DTYPE_F32 0 /* complex64 statevector  */
 #define QMC_DTYPE_F64 1 /* complex128 statevector */
 
-#define QMC_MAX_SPINS 34       /* single-GPU statevector limit (2^34 complex64 = 128 GiB) */
+#define QMC_MAX_SPINS 40       /* model limit; one GPU holds a statevector up to n = 34 (2^34 complex64 = 128 GiB) */
+#define QMC_MAX_LOCAL_SPINS 34
 #define QMC_SMEM_MAX_SPINS_F32 13 /* whole statevector in shared memory, one CTA per chain */
 #define QMC_SMEM_MAX_SPINS_F64 12
 

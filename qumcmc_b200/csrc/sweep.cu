@@ -54,7 +54,9 @@ struct ChainParams {
 };
 
 struct SweepArgs {
-    int n;
+    int n;                    // index qubits of the local statevector (addressing)
+    int n_total;              // all qubits incl. global (sharded) ones; == n on one GPU
+    unsigned long long gbits; // value of the global qubits, already shifted to bit n
     float2 *state;            // [chains][2^n]
     ChainParams *params;      // [chains]
     // on-the-fly phase exponent: D_fx(idx) = A + sum_b z_b F_b + R(j) per register layout;
@@ -285,17 +287,18 @@ struct LoQ6 { __device__ __forceinline__ int operator()(int b) const { return 6 
 // Final LO computation for (chain, tile): leaves the final amplitudes of the tile in B layout.
 // Used by the last sweep (segment sums) and by the sampler (recompute of the selected tile).
 __device__ __forceinline__ void lo_final_tile(A64 (&v)[64], float2 *sm, const float2 *__restrict__ state_chain,
-                                              int64_t tile, int tid, int n, const ChainParams &cp) {
+                                              int64_t tile, int tid, int n, const ChainParams &cp,
+                                              unsigned long long gb = 0ULL) {
     if (cp.r == 1) {
-        init_product(v, ((uint64_t)tile << TILE_BITS) | ((uint64_t)tid << 6), n, cp, LoQ0());
+        init_product(v, gb | ((uint64_t)tile << TILE_BITS) | ((uint64_t)tid << 6), n, cp, LoQ0());
         return;
     }
     lo_load_a(v, state_chain + (tile << TILE_BITS), tid);
-    bfly6<63>(v, cp, LoQ6(), parity64(((unsigned long long)tile << TILE_BITS) | (unsigned)lo_base_a(tid)));
+    bfly6<63>(v, cp, LoQ6(), parity64(gb | ((unsigned long long)tile << TILE_BITS) | (unsigned)lo_base_a(tid)));
     lo_a_to_smem(v, sm, tid);
     __syncthreads();
     lo_smem_to_b(v, sm, tid);
-    bfly6<63>(v, cp, LoQ0(), parity64(((unsigned long long)tile << TILE_BITS) | ((unsigned)tid << 6)));
+    bfly6<63>(v, cp, LoQ0(), parity64(gb | ((unsigned long long)tile << TILE_BITS) | ((unsigned)tid << 6)));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(NT, 3) lo_sweep_kernel(const SweepArgs a, cons
     float2 *state = a.state + (chain << n);
     A64 v[64];
     if (ROLE == LO_FINAL) {
-        lo_final_tile(v, sm, state, tile, tid, n, cp);
+        lo_final_tile(v, sm, state, tile, tid, a.n_total, cp, a.gbits);
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < 64; ++j) s += norm2(v[j]);
@@ -389,15 +392,15 @@ __global__ void __launch_bounds__(NT, 3) lo_sweep_kernel(const SweepArgs a, cons
             float2 *ao = a.amps_out + (chain << n) + (tile << TILE_BITS) + (tid << 6);
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
-                const bool odd = ((__builtin_popcount(j) & 1) ^ parity64(((unsigned long long)tile << TILE_BITS) | ((unsigned)tid << 6))) != 0;
+                const bool odd = ((__builtin_popcount(j) & 1) ^ parity64(a.gbits | ((unsigned long long)tile << TILE_BITS) | ((unsigned)tid << 6))) != 0;
                 const float2 f = upk(v[j]);
                 ao[j] = odd ? make_float2(f.y, f.x) : f;
             }
         }
         return;
     }
-    const int par_a = parity64(((unsigned long long)tile << TILE_BITS) | (unsigned)lo_base_a(tid));
-    const int par_b = parity64(((unsigned long long)tile << TILE_BITS) | ((unsigned)tid << 6));
+    const int par_a = parity64(a.gbits | ((unsigned long long)tile << TILE_BITS) | (unsigned)lo_base_a(tid));
+    const int par_b = parity64(a.gbits | ((unsigned long long)tile << TILE_BITS) | ((unsigned)tid << 6));
     if (ROLE == LO_SINGLE) {
         lo_load_a(v, state + (tile << TILE_BITS), tid);
         bfly6<63>(v, cp, LoQ6(), par_a);
@@ -703,8 +706,9 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
     const int64_t tile = blockIdx.x;
     const int64_t chain = order[list_off + blockIdx.y];
     if (ROLE != HI6_SINGLE) {
-        for (int i = tid; i < n * n; i += NT) smd[i] = g.Jq[i];
-        for (int i = tid; i < n; i += NT) smd[n * n + i] = g.hq[i];
+        const int nt_ = a.n_total;
+        for (int i = tid; i < nt_ * nt_; i += NT) smd[i] = g.Jq[i];
+        for (int i = tid; i < nt_; i += NT) smd[nt_ * nt_ + i] = g.hq[i];
     }
     stage_params(cp_s, a.params + chain, tid);  // barrier inside
     const ChainParams &cp = cp_s;
@@ -715,7 +719,9 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
     const int64_t base = (int64_t)(tid & 31) | ((int64_t)(tid >> 5) << 5) | ((tile & (((int64_t)1 << low_bits) - 1)) << 7) |
                          ((tile >> low_bits) << (p + 6));
     A64 *state = reinterpret_cast<A64 *>(a.state + (chain << n)) + base;
-    const int tpar = parity64((unsigned long long)base);
+    const unsigned long long full = (unsigned long long)base | a.gbits;  // incl. the global (sharded) qubits
+    const int nt = a.n_total;
+    const int tpar = parity64(full);
     const int64_t stride = (int64_t)1 << p;
     const HiP qp{p};
     // phase exponent fields first (fp64, registers still free): A = sum_{a<b fixed} Jq z z + sum_{a fixed} hq z,
@@ -724,21 +730,21 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
     af.a0 = make_int4(0, 0, 0, 0);
     af.a1 = af.a0;
     if (ROLE != HI6_SINGLE && cp.active) {
-        const double *Jq = smd, *hq = smd + n * n;
+        const double *Jq = smd, *hq = smd + nt * nt;
         double A = 0.0, F[6];
 #pragma unroll
         for (int b = 0; b < 6; ++b) F[b] = hq[p + b];
-        for (int q = 0; q < n; ++q) {
+        for (int q = 0; q < nt; ++q) {
             if (q >= p && q < p + 6) continue;
-            const double zq = ((base >> q) & 1) ? -1.0 : 1.0;
+            const double zq = ((full >> q) & 1ULL) ? -1.0 : 1.0;
             double acc = hq[q];
-            for (int q2 = q + 1; q2 < n; ++q2) {
+            for (int q2 = q + 1; q2 < nt; ++q2) {
                 if (q2 >= p && q2 < p + 6) continue;
-                acc += ((base >> q2) & 1) ? -Jq[q * n + q2] : Jq[q * n + q2];
+                acc += ((full >> q2) & 1ULL) ? -Jq[q * nt + q2] : Jq[q * nt + q2];
             }
             A += zq * acc;
 #pragma unroll
-            for (int b = 0; b < 6; ++b) F[b] += Jq[q * n + p + b] * zq;
+            for (int b = 0; b < 6; ++b) F[b] += Jq[q * nt + p + b] * zq;
         }
         af.a0 = make_int4((int)rint(A * g.fx_scale), (int)rint(F[0] * g.fx_scale), (int)rint(F[1] * g.fx_scale),
                           (int)rint(F[2] * g.fx_scale));
@@ -746,7 +752,7 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
     }
     A64 v[64];
     if (ROLE == HI6_FIRST) {
-        init_product(v, (uint64_t)base, n, cp, qp);
+        init_product(v, full, nt, cp, qp);
     } else {
         const A64 *src = state;
 #pragma unroll
@@ -1270,7 +1276,7 @@ static int launch_hi(int n, const SweepArgs &a, const int *order, int off, int64
 template <int ROLE, int ACT>
 static int launch_hi6_ra(const SweepArgs &a, const Hi6Args &g, const int *order, int off, int64_t tiles, int count,
                          cudaStream_t st) {
-    const size_t smem = ROLE == HI6_SINGLE ? 0 : sizeof(double) * (size_t)(a.n * a.n + a.n);
+    const size_t smem = ROLE == HI6_SINGLE ? 0 : sizeof(double) * (size_t)(a.n_total * a.n_total + a.n_total);
     hi6_sweep_kernel<ROLE, ACT><<<dim3((unsigned)tiles, (unsigned)count), NT, smem, st>>>(a, g, order, off);
     return QMC_OK;
 }
@@ -1419,7 +1425,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         h.hamming_hist = hamming_hist ? hamming_hist + c0 * (n + 1) : nullptr;
         h.hist = w->hist;
         SweepArgs a;
-        a.n = n; a.state = w->state; a.params = w->params; a.af_lo = w->af_lo; a.af_hia = w->af_hia; a.af_hib = w->af_hib;
+        a.n = n; a.n_total = n; a.gbits = 0ULL; a.state = w->state; a.params = w->params; a.af_lo = w->af_lo; a.af_hia = w->af_hia; a.af_hib = w->af_hib;
         memcpy(a.dr_lo, w->dr_lo, sizeof(a.dr_lo)); memcpy(a.dr_hia, w->dr_hia, sizeof(a.dr_hia)); memcpy(a.dr_hib, w->dr_hib, sizeof(a.dr_hib));
         a.segsum = w->segsum;
         a.probs_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float *>(probs_out) : nullptr;
