@@ -50,6 +50,7 @@ struct ChainParams {
     float scale; // prod_q cos(theta_q)
     int active;  // phase layer present
     float tq[QMC_MAX_SPINS];  // tan(theta_q), theta_q = gamma w_q dt
+    float2 tpair[QMC_MAX_SPINS][2];  // [q][0] = (t, -t), [q][1] = (-t, t): packed FFMA2 multipliers
 };
 
 struct SweepArgs {
@@ -94,28 +95,27 @@ __device__ __forceinline__ float norm2(A64 a) {
     return f.x * f.x + f.y * f.y;
 }
 
-// Storage convention of the sweep path: amplitude a(idx) is held as S(idx) = (-i)^popcount(idx) * a(idx) -- in
-// registers, shared memory and HBM alike.  In that basis exp(-i theta X_q) is a real rotation, so the tan-form
-// butterfly a' = a - i t b ; b' = b - i t a  becomes, for the partner with qubit q clear (lo) / set (hi),
-//     S_lo' = S_lo + t * S_hi        S_hi' = S_hi - t * S_lo
-// identically on the real and imaginary halves: two packed FFMA2 whose multiplier is one scalar that is the same
-// for every thread of the CTA (SASS: FFMA2 Rd, Rt.F32, Rw, Ru -- scalar broadcast, two 64-bit operand reads;
-// measured 5.2 cycles/butterfly/sub-partition against 8.0 for per-thread (t, -t) pairs, benchmarks/micro/).
-// Diagonal factors (the phase layer) commute with the basis change, and |S|^2 = |a|^2.
-// reg bit b <-> qubit qpos(b).
+// Storage convention of the sweep path: amplitude idx is held as (re, im) when popcount(idx) is even and
+// as (im, re) when it is odd -- in registers, shared memory and HBM alike.  Butterfly partners always
+// differ in parity, so a' = a - i t b ; b' = b - i t a becomes two packed FFMA2 (fma.rn.f32x2, sm_100):
+//   even' = even + (t, -t) * odd_stored      odd_stored' = odd_stored + (-t, t) * even
+// `tpar` = parity of the thread's base index (all index bits outside the 6 register bits).
+// reg bit b <-> qubit qpos(b); multiplier pairs are fetched per stage as opaque 64-bit values
+// ([q][0] = (t,-t), [q][1] = (-t,t); a thread of odd base parity uses them crosswise).
 template <int ACTIVE, typename QP>
-__device__ __forceinline__ void bfly6(A64 (&v)[64], const ChainParams &cp, QP qpos) {
+__device__ __forceinline__ void bfly6(A64 (&v)[64], const ChainParams &cp, QP qpos, const int tpar) {
 #pragma unroll
     for (int b = 0; b < 6; ++b) {
         if (!((ACTIVE >> b) & 1)) continue;
-        const float t = cp.tq[qpos(b)];
-        const A64 TP = pk(t, t), TN = pk(-t, -t);
+        const A64 *p = reinterpret_cast<const A64 *>(&cp.tpair[qpos(b)][0]);
+        const A64 TA = p[tpar], TB = p[tpar ^ 1];
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
             if (j & (1 << b)) continue;
+            const bool odd = (__builtin_popcount(j) & 1) != 0;  // folds: j is a compile-time constant
             const A64 u = v[j], w = v[j | (1 << b)];
-            v[j] = fma2(TP, w, u);
-            v[j | (1 << b)] = fma2(TN, u, w);
+            v[j] = fma2(odd ? TB : TA, w, u);
+            v[j | (1 << b)] = fma2(odd ? TA : TB, u, w);
         }
     }
 }
@@ -141,22 +141,18 @@ __device__ __forceinline__ void apply_scale(A64 &a, const float g) {
     a = pk(v.x * g, v.y * g);
 }
 
-// z * i^k for k mod 4 (conversion between stored S(idx) and a(idx) = i^popcount(idx) S(idx))
-__device__ __forceinline__ float2 times_i_pow(float2 z, int k) {
-    switch (k & 3) {
-        case 0: return z;
-        case 1: return make_float2(-z.y, z.x);
-        case 2: return make_float2(-z.x, -z.y);
-        default: return make_float2(z.y, -z.x);
+// amplitude of M|s0> at index idx (tan form incl. the layer scale):
+//   scale * prod_{q in idx^s0} (-i t_q)
+__device__ __forceinline__ float2 product_state_amp(float mag, int d) {
+    switch (d & 3) {
+        case 0: return make_float2(mag, 0.f);
+        case 1: return make_float2(0.f, -mag);
+        case 2: return make_float2(-mag, 0.f);
+        default: return make_float2(0.f, mag);
     }
 }
 
-// Shared-memory swizzle of the LO transposition: XOR the 4 low index bits with bits 6..9.  A-layout accesses
-// (lanes on bits 0..4, register bits 6..11 fixed per instruction) stay a permutation inside each aligned group of
-// 16 slots; B-layout accesses (lane stride 64 slots) hit 16 distinct 8-byte slots per half-warp: both
-// conflict-free with 64-bit accesses.  (128-bit B accesses would pin amplitude pairs (j, j+1) to aligned register
-// quads, which costs ~400 MOVs around the qubit-0 butterflies.)
-__device__ __forceinline__ int lo_swz(int local) { return local ^ ((local >> 6) & 15); }
+__device__ __forceinline__ int lo_swz(int local) { return local ^ (((local >> 6) & 7) << 1); }
 
 // ------------------------------------------------------------------------------------------
 // LO tile: 2^13 contiguous amplitudes, qubits 0..11 butterflied.
@@ -178,46 +174,31 @@ __device__ __forceinline__ void lo_store_a(const A64 (&v)[64], float2 *__restric
 #pragma unroll
     for (int j = 0; j < 64; ++j) p[j << 6] = v[j];
 }
-// The swizzled slot of (thread-fixed bits | register bits) needs one XOR per value of (j & 15); the four
-// registers sharing it sit at compile-time offsets, so each transposition costs 16 address computations.
 __device__ __forceinline__ void lo_a_to_smem(const A64 (&v)[64], float2 *sm_, int tid) {
     A64 *sm = reinterpret_cast<A64 *>(sm_);
     const int base = lo_base_a(tid);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        A64 *p = sm + (base ^ k);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) p[(k + 16 * q) << 6] = v[k + 16 * q];
-    }
+    for (int j = 0; j < 64; ++j) sm[lo_swz(base | (j << 6))] = v[j];
 }
 __device__ __forceinline__ void lo_smem_to_a(A64 (&v)[64], const float2 *sm_, int tid) {
     const A64 *sm = reinterpret_cast<const A64 *>(sm_);
     const int base = lo_base_a(tid);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const A64 *p = sm + (base ^ k);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[k + 16 * q] = p[(k + 16 * q) << 6];
-    }
+    for (int j = 0; j < 64; ++j) v[j] = sm[lo_swz(base | (j << 6))];
 }
 __device__ __forceinline__ void lo_b_to_smem(const A64 (&v)[64], float2 *sm_, int tid) {
-    A64 *sm = reinterpret_cast<A64 *>(sm_) + (tid << 6);
-    const int t4 = tid & 15;
+    A64 *sm = reinterpret_cast<A64 *>(sm_);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        A64 *p = sm + (k ^ t4);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) p[16 * q] = v[k + 16 * q];
-    }
+    for (int j = 0; j < 64; j += 2)
+        *reinterpret_cast<ulonglong2 *>(&sm[lo_swz((tid << 6) | j)]) = make_ulonglong2(v[j], v[j + 1]);
 }
 __device__ __forceinline__ void lo_smem_to_b(A64 (&v)[64], const float2 *sm_, int tid) {
-    const A64 *sm = reinterpret_cast<const A64 *>(sm_) + (tid << 6);
-    const int t4 = tid & 15;
+    const A64 *sm = reinterpret_cast<const A64 *>(sm_);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const A64 *p = sm + (k ^ t4);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[k + 16 * q] = p[16 * q];
+    for (int j = 0; j < 64; j += 2) {
+        const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(&sm[lo_swz((tid << 6) | j)]);
+        v[j] = x.x;
+        v[j + 1] = x.y;
     }
 }
 
@@ -238,75 +219,88 @@ __device__ __forceinline__ PhaseAF load_af(const int4 *__restrict__ af, int64_t 
     r.a1 = __ldg(af + 2 * f + 1);
     return r;
 }
-// Per-CTA table hs[0..63] of the Gray-order increments of R(j) in 32-bit turns (c/(2 pi) * dR, wraps mod 1 turn).
-// cfx/shift are read straight from the chain's parameter record so that the table is complete at the barrier that
-// ends the parameter staging.
+// Per-CTA table of the Gray-order increments of R(j) in 32-bit turns (c/(2 pi) * dR, wraps mod 1 turn),
+// hs[0..63] as is and hs[64..127] negated (threads of odd base parity run the whole recurrence negated,
+// see phase_gray).  cfx/shift are read straight from the chain's parameter record so that the table is
+// complete at the barrier that ends the parameter staging.
 __device__ __forceinline__ int turns32(int dfx, int cfx, int shift) {
     return (int)(unsigned int)(((long long)dfx * (long long)cfx) >> shift);
 }
+template <int NTH>
 __device__ __forceinline__ void build_hs(int *hs, const int (&dr)[64], const ChainParams *cpg, int tid) {
-    if (tid < 64) hs[tid] = turns32(dr[tid], cpg->cfx, cpg->shift);
+    const int cfx = cpg->cfx, shift = cpg->shift;
+#pragma unroll
+    for (int i = tid; i < 128; i += NTH) {
+        const int t = turns32(dr[i & 63], cfx, shift);
+        hs[i] = (i & 64) ? -t : t;
+    }
 }
 
 // K1 for the thread's 64 amplitudes.  The phase angle is accumulated directly in 32-bit integer turns along the
 // Gray-code order: t(j') = t(j) +/- G_b + H_i with G_b = turns(2 F_b) (per thread) and H_i = turns(dR_i) (per
 // chain, shared memory) -- one IADD3 per amplitude, wrap-around = mod 2 pi for free, rounding <= 64 * 2^-33 turn.
-// FOLD: the per-layer normalisation prod cos(theta_q) has been folded into the initial product state
-// (cp.scale = scale^r), so the factor has unit modulus; otherwise it is scale * exp(i phi).
-// No branch on cp.active: an absent phase layer has cfx = 0, i.e. every factor is exactly (1, 0).  (A branch here
-// forces the register allocator to re-home all 64 amplitudes at the join: ~450 MOV / XOR-swap instructions.)
+// Amplitudes of odd index parity are stored swapped, for which multiplying by exp(i phi) is the same
+// formula with phi -> -phi: compile-time parity of j picks the sign of sin, the base parity tpar negates
+// the whole recurrence.  FOLD: the per-layer normalisation prod cos(theta_q) has been folded into the initial
+// product state (cp.scale = scale^r), so the factor has unit modulus; otherwise it is scale * exp(i phi).
 template <bool FOLD>
 __device__ __forceinline__ void phase_gray(A64 (&v)[64], const PhaseAF af, const int *hs_all, const int dr0,
-                                           const ChainParams &cp) {
-    const int cfx = cp.cfx, shift = cp.shift;
-    const int F[6] = {af.a0.y, af.a0.z, af.a0.w, af.a1.x, af.a1.y, af.a1.z};
-    int G[6];
+                                           const ChainParams &cp, const int tpar) {
+    if (cp.active) {
+        const int cfx = tpar ? -cp.cfx : cp.cfx, shift = cp.shift;
+        const int F[6] = {af.a0.y, af.a0.z, af.a0.w, af.a1.x, af.a1.y, af.a1.z};
+        int G[6];
 #pragma unroll
-    for (int b = 0; b < 6; ++b) G[b] = turns32(2 * F[b], cfx, shift);
-    int t = turns32(af.a0.x + F[0] + F[1] + F[2] + F[3] + F[4] + F[5] + dr0, cfx, shift);
-    const int4 *hs = reinterpret_cast<const int4 *>(hs_all);
-    const float sc = cp.scale;
-    int4 hn = hs[0];
+        for (int b = 0; b < 6; ++b) G[b] = turns32(2 * F[b], cfx, shift);
+        int t = turns32(af.a0.x + F[0] + F[1] + F[2] + F[3] + F[4] + F[5] + dr0, cfx, shift);
+        const int4 *hs = reinterpret_cast<const int4 *>(hs_all + (tpar << 6));
+        const float sc = cp.scale;
+        int4 hn = hs[0];
 #pragma unroll
-    for (int i4 = 0; i4 < 16; ++i4) {
-        const int4 h4 = hn;  // increments H_{4 i4 .. 4 i4 + 3}; the step i -> i+1 adds H_{i+1}
-        if (i4 < 15) hn = hs[i4 + 1];
+        for (int i4 = 0; i4 < 16; ++i4) {
+            const int4 h4 = hn;  // increments H_{4 i4 .. 4 i4 + 3}; the step i -> i+1 adds H_{i+1}
+            if (i4 < 15) hn = hs[i4 + 1];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = 4 * i4 + k;
-            const int j = i ^ (i >> 1);
-            float sn, cs;
-            __sincosf((float)t * 1.4629180792671596e-09f, &sn, &cs);  // 2 pi / 2^32
-            if (!FOLD) {
-                sn *= sc;
-                cs *= sc;
-            }
-            const float2 a = upk(v[j]);
-            v[j] = pk(a.x * cs - a.y * sn, a.y * cs + a.x * sn);
-            if (i < 63) {
-                const int i1 = i + 1;
-                const int b = (i1 & 1) ? 0 : (i1 & 2) ? 1 : (i1 & 4) ? 2 : (i1 & 8) ? 3 : (i1 & 16) ? 4 : 5;
-                const int jn = i1 ^ (i1 >> 1);
-                const int h = (k == 0) ? h4.y : (k == 1) ? h4.z : (k == 2) ? h4.w : hn.x;
-                t = ((jn >> b) & 1) ? t - G[b] + h : t + G[b] + h;
+            for (int k = 0; k < 4; ++k) {
+                const int i = 4 * i4 + k;
+                const int j = i ^ (i >> 1);
+                const bool odd = (__builtin_popcount(j) & 1) != 0;
+                float sn, cs;
+                __sincosf((float)t * 1.4629180792671596e-09f, &sn, &cs);  // 2 pi / 2^32
+                if (!FOLD) {
+                    sn *= sc;
+                    cs *= sc;
+                }
+                const float2 a = upk(v[j]);
+                v[j] = odd ? pk(a.x * cs + a.y * sn, a.y * cs - a.x * sn) : pk(a.x * cs - a.y * sn, a.y * cs + a.x * sn);
+                if (i < 63) {
+                    const int i1 = i + 1;
+                    const int b = (i1 & 1) ? 0 : (i1 & 2) ? 1 : (i1 & 4) ? 2 : (i1 & 8) ? 3 : (i1 & 16) ? 4 : 5;
+                    const int jn = i1 ^ (i1 >> 1);
+                    const int h = (k == 0) ? h4.y : (k == 1) ? h4.z : (k == 2) ? h4.w : hn.x;
+                    t = ((jn >> b) & 1) ? t - G[b] + h : t + G[b] + h;
+                }
             }
         }
+    } else if (!FOLD) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) apply_scale(v[j], cp.scale);
     }
 }
 
-// M|s0> restricted to this thread's 64 amplitudes; reg bit b <-> global qubit qpos[b].
-//   a(idx) = scale * prod_{q in idx^s0} (-i t_q)   =>   S(idx) = (-i)^popcount(s0) * (-1)^popcount(idx & ~s0) * |..|
-// i.e. real up to the global factor (-i)^popcount(s0).
+// M|s0> restricted to this thread's 64 amplitudes; reg bit b <-> global qubit qpos[b]
 template <typename QP>
 __device__ __forceinline__ void init_product(A64 (&v)[64], uint64_t base_idx, int n, const ChainParams &cp, QP qpos) {
+    const int tpar = parity64(base_idx);
+    // fixed part: all qubits outside the register bits
     uint64_t regmask = 0;
 #pragma unroll
     for (int b = 0; b < 6; ++b) regmask |= 1ULL << qpos(b);
     const uint64_t diff = (base_idx ^ cp.cur) & ~regmask;
-    float mag0 = (__popcll(base_idx & ~cp.cur & ~regmask) & 1) ? -cp.scale : cp.scale;
+    float mag0 = cp.scale;
     for (int q = 0; q < n; ++q)
         if ((diff >> q) & 1ULL) mag0 *= cp.tq[q];
-    const float2 g = times_i_pow(make_float2(1.f, 0.f), -(int)__popcll(cp.cur));  // (-i)^popcount(s0)
+    const int d0 = __popcll(diff);
     float f[6];
     int sbit[6];
 #pragma unroll
@@ -317,13 +311,16 @@ __device__ __forceinline__ void init_product(A64 (&v)[64], uint64_t base_idx, in
 #pragma unroll
     for (int j = 0; j < 64; ++j) {
         float mag = mag0;
+        int d = d0;
 #pragma unroll
         for (int b = 0; b < 6; ++b) {
-            const int jb = (j >> b) & 1;
-            mag *= (jb ^ sbit[b]) ? f[b] : 1.0f;      // qubit differs from s0: factor t_q
-            mag = (jb & (sbit[b] ^ 1)) ? -mag : mag;  // bit set in idx but not in s0: sign
+            const int differs = ((j >> b) & 1) ^ sbit[b];
+            mag *= differs ? f[b] : 1.0f;
+            d += differs;
         }
-        v[j] = pk(mag * g.x, mag * g.y);
+        const float2 amp = product_state_amp(mag, d);
+        const bool odd = ((__builtin_popcount(j) & 1) ^ tpar) != 0;
+        v[j] = odd ? pk(amp.y, amp.x) : pk(amp.x, amp.y);
     }
 }
 
@@ -344,11 +341,11 @@ __device__ __forceinline__ void lo_final_tile(A64 (&v)[64], float2 *sm, const fl
         return;
     }
     lo_load_a(v, state_chain + (tile << TB), tid);
-    bfly6<63>(v, cp, LoQ6());
+    bfly6<63>(v, cp, LoQ6(), parity64(gb | ((unsigned long long)tile << TB) | (unsigned)lo_base_a(tid)));
     lo_a_to_smem(v, sm, tid);
     __syncthreads();
     lo_smem_to_b(v, sm, tid);
-    bfly6<63>(v, cp, LoQ0());
+    bfly6<63>(v, cp, LoQ0(), parity64(gb | ((unsigned long long)tile << TB) | ((unsigned)tid << 6)));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -434,11 +431,11 @@ __device__ __forceinline__ void stage_params(ChainParams &dst_s, const ChainPara
 enum { LO_FIRST = 0, LO_MID = 1, LO_FINAL = 2, LO_SINGLE = 3 };  // SINGLE: M_lo only (3+ qubit groups)
 
 template <int ROLE, int NTH, bool FOLD>
-__global__ void __launch_bounds__(NTH, 384 / NTH) lo_sweep_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off) {
+__global__ void __launch_bounds__(NTH, 256 / NTH) lo_sweep_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off) {
     constexpr int TB = NTH == 128 ? 13 : 12;  // tile bits
     extern __shared__ __align__(16) float2 sm[];
     __shared__ ChainParams cp_s;
-    __shared__ __align__(16) int hs_s[64];
+    __shared__ __align__(16) int hs_s[128];
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t chain = order[list_off + blockIdx.y];
@@ -450,7 +447,7 @@ __global__ void __launch_bounds__(NTH, 384 / NTH) lo_sweep_kernel(const SweepArg
         int64_t pc, pt;
         if (pf_target(a, order, list_off, pc, pt)) l2_prefetch_bulk(a.state + (pc << n) + (pt << TB), (1u << TB) * 8);
     }
-    if (ROLE == LO_FIRST || ROLE == LO_MID) build_hs(hs_s, a.dr_lo, a.params + chain, tid);
+    if (ROLE == LO_FIRST || ROLE == LO_MID) build_hs<NTH>(hs_s, a.dr_lo, a.params + chain, tid);
     stage_params<NTH>(cp_s, a.params + chain, tid);
     const ChainParams &cp = cp_s;
     if (ROLE == LO_FINAL) {
@@ -467,18 +464,23 @@ __global__ void __launch_bounds__(NTH, 384 / NTH) lo_sweep_kernel(const SweepArg
         if (a.amps_out) {
             float2 *ao = a.amps_out + (chain << n) + (tile << TB) + (tid << 6);
 #pragma unroll
-            const int kb = __popcll(a.gbits | ((unsigned long long)tile << TB) | ((unsigned)tid << 6));
-            for (int j = 0; j < 64; ++j) ao[j] = times_i_pow(upk(v[j]), kb + __builtin_popcount(j));  // a = i^popcount S
+            for (int j = 0; j < 64; ++j) {
+                const bool odd = ((__builtin_popcount(j) & 1) ^ parity64(a.gbits | ((unsigned long long)tile << TB) | ((unsigned)tid << 6))) != 0;
+                const float2 f = upk(v[j]);
+                ao[j] = odd ? make_float2(f.y, f.x) : f;
+            }
         }
         return;
     }
+    const int par_a = parity64(a.gbits | ((unsigned long long)tile << TB) | (unsigned)lo_base_a(tid));
+    const int par_b = parity64(a.gbits | ((unsigned long long)tile << TB) | ((unsigned)tid << 6));
     if (ROLE == LO_SINGLE) {
         lo_load_a(v, state + (tile << TB), tid);
-        bfly6<63>(v, cp, LoQ6());
+        bfly6<63>(v, cp, LoQ6(), par_a);
         lo_a_to_smem(v, sm, tid);
         __syncthreads();
         lo_smem_to_b(v, sm, tid);
-        bfly6<63>(v, cp, LoQ0());
+        bfly6<63>(v, cp, LoQ0(), par_b);
         lo_b_to_smem(v, sm, tid);  // each thread rewrites exactly the slots it read
         __syncthreads();
         lo_smem_to_a(v, sm, tid);
@@ -489,86 +491,27 @@ __global__ void __launch_bounds__(NTH, 384 / NTH) lo_sweep_kernel(const SweepArg
     if (ROLE == LO_FIRST) {
         init_product(v, ((uint64_t)tile << TB) | ((uint64_t)tid << 6), n, cp, LoQ0());
     } else {
-        bfly6<63>(v, cp, LoQ6());
+        bfly6<63>(v, cp, LoQ6(), par_a);
         lo_a_to_smem(v, sm, tid);
         __syncthreads();
         lo_smem_to_b(v, sm, tid);
-        bfly6<63>(v, cp, LoQ0());
+        bfly6<63>(v, cp, LoQ0(), par_b);
     }
-    phase_gray<FOLD>(v, af, hs_s, a.dr_lo[0], cp);
-    bfly6<63>(v, cp, LoQ0());
+    phase_gray<FOLD>(v, af, hs_s, a.dr_lo[0], cp, par_b);
+    bfly6<63>(v, cp, LoQ0(), par_b);
     lo_b_to_smem(v, sm, tid);  // each thread rewrites exactly the slots it read: no barrier needed before
     __syncthreads();
     lo_smem_to_a(v, sm, tid);
-    bfly6<63>(v, cp, LoQ6());
+    bfly6<63>(v, cp, LoQ6(), par_a);
     lo_store_a(v, state + (tile << TB), tid);
 }
-
-#ifdef QMC_PROBES
-// Diagnostics only (make PROBES=1 / benchmarks/probe_sweep.cu; never in the shipped library): the LO MID sweep
-// with parts removed.  MODE bits: 1 = HBM loads + stores, 2 = butterflies, 4 = phase layer, 8 = transpositions.
-// Without bit 1 the store is predicated on a value the compiler cannot prove, so the arithmetic stays.
-template <int MODE, int MINB, int TPC = 1>
-__global__ void __launch_bounds__(NT, MINB) lo_probe_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off) {
-    extern __shared__ __align__(16) float2 sm[];
-    __shared__ ChainParams cp_s;
-    __shared__ __align__(16) int hs_s[64];
-    const int tid = threadIdx.x;
-    const int64_t chain = order[list_off + blockIdx.y];
-    const int n = a.n;
-    float2 *state = a.state + (chain << n);
-    build_hs(hs_s, a.dr_lo, a.params + chain, tid);
-    stage_params<NT>(cp_s, a.params + chain, tid);
-    const ChainParams &cp = cp_s;
-#pragma unroll 1
-    for (int it = 0; it < TPC; ++it) {
-        const int64_t tile = (int64_t)blockIdx.x * TPC + it;
-        A64 v[64];
-        if (MODE & 1) {
-            lo_load_a(v, state + (tile << 13), tid);
-            if (tid == 0) {
-                int64_t pc, pt;
-                if (pf_target(a, order, list_off, pc, pt)) l2_prefetch_bulk(a.state + (pc << n) + (pt << 13), TILE * 8);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = pk((float)(tid + j), 1.0f);
-        }
-        const PhaseAF af = load_af(a.af_lo, tile * NT + tid);
-        if (MODE & 2) bfly6<63>(v, cp, LoQ6());
-        if (MODE & 8) {
-            if (TPC > 1) __syncthreads();
-            lo_a_to_smem(v, sm, tid);
-            __syncthreads();
-            lo_smem_to_b(v, sm, tid);
-        }
-        if (MODE & 2) bfly6<63>(v, cp, LoQ0());
-        if (MODE & 4) phase_gray<true>(v, af, hs_s, a.dr_lo[0], cp);
-        if (MODE & 2) bfly6<63>(v, cp, LoQ0());
-        if (MODE & 8) {
-            lo_b_to_smem(v, sm, tid);
-            __syncthreads();
-            lo_smem_to_a(v, sm, tid);
-        }
-        if (MODE & 2) bfly6<63>(v, cp, LoQ6());
-        if (MODE & 1) {
-            lo_store_a(v, state + (tile << 13), tid);
-        } else {
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) acc += norm2(v[j]);
-            if (acc == 1.2345e-30f) lo_store_a(v, state + (tile << 13), tid);
-        }
-    }
-}
-#endif
 
 template <int W, bool FIRST, bool FOLD>
 __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off) {
     using G = HiGeom<W>;
     extern __shared__ __align__(16) float2 sm[];
     __shared__ ChainParams cp_s;
-    __shared__ __align__(16) int hs_s[64];
+    __shared__ __align__(16) int hs_s[128];
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t chain = order[list_off + blockIdx.y];
@@ -587,7 +530,7 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
             for (int r = tid; r < ROWS; r += NT) l2_prefetch_bulk(src + ((int64_t)r << 12), ROW_BYTES);
         }
     }
-    build_hs(hs_s, G::two_rounds ? a.dr_hib : a.dr_hia, a.params + chain, tid);
+    build_hs<NT>(hs_s, G::two_rounds ? a.dr_hib : a.dr_hia, a.params + chain, tid);
     stage_params(cp_s, a.params + chain, tid);
     const ChainParams &cp = cp_s;
     const PhaseAF af = load_af(G::two_rounds ? a.af_hib : a.af_hia, tile * NT + tid);
@@ -596,33 +539,33 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
         if (FIRST) {
             init_product(v, (uint64_t)base_b, n, cp, HiQB<W>());
         } else {
-            bfly6<G::active_a>(v, cp, HiQA<W>());
+            bfly6<G::active_a>(v, cp, HiQA<W>(), parity64((unsigned long long)base_a));
 #pragma unroll
             for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(sm)[hi_loc_a(tid, j)] = v[j];
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < 64; ++j) v[j] = reinterpret_cast<const A64 *>(sm)[hi_loc_b(tid, j)];
-            bfly6<G::active_b>(v, cp, HiQB<W>());
+            bfly6<G::active_b>(v, cp, HiQB<W>(), parity64((unsigned long long)base_b));
             __syncthreads();
         }
-        phase_gray<FOLD>(v, af, hs_s, a.dr_hib[0], cp);
-        bfly6<G::active_b>(v, cp, HiQB<W>());
+        phase_gray<FOLD>(v, af, hs_s, a.dr_hib[0], cp, parity64((unsigned long long)base_b));
+        bfly6<G::active_b>(v, cp, HiQB<W>(), parity64((unsigned long long)base_b));
 #pragma unroll
         for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(sm)[hi_loc_b(tid, j)] = v[j];
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < 64; ++j) v[j] = reinterpret_cast<const A64 *>(sm)[hi_loc_a(tid, j)];
-        bfly6<G::active_a>(v, cp, HiQA<W>());
+        bfly6<G::active_a>(v, cp, HiQA<W>(), parity64((unsigned long long)base_a));
 #pragma unroll
         for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(state)[base_a + G::off_a(j)] = v[j];
     } else {
         if (FIRST) {
             init_product(v, (uint64_t)base_a, n, cp, HiQA<W>());
         } else {
-            bfly6<G::active_a>(v, cp, HiQA<W>());
+            bfly6<G::active_a>(v, cp, HiQA<W>(), parity64((unsigned long long)base_a));
         }
-        phase_gray<FOLD>(v, af, hs_s, a.dr_hia[0], cp);
-        bfly6<G::active_a>(v, cp, HiQA<W>());
+        phase_gray<FOLD>(v, af, hs_s, a.dr_hia[0], cp, parity64((unsigned long long)base_a));
+        bfly6<G::active_a>(v, cp, HiQA<W>(), parity64((unsigned long long)base_a));
 #pragma unroll
         for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(state)[base_a + G::off_a(j)] = v[j];
     }
@@ -656,12 +599,12 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
                                                           const int list_off) {
     extern __shared__ __align__(16) double smd[];  // Jq[n*n], hq[n]
     __shared__ ChainParams cp_s;
-    __shared__ __align__(16) int hs_s[64];
+    __shared__ __align__(16) int hs_s[128];
     const int tid = threadIdx.x;
     const int n = a.n;
     const int64_t tile = blockIdx.x;
     const int64_t chain = order[list_off + blockIdx.y];
-    if (ROLE != HI6_SINGLE) build_hs(hs_s, g.dr, a.params + chain, tid);
+    if (ROLE != HI6_SINGLE) build_hs<NT>(hs_s, g.dr, a.params + chain, tid);
     if (ROLE != HI6_SINGLE) {
         const int nt_ = a.n_total;
         for (int i = tid; i < nt_ * nt_; i += NT) smd[i] = g.Jq[i];
@@ -678,6 +621,7 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
     A64 *state = reinterpret_cast<A64 *>(a.state + (chain << n)) + base;
     const unsigned long long full = (unsigned long long)base | a.gbits;  // incl. the global (sharded) qubits
     const int nt = a.n_total;
+    const int tpar = parity64(full);
     const int64_t stride = (int64_t)1 << p;
     const HiP qp{p};
     // phase exponent fields first (fp64, registers still free): A = sum_{a<b fixed} Jq z z + sum_{a fixed} hq z,
@@ -716,11 +660,11 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
             v[j] = *src;
             src += stride;
         }
-        bfly6<ACTIVE>(v, cp, qp);
+        bfly6<ACTIVE>(v, cp, qp, tpar);
     }
     if (ROLE != HI6_SINGLE) {
-        phase_gray<false>(v, af, hs_s, g.dr[0], cp);
-        bfly6<ACTIVE>(v, cp, qp);
+        phase_gray<false>(v, af, hs_s, g.dr[0], cp, tpar);
+        bfly6<ACTIVE>(v, cp, qp, tpar);
     }
     A64 *dst = state;
 #pragma unroll
@@ -798,6 +742,10 @@ __device__ void fill_proposal_params(ChainParams &cp, const HopArgs &h, double g
         scale *= c;
     }
     cp.scale = h.fold ? (float)pow(scale, (double)cp.r) : (float)scale;
+    for (int q = 0; q < QMC_MAX_SPINS; ++q) {
+        cp.tpair[q][0] = make_float2(cp.tq[q], -cp.tq[q]);
+        cp.tpair[q][1] = make_float2(-cp.tq[q], cp.tq[q]);
+    }
     const double cprime = (1.0 - gamma) * h.alpha * h.dt * 0.15915494309189533577;  // c / (2 pi)
     cp.active = h.phase_active && cp.r > 1 && cprime != 0.0;
     int m = 0;
@@ -1185,23 +1133,6 @@ template <int ROLE>
 static int launch_lo(const SweepTune &tu, const SweepArgs &a, const int *order, int off, int64_t tiles, int count,
                      cudaStream_t st) {
     constexpr bool PHASED = ROLE == LO_FIRST || ROLE == LO_MID;  // roles without a phase layer ignore `fold`
-#ifdef QMC_PROBES
-    if (ROLE == LO_MID) {
-        const char *pe = getenv("QUMCMC_SWEEP_PROBE");
-        const int mode = pe ? atoi(pe) : 0;
-        static bool done1 = false, done2 = false;
-        if (mode == 1) {
-            set_smem_once(lo_probe_kernel<9, 3>, done1);
-            lo_probe_kernel<9, 3><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off);
-            return QMC_OK;
-        }
-        if (mode == 2) {
-            set_smem_once(lo_probe_kernel<14, 3>, done2);
-            lo_probe_kernel<14, 3><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off);
-            return QMC_OK;
-        }
-    }
-#endif
     if (ROLE == LO_SINGLE) return launch_lo_v<ROLE, 128, false>(a, order, off, tiles, count, st);
     if (tu.lo64) {
         if (PHASED && tu.fold) return launch_lo_v<ROLE, 64, PHASED>(a, order, off, tiles, count, st);
