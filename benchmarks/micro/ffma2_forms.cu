@@ -14,6 +14,9 @@ __device__ __forceinline__ A64 fma2(A64 a, A64 b, A64 c) { A64 d; asm("fma.rn.f3
 // VAR 4: VAR 0 with a per-thread sign on t (what the parity-swapped layout needs in the sweep kernels)
 // VAR 5: odd-parity amplitudes stored as -i*x: skew update v[j] += s v[p]; v[p] -= s v[j], s per thread (scalar broadcast)
 // VAR 6: VAR 5 with s = kernel parameter
+// VAR 7: VAR 5 layout, one multiplier per CTA read from __constant__ memory at a block-uniform index
+__constant__ float c_tab[4096];
+
 template <int VAR>
 __global__ void __launch_bounds__(128, 3) k(float *out, long long *cyc, float t, int iters) {
     __shared__ float ts[64];
@@ -30,6 +33,7 @@ __global__ void __launch_bounds__(128, 3) k(float *out, long long *cyc, float t,
             float tt = t;
             if (VAR == 2 || VAR == 3) tt = ts[(it + b) & 63];
             if (VAR == 4 || VAR == 5) tt = ts[(it + b) & 63] * sgn;
+            if (VAR == 7) tt = c_tab[(blockIdx.x + iters + b) & 4095];
             const A64 TA = pk(tt, -tt), TB = pk(-tt, tt), TT = pk(tt, tt), TN = pk(-tt, -tt);
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
@@ -39,7 +43,7 @@ __global__ void __launch_bounds__(128, 3) k(float *out, long long *cyc, float t,
                 if (VAR == 0 || VAR == 2 || VAR == 4) {
                     v[j] = fma2(TA, w, u);
                     v[p] = fma2(TB, u, w);
-                } else if (VAR == 5 || VAR == 6) {
+                } else if (VAR == 5 || VAR == 6 || VAR == 7) {
                     const bool odd = (__builtin_popcount(j) & 1) != 0;
                     v[j] = fma2(odd ? TN : TT, w, u);
                     v[p] = fma2(odd ? TT : TN, u, w);
@@ -91,6 +95,7 @@ void run(const char *name, int per_sm, int iters) {
     cudaFree(out); cudaFree(cyc);
 }
 int main() {
+    { float h[4096]; for (int i = 0; i < 4096; ++i) h[i] = 0.3f + 1e-5f * i; cudaMemcpyToSymbol(c_tab, h, sizeof(h)); }
     for (int w = 1; w <= 3; w += 2) {
         run<0>("swapped storage, t = kernel param", w, 4000);
         run<1>("natural storage + half swap, t = kernel param", w, 4000);
@@ -99,6 +104,7 @@ int main() {
         run<4>("swapped storage, t from smem * per-thread sign", w, 4000);
         run<5>("-i storage (skew form), s from smem * per-thread sign", w, 4000);
         run<6>("-i storage (skew form), s = kernel param", w, 4000);
+        run<7>("skew form, s = __constant__[block-uniform index]", w, 4000);
     }
     return 0;
 }

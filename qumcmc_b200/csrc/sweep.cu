@@ -52,6 +52,12 @@ struct ChainParams {
     float tq[QMC_MAX_SPINS];  // tan(theta_q), theta_q = gamma w_q dt
 };
 
+// Fast path only: tan(gamma w dt) of the chain at position i of order[] (one value per chain: every qubit carries
+// the same mixer weight).  Read at a block-uniform index, so it lands in a uniform register and feeds FFMA2 as a
+// scalar-broadcast operand (4.5 cycles/butterfly/sub-partition against 5.2 from a vector register).
+constexpr int CTAN_MAX = 12288;
+__constant__ float c_tan[CTAN_MAX];
+
 struct SweepArgs {
     int n;                    // index qubits of the local statevector (addressing)
     int n_total;              // all qubits incl. global (sharded) ones; == n on one GPU
@@ -103,12 +109,12 @@ __device__ __forceinline__ float norm2(A64 a) {
 // measured 5.2 cycles/butterfly/sub-partition against 8.0 for per-thread (t, -t) pairs, benchmarks/micro/).
 // Diagonal factors (the phase layer) commute with the basis change, and |S|^2 = |a|^2.
 // reg bit b <-> qubit qpos(b).
-template <int ACTIVE, typename QP>
-__device__ __forceinline__ void bfly6(A64 (&v)[64], const ChainParams &cp, QP qpos) {
+template <int ACTIVE, bool FAST = false, typename QP>
+__device__ __forceinline__ void bfly6(A64 (&v)[64], const ChainParams &cp, QP qpos, const float t_uniform = 0.f) {
 #pragma unroll
     for (int b = 0; b < 6; ++b) {
         if (!((ACTIVE >> b) & 1)) continue;
-        const float t = cp.tq[qpos(b)];
+        const float t = FAST ? t_uniform : cp.tq[qpos(b)];
         const A64 TP = pk(t, t), TN = pk(-t, -t);
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
@@ -334,21 +340,22 @@ struct LoQ6 { __device__ __forceinline__ int operator()(int b) const { return 6 
 // Used by the last sweep (segment sums) and by the sampler (recompute of the selected tile).
 // A LO tile is NTH * 64 contiguous amplitudes: 2^13 for 128 threads, 2^12 for 64 threads (bit 12 is a pure
 // batch bit of the LO butterflies, so a 128-thread tile is two independent 64-thread tiles).
-template <int NTH>
+// R1: proposal with a single mixer layer -- the final state is the analytic product state (no sweep ran before).
+template <int NTH, bool FAST, bool R1>
 __device__ __forceinline__ void lo_final_tile(A64 (&v)[64], float2 *sm, const float2 *__restrict__ state_chain,
                                               int64_t tile, int tid, int n, const ChainParams &cp,
-                                              unsigned long long gb = 0ULL) {
+                                              unsigned long long gb = 0ULL, const float tu = 0.f) {
     constexpr int TB = NTH == 128 ? 13 : 12;
-    if (cp.r == 1) {
+    if (R1) {
         init_product(v, gb | ((uint64_t)tile << TB) | ((uint64_t)tid << 6), n, cp, LoQ0());
         return;
     }
     lo_load_a(v, state_chain + (tile << TB), tid);
-    bfly6<63>(v, cp, LoQ6());
+    bfly6<63, FAST>(v, cp, LoQ6(), tu);
     lo_a_to_smem(v, sm, tid);
     __syncthreads();
     lo_smem_to_b(v, sm, tid);
-    bfly6<63>(v, cp, LoQ0());
+    bfly6<63, FAST>(v, cp, LoQ0(), tu);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -431,10 +438,11 @@ __device__ __forceinline__ void stage_params(ChainParams &dst_s, const ChainPara
     __syncthreads();
 }
 
-enum { LO_FIRST = 0, LO_MID = 1, LO_FINAL = 2, LO_SINGLE = 3 };  // SINGLE: M_lo only (3+ qubit groups)
+enum { LO_FIRST = 0, LO_MID = 1, LO_FINAL = 2, LO_SINGLE = 3, LO_FINAL1 = 4 };  // SINGLE: M_lo only (3+ qubit groups); FINAL1: r == 1
 
-template <int ROLE, int NTH, bool FOLD>
-__global__ void __launch_bounds__(NTH, 384 / NTH) lo_sweep_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off) {
+// FAST = normalisation folded into the initial product state + one mixer multiplier per chain from c_tan[]
+template <int ROLE, int NTH, bool FAST>
+__global__ void __launch_bounds__(NTH, 384 / NTH) lo_sweep_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off, const int ct_off) {
     constexpr int TB = NTH == 128 ? 13 : 12;  // tile bits
     extern __shared__ __align__(16) float2 sm[];
     __shared__ ChainParams cp_s;
@@ -442,19 +450,21 @@ __global__ void __launch_bounds__(NTH, 384 / NTH) lo_sweep_kernel(const SweepArg
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t chain = order[list_off + blockIdx.y];
+    // ct_off == list_off: passed separately so that this index stays pure uniform-datapath arithmetic (LDCU -> UR)
+    const float tu = FAST ? c_tan[ct_off + blockIdx.y] : 0.f;
     const int n = a.n;
     float2 *state = a.state + (chain << n);
     A64 v[64];
     if (ROLE == LO_MID) lo_load_a(v, state + (tile << TB), tid);  // in flight while the parameters are staged
-    if (ROLE != LO_FIRST && tid == 0) {
+    if (ROLE != LO_FIRST && ROLE != LO_FINAL1 && tid == 0) {
         int64_t pc, pt;
         if (pf_target(a, order, list_off, pc, pt)) l2_prefetch_bulk(a.state + (pc << n) + (pt << TB), (1u << TB) * 8);
     }
     if (ROLE == LO_FIRST || ROLE == LO_MID) build_hs(hs_s, a.dr_lo, a.params + chain, tid);
     stage_params<NTH>(cp_s, a.params + chain, tid);
     const ChainParams &cp = cp_s;
-    if (ROLE == LO_FINAL) {
-        lo_final_tile<NTH>(v, sm, state, tile, tid, a.n_total, cp, a.gbits);
+    if (ROLE == LO_FINAL || ROLE == LO_FINAL1) {
+        lo_final_tile<NTH, FAST, ROLE == LO_FINAL1>(v, sm, state, tile, tid, a.n_total, cp, a.gbits, tu);
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < 64; ++j) s += norm2(v[j]);
@@ -474,11 +484,11 @@ __global__ void __launch_bounds__(NTH, 384 / NTH) lo_sweep_kernel(const SweepArg
     }
     if (ROLE == LO_SINGLE) {
         lo_load_a(v, state + (tile << TB), tid);
-        bfly6<63>(v, cp, LoQ6());
+        bfly6<63, FAST>(v, cp, LoQ6(), tu);
         lo_a_to_smem(v, sm, tid);
         __syncthreads();
         lo_smem_to_b(v, sm, tid);
-        bfly6<63>(v, cp, LoQ0());
+        bfly6<63, FAST>(v, cp, LoQ0(), tu);
         lo_b_to_smem(v, sm, tid);  // each thread rewrites exactly the slots it read
         __syncthreads();
         lo_smem_to_a(v, sm, tid);
@@ -489,18 +499,18 @@ __global__ void __launch_bounds__(NTH, 384 / NTH) lo_sweep_kernel(const SweepArg
     if (ROLE == LO_FIRST) {
         init_product(v, ((uint64_t)tile << TB) | ((uint64_t)tid << 6), n, cp, LoQ0());
     } else {
-        bfly6<63>(v, cp, LoQ6());
+        bfly6<63, FAST>(v, cp, LoQ6(), tu);
         lo_a_to_smem(v, sm, tid);
         __syncthreads();
         lo_smem_to_b(v, sm, tid);
-        bfly6<63>(v, cp, LoQ0());
+        bfly6<63, FAST>(v, cp, LoQ0(), tu);
     }
-    phase_gray<FOLD>(v, af, hs_s, a.dr_lo[0], cp);
-    bfly6<63>(v, cp, LoQ0());
+    phase_gray<FAST>(v, af, hs_s, a.dr_lo[0], cp);
+    bfly6<63, FAST>(v, cp, LoQ0(), tu);
     lo_b_to_smem(v, sm, tid);  // each thread rewrites exactly the slots it read: no barrier needed before
     __syncthreads();
     lo_smem_to_a(v, sm, tid);
-    bfly6<63>(v, cp, LoQ6());
+    bfly6<63, FAST>(v, cp, LoQ6(), tu);
     lo_store_a(v, state + (tile << TB), tid);
 }
 
@@ -563,8 +573,8 @@ __global__ void __launch_bounds__(NT, MINB) lo_probe_kernel(const SweepArgs a, c
 }
 #endif
 
-template <int W, bool FIRST, bool FOLD>
-__global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off) {
+template <int W, bool FIRST, bool FAST>
+__global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off, const int ct_off) {
     using G = HiGeom<W>;
     extern __shared__ __align__(16) float2 sm[];
     __shared__ ChainParams cp_s;
@@ -572,6 +582,8 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t chain = order[list_off + blockIdx.y];
+    // ct_off == list_off: passed separately so that this index stays pure uniform-datapath arithmetic (LDCU -> UR)
+    const float tu = FAST ? c_tan[ct_off + blockIdx.y] : 0.f;
     const int n = a.n;
     float2 *state = a.state + (chain << n);
     A64 v[64];
@@ -596,33 +608,33 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
         if (FIRST) {
             init_product(v, (uint64_t)base_b, n, cp, HiQB<W>());
         } else {
-            bfly6<G::active_a>(v, cp, HiQA<W>());
+            bfly6<G::active_a, FAST>(v, cp, HiQA<W>(), tu);
 #pragma unroll
             for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(sm)[hi_loc_a(tid, j)] = v[j];
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < 64; ++j) v[j] = reinterpret_cast<const A64 *>(sm)[hi_loc_b(tid, j)];
-            bfly6<G::active_b>(v, cp, HiQB<W>());
+            bfly6<G::active_b, FAST>(v, cp, HiQB<W>(), tu);
             __syncthreads();
         }
-        phase_gray<FOLD>(v, af, hs_s, a.dr_hib[0], cp);
-        bfly6<G::active_b>(v, cp, HiQB<W>());
+        phase_gray<FAST>(v, af, hs_s, a.dr_hib[0], cp);
+        bfly6<G::active_b, FAST>(v, cp, HiQB<W>(), tu);
 #pragma unroll
         for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(sm)[hi_loc_b(tid, j)] = v[j];
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < 64; ++j) v[j] = reinterpret_cast<const A64 *>(sm)[hi_loc_a(tid, j)];
-        bfly6<G::active_a>(v, cp, HiQA<W>());
+        bfly6<G::active_a, FAST>(v, cp, HiQA<W>(), tu);
 #pragma unroll
         for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(state)[base_a + G::off_a(j)] = v[j];
     } else {
         if (FIRST) {
             init_product(v, (uint64_t)base_a, n, cp, HiQA<W>());
         } else {
-            bfly6<G::active_a>(v, cp, HiQA<W>());
+            bfly6<G::active_a, FAST>(v, cp, HiQA<W>(), tu);
         }
-        phase_gray<FOLD>(v, af, hs_s, a.dr_hia[0], cp);
-        bfly6<G::active_a>(v, cp, HiQA<W>());
+        phase_gray<FAST>(v, af, hs_s, a.dr_hia[0], cp);
+        bfly6<G::active_a, FAST>(v, cp, HiQA<W>(), tu);
 #pragma unroll
         for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(state)[base_a + G::off_a(j)] = v[j];
     }
@@ -734,7 +746,8 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
 // sorted by r descending.  The host replays the same Philox draws to know the class sizes.
 constexpr int SCHED_RMAX = 2047;
 __global__ void __launch_bounds__(1024) schedule_kernel(const ChainParams *__restrict__ params, int64_t n_chains,
-                                                        int r_cap, int *__restrict__ order, int by_parity) {
+                                                        int r_cap, int *__restrict__ order, int by_parity,
+                                                        float *__restrict__ tan_sorted) {
     __shared__ int hist[SCHED_RMAX + 1];
     __shared__ int start[SCHED_RMAX + 1];
     for (int i = threadIdx.x; i <= r_cap; i += blockDim.x) hist[i] = 0;
@@ -755,7 +768,9 @@ __global__ void __launch_bounds__(1024) schedule_kernel(const ChainParams *__res
     __syncthreads();
     for (int64_t c = threadIdx.x; c < n_chains; c += blockDim.x) {
         const int r = params[c].r;
-        order[start[r] + atomicAdd(&hist[r], 1)] = (int)c;
+        const int pos = start[r] + atomicAdd(&hist[r], 1);
+        order[pos] = (int)c;
+        if (tan_sorted) tan_sorted[pos] = params[c].tq[0];  // fast path: the same multiplier on every qubit
     }
 }
 
@@ -908,7 +923,8 @@ __global__ void __launch_bounds__(NT) sample_accept_kernel(const SweepArgs a, co
     const int64_t tile = sg / NT;
     const int owner = (int)(sg % NT);
     A64 v[64];
-    lo_final_tile<NT>(v, sm, a.state + ((int64_t)chain << n), tile, tid, n, cp);
+    if (cp.r == 1) lo_final_tile<NT, false, true>(v, sm, a.state + ((int64_t)chain << n), tile, tid, n, cp);
+    else lo_final_tile<NT, false, false>(v, sm, a.state + ((int64_t)chain << n), tile, tid, n, cp);
     if (tid == owner) {
         const double rem = s_rem;
         double c = 0.0;
@@ -1022,6 +1038,7 @@ struct SweepWorkspace {
     float *segsum = nullptr;
     int *hist = nullptr;
     int *order = nullptr;
+    float *tan_sorted = nullptr;  // fast path: per-position mixer multiplier, copied into c_tan[] every hop
     int4 *af_lo = nullptr, *af_hia = nullptr, *af_hib = nullptr;
     int dr_lo[64], dr_hia[64], dr_hib[64];
     bool tables_ready = false;
@@ -1040,6 +1057,7 @@ void qmc_sweep_free(qmc_model *m) {
     cudaFree(w->segsum);
     cudaFree(w->hist);
     cudaFree(w->order);
+    cudaFree(w->tan_sorted);
     cudaFree(w->af_lo);
     cudaFree(w->af_hia);
     cudaFree(w->af_hib);
@@ -1142,14 +1160,15 @@ static int ensure_workspace(qmc_model *m, int64_t chains, cudaStream_t st) {
     }
     if (chains > w->cap_chains) {
         QMC_CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(w->state); cudaFree(w->params); cudaFree(w->segsum); cudaFree(w->hist); cudaFree(w->order);
-        w->state = nullptr; w->params = nullptr; w->segsum = nullptr; w->hist = nullptr; w->order = nullptr;
+        cudaFree(w->state); cudaFree(w->params); cudaFree(w->segsum); cudaFree(w->hist); cudaFree(w->order); cudaFree(w->tan_sorted);
+        w->state = nullptr; w->params = nullptr; w->segsum = nullptr; w->hist = nullptr; w->order = nullptr; w->tan_sorted = nullptr;
         w->cap_chains = 0;
         QMC_CUDA_TRY(cudaMalloc(&w->state, sizeof(float2) * (size_t)N * chains));
         QMC_CUDA_TRY(cudaMalloc(&w->params, sizeof(ChainParams) * chains));
         QMC_CUDA_TRY(cudaMalloc(&w->segsum, sizeof(float) * (size_t)(N >> 6) * chains));
         QMC_CUDA_TRY(cudaMalloc(&w->hist, sizeof(int) * (size_t)(n + 1) * chains));
         QMC_CUDA_TRY(cudaMalloc(&w->order, sizeof(int) * (size_t)chains));
+        QMC_CUDA_TRY(cudaMalloc(&w->tan_sorted, sizeof(float) * (size_t)chains));
         w->cap_chains = chains;
     }
     return QMC_OK;
@@ -1164,27 +1183,23 @@ static int set_smem_once(K kernel, bool &done, int bytes = TILE * 8) {
     return QMC_OK;
 }
 
-// Launch-time variants: fold = normalisation folded into the initial product state (phase factors of unit
-// modulus); lo64 = LO tiles of 2^12 amplitudes on 64-thread CTAs (6 resident per SM instead of 3 of 2^13).
+// Launch-time variant: fast = normalisation folded into the initial product state (phase factors of unit modulus)
+// and one mixer multiplier per chain served from the constant bank (c_tan[], position-indexed).
 struct SweepTune {
-    bool fold = false;
-    bool lo64 = false;
+    bool fast = false;
 };
 
-template <int ROLE, int NTH, bool FOLD>
+template <int ROLE, bool FAST>
 static int launch_lo_v(const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
     static bool done = false;
-    constexpr int SMEM = NTH * 64 * 8;
-    int rc = set_smem_once(lo_sweep_kernel<ROLE, NTH, FOLD>, done, SMEM);
+    int rc = set_smem_once(lo_sweep_kernel<ROLE, NT, FAST>, done);
     if (rc != QMC_OK) return rc;
-    const int64_t t = tiles * (128 / NTH);  // `tiles` counts 2^13-amplitude tiles
-    lo_sweep_kernel<ROLE, NTH, FOLD><<<dim3((unsigned)t, (unsigned)count), NTH, SMEM, st>>>(a, order, off);
+    lo_sweep_kernel<ROLE, NT, FAST><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off, off);
     return QMC_OK;
 }
 template <int ROLE>
 static int launch_lo(const SweepTune &tu, const SweepArgs &a, const int *order, int off, int64_t tiles, int count,
                      cudaStream_t st) {
-    constexpr bool PHASED = ROLE == LO_FIRST || ROLE == LO_MID;  // roles without a phase layer ignore `fold`
 #ifdef QMC_PROBES
     if (ROLE == LO_MID) {
         const char *pe = getenv("QUMCMC_SWEEP_PROBE");
@@ -1202,34 +1217,30 @@ static int launch_lo(const SweepTune &tu, const SweepArgs &a, const int *order, 
         }
     }
 #endif
-    if (ROLE == LO_SINGLE) return launch_lo_v<ROLE, 128, false>(a, order, off, tiles, count, st);
-    if (tu.lo64) {
-        if (PHASED && tu.fold) return launch_lo_v<ROLE, 64, PHASED>(a, order, off, tiles, count, st);
-        return launch_lo_v<ROLE, 64, false>(a, order, off, tiles, count, st);
-    }
-    if (PHASED && tu.fold) return launch_lo_v<ROLE, 128, PHASED>(a, order, off, tiles, count, st);
-    return launch_lo_v<ROLE, 128, false>(a, order, off, tiles, count, st);
+    if (ROLE != LO_SINGLE && ROLE != LO_FINAL1 && tu.fast)
+        return launch_lo_v<ROLE, ROLE != LO_SINGLE && ROLE != LO_FINAL1>(a, order, off, tiles, count, st);
+    return launch_lo_v<ROLE, false>(a, order, off, tiles, count, st);
 }
 
-template <int W, bool FIRST, bool FOLD>
+template <int W, bool FIRST, bool FAST>
 static int launch_hi_w(const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
     static bool done = false;
-    int rc = set_smem_once(hi_sweep_kernel<W, FIRST, FOLD>, done);
+    int rc = set_smem_once(hi_sweep_kernel<W, FIRST, FAST>, done);
     if (rc != QMC_OK) return rc;
-    hi_sweep_kernel<W, FIRST, FOLD><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off);
+    hi_sweep_kernel<W, FIRST, FAST><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off, off);
     return QMC_OK;
 }
 
-template <bool FIRST, bool FOLD>
+template <bool FIRST, bool FAST>
 static int launch_hi_f(int n, const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
     switch (n - LO_BITS) {
-        case 2: return launch_hi_w<2, FIRST, FOLD>(a, order, off, tiles, count, st);
-        case 3: return launch_hi_w<3, FIRST, FOLD>(a, order, off, tiles, count, st);
-        case 4: return launch_hi_w<4, FIRST, FOLD>(a, order, off, tiles, count, st);
-        case 5: return launch_hi_w<5, FIRST, FOLD>(a, order, off, tiles, count, st);
-        case 6: return launch_hi_w<6, FIRST, FOLD>(a, order, off, tiles, count, st);
-        case 7: return launch_hi_w<7, FIRST, FOLD>(a, order, off, tiles, count, st);
-        case 8: return launch_hi_w<8, FIRST, FOLD>(a, order, off, tiles, count, st);
+        case 2: return launch_hi_w<2, FIRST, FAST>(a, order, off, tiles, count, st);
+        case 3: return launch_hi_w<3, FIRST, FAST>(a, order, off, tiles, count, st);
+        case 4: return launch_hi_w<4, FIRST, FAST>(a, order, off, tiles, count, st);
+        case 5: return launch_hi_w<5, FIRST, FAST>(a, order, off, tiles, count, st);
+        case 6: return launch_hi_w<6, FIRST, FAST>(a, order, off, tiles, count, st);
+        case 7: return launch_hi_w<7, FIRST, FAST>(a, order, off, tiles, count, st);
+        case 8: return launch_hi_w<8, FIRST, FAST>(a, order, off, tiles, count, st);
     }
     qmc_set_error("sweep path: n=%d outside [14, 20]", n);
     return QMC_ERR_UNSUPPORTED;
@@ -1237,7 +1248,7 @@ static int launch_hi_f(int n, const SweepArgs &a, const int *order, int off, int
 template <bool FIRST>
 static int launch_hi(const SweepTune &tu, int n, const SweepArgs &a, const int *order, int off, int64_t tiles, int count,
                      cudaStream_t st) {
-    return tu.fold ? launch_hi_f<FIRST, true>(n, a, order, off, tiles, count, st)
+    return tu.fast ? launch_hi_f<FIRST, true>(n, a, order, off, tiles, count, st)
                    : launch_hi_f<FIRST, false>(n, a, order, off, tiles, count, st);
 }
 
@@ -1273,7 +1284,7 @@ static int run_generic_schedule(int n, int r, const SweepArgs &a, const std::vec
     const int K = (int)groups.size();
     if (r <= 1) {
         ++launched;
-        return launch_lo<LO_FINAL>(SweepTune(), a, order, off, tiles, count, st);
+        return launch_lo<LO_FINAL1>(SweepTune(), a, order, off, tiles, count, st);
     }
     rc = launch_hi6<HI6_FIRST>(acts[0], a, groups[0], order, off, tiles, count, st);
     ++launched;
@@ -1332,6 +1343,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     const size_t have = w0 ? (size_t)w0->cap_chains * per_chain : 0;
     int64_t cap = (int64_t)(((double)(free_b + have) * 0.85) / (double)per_chain);
     if (cap > 65535) cap = 65535;  // gridDim.y
+    if (!generic && cap > CTAN_MAX) cap = CTAN_MAX;  // one c_tan[] entry per chain of a batch (fast path)
     QMC_REQUIRE(cap >= 1, QMC_ERR_CUDA, "not enough device memory for one 2^%d statevector", n);
     const int64_t batch = std::min<int64_t>(cap, n_chains);
     int rc = ensure_workspace(m, batch, st);
@@ -1359,8 +1371,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     // tuning knobs (defaults = measured best on B200; the env overrides exist for A/B runs and profiling)
     const char *pf_env = getenv("QUMCMC_SWEEP_PF");
     const int pf_dist = pf_env ? atoi(pf_env) : 222;
-    const char *lo64_env = getenv("QUMCMC_SWEEP_LO64");
-    const char *fold_env = getenv("QUMCMC_SWEEP_FOLD");
+    const char *fast_env = getenv("QUMCMC_SWEEP_FAST");
     const int r_cap = qmc_trotter_steps(11, dt);
     int r_max = r_cap;
     std::vector<int> r_host;
@@ -1377,7 +1388,6 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     // Folding the normalisation (prod_q cos theta_q)^r into the initial product state is exact as long as that
     // factor stays far inside the fp32 range: bound it from below over every (gamma, r) this call can draw.
     SweepTune tune;
-    tune.lo64 = lo64_env ? lo64_env[0] == '1' : false;
     {
         double log_min = 0.0;  // min over proposals of r * sum_q log|cos(gamma w_q dt)|
         auto log_scale = [&](double gamma, int grp) {
@@ -1402,8 +1412,16 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
             for (int64_t c = 0; c < n_chains; ++c)
                 log_min = std::min(log_min, std::max(1, r_host[c]) * log_scale(g_host[c], grp_host[c]));
         }
-        tune.fold = !generic && log_min > log(1e-24);
-        if (fold_env) tune.fold = tune.fold && fold_env[0] == '1';
+        // ... and the constant-bank multiplier needs one tan(gamma w dt) per chain: every group must put the same
+        // weight on all n qubits (GenericMixer.OneBodyMixer and sums of it), and the batch must fit c_tan[].
+        bool uniform_w = true;
+        for (int grp = 0; grp < m->n_groups && uniform_w; ++grp) {
+            const int k0 = m->group_off[grp], k1 = m->group_off[grp + 1];
+            uniform_w = (k1 - k0 == n);
+            for (int k = k0; k < k1 && uniform_w; ++k) uniform_w = m->weights[k] == m->weights[k0];
+        }
+        tune.fast = !generic && log_min > log(1e-24) && uniform_w && batch <= CTAN_MAX;
+        if (fast_env) tune.fast = tune.fast && fast_env[0] == '1';
     }
 
     QMC_REQUIRE(r_max <= SCHED_RMAX, QMC_ERR_UNSUPPORTED, "delta_time=%g gives up to %d Trotter layers (> %d)", dt, r_max, SCHED_RMAX);
@@ -1411,7 +1429,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     for (int64_t c0 = 0; c0 < n_chains; c0 += batch) {
         const int64_t nc = std::min<int64_t>(batch, n_chains - c0);
         HopArgs h;
-        h.n = n; h.mode = mode; h.n_groups = m->n_groups; h.phase_active = m->phase_active; h.k_fx = w->k_fx; h.fold = tune.fold ? 1 : 0;
+        h.n = n; h.mode = mode; h.n_groups = m->n_groups; h.phase_active = m->phase_active; h.k_fx = w->k_fx; h.fold = tune.fast ? 1 : 0;
         h.n_chains = nc; h.n_hops = n_hops; h.hop = 0;
         h.chain_id0 = chain_id0 + (uint64_t)c0; h.seed = seed; h.hop0 = hop0;
         h.temperature = temperature; h.g_lo = g_lo; h.g_hi = g_hi; h.dt = dt; h.alpha = m->alpha;
@@ -1444,7 +1462,11 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         for (int64_t hop = 0; hop < hops; ++hop) {
             h.hop = hop;
             hop_prepare_kernel<<<gb, 128, 0, st>>>(h, w->params);
-            schedule_kernel<<<1, 1024, 0, st>>>(w->params, nc, r_max, w->order, generic ? 0 : 1);
+            schedule_kernel<<<1, 1024, 0, st>>>(w->params, nc, r_max, w->order, generic ? 0 : 1,
+                                                tune.fast ? w->tan_sorted : nullptr);
+            if (tune.fast)
+                QMC_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tan, w->tan_sorted, sizeof(float) * (size_t)nc, 0,
+                                                     cudaMemcpyDeviceToDevice, st));
             m->launches += 2;
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (m->profile) {
@@ -1494,7 +1516,8 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                         ++launched;
                     }
                     if (lo_eq > 0) {
-                        rc = launch_lo<LO_FINAL>(tune, a, w->order, lo_base + lo_gt, tiles, lo_eq, st);
+                        rc = step == 1 ? launch_lo<LO_FINAL1>(tune, a, w->order, lo_base + lo_gt, tiles, lo_eq, st)
+                                       : launch_lo<LO_FINAL>(tune, a, w->order, lo_base + lo_gt, tiles, lo_eq, st);
                         if (rc != QMC_OK) return rc;
                         ++launched;
                     }
