@@ -129,6 +129,36 @@ int qmc_run_chains_host(qmc_model *m, int64_t n_chains, int64_t n_hops, const ui
                         uint64_t *final_state_host, int64_t *acc_count_host,
                         int64_t *hamming_hist_host);
 
+/* ---- Sharded statevector: n > 34, or any n with 18 <= n - log2(world) <= 34 ------------------------------
+ * Replaces run_qmcmc_quantum_ckt (qumcmc/quantum_mcmc_routines.py:110-156) when 2^n amplitudes do not fit one GPU:
+ * rank R of 2^g holds the amplitudes whose top g index bits equal R (2^(n-g) complex64, caller-owned buffer).
+ * The proposal U = M (P M)^(r-1) is a sequence of local passes (qmc_shard_op, one kernel each) and all-to-all
+ * exchanges on equal chunks, which swap the top g local index bits with the rank bits; the CALLER performs the
+ * exchange (torch.distributed / NCCL all_to_all_single between two state buffers) and passes the layout parity
+ * (0 = no / even number of exchanges so far, 1 = odd) to every op.  The library tracks which logical qubit sits at
+ * which position for each layout and never swaps back.  Op sequence for r >= 2 (K = qmc_shard_num_groups):
+ *   FIRST(top) ; then per layer j = 2..r:  [LO_SINGLE unless j == r] SINGLE(k = 1..K-1) <exchange>
+ *                                          MID(top, pre = g) if j < r   else   SINGLE(top, pre = g) LO_FINAL
+ * and LO_FINAL alone for r == 1.  qumcmc_b200/distributed.py (sharded_plan) generates exactly this list.
+ * After LO_FINAL: qmc_shard_norm -> local sum |a|^2; ranks all-gather the W sums, the owner of u * total calls
+ * qmc_shard_select and broadcasts the measured index. */
+typedef struct qmc_shard qmc_shard;
+#define QMC_SHARD_OP_FIRST 0
+#define QMC_SHARD_OP_MID 1
+#define QMC_SHARD_OP_SINGLE 2
+#define QMC_SHARD_OP_LO_SINGLE 3
+#define QMC_SHARD_OP_LO_FINAL 4
+int qmc_shard_create(qmc_shard **out, qmc_model *m, int rank, int log2_world);
+int qmc_shard_destroy(qmc_shard *sh);
+int qmc_shard_num_groups(const qmc_shard *sh);
+/* Parameters of the next proposal: start state s (logical basis index), gamma, r mixer layers, mixer group. */
+int qmc_shard_begin(qmc_shard *sh, uint64_t s, double gamma, int r, double delta_time, int group);
+int qmc_shard_op(qmc_shard *sh, int op, int k, int pre, int layout, void *state_dev, void *stream);
+int qmc_shard_norm(qmc_shard *sh, double *total_dev, void *stream);
+int qmc_shard_select(qmc_shard *sh, void *state_dev, double target, int layout, uint64_t *index_dev, void *stream);
+/* Test hook: LO_FINAL that also writes |a|^2 of the local shard (2^(n-g) floats, local index order). */
+int qmc_shard_final_probs(qmc_shard *sh, int layout, void *state_dev, float *probs_dev, void *stream);
+
 /* Introspection for benchmarks/tests. */
 int qmc_model_num_spins(const qmc_model *m);
 /* Number of kernels this library has launched on behalf of handle m since creation. */

@@ -24,7 +24,9 @@ DTYPE_F32 = 0
 DTYPE_F64 = 1
 SMEM_MAX_SPINS_F32 = 13
 SMEM_MAX_SPINS_F64 = 12
-MAX_SPINS = 34
+MAX_SPINS = 40          # model limit; one GPU holds a statevector up to MAX_LOCAL_SPINS qubits
+MAX_LOCAL_SPINS = 34
+SHARD_OP_FIRST, SHARD_OP_MID, SHARD_OP_SINGLE, SHARD_OP_LO_SINGLE, SHARD_OP_LO_FINAL = range(5)
 
 # every symbol include/qumcmc_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
@@ -33,6 +35,8 @@ EXPORTS = [
     "qmc_exact_partial", "qmc_exact_probs_range",
     "qmc_transition_probs", "qmc_propose", "qmc_run_chains", "qmc_run_chains_host",
     "qmc_model_num_spins", "qmc_model_launch_count", "qmc_profile_enable", "qmc_profile_read",
+    "qmc_shard_create", "qmc_shard_destroy", "qmc_shard_num_groups", "qmc_shard_begin", "qmc_shard_op",
+    "qmc_shard_norm", "qmc_shard_select", "qmc_shard_final_probs",
 ]
 
 
@@ -93,6 +97,14 @@ def lib() -> C.CDLL:
     L.qmc_model_launch_count.restype = C.c_int64
     L.qmc_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.qmc_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.qmc_shard_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int]
+    L.qmc_shard_destroy.argtypes = [C.c_void_p]
+    L.qmc_shard_num_groups.argtypes = [C.c_void_p]
+    L.qmc_shard_begin.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_int, C.c_double, C.c_int]
+    L.qmc_shard_op.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.qmc_shard_norm.argtypes = [C.c_void_p, dp, vp]
+    L.qmc_shard_select.argtypes = [C.c_void_p, vp, C.c_double, C.c_int, u64p, vp]
+    L.qmc_shard_final_probs.argtypes = [C.c_void_p, C.c_int, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("qmc_last_error", "qmc_model_launch_count"):

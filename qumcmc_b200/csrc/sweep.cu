@@ -663,7 +663,9 @@ struct Hi6Args {
     double fx_scale;        // 2^k_fx
 };
 
-template <int ROLE, int ACT>
+// PRE = active (top) register qubits of the half-layer before the phase, when it differs from ACT: the sharded path
+// mixes only the g qubits that the preceding all-to-all brought in, then all six after the phase.
+template <int ROLE, int ACT, int PRE = ACT>
 __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, const Hi6Args g, const int *__restrict__ order,
                                                           const int list_off) {
     extern __shared__ __align__(16) double smd[];  // Jq[n*n], hq[n]
@@ -683,6 +685,7 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
     const ChainParams &cp = cp_s;
     const int p = g.p;
     constexpr int ACTIVE = 63 & ~((1 << (6 - ACT)) - 1);
+    constexpr int ACTIVE_PRE = 63 & ~((1 << (6 - PRE)) - 1);
     // index bits: lane 0..4, warp bits 5,6, tile-low bits 7..p-1, register bits p..p+5, tile-high bits p+6..n-1
     const int low_bits = p - 7;
     const int64_t base = (int64_t)(tid & 31) | ((int64_t)(tid >> 5) << 5) | ((tile & (((int64_t)1 << low_bits) - 1)) << 7) |
@@ -728,7 +731,7 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
             v[j] = *src;
             src += stride;
         }
-        bfly6<ACTIVE>(v, cp, qp);
+        bfly6<ACTIVE_PRE>(v, cp, qp);
     }
     if (ROLE != HI6_SINGLE) {
         phase_gray<false>(v, af, hs_s, g.dr[0], cp);
@@ -1274,6 +1277,22 @@ static int launch_hi6(int act, const SweepArgs &a, const Hi6Args &g, const int *
     return QMC_ERR_BADARG;
 }
 
+// MID on the top group of a shard: before the phase only the `pre` swapped-in (top) qubits are mixed
+static int launch_hi6_pre(int pre, const SweepArgs &a, const Hi6Args &g, const int *order, int off, int64_t tiles, int count,
+                          cudaStream_t st) {
+    const size_t smem = sizeof(double) * (size_t)(a.n_total * a.n_total + a.n_total);
+    switch (pre) {
+        case 1: hi6_sweep_kernel<HI6_MID, 6, 1><<<dim3((unsigned)tiles, (unsigned)count), NT, smem, st>>>(a, g, order, off); return QMC_OK;
+        case 2: hi6_sweep_kernel<HI6_MID, 6, 2><<<dim3((unsigned)tiles, (unsigned)count), NT, smem, st>>>(a, g, order, off); return QMC_OK;
+        case 3: hi6_sweep_kernel<HI6_MID, 6, 3><<<dim3((unsigned)tiles, (unsigned)count), NT, smem, st>>>(a, g, order, off); return QMC_OK;
+        case 4: hi6_sweep_kernel<HI6_MID, 6, 4><<<dim3((unsigned)tiles, (unsigned)count), NT, smem, st>>>(a, g, order, off); return QMC_OK;
+        case 5: hi6_sweep_kernel<HI6_MID, 6, 5><<<dim3((unsigned)tiles, (unsigned)count), NT, smem, st>>>(a, g, order, off); return QMC_OK;
+        case 6: hi6_sweep_kernel<HI6_MID, 6, 6><<<dim3((unsigned)tiles, (unsigned)count), NT, smem, st>>>(a, g, order, off); return QMC_OK;
+    }
+    qmc_set_error("hi6 sweep: %d swapped-in qubits", pre);
+    return QMC_ERR_BADARG;
+}
+
 // Sweep list of one proposal with r mixer layers on the generic path (LO group + K >= 2 HI6 groups):
 //   HI6_FIRST(g0); per middle layer: LO_SINGLE, HI6_SINGLE for the other groups, HI6_MID on the next
 //   group (which carries its M into the following layer); last layer: HI6_SINGLE..., LO_FINAL.
@@ -1564,5 +1583,377 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
             w->ev.clear();
         }
     }
+    return QMC_OK;
+}
+
+
+// ==========================================================================================
+// Sharded statevector (qmc_shard_*): rank R of 2^g holds the 2^nl amplitudes whose top g index bits equal R.
+// Everything below works in PHYSICAL coordinates: position a < nl is bit a of the local index, position nl + j is
+// bit j of the rank.  An all-to-all on equal chunks exchanges the top g local positions with the rank positions;
+// the library never un-swaps, it only tracks which logical qubit sits at each position (layout 0 = identity,
+// layout 1 = after an odd number of exchanges) and feeds the kernels permuted parameters: couplings Jq', hq',
+// mixer multipliers tq' and the start state cur'.  (popcount -- the storage convention -- is permutation invariant.)
+// One op = one kernel launch over the local shard; the caller (qumcmc_b200/distributed.py) strings ops and
+// exchanges together, see sharded_plan().
+// ==========================================================================================
+struct qmc_shard {
+    qmc_model *m = nullptr;
+    int rank = 0, g = 0, nl = 0, n = 0;
+    ChainParams *params = nullptr;  // one record (device)
+    int *order = nullptr;           // {0}
+    float *segsum = nullptr;        // [2^(nl-6)]
+    double *total = nullptr;        // scratch for the norm
+    double *dJq[2] = {nullptr, nullptr}, *dhq[2] = {nullptr, nullptr};
+    std::vector<double> Jq[2], hq[2];
+    std::vector<int> perm[2];       // perm[layout][position] = logical qubit
+    std::vector<Hi6Args> groups[2];
+    std::vector<int> acts;
+    double fx_scale = 1.0;
+    int k_fx = 0;
+    ChainParams host_cp[2];         // physical-coordinate parameters of the current proposal, per layout
+    int r = 0;
+};
+
+namespace {
+
+__global__ void shard_norm_kernel(const float *__restrict__ seg, int64_t nseg, double *__restrict__ total) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nseg; i += (int64_t)gridDim.x * blockDim.x)
+        s += (double)seg[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(total, red[0]);
+}
+
+// Inverse CDF over the local shard: the amplitude index at which the running sum of |a|^2 (segment sums in
+// segsum, segment = 64 amplitudes) passes `target`.  Phase 1: per-block partial sums of contiguous segment ranges.
+constexpr int SEL_BLOCKS = 1024;
+__global__ void shard_block_sums_kernel(const float *__restrict__ seg, int64_t nseg, double *__restrict__ bsum) {
+    __shared__ double red[256];
+    const int64_t per = (nseg + SEL_BLOCKS - 1) / SEL_BLOCKS;
+    const int64_t b0 = blockIdx.x * per, b1 = b0 + per < nseg ? b0 + per : nseg;
+    double s = 0.0;
+    for (int64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) s += (double)seg[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bsum[blockIdx.x] = red[0];
+}
+// Phase 2 (one thread): block, then segment inside the block; writes the segment and the remainder.
+__global__ void shard_pick_segment_kernel(const float *__restrict__ seg, int64_t nseg, const double *__restrict__ bsum,
+                                          double target, long long *__restrict__ sel_seg, double *__restrict__ rem) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int64_t per = (nseg + SEL_BLOCKS - 1) / SEL_BLOCKS;
+    const int nblk = (int)((nseg + per - 1) / per);
+    double c = 0.0;
+    int blk = nblk - 1;
+    for (int b = 0; b < nblk; ++b) {
+        if (target < c + bsum[b] || b == nblk - 1) {
+            blk = b;
+            break;
+        }
+        c += bsum[b];
+    }
+    const int64_t b0 = blk * per, b1 = b0 + per < nseg ? b0 + per : nseg;
+    int64_t sel = b1 - 1;
+    double before = c;
+    for (int64_t i = b0; i < b1; ++i) {
+        const double x = (double)seg[i];
+        if (target < c + x || i == b1 - 1) {  // rounding tail: last segment of the block
+            sel = i;
+            before = c;
+            break;
+        }
+        c += x;
+    }
+    *sel_seg = sel;
+    *rem = target - before;
+}
+// Phase 3: recompute the final amplitudes of the tile that holds the segment, resolve the index inside it.
+__global__ void __launch_bounds__(NT) shard_resolve_kernel(const SweepArgs a, const long long *__restrict__ sel_seg,
+                                                           const double *__restrict__ rem_p, unsigned long long *out) {
+    extern __shared__ __align__(16) float2 sm[];
+    __shared__ ChainParams cp_s;
+    const int tid = threadIdx.x;
+    stage_params(cp_s, a.params, tid);
+    const ChainParams &cp = cp_s;
+    const int64_t sg = *sel_seg;
+    const int64_t tile = sg / NT;
+    const int owner = (int)(sg % NT);
+    A64 v[64];
+    if (cp.r == 1) lo_final_tile<NT, false, true>(v, sm, a.state, tile, tid, a.n_total, cp, a.gbits);
+    else lo_final_tile<NT, false, false>(v, sm, a.state, tile, tid, a.n_total, cp, a.gbits);
+    if (tid == owner) {
+        const double rem = *rem_p;
+        double c = 0.0;
+        int selj = 63;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            c += (double)norm2(v[j]);
+            if (selj == 63 && rem < c) selj = j;
+        }
+        *out = ((unsigned long long)tile << TILE_BITS) | ((unsigned long long)owner << 6) | (unsigned long long)selj;
+    }
+}
+
+}  // namespace
+
+static void shard_fill_params(qmc_shard *sh, uint64_t s, double gamma, int r, double dt, int grp) {
+    const qmc_model *m = sh->m;
+    const int n = sh->n;
+    double tq[QMC_MAX_SPINS];
+    for (int q = 0; q < QMC_MAX_SPINS; ++q) tq[q] = 0.0;
+    double scale = 1.0;
+    for (int k = m->group_off[grp]; k < m->group_off[grp + 1]; ++k) {
+        int q = 0;
+        while (!((m->masks[k] >> q) & 1ULL)) ++q;
+        const double th = gamma * m->weights[k] * dt;
+        tq[q] = sin(th) / cos(th);
+        scale *= cos(th);
+    }
+    const double cprime = (1.0 - gamma) * m->alpha * dt * 0.15915494309189533577;
+    const int rr = r < 1 ? 1 : r;
+    const int active = m->phase_active && rr > 1 && cprime != 0.0;
+    int mm = 0;
+    if (active) {
+        mm = (int)floor(log2(2147483647.0 / fabs(cprime)));
+        if (mm > 40) mm = 40;
+        if (mm < 0) mm = 0;
+    }
+    for (int L = 0; L < 2; ++L) {
+        ChainParams &cp = sh->host_cp[L];
+        memset(&cp, 0, sizeof(cp));
+        unsigned long long cur = 0ULL;
+        for (int a = 0; a < n; ++a) {
+            const int lq = sh->perm[L][a];
+            cp.tq[a] = (float)tq[lq];
+            if ((s >> lq) & 1ULL) cur |= 1ULL << a;
+        }
+        cp.cur = cur;
+        cp.r = rr;
+        cp.group = grp;
+        cp.scale = (float)scale;
+        cp.active = active;
+        cp.cfx = active ? (int)rint(ldexp(cprime, mm)) : 0;
+        cp.shift = sh->k_fx + mm - 32;
+    }
+    sh->r = rr;
+}
+
+extern "C" int qmc_shard_create(qmc_shard **out, qmc_model *m, int rank, int log2_world) {
+    QMC_REQUIRE(out && m, QMC_ERR_BADARG, "qmc_shard_create: null argument");
+    const int n = m->n, g = log2_world, nl = n - g;
+    QMC_REQUIRE(g >= 1 && g <= 6 && rank >= 0 && rank < (1 << g), QMC_ERR_BADARG, "qmc_shard_create: rank %d of 2^%d", rank, g);
+    QMC_REQUIRE(nl >= 18 && nl <= QMC_MAX_LOCAL_SPINS, QMC_ERR_UNSUPPORTED,
+                "sharded statevector: %d local qubits outside [18, %d] (n=%d over 2^%d ranks)", nl, QMC_MAX_LOCAL_SPINS, n, g);
+    QMC_REQUIRE(m->all_one_body, QMC_ERR_UNSUPPORTED, "sharded statevector: one-body X mixers only");
+    QMC_CUDA_TRY(cudaSetDevice(m->device));
+    qmc_shard *sh = new qmc_shard();
+    sh->m = m; sh->rank = rank; sh->g = g; sh->nl = nl; sh->n = n;
+    // logical couplings in qubit order: qubit a = spin n-1-a (quantum_mcmc_routines.py:75,87)
+    std::vector<double> Jl((size_t)n * n), hl(n);
+    double dmax = 0.0;
+    for (int a = 0; a < n; ++a) {
+        hl[a] = m->host_ch[n - 1 - a];
+        dmax += fabs(hl[a]);
+        for (int b = 0; b < n; ++b) {
+            Jl[(size_t)a * n + b] = m->host_cJ[(size_t)(n - 1 - a) * n + (n - 1 - b)];
+            if (b > a) dmax += fabs(Jl[(size_t)a * n + b]);
+        }
+    }
+    if (dmax < 1e-300) dmax = 1.0;
+    sh->k_fx = (int)floor(log2(2147483647.0 / (dmax * 1.0000001))) - 1;
+    if (sh->k_fx > 30) sh->k_fx = 30;
+    sh->fx_scale = ldexp(1.0, sh->k_fx);
+    // group geometry (positions): top group full, the partial group lowest; LO = positions 0..11
+    const int hi_qubits = nl - LO_BITS, K = (hi_qubits + 5) / 6;
+    std::vector<int> ps;
+    for (int k = 0; k < K; ++k) {  // k = 0 is the top group
+        const bool lowest = (k == K - 1);
+        const int act = lowest ? hi_qubits - 6 * (K - 1) : 6;
+        ps.push_back(lowest ? LO_BITS + act - 6 : nl - 6 * (k + 1));
+        sh->acts.push_back(act);
+    }
+    for (int L = 0; L < 2; ++L) {
+        sh->perm[L].resize(n);
+        for (int a = 0; a < n; ++a) sh->perm[L][a] = a;
+        if (L == 1)
+            for (int j = 0; j < g; ++j) std::swap(sh->perm[L][nl - g + j], sh->perm[L][nl + j]);
+        sh->Jq[L].assign((size_t)n * n, 0.0);
+        sh->hq[L].assign(n, 0.0);
+        for (int a = 0; a < n; ++a) {
+            sh->hq[L][a] = hl[sh->perm[L][a]];
+            for (int b = 0; b < n; ++b) sh->Jq[L][(size_t)a * n + b] = Jl[(size_t)sh->perm[L][a] * n + sh->perm[L][b]];
+        }
+        QMC_CUDA_TRY(cudaMalloc(&sh->dJq[L], sizeof(double) * (size_t)n * n));
+        QMC_CUDA_TRY(cudaMalloc(&sh->dhq[L], sizeof(double) * (size_t)n));
+        QMC_CUDA_TRY(cudaMemcpy(sh->dJq[L], sh->Jq[L].data(), sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
+        QMC_CUDA_TRY(cudaMemcpy(sh->dhq[L], sh->hq[L].data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+        for (int k = 0; k < K; ++k) {
+            Hi6Args ga;
+            ga.p = ps[k];
+            const int pos[6] = {ga.p, ga.p + 1, ga.p + 2, ga.p + 3, ga.p + 4, ga.p + 5};
+            gray_increments(sh->Jq[L], n, sh->fx_scale, pos, ga.dr);
+            ga.Jq = sh->dJq[L];
+            ga.hq = sh->dhq[L];
+            ga.fx_scale = sh->fx_scale;
+            sh->groups[L].push_back(ga);
+        }
+    }
+    QMC_CUDA_TRY(cudaMalloc(&sh->params, sizeof(ChainParams)));
+    QMC_CUDA_TRY(cudaMalloc(&sh->order, sizeof(int)));
+    QMC_CUDA_TRY(cudaMemset(sh->order, 0, sizeof(int)));
+    QMC_CUDA_TRY(cudaMalloc(&sh->segsum, sizeof(float) * ((size_t)1 << (nl - 6))));
+    QMC_CUDA_TRY(cudaMalloc(&sh->total, sizeof(double) * (SEL_BLOCKS + 4)));
+    static bool attr = false;
+    if (!attr) {
+        QMC_CUDA_TRY(cudaFuncSetAttribute(shard_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 8));
+        attr = true;
+    }
+    *out = sh;
+    return QMC_OK;
+}
+
+extern "C" int qmc_shard_destroy(qmc_shard *sh) {
+    if (!sh) return QMC_OK;
+    cudaFree(sh->params); cudaFree(sh->order); cudaFree(sh->segsum); cudaFree(sh->total);
+    for (int L = 0; L < 2; ++L) { cudaFree(sh->dJq[L]); cudaFree(sh->dhq[L]); }
+    delete sh;
+    return QMC_OK;
+}
+
+extern "C" int qmc_shard_num_groups(const qmc_shard *sh) { return sh ? (int)sh->acts.size() : 0; }
+
+extern "C" int qmc_shard_begin(qmc_shard *sh, uint64_t s, double gamma, int r, double delta_time, int group) {
+    QMC_REQUIRE(sh, QMC_ERR_BADARG, "qmc_shard_begin: null handle");
+    QMC_REQUIRE(group >= 0 && group < sh->m->n_groups, QMC_ERR_BADARG, "qmc_shard_begin: group %d of %d", group, sh->m->n_groups);
+    QMC_REQUIRE(delta_time > 0.0 && r >= 1, QMC_ERR_BADARG, "qmc_shard_begin: r=%d, delta_time=%g", r, delta_time);
+    QMC_REQUIRE(sh->n >= 64 || s < (1ULL << sh->n), QMC_ERR_BADARG, "qmc_shard_begin: state out of range");
+    shard_fill_params(sh, s, gamma, r, delta_time, group);
+    return QMC_OK;
+}
+
+// One local pass.  op: 0 FIRST(top group: analytic M|s>, P, M_top) | 1 MID(top group: M_top restricted to the
+// `pre` swapped-in qubits, P, M_top) | 2 SINGLE(group k, its active qubits; k == 0 with pre > 0: only the `pre`
+// swapped-in qubits) | 3 LO_SINGLE | 4 LO_FINAL (segment sums; r == 1: of the analytic product state).
+extern "C" int qmc_shard_op(qmc_shard *sh, int op, int k, int pre, int layout, void *state_dev, void *stream) {
+    QMC_REQUIRE(sh && state_dev, QMC_ERR_BADARG, "qmc_shard_op: null argument");
+    QMC_REQUIRE(layout == 0 || layout == 1, QMC_ERR_BADARG, "qmc_shard_op: layout %d", layout);
+    const int K = (int)sh->acts.size();
+    QMC_REQUIRE(k >= 0 && k < K, QMC_ERR_BADARG, "qmc_shard_op: group %d of %d", k, K);
+    QMC_CUDA_TRY(cudaSetDevice(sh->m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    QMC_CUDA_TRY(cudaMemcpyAsync(sh->params, &sh->host_cp[layout], sizeof(ChainParams), cudaMemcpyHostToDevice, st));
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = sh->nl; a.n_total = sh->n; a.gbits = (unsigned long long)sh->rank << sh->nl;
+    a.state = reinterpret_cast<float2 *>(state_dev);
+    a.params = sh->params;
+    a.segsum = sh->segsum;
+    a.pf_dist = 0;
+    const int64_t tiles = (int64_t)1 << (sh->nl - TILE_BITS);
+    const Hi6Args &ga = sh->groups[layout][k];
+    int rc = QMC_OK;
+    switch (op) {
+        case 0:
+            QMC_REQUIRE(k == 0, QMC_ERR_BADARG, "qmc_shard_op: FIRST runs on the top group");
+            rc = launch_hi6<HI6_FIRST>(6, a, ga, sh->order, 0, tiles, 1, st);
+            break;
+        case 1:
+            QMC_REQUIRE(k == 0 && pre == sh->g, QMC_ERR_BADARG, "qmc_shard_op: MID runs on the top group with pre = log2(world)");
+            rc = launch_hi6_pre(pre, a, ga, sh->order, 0, tiles, 1, st);
+            break;
+        case 2:
+            rc = launch_hi6<HI6_SINGLE>(k == 0 && pre > 0 ? pre : sh->acts[k], a, ga, sh->order, 0, tiles, 1, st);
+            break;
+        case 3:
+            rc = launch_lo<LO_SINGLE>(SweepTune(), a, sh->order, 0, tiles, 1, st);
+            break;
+        case 4:
+            rc = sh->r == 1 ? launch_lo<LO_FINAL1>(SweepTune(), a, sh->order, 0, tiles, 1, st)
+                            : launch_lo<LO_FINAL>(SweepTune(), a, sh->order, 0, tiles, 1, st);
+            break;
+        default:
+            qmc_set_error("qmc_shard_op: unknown op %d", op);
+            return QMC_ERR_BADARG;
+    }
+    if (rc != QMC_OK) return rc;
+    sh->m->launches++;
+    QMC_CUDA_TRY(cudaGetLastError());
+    return QMC_OK;
+}
+
+// sum of |a|^2 over the local shard (after LO_FINAL) -> total_dev[0]
+extern "C" int qmc_shard_norm(qmc_shard *sh, double *total_dev, void *stream) {
+    QMC_REQUIRE(sh && total_dev, QMC_ERR_BADARG, "qmc_shard_norm: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    QMC_CUDA_TRY(cudaMemsetAsync(total_dev, 0, sizeof(double), st));
+    shard_norm_kernel<<<148 * 4, 256, 0, st>>>(sh->segsum, (int64_t)1 << (sh->nl - 6), total_dev);
+    sh->m->launches++;
+    QMC_CUDA_TRY(cudaGetLastError());
+    return QMC_OK;
+}
+
+// Owner rank only: local index (physical -> logical) at which the local running sum passes `target`
+// (0 <= target < local total).  index_dev[0] = LOGICAL basis index of the measured bitstring.
+extern "C" int qmc_shard_select(qmc_shard *sh, void *state_dev, double target, int layout, uint64_t *index_dev, void *stream) {
+    QMC_REQUIRE(sh && state_dev && index_dev, QMC_ERR_BADARG, "qmc_shard_select: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nseg = (int64_t)1 << (sh->nl - 6);
+    double *bsum = sh->total;  // [SEL_BLOCKS], then sel_seg, rem, out
+    long long *sel_seg = reinterpret_cast<long long *>(sh->total + SEL_BLOCKS);
+    double *rem = sh->total + SEL_BLOCKS + 1;
+    unsigned long long *phys = reinterpret_cast<unsigned long long *>(sh->total + SEL_BLOCKS + 2);
+    QMC_CUDA_TRY(cudaMemcpyAsync(sh->params, &sh->host_cp[layout], sizeof(ChainParams), cudaMemcpyHostToDevice, st));
+    shard_block_sums_kernel<<<SEL_BLOCKS, 256, 0, st>>>(sh->segsum, nseg, bsum);
+    shard_pick_segment_kernel<<<1, 32, 0, st>>>(sh->segsum, nseg, bsum, target, sel_seg, rem);
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = sh->nl; a.n_total = sh->n; a.gbits = (unsigned long long)sh->rank << sh->nl;
+    a.state = reinterpret_cast<float2 *>(state_dev);
+    a.params = sh->params;
+    shard_resolve_kernel<<<1, NT, TILE * 8, st>>>(a, sel_seg, rem, phys);
+    sh->m->launches += 3;
+    QMC_CUDA_TRY(cudaGetLastError());
+    unsigned long long hphys = 0ULL;
+    QMC_CUDA_TRY(cudaMemcpyAsync(&hphys, phys, sizeof(hphys), cudaMemcpyDeviceToHost, st));
+    QMC_CUDA_TRY(cudaStreamSynchronize(st));
+    const unsigned long long full = hphys | ((unsigned long long)sh->rank << sh->nl);
+    unsigned long long logical = 0ULL;
+    for (int a2 = 0; a2 < sh->n; ++a2)
+        if ((full >> a2) & 1ULL) logical |= 1ULL << sh->perm[layout][a2];
+    QMC_CUDA_TRY(cudaMemcpyAsync(index_dev, &logical, sizeof(logical), cudaMemcpyHostToDevice, st));
+    QMC_CUDA_TRY(cudaStreamSynchronize(st));
+    return QMC_OK;
+}
+
+extern "C" int qmc_shard_final_probs(qmc_shard *sh, int layout, void *state_dev, float *probs_dev, void *stream) {
+    QMC_REQUIRE(sh && state_dev && probs_dev, QMC_ERR_BADARG, "qmc_shard_final_probs: null argument");
+    QMC_REQUIRE(layout == 0 || layout == 1, QMC_ERR_BADARG, "qmc_shard_final_probs: layout %d", layout);
+    QMC_CUDA_TRY(cudaSetDevice(sh->m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    QMC_CUDA_TRY(cudaMemcpyAsync(sh->params, &sh->host_cp[layout], sizeof(ChainParams), cudaMemcpyHostToDevice, st));
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = sh->nl; a.n_total = sh->n; a.gbits = (unsigned long long)sh->rank << sh->nl;
+    a.state = reinterpret_cast<float2 *>(state_dev);
+    a.params = sh->params;
+    a.segsum = sh->segsum;
+    a.probs_out = probs_dev;
+    const int64_t tiles = (int64_t)1 << (sh->nl - TILE_BITS);
+    int rc = sh->r == 1 ? launch_lo<LO_FINAL1>(SweepTune(), a, sh->order, 0, tiles, 1, st)
+                        : launch_lo<LO_FINAL>(SweepTune(), a, sh->order, 0, tiles, 1, st);
+    if (rc != QMC_OK) return rc;
+    sh->m->launches++;
+    QMC_CUDA_TRY(cudaGetLastError());
     return QMC_OK;
 }

@@ -1,0 +1,189 @@
+"""Statevectors sharded over GPUs by global qubits (BASELINE config C5: n >= 35 over 8 B200).
+
+Rank ``R`` of ``W = 2^g`` holds the ``2^(n-g)`` amplitudes whose top ``g`` index bits equal ``R``.  One proposal
+``U = M (P M)^(r-1)`` of ``run_qmcmc_quantum_ckt`` (/root/reference/qumcmc/quantum_mcmc_routines.py:110-156) becomes a
+list of local passes (``qmc_shard_op``: one CUDA kernel over the local shard each) and all-to-all exchanges on equal
+chunks -- an ``all_to_all_single`` between two state buffers swaps the top ``g`` local index bits with the rank
+bits, so the qubits that were global become local and get mixed by the next pass.  The layout is never swapped
+back: the library keeps the logical-qubit-at-position map for both layout parities.
+
+``sharded_plan`` is the schedule; ``ShardHandle`` wraps the C-ABI; ``ShardedProposer`` runs it over
+``torch.distributed`` (NCCL on GPUs).  Sampling: every rank reduces its local sum of |a|^2, the W sums are
+all-gathered, the rank that owns ``u * total`` resolves the index and broadcasts it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _device, _lib
+
+FIRST, MID, SINGLE, LO_SINGLE, LO_FINAL, EXCHANGE = "first", "mid", "single", "lo_single", "lo_final", "exchange"
+_OPCODE = {FIRST: _lib.SHARD_OP_FIRST, MID: _lib.SHARD_OP_MID, SINGLE: _lib.SHARD_OP_SINGLE,
+           LO_SINGLE: _lib.SHARD_OP_LO_SINGLE, LO_FINAL: _lib.SHARD_OP_LO_FINAL}
+
+
+def sharded_plan(r: int, n_groups: int, log2_world: int) -> List[Tuple[str, int, int]]:
+    """Op list ``(kind, group, pre)`` of one proposal with ``r`` mixer layers.
+
+    Positions 0..11 are the LO group; ``n_groups`` register groups of 6 cover the remaining local positions, group 0
+    on top (it contains the ``g`` positions an exchange swaps with the rank bits).  Layer 1 is analytic (FIRST builds
+    M|s> over all n qubits).  Every later layer j: the top group was mixed by the preceding FIRST/MID pass (after
+    its phase), the other groups by SINGLE passes, the g global qubits after the exchange brought them in -- as the
+    restricted first half of the next MID (which also carries the phase layer and layer j+1 of the top group), or,
+    in the last layer, a restricted SINGLE followed by the read-only LO_FINAL that emits the |a|^2 segment sums.
+    """
+    if r <= 1:
+        return [(LO_FINAL, 0, 0)]
+    ops: List[Tuple[str, int, int]] = [(FIRST, 0, 0)]
+    for layer in range(2, r + 1):
+        last = layer == r
+        if not last:
+            ops.append((LO_SINGLE, 0, 0))
+        ops.extend((SINGLE, k, 0) for k in range(1, n_groups))
+        ops.append((EXCHANGE, 0, 0))
+        if last:
+            ops.append((SINGLE, 0, log2_world))
+            if (r - 1) % 2 == 1:  # end in the identity layout: the measurement CDF then runs in index order, like the
+                ops.append((EXCHANGE, 0, 0))  # reference's sequential sampler, and every proposal starts from layout 0
+            ops.append((LO_FINAL, 0, 0))
+        else:
+            ops.append((MID, 0, log2_world))
+    return ops
+
+
+def shard_geometry(n_local: int) -> List[Tuple[int, int]]:
+    """Active position range [lo, hi) of every register group, top group first (mirrors qmc_shard_create):
+    positions 0..11 belong to the LO passes, full groups of 6 stack down from the top, the partial group is lowest."""
+    hi_qubits = n_local - 12
+    K = (hi_qubits + 5) // 6
+    out = []
+    for k in range(K):
+        if k == K - 1:
+            out.append((12, 12 + hi_qubits - 6 * (K - 1)))
+        else:
+            out.append((n_local - 6 * (k + 1), n_local - 6 * k))
+    return out
+
+
+def plan_traffic_bytes(ops: Sequence[Tuple[str, int, int]], n_local: int, world: int) -> Tuple[float, float]:
+    """(HBM bytes moved by the local passes, bytes sent over NVLink) per rank for a plan."""
+    amp = 8.0 * (1 << n_local)
+    hbm = nv = 0.0
+    for kind, _, _ in ops:
+        if kind == EXCHANGE:
+            nv += amp * (world - 1) / world
+            hbm += 2.0 * amp
+        elif kind == FIRST:
+            hbm += amp
+        elif kind == LO_FINAL:
+            hbm += amp
+        else:
+            hbm += 2.0 * amp
+    return hbm, nv
+
+
+class ShardHandle:
+    """``qmc_shard`` of one rank: local passes, norm and inverse-CDF selection on that rank's buffers."""
+
+    def __init__(self, model, mixer, rank: int, log2_world: int, device: int = 0):
+        self.model, self.rank, self.g, self.device = model, int(rank), int(log2_world), int(device)
+        self.n = model.num_spins
+        self.n_local = self.n - self.g
+        self.dm = model.device_model(device)
+        self.dm.set_mixer(mixer)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().qmc_shard_create(C.byref(h), self.dm.handle, self.rank, self.g))
+        self.handle = h
+        self.n_groups = int(_lib.lib().qmc_shard_num_groups(h))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.lib().qmc_shard_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def begin(self, s: int, gamma: float, r: int, delta_time: float, group: int = 0):
+        _lib.check(_lib.lib().qmc_shard_begin(self.handle, int(s), float(gamma), int(r), float(delta_time), int(group)))
+
+    def op(self, kind: str, k: int, pre: int, layout: int, state) -> None:
+        _lib.check(_lib.lib().qmc_shard_op(self.handle, _OPCODE[kind], int(k), int(pre), int(layout), state.data_ptr(),
+                                           _device.current_stream_ptr(self.device)))
+
+    def norm(self, total) -> None:
+        _lib.check(_lib.lib().qmc_shard_norm(self.handle, total.data_ptr(), _device.current_stream_ptr(self.device)))
+
+    def final_probabilities(self, state, layout: int, probs) -> None:
+        """Test hook: |a|^2 of the local shard after the last mixer half-layer (float32, local index order)."""
+        _lib.check(_lib.lib().qmc_shard_final_probs(self.handle, int(layout), state.data_ptr(), probs.data_ptr(),
+                                                    _device.current_stream_ptr(self.device)))
+
+    def select(self, state, target: float, layout: int, index) -> None:
+        _lib.check(_lib.lib().qmc_shard_select(self.handle, state.data_ptr(), float(target), int(layout),
+                                               index.data_ptr(), _device.current_stream_ptr(self.device)))
+
+
+def pick_owner(totals: np.ndarray, u: float) -> Tuple[int, float]:
+    """Rank whose slice of the global running sum of |a|^2 contains ``u * total`` and the target inside it.
+    Ranks are in index order (rank = top bits), matching the sequential cumulative sum of
+    QuantumState.sampling (call at qumcmc/quantum_mcmc_routines.py:153)."""
+    totals = np.asarray(totals, dtype=np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(totals)])
+    target = float(u) * cum[-1]
+    owner = int(np.searchsorted(cum[1:], target, side="right"))
+    owner = min(owner, len(totals) - 1)
+    return owner, target - cum[owner]
+
+
+class ShardedProposer:
+    """One process per GPU (torchrun); every rank calls :meth:`propose` with the same arguments and gets the same
+    measured bitstring back."""
+
+    def __init__(self, model, mixer, device: int = 0, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        g = self.world.bit_length() - 1
+        if self.world < 2 or (1 << g) != self.world:
+            raise ValueError(f"world size must be a power of two >= 2 (got {self.world})")
+        self.handle = ShardHandle(model, mixer, self.rank, g, device)
+        dev = _device.require_cuda(device)
+        self.dev = dev
+        amps = 1 << self.handle.n_local
+        self.buf = [torch.empty(amps, dtype=torch.complex64, device=dev) for _ in range(2)]
+        self.cur = 0
+        self.layout = 0
+        self.total = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.index = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.exchanges = 0
+
+    def propose(self, s: int, gamma: float, r: int, u: float, delta_time: float = 0.8, group_id: int = 0) -> int:
+        torch, dist, h = _device._torch(), self.dist, self.handle
+        h.begin(s, gamma, r, delta_time, group_id)
+        for kind, k, pre in sharded_plan(r, h.n_groups, h.g):
+            if kind == EXCHANGE:
+                dist.all_to_all_single(self.buf[1 - self.cur], self.buf[self.cur], group=self.group)
+                self.cur ^= 1
+                self.layout ^= 1
+                self.exchanges += 1
+            else:
+                h.op(kind, k, pre, self.layout, self.buf[self.cur])
+        h.norm(self.total)
+        totals = [torch.empty_like(self.total) for _ in range(self.world)]
+        dist.all_gather(totals, self.total, group=self.group)
+        owner, target = pick_owner(np.array([float(t.item()) for t in totals]), u)
+        if self.rank == owner:
+            h.select(self.buf[self.cur], target, self.layout, self.index)
+        dist.broadcast(self.index, src=dist.get_global_rank(self.group, owner) if self.group is not None else owner,
+                       group=self.group)
+        return int(self.index.item()) & ((1 << h.n) - 1) if h.n < 63 else int(self.index.item())
+

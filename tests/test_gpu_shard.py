@@ -1,0 +1,135 @@
+"""GPU parity for the sharded statevector ops (qmc_shard_*, config C5).
+
+Single-GPU tests emulate W ranks in one process: W handles, W pairs of buffers on cuda:0, the exchange done with
+the same chunk transpose an all_to_all_single performs.  The NCCL test needs >= 2 GPUs (gpurun --gpus 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import oracle
+from tests import models
+from tests.shard_sim import logical_indices
+
+pytestmark = pytest.mark.gpu
+
+
+def _emulated_proposal(n, g, r, s, gamma, seed=11, us=()):
+    import torch
+    import qumcmc_b200 as q
+    from qumcmc_b200.sharded import EXCHANGE, ShardHandle, pick_owner, sharded_plan
+    J, h = models.packaged_random_model(n, seed)
+    model = q.IsingEnergyFunction(J, h)
+    mixer = q.GenericMixer.OneBodyMixer(n)
+    W, nl = 1 << g, n - g
+    dev = torch.device("cuda", 0)
+    hs = [ShardHandle(model, mixer, R, g, 0) for R in range(W)]
+    bufs = [torch.zeros(1 << nl, dtype=torch.complex64, device=dev) for _ in range(W)]
+    for hd in hs:
+        hd.begin(s, gamma, r, 0.8)
+    layout = 0
+    for kind, k, pre in sharded_plan(r, hs[0].n_groups, g):
+        if kind == EXCHANGE:
+            stacked = torch.stack([b.view(W, -1) for b in bufs])                  # [rank][chunk][...]
+            bufs = [stacked[:, R, :].contiguous().view(-1) for R in range(W)]
+            layout ^= 1
+        else:
+            for R, hd in enumerate(hs):
+                hd.op(kind, k, pre, layout, bufs[R])
+    totals = []
+    for R, hd in enumerate(hs):
+        t = torch.zeros(1, dtype=torch.float64, device=dev)
+        hd.norm(t)
+        totals.append(float(t.item()))
+    p = np.zeros(1 << n)
+    for R, hd in enumerate(hs):
+        pr = torch.empty(1 << nl, dtype=torch.float32, device=dev)
+        hd.final_probabilities(bufs[R], layout, pr)
+        p[logical_indices(R, nl, g, layout)] = pr.cpu().numpy().astype(np.float64)
+    picks = []
+    for u in us:
+        owner, target = pick_owner(np.array(totals), u)
+        idx = torch.zeros(1, dtype=torch.int64, device=dev)
+        hs[owner].select(bufs[owner], target, layout, idx)
+        picks.append(int(idx.item()))
+    for hd in hs:
+        hd.close()
+    return J, h, p, totals, layout, picks
+
+
+@pytest.mark.parametrize("n,g,r", [(19, 1, 1), (19, 1, 2), (19, 1, 3), (20, 2, 4), (21, 1, 5), (22, 3, 6), (25, 1, 3)])
+def test_shard_ops_match_oracle(n, g, r):
+    rng = np.random.default_rng(1000 * n + 10 * g + r)
+    s = int(rng.integers(0, 1 << n))
+    gamma = float(rng.uniform(0.25, 0.6))
+    us = [0.0, 0.25, 0.5, 0.77, 0.999999]
+    J, h, p, totals, layout, picks = _emulated_proposal(n, g, r, s, gamma, us=us)
+    assert layout == 0
+    masks, w = models.one_body(n)
+    ref = oracle.transition_probs(J, h, oracle.alpha(J, h), gamma, 0.8, r, masks, w, s, gatewise=False)
+    assert abs(sum(totals) - 1.0) < 1e-5
+    assert np.abs(p - ref).max() < 1e-6                                      # north-star tolerance (fp32)
+    # measurement: sequential inverse CDF in index order over the probabilities this path produced
+    cdf = np.cumsum(p)
+    for u, got in zip(us, picks):
+        want = int(np.searchsorted(cdf, u * cdf[-1], side="right"))
+        if got != want:  # u within fp32 summation rounding of a CDF boundary
+            lo, hi = min(got, want), max(got, want)
+            assert abs(cdf[hi - 1] - u * cdf[-1]) < 1e-6 * cdf[-1] or abs(cdf[lo] - u * cdf[-1]) < 1e-6 * cdf[-1], (u, got, want)
+
+
+def test_shard_rejects_bad_configurations():
+    import qumcmc_b200 as q
+    from qumcmc_b200 import _lib
+    from qumcmc_b200.sharded import ShardHandle
+    J, h = models.packaged_random_model(18, 3)
+    with pytest.raises(_lib.QmcUnsupported):                                  # 17 local qubits: below the tile geometry
+        ShardHandle(q.IsingEnergyFunction(J, h), q.GenericMixer.OneBodyMixer(18), 0, 1, 0)
+    J, h = models.packaged_random_model(19, 3)
+    with pytest.raises(ValueError):
+        ShardHandle(q.IsingEnergyFunction(J, h), q.GenericMixer.OneBodyMixer(19), 2, 1, 0)   # rank outside the world
+
+
+def _nccl_worker(rank, world, port, n, cases, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import qumcmc_b200 as qq
+        from qumcmc_b200.sharded import ShardedProposer
+        J, h = models.packaged_random_model(n, 11)
+        prop = ShardedProposer(qq.IsingEnergyFunction(J, h), qq.GenericMixer.OneBodyMixer(n), device=rank)
+        out = [prop.propose(s, gamma, r, u) for (s, gamma, r, u) in cases]
+        q.put((rank, out, prop.exchanges))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_nccl_world2_matches_emulation():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    n, world = 21, 2
+    rng = np.random.default_rng(5)
+    cases = [(int(rng.integers(0, 1 << n)), float(rng.uniform(0.25, 0.6)), int(r), float(rng.uniform(0, 1)))
+             for r in (1, 2, 3, 6)]
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(rk, world, port, n, cases, q)) for rk in range(world)]
+    for p_ in procs:
+        p_.start()
+    res = sorted((q.get(timeout=600) for _ in range(world)), key=lambda t: t[0])
+    for p_ in procs:
+        p_.join(timeout=120)
+        assert p_.exitcode == 0
+    assert res[0][1] == res[1][1]                                             # every rank reports the same bitstring
+    for (s, gamma, r, u), got in zip(cases, res[0][1]):
+        _, _, _, _, _, picks = _emulated_proposal(n, 1, r, s, gamma, us=[u])
+        assert got == picks[0]
