@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Config C5: statevector sharded over the GPUs of one node by global qubits (NCCL all-to-all qubit swaps) plus
+the sharded exact enumeration (all-gather of (max, sumexp) pairs = the allreduce for Z).
+
+    torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 benchmarks/sharded_bench.py --spins 36 --layers 2 5
+
+One JSON line per layer count on rank 0: seconds per proposal (device events, max over ranks), HBM GB/s of the local
+passes, NVLink GB/s per rank of the exchanges, total norm, measured index (identical on every rank)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--spins", dest="n", type=int, default=36)
+    ap.add_argument("--layers", type=int, nargs="+", default=[2, 5])
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--logz", action="store_true")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+
+    rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import qumcmc_b200 as q
+    from qumcmc_b200.distributed import exact_logz_sharded
+    from qumcmc_b200.sharded import EXCHANGE, ShardedProposer, plan_traffic_bytes, sharded_plan
+
+    model = q.random_ising_model(args.n, 1)
+    prop = ShardedProposer(model, q.GenericMixer.OneBodyMixer(args.n), device=local)
+    h = prop.handle
+    s = 0x5EED5EED5 & ((1 << args.n) - 1)
+
+    # time the exchanges separately: wrap all_to_all_single with events
+    a2a_ms = [0.0]
+    orig = dist.all_to_all_single
+
+    def timed_a2a(out, inp, group=None):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(out, inp, group=group)
+        e1.record()
+        pend.append((e0, e1))
+
+    pend = []
+    dist.all_to_all_single = timed_a2a
+    for r in args.layers:
+        prop.propose(s, 0.45, r, 0.5)  # warm-up (allocations, NCCL channels)
+        pend.clear()
+        times, idxs = [], []
+        for rep in range(args.reps):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            idx = prop.propose(s, 0.45, r, 0.37 + 0.1 * rep)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()))
+            idxs.append(idx)
+        ex_ms = sum(a.elapsed_time(b) for a, b in pend) / args.reps
+        t_ex = torch.tensor([ex_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t_ex, op=dist.ReduceOp.MAX)
+        ops = sharded_plan(r, h.n_groups, h.g)
+        hbm, nv = plan_traffic_bytes(ops, h.n_local, world)
+        n_ex = sum(1 for o in ops if o[0] == EXCHANGE)
+        hbm_local = hbm - 2.0 * 8.0 * (1 << h.n_local) * n_ex  # without the copies NCCL makes
+        tot = [torch.empty_like(prop.total) for _ in range(world)]
+        dist.all_gather(tot, prop.total)
+        ms = min(times)
+        if rank == 0:
+            print(json.dumps({
+                "config": "C5 sharded statevector", "n": args.n, "world": world, "n_local": h.n_local, "layers": r,
+                "seconds_per_proposal": ms * 1e-3, "exchange_seconds": float(t_ex.item()) * 1e-3, "exchanges": n_ex,
+                "local_passes": len(ops) - n_ex,
+                "local_pass_hbm_GBps": hbm_local / 1e9 / max(1e-9, (ms - float(t_ex.item())) * 1e-3),
+                "nvlink_GBps_per_rank": (nv / 1e9) / max(1e-9, float(t_ex.item()) * 1e-3),
+                "total_norm": float(sum(float(t.item()) for t in tot)), "index": idxs[-1],
+                "state_GiB_per_rank": 8.0 * (1 << h.n_local) / 2 ** 30}), flush=True)
+    dist.all_to_all_single = orig
+    if args.logz:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lz = exact_logz_sharded(model, 1.0, device=local)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if rank == 0:
+            print(json.dumps({"config": "C5 sharded exact log Z", "n": args.n, "world": world, "logZ": lz, "seconds": dt,
+                              "Gstates_per_s": (1 << args.n) / dt / 1e9}), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -132,6 +132,9 @@ struct qmc_model {
     int max_terms_in_group = 0;
     bool all_one_body = false;        // every term has popcount 1 and each qubit appears at most once per group
     std::vector<double> host_J, host_h, host_cJ, host_ch;
+    // fast exact enumerator: symmetrised couplings / fields in qubit order, constant 0.5 * trace(J)
+    double *dJp = nullptr, *dhq_e = nullptr;
+    double fast_e0 = 0.0;
     // large-n path
     SweepWorkspace *sweep = nullptr;
     // stats

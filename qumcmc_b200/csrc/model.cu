@@ -6,6 +6,7 @@
 //   fn_qckt_problem_half (phase exponent D)   qumcmc/quantum_mcmc_routines.py:54-91
 //   Exact_Sampling.get_boltzmann_distribution qumcmc/energy_models.py:218-275
 #include <math.h>
+#include <algorithm>
 #include <stdarg.h>
 
 #include "common.cuh"
@@ -146,6 +147,86 @@ __global__ void __launch_bounds__(256) exact_finalize_kernel(const LseState *__r
     }
 }
 
+// K5 fast path (log Z only / probabilities only -- whenever the energies themselves are not materialised).
+// Split the index into hi = idx >> 8 and lo = idx & 255 and write, in qubit order (qubit a = bit a, s_a = +-1),
+//     E(idx) = A(hi) + sum_{b<8} s_b(lo) F_b(hi) + R(lo),
+//     A  = e0 + sum_{a>=8} h_a s_a + sum_{8<=a<a'} Jp_aa' s_a s_a'      F_b = h_b + sum_{a>=8} Jp_ab s_a
+//     R  = sum_{b<b'<8} Jp_bb' s_b s_b'        Jp = (J + J^T)/2 off the diagonal,  e0 = sum_a J_aa / 2.
+// A CTA owns 2^16 consecutive indices: thread t first evaluates (A, F_0..F_7) of hi-block t into shared memory
+// (O(n^2) once per 256 states), then walks the 256 hi-blocks with lo = t fixed: 8 fused adds + one exp per state,
+// coalesced stores.  Same energies as the ordered evaluation up to fp64 rounding of a different summation order
+// (~1e-15 relative), which is why the path that returns energies keeps the oracle's order instead.
+constexpr int FAST_LO = 8, FAST_BLOCK = 1 << 16;
+template <bool PROBS>
+__global__ void __launch_bounds__(256) exact_fast_kernel(int n, const double *__restrict__ Jp, const double *__restrict__ hq,
+                                                         double e0, double beta, int64_t begin, int64_t n_blocks,
+                                                         LseState *__restrict__ partials, const double *__restrict__ logZ,
+                                                         double logZ_value, double *__restrict__ probs) {
+    extern __shared__ double sm[];
+    double *sJ = sm, *sh = sm + n * n, *sA = sh + n, *sF = sA + 256;  // sF[b * 256 + hi_local]
+    const int t = threadIdx.x;
+    for (int i = t; i < n * n; i += 256) sJ[i] = Jp[i];
+    for (int i = t; i < n; i += 256) sh[i] = hq[i];
+    __syncthreads();
+    // this thread's lo pattern: signs and the intra-lo couplings R(lo)
+    double sg[FAST_LO];
+#pragma unroll
+    for (int b = 0; b < FAST_LO; ++b) sg[b] = ((t >> b) & 1) ? 1.0 : -1.0;
+    double R = 0.0;
+#pragma unroll
+    for (int b = 0; b < FAST_LO; ++b)
+#pragma unroll
+        for (int b2 = b + 1; b2 < FAST_LO; ++b2) R += sJ[b * n + b2] * sg[b] * sg[b2];
+    const double lz = PROBS ? (logZ ? logZ[0] : logZ_value) : 0.0;
+    LseState acc = {-INFINITY, 0.0};
+    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const uint64_t base = (uint64_t)begin + (uint64_t)blk * FAST_BLOCK;
+        {   // (A, F) of hi-block t
+            const uint64_t idx = base + ((uint64_t)t << FAST_LO);
+            double A = e0, F[FAST_LO];
+#pragma unroll
+            for (int b = 0; b < FAST_LO; ++b) F[b] = sh[b];
+            for (int a = FAST_LO; a < n; ++a) {
+                const double sa = ((idx >> a) & 1ULL) ? 1.0 : -1.0;
+                double row = sh[a];
+                for (int a2 = a + 1; a2 < n; ++a2) row += ((idx >> a2) & 1ULL) ? sJ[a * n + a2] : -sJ[a * n + a2];
+                A += sa * row;
+#pragma unroll
+                for (int b = 0; b < FAST_LO; ++b) F[b] += sJ[b * n + a] * sa;
+            }
+            __syncthreads();  // previous block's readers are done
+            sA[t] = A;
+#pragma unroll
+            for (int b = 0; b < FAST_LO; ++b) sF[b * 256 + t] = F[b];
+            __syncthreads();
+        }
+        for (int hl = 0; hl < 256; ++hl) {
+            double e = sA[hl] + R;
+#pragma unroll
+            for (int b = 0; b < FAST_LO; ++b) e += sg[b] * sF[b * 256 + hl];
+            const double x = -beta * e;
+            if (PROBS) {
+                probs[(base - (uint64_t)begin) + ((uint64_t)hl << FAST_LO) + t] = exp(x - lz);
+            } else if (x > acc.m) {
+                acc.s = acc.s * exp(acc.m - x) + 1.0;
+                acc.m = x;
+            } else {
+                acc.s += exp(x - acc.m);
+            }
+        }
+    }
+    if (!PROBS) {
+        __shared__ LseState red[256];
+        red[t] = acc;
+        __syncthreads();
+        for (int off = 128; off > 0; off >>= 1) {
+            if (t < off) red[t] = lse_merge(red[t], red[t + off]);
+            __syncthreads();
+        }
+        if (t == 0) partials[blockIdx.x] = red[0];
+    }
+}
+
 // p = exp(-beta*E - logZ); E read back if materialised, recomputed otherwise.
 __global__ void __launch_bounds__(256) exact_probs_kernel(int n, const double *__restrict__ J,
                                                           const double *__restrict__ h, double beta,
@@ -176,6 +257,31 @@ static int grid_for(int64_t items, int block, int sms = 148, int per_sm = 8) {
     if (g < 1) g = 1;
     return (int)g;
 }
+
+// Jp / hq / e0 of the fast enumerator (qubit order: qubit a = spin n-1-a), uploaded once per model
+static int ensure_fast_tables(qmc_model *m) {
+    if (m->dJp) return QMC_OK;
+    const int n = m->n;
+    std::vector<double> Jp((size_t)n * n, 0.0), hq(n);
+    double e0 = 0.0;
+    for (int a = 0; a < n; ++a) {
+        hq[a] = m->host_h[n - 1 - a];
+        e0 += 0.5 * m->host_J[(size_t)(n - 1 - a) * n + (n - 1 - a)];
+        for (int b = 0; b < n; ++b)
+            if (a != b)
+                Jp[(size_t)a * n + b] = 0.5 * (m->host_J[(size_t)(n - 1 - a) * n + (n - 1 - b)] + m->host_J[(size_t)(n - 1 - b) * n + (n - 1 - a)]);
+    }
+    m->fast_e0 = e0;
+    QMC_CUDA_TRY(cudaMalloc(&m->dJp, sizeof(double) * (size_t)n * n));
+    QMC_CUDA_TRY(cudaMalloc(&m->dhq_e, sizeof(double) * (size_t)n));
+    QMC_CUDA_TRY(cudaMemcpy(m->dJp, Jp.data(), sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
+    QMC_CUDA_TRY(cudaMemcpy(m->dhq_e, hq.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    return QMC_OK;
+}
+static bool fast_range_ok(const qmc_model *m, uint64_t begin, int64_t count) {
+    return m->n >= 16 && count > 0 && begin % FAST_BLOCK == 0 && count % FAST_BLOCK == 0;
+}
+static size_t fast_smem(int n) { return sizeof(double) * (size_t)(n * n + n + 256 + FAST_LO * 256); }
 
 int qmc_launch_energies(qmc_model *m, const uint64_t *idx_dev, int64_t count, double *E_dev, cudaStream_t st) {
     if (count == 0) return QMC_OK;
@@ -285,6 +391,8 @@ extern "C" int qmc_model_destroy(qmc_model *m) {
     cudaFree(m->dJ);
     cudaFree(m->dh);
     cudaFree(m->dD);
+    cudaFree(m->dJp);
+    cudaFree(m->dhq_e);
     cudaFree(m->dE);
     cudaFree(m->d_group_off);
     cudaFree(m->d_masks);
@@ -399,12 +507,27 @@ extern "C" int qmc_exact_sampling(qmc_model *m, double beta, double *logZ_dev, d
     const int grid = grid_for(N, 256);
     LseState *partials = nullptr;
     QMC_CUDA_TRY(cudaMallocAsync(&partials, sizeof(LseState) * grid, st));
-    exact_enumerate_kernel<<<grid, 256, smem, st>>>(n, m->dJ, m->dh, beta, 0, N, energies_dev, partials);
-    exact_finalize_kernel<<<1, 256, 0, st>>>(partials, grid, logZ_dev, nullptr);
-    m->launches += 2;
-    if (probs_dev) {
-        exact_probs_kernel<<<grid, 256, smem, st>>>(n, m->dJ, m->dh, beta, 0, N, energies_dev, logZ_dev, 0.0, probs_dev);
-        m->launches++;
+    const bool fast = !energies_dev && fast_range_ok(m, 0, N);
+    if (fast) {
+        int rc = ensure_fast_tables(m);
+        if (rc != QMC_OK) return rc;
+        const int64_t nb = N / FAST_BLOCK;
+        const int fgrid = (int)std::min<int64_t>(nb, grid);
+        exact_fast_kernel<false><<<fgrid, 256, fast_smem(n), st>>>(n, m->dJp, m->dhq_e, m->fast_e0, beta, 0, nb, partials, nullptr, 0.0, nullptr);
+        exact_finalize_kernel<<<1, 256, 0, st>>>(partials, fgrid, logZ_dev, nullptr);
+        m->launches += 2;
+        if (probs_dev) {
+            exact_fast_kernel<true><<<fgrid, 256, fast_smem(n), st>>>(n, m->dJp, m->dhq_e, m->fast_e0, beta, 0, nb, nullptr, logZ_dev, 0.0, probs_dev);
+            m->launches++;
+        }
+    } else {
+        exact_enumerate_kernel<<<grid, 256, smem, st>>>(n, m->dJ, m->dh, beta, 0, N, energies_dev, partials);
+        exact_finalize_kernel<<<1, 256, 0, st>>>(partials, grid, logZ_dev, nullptr);
+        m->launches += 2;
+        if (probs_dev) {
+            exact_probs_kernel<<<grid, 256, smem, st>>>(n, m->dJ, m->dh, beta, 0, N, energies_dev, logZ_dev, 0.0, probs_dev);
+            m->launches++;
+        }
     }
     QMC_CUDA_TRY(cudaGetLastError());
     QMC_CUDA_TRY(cudaFreeAsync(partials, st));
@@ -423,8 +546,17 @@ extern "C" int qmc_exact_partial(qmc_model *m, double beta, uint64_t idx_begin, 
     const int grid = grid_for(idx_count, 256);
     LseState *partials = nullptr;
     QMC_CUDA_TRY(cudaMallocAsync(&partials, sizeof(LseState) * grid, st));
-    exact_enumerate_kernel<<<grid, 256, smem, st>>>(n, m->dJ, m->dh, beta, (int64_t)idx_begin, idx_count, energies_dev, partials);
-    exact_finalize_kernel<<<1, 256, 0, st>>>(partials, grid, nullptr, lse_pair_dev);
+    if (!energies_dev && fast_range_ok(m, idx_begin, idx_count)) {
+        int rc = ensure_fast_tables(m);
+        if (rc != QMC_OK) return rc;
+        const int64_t nb = idx_count / FAST_BLOCK;
+        const int fgrid = (int)std::min<int64_t>(nb, grid);
+        exact_fast_kernel<false><<<fgrid, 256, fast_smem(n), st>>>(n, m->dJp, m->dhq_e, m->fast_e0, beta, (int64_t)idx_begin, nb, partials, nullptr, 0.0, nullptr);
+        exact_finalize_kernel<<<1, 256, 0, st>>>(partials, fgrid, nullptr, lse_pair_dev);
+    } else {
+        exact_enumerate_kernel<<<grid, 256, smem, st>>>(n, m->dJ, m->dh, beta, (int64_t)idx_begin, idx_count, energies_dev, partials);
+        exact_finalize_kernel<<<1, 256, 0, st>>>(partials, grid, nullptr, lse_pair_dev);
+    }
     m->launches += 2;
     QMC_CUDA_TRY(cudaGetLastError());
     QMC_CUDA_TRY(cudaFreeAsync(partials, st));
@@ -439,8 +571,17 @@ extern "C" int qmc_exact_probs_range(qmc_model *m, double beta, double logZ, uin
     QMC_CUDA_TRY(cudaSetDevice(m->device));
     const int n = m->n;
     const size_t smem = sizeof(double) * (size_t)(n * n + n);
-    exact_probs_kernel<<<grid_for(idx_count, 256), 256, smem, (cudaStream_t)stream>>>(n, m->dJ, m->dh, beta, (int64_t)idx_begin, idx_count,
-                                                                                     energies_dev, nullptr, logZ, probs_dev);
+    if (!energies_dev && fast_range_ok(m, idx_begin, idx_count)) {
+        int rc = ensure_fast_tables(m);
+        if (rc != QMC_OK) return rc;
+        const int64_t nb = idx_count / FAST_BLOCK;
+        const int fgrid = (int)std::min<int64_t>(nb, grid_for(idx_count, 256));
+        exact_fast_kernel<true><<<fgrid, 256, fast_smem(n), (cudaStream_t)stream>>>(n, m->dJp, m->dhq_e, m->fast_e0, beta, (int64_t)idx_begin, nb,
+                                                                                    nullptr, nullptr, logZ, probs_dev);
+    } else {
+        exact_probs_kernel<<<grid_for(idx_count, 256), 256, smem, (cudaStream_t)stream>>>(n, m->dJ, m->dh, beta, (int64_t)idx_begin, idx_count,
+                                                                                         energies_dev, nullptr, logZ, probs_dev);
+    }
     m->launches++;
     QMC_CUDA_TRY(cudaGetLastError());
     return QMC_OK;

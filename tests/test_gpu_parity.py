@@ -331,3 +331,43 @@ def test_exact_partial_ranges_combine_to_full_logz():
         assert np.abs(pr.cpu().numpy() - ex.probs[a:b]).max() < 1e-15
         pairs.append(pair.cpu().numpy())
     assert combine_logsumexp(np.stack(pairs)) == pytest.approx(ex.logZ, rel=1e-14)
+
+
+@pytest.mark.parametrize("n", [16, 19])
+def test_exact_fast_enumerator_matches_ordered_path(n):
+    """log Z only / probabilities only take the hi/lo-split enumerator (O(1) energy per state); it must agree with
+    the ordered evaluation (bit-exact energies) to fp64 rounding, also for a non-symmetric J with a diagonal."""
+    import torch
+    from qumcmc_b200 import _lib
+    from qumcmc_b200.distributed import combine_logsumexp
+    rng = np.random.default_rng(n)
+    J = rng.uniform(-1, 1, size=(n, n))            # neither symmetric nor zero-diagonal: get_energy takes any J
+    h = rng.normal(0, 0.5, size=n)
+    m = _model(J, h)
+    beta = 1.3
+    dm = m.device_model(0)
+    dev = torch.device("cuda", 0)
+    N = 1 << n
+    lz_o = torch.zeros(1, dtype=torch.float64, device=dev)
+    en = torch.zeros(N, dtype=torch.float64, device=dev)
+    _lib.check(_lib.lib().qmc_exact_sampling(dm.handle, beta, lz_o.data_ptr(), en.data_ptr(), None, None))
+    lz_f = torch.zeros(1, dtype=torch.float64, device=dev)
+    pr = torch.zeros(N, dtype=torch.float64, device=dev)
+    _lib.check(_lib.lib().qmc_exact_sampling(dm.handle, beta, lz_f.data_ptr(), None, pr.data_ptr(), None))
+    torch.cuda.synchronize()
+    E = en.cpu().numpy()
+    assert np.array_equal(E[:64], np.array([oracle.energy(J, h, i) for i in range(64)]))
+    assert abs(lz_f.item() - lz_o.item()) < 1e-12
+    ref_p = np.exp(-beta * E - lz_o.item())
+    assert np.abs(pr.cpu().numpy() - ref_p).max() < 1e-13 * max(1.0, ref_p.max())
+    # fast-eligible ranges (multiples of 2^16) through the sharded entry points
+    pairs = []
+    for a in range(0, N, N // 2):
+        pair = torch.empty(2, dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().qmc_exact_partial(dm.handle, beta, a, N // 2, pair.data_ptr(), None, None))
+        p2 = torch.empty(N // 2, dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().qmc_exact_probs_range(dm.handle, beta, lz_o.item(), a, N // 2, None, p2.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert np.abs(p2.cpu().numpy() - ref_p[a:a + N // 2]).max() < 1e-13 * max(1.0, ref_p.max())
+        pairs.append(pair.cpu().numpy())
+    assert combine_logsumexp(np.stack(pairs)) == pytest.approx(lz_o.item(), abs=1e-12)
