@@ -154,6 +154,18 @@ int qmc_shard_num_groups(const qmc_shard *sh);
 /* Parameters of the next proposal: start state s (logical basis index), gamma, r mixer layers, mixer group. */
 int qmc_shard_begin(qmc_shard *sh, uint64_t s, double gamma, int r, double delta_time, int group);
 int qmc_shard_op(qmc_shard *sh, int op, int k, int pre, int layout, void *state_dev, void *stream);
+/* Fused pass + exchange: the pass stores every amplitude straight into buffer `dst_which` of the rank that owns it
+ * after the qubit swap (peer-mapped pointers over NVLink, set once with qmc_shard_set_peers: 2^g device-accessible
+ * addresses of buffer `which` of every rank).  Replaces "pass; all_to_all_single" by "pass_exchange; barrier". */
+int qmc_shard_set_peers(qmc_shard *sh, int which, void *const *ptrs_host);
+int qmc_enable_peer_access(int device, int peer);
+/* CUDA IPC plumbing for the peer tables: export = handle of the allocation containing dev_ptr + offset inside it;
+ * open = map it into `device`'s context in another process (cached per allocation); close_all unmaps. */
+#define QMC_IPC_HANDLE_BYTES 64
+int qmc_ipc_export(int device, void *dev_ptr, void *handle_out /* 64 bytes */, uint64_t *offset_out);
+int qmc_ipc_open(int device, const void *handle, uint64_t offset, void **ptr_out);
+int qmc_ipc_close_all(void);
+int qmc_shard_op_exchange(qmc_shard *sh, int op, int k, int pre, int layout, void *state_dev, int dst_which, void *stream);
 int qmc_shard_norm(qmc_shard *sh, double *total_dev, void *stream);
 int qmc_shard_select(qmc_shard *sh, void *state_dev, double target, int layout, uint64_t *index_dev, void *stream);
 /* Test hook: LO_FINAL that also writes |a|^2 of the local shard (2^(n-g) floats, local index order). */

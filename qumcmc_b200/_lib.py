@@ -26,6 +26,7 @@ SMEM_MAX_SPINS_F32 = 13
 SMEM_MAX_SPINS_F64 = 12
 MAX_SPINS = 40          # model limit; one GPU holds a statevector up to MAX_LOCAL_SPINS qubits
 MAX_LOCAL_SPINS = 34
+IPC_HANDLE_BYTES = 64
 SHARD_OP_FIRST, SHARD_OP_MID, SHARD_OP_SINGLE, SHARD_OP_LO_SINGLE, SHARD_OP_LO_FINAL = range(5)
 
 # every symbol include/qumcmc_b200.h declares (tests check the library exports all of them)
@@ -36,7 +37,8 @@ EXPORTS = [
     "qmc_transition_probs", "qmc_propose", "qmc_run_chains", "qmc_run_chains_host",
     "qmc_model_num_spins", "qmc_model_launch_count", "qmc_profile_enable", "qmc_profile_read",
     "qmc_shard_create", "qmc_shard_destroy", "qmc_shard_num_groups", "qmc_shard_begin", "qmc_shard_op",
-    "qmc_shard_norm", "qmc_shard_select", "qmc_shard_final_probs",
+    "qmc_shard_norm", "qmc_shard_select", "qmc_shard_final_probs", "qmc_shard_set_peers", "qmc_shard_op_exchange",
+    "qmc_enable_peer_access", "qmc_ipc_export", "qmc_ipc_open", "qmc_ipc_close_all",
 ]
 
 
@@ -105,6 +107,12 @@ def lib() -> C.CDLL:
     L.qmc_shard_norm.argtypes = [C.c_void_p, dp, vp]
     L.qmc_shard_select.argtypes = [C.c_void_p, vp, C.c_double, C.c_int, u64p, vp]
     L.qmc_shard_final_probs.argtypes = [C.c_void_p, C.c_int, vp, vp, vp]
+    L.qmc_shard_set_peers.argtypes = [C.c_void_p, C.c_int, vp]
+    L.qmc_enable_peer_access.argtypes = [C.c_int, C.c_int]
+    L.qmc_ipc_export.argtypes = [C.c_int, vp, vp, u64p]
+    L.qmc_ipc_open.argtypes = [C.c_int, vp, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.qmc_ipc_close_all.argtypes = []
+    L.qmc_shard_op_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("qmc_last_error", "qmc_model_launch_count"):

@@ -72,6 +72,11 @@ struct SweepArgs {
     float *probs_out;         // PROBS mode: unnormalised |a|^2 (index order) or null
     float2 *amps_out;
     int pf_dist;              // > 0: each CTA L2-prefetches the tile of the CTA launched pf_dist later (in launch order)
+    // Fused exchange (sharded statevector): when xchg_peers != null the pass stores amplitude L of this rank to
+    // xchg_peers[L >> xchg_shift][(L & low) | (xchg_rank << xchg_shift)] -- the all-to-all that swaps the top local
+    // index bits with the rank bits, done by the sweep's own stores over NVLink peer mappings (no staging copy).
+    float2 *const *xchg_peers;
+    int xchg_shift, xchg_rank;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -403,6 +408,11 @@ __device__ __forceinline__ int64_t hi_base_b(int tid, int64_t tile) {
 __device__ __forceinline__ int hi_loc_a(int tid, int j) { return (tid & 31) | ((tid >> 5) << 5) | (j << 7); }
 __device__ __forceinline__ int hi_loc_b(int tid, int j) { return (tid & 31) | (j << 5) | ((tid >> 5) << 11); }
 
+__device__ __forceinline__ A64 *xchg_addr(const SweepArgs &a, int64_t local_idx) {
+    const int64_t low = local_idx & (((int64_t)1 << a.xchg_shift) - 1);
+    return reinterpret_cast<A64 *>(a.xchg_peers[local_idx >> a.xchg_shift]) + (low | ((int64_t)a.xchg_rank << a.xchg_shift));
+}
+
 // L2 prefetch of the tile a later CTA of the same launch will read (CTAs start in linear blockIdx order,
 // x fastest): with 3 resident CTAs per SM the CTA `pf_dist` ahead starts roughly when this one retires,
 // so its loads hit L2 instead of waiting on HBM with nothing else to overlap.
@@ -492,7 +502,13 @@ __global__ void __launch_bounds__(NTH, 384 / NTH) lo_sweep_kernel(const SweepArg
         lo_b_to_smem(v, sm, tid);  // each thread rewrites exactly the slots it read
         __syncthreads();
         lo_smem_to_a(v, sm, tid);
-        lo_store_a(v, state + (tile << TB), tid);
+        if (a.xchg_peers) {  // the whole tile shares its top index bits: one destination rank per CTA
+            A64 *dst = xchg_addr(a, tile << TB) + lo_base_a(tid);
+#pragma unroll
+            for (int j = 0; j < 64; ++j) dst[j << 6] = v[j];
+        } else {
+            lo_store_a(v, state + (tile << TB), tid);
+        }
         return;
     }
     const PhaseAF af = load_af(a.af_lo, tile * NTH + tid);  // issued before the amplitude loads are consumed
@@ -737,11 +753,16 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
         phase_gray<false>(v, af, hs_s, g.dr[0], cp);
         bfly6<ACTIVE>(v, cp, qp);
     }
-    A64 *dst = state;
+    if (a.xchg_peers) {  // register qubits may include the swapped positions: destination resolved per amplitude
 #pragma unroll
-    for (int j = 0; j < 64; ++j) {
-        *dst = v[j];
-        dst += stride;
+        for (int j = 0; j < 64; ++j) *xchg_addr(a, base + j * stride) = v[j];
+    } else {
+        A64 *dst = state;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            *dst = v[j];
+            dst += stride;
+        }
     }
 }
 
@@ -1470,6 +1491,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         memcpy(a.dr_lo, w->dr_lo, sizeof(a.dr_lo)); memcpy(a.dr_hia, w->dr_hia, sizeof(a.dr_hia)); memcpy(a.dr_hib, w->dr_hib, sizeof(a.dr_hib));
         a.segsum = w->segsum;
         a.pf_dist = pf_dist;
+        a.xchg_peers = nullptr; a.xchg_shift = 0; a.xchg_rank = 0;
         a.probs_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float *>(probs_out) : nullptr;
         a.amps_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float2 *>(amps_out) : nullptr;
         // PROBS with amps only: still need a probs-free normalisation; handled by the normalise kernel
@@ -1612,6 +1634,7 @@ struct qmc_shard {
     double fx_scale = 1.0;
     int k_fx = 0;
     ChainParams host_cp[2];         // physical-coordinate parameters of the current proposal, per layout
+    float2 **d_peers[2] = {nullptr, nullptr};  // device tables: pointer to buffer `which` of every rank
     int r = 0;
 };
 
@@ -1826,7 +1849,7 @@ extern "C" int qmc_shard_create(qmc_shard **out, qmc_model *m, int rank, int log
 extern "C" int qmc_shard_destroy(qmc_shard *sh) {
     if (!sh) return QMC_OK;
     cudaFree(sh->params); cudaFree(sh->order); cudaFree(sh->segsum); cudaFree(sh->total);
-    for (int L = 0; L < 2; ++L) { cudaFree(sh->dJq[L]); cudaFree(sh->dhq[L]); }
+    for (int L = 0; L < 2; ++L) { cudaFree(sh->dJq[L]); cudaFree(sh->dhq[L]); cudaFree(sh->d_peers[L]); }
     delete sh;
     return QMC_OK;
 }
@@ -1845,8 +1868,11 @@ extern "C" int qmc_shard_begin(qmc_shard *sh, uint64_t s, double gamma, int r, d
 // One local pass.  op: 0 FIRST(top group: analytic M|s>, P, M_top) | 1 MID(top group: M_top restricted to the
 // `pre` swapped-in qubits, P, M_top) | 2 SINGLE(group k, its active qubits; k == 0 with pre > 0: only the `pre`
 // swapped-in qubits) | 3 LO_SINGLE | 4 LO_FINAL (segment sums; r == 1: of the analytic product state).
-extern "C" int qmc_shard_op(qmc_shard *sh, int op, int k, int pre, int layout, void *state_dev, void *stream) {
+static int shard_op_impl(qmc_shard *sh, int op, int k, int pre, int layout, void *state_dev, int dst_which, void *stream) {
     QMC_REQUIRE(sh && state_dev, QMC_ERR_BADARG, "qmc_shard_op: null argument");
+    QMC_REQUIRE(dst_which < 0 || (dst_which < 2 && sh->d_peers[dst_which]), QMC_ERR_BADARG,
+                "qmc_shard_op_exchange: peer table %d not set (qmc_shard_set_peers)", dst_which);
+    QMC_REQUIRE(dst_which < 0 || op != 4, QMC_ERR_BADARG, "qmc_shard_op_exchange: LO_FINAL does not write the state");
     QMC_REQUIRE(layout == 0 || layout == 1, QMC_ERR_BADARG, "qmc_shard_op: layout %d", layout);
     const int K = (int)sh->acts.size();
     QMC_REQUIRE(k >= 0 && k < K, QMC_ERR_BADARG, "qmc_shard_op: group %d of %d", k, K);
@@ -1860,6 +1886,11 @@ extern "C" int qmc_shard_op(qmc_shard *sh, int op, int k, int pre, int layout, v
     a.params = sh->params;
     a.segsum = sh->segsum;
     a.pf_dist = 0;
+    if (dst_which >= 0) {
+        a.xchg_peers = sh->d_peers[dst_which];
+        a.xchg_shift = sh->nl - sh->g;
+        a.xchg_rank = sh->rank;
+    }
     const int64_t tiles = (int64_t)1 << (sh->nl - TILE_BITS);
     const Hi6Args &ga = sh->groups[layout][k];
     int rc = QMC_OK;
@@ -1890,6 +1921,31 @@ extern "C" int qmc_shard_op(qmc_shard *sh, int op, int k, int pre, int layout, v
     sh->m->launches++;
     QMC_CUDA_TRY(cudaGetLastError());
     return QMC_OK;
+}
+
+extern "C" int qmc_shard_op(qmc_shard *sh, int op, int k, int pre, int layout, void *state_dev, void *stream) {
+    return shard_op_impl(sh, op, k, pre, layout, state_dev, -1, stream);
+}
+
+// Device-accessible address of buffer `which` (0/1) of every rank, this rank's own included (peer mappings from
+// CUDA IPC / torch shared CUDA tensors; on one GPU plain pointers).  Host array of 2^g pointers.
+extern "C" int qmc_shard_set_peers(qmc_shard *sh, int which, void *const *ptrs_host) {
+    QMC_REQUIRE(sh && ptrs_host && (which == 0 || which == 1), QMC_ERR_BADARG, "qmc_shard_set_peers: bad argument");
+    QMC_CUDA_TRY(cudaSetDevice(sh->m->device));
+    const size_t bytes = sizeof(void *) * ((size_t)1 << sh->g);
+    if (!sh->d_peers[which]) QMC_CUDA_TRY(cudaMalloc(&sh->d_peers[which], bytes));
+    QMC_CUDA_TRY(cudaMemcpy(sh->d_peers[which], ptrs_host, bytes, cudaMemcpyHostToDevice));
+    return QMC_OK;
+}
+
+// The pass `op` with its stores redirected into buffer `dst_which` of the owning ranks: local pass + all-to-all in
+// one kernel.  The caller puts a barrier across ranks between this call and the first read of the destination
+// buffers (and nothing else: the buffers alternate, so the previous contents of `dst_which` were last read before
+// the previous barrier).
+extern "C" int qmc_shard_op_exchange(qmc_shard *sh, int op, int k, int pre, int layout, void *state_dev, int dst_which,
+                                     void *stream) {
+    QMC_REQUIRE(dst_which == 0 || dst_which == 1, QMC_ERR_BADARG, "qmc_shard_op_exchange: dst_which %d", dst_which);
+    return shard_op_impl(sh, op, k, pre, layout, state_dev, dst_which, stream);
 }
 
 // sum of |a|^2 over the local shard (after LO_FINAL) -> total_dev[0]
@@ -1955,5 +2011,84 @@ extern "C" int qmc_shard_final_probs(qmc_shard *sh, int layout, void *state_dev,
     if (rc != QMC_OK) return rc;
     sh->m->launches++;
     QMC_CUDA_TRY(cudaGetLastError());
+    return QMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// CUDA IPC for the fused exchange.  A peer's state buffer has to be mapped into THIS device's context (a mapping
+// opened under the owner's device index, which is what torch's shared-CUDA-tensor machinery does, is not reachable
+// from kernels running on this device).  Export: handle of the allocation that contains dev_ptr + the offset inside
+// it (the caller's allocator may sub-allocate); open: map under `device` with lazy peer access; every distinct
+// allocation is opened once per process and cached.
+// ------------------------------------------------------------------------------------------
+typedef int (*cuMemGetAddressRange_fn)(unsigned long long *pbase, size_t *psize, unsigned long long dptr);
+
+extern "C" int qmc_ipc_export(int device, void *dev_ptr, void *handle_out, uint64_t *offset_out) {
+    QMC_REQUIRE(dev_ptr && handle_out && offset_out, QMC_ERR_BADARG, "qmc_ipc_export: null argument");
+    QMC_CUDA_TRY(cudaSetDevice(device));
+    static cuMemGetAddressRange_fn get_range = nullptr;
+    if (!get_range) {
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        QMC_CUDA_TRY(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &qr));
+        QMC_REQUIRE(fp && qr == cudaDriverEntryPointSuccess, QMC_ERR_CUDA, "cuMemGetAddressRange entry point not found");
+        get_range = reinterpret_cast<cuMemGetAddressRange_fn>(fp);
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    const int drc = get_range(&base, &size, (unsigned long long)(uintptr_t)dev_ptr);
+    QMC_REQUIRE(drc == 0, QMC_ERR_CUDA, "cuMemGetAddressRange -> %d", drc);
+    cudaIpcMemHandle_t h;
+    QMC_CUDA_TRY(cudaIpcGetMemHandle(&h, reinterpret_cast<void *>((uintptr_t)base)));
+    static_assert(sizeof(h) == QMC_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    memcpy(handle_out, &h, sizeof(h));
+    *offset_out = (uint64_t)((uintptr_t)dev_ptr - (uintptr_t)base);
+    return QMC_OK;
+}
+
+static std::vector<std::pair<std::string, void *>> g_ipc_open;  // (device:handle bytes) -> mapped base
+
+extern "C" int qmc_ipc_open(int device, const void *handle, uint64_t offset, void **ptr_out) {
+    QMC_REQUIRE(handle && ptr_out, QMC_ERR_BADARG, "qmc_ipc_open: null argument");
+    QMC_CUDA_TRY(cudaSetDevice(device));
+    std::string key(reinterpret_cast<const char *>(handle), QMC_IPC_HANDLE_BYTES);
+    key.push_back((char)device);
+    for (auto &e : g_ipc_open)
+        if (e.first == key) {
+            *ptr_out = static_cast<char *>(e.second) + offset;
+            return QMC_OK;
+        }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *base = nullptr;
+    QMC_CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    g_ipc_open.emplace_back(key, base);
+    *ptr_out = static_cast<char *>(base) + offset;
+    return QMC_OK;
+}
+
+// Unmap everything qmc_ipc_open mapped in this process (call before the owners free their buffers).
+extern "C" int qmc_ipc_close_all(void) {
+    for (auto &e : g_ipc_open) {
+        cudaSetDevice((int)e.first.back());
+        cudaIpcCloseMemHandle(e.second);
+    }
+    g_ipc_open.clear();
+    return QMC_OK;
+}
+
+// cudaDeviceEnablePeerAccess(peer) on `device` (idempotent): the fused exchange stores to peer-mapped buffers
+extern "C" int qmc_enable_peer_access(int device, int peer) {
+    if (device == peer) return QMC_OK;
+    QMC_CUDA_TRY(cudaSetDevice(device));
+    int can = 0;
+    QMC_CUDA_TRY(cudaDeviceCanAccessPeer(&can, device, peer));
+    QMC_REQUIRE(can, QMC_ERR_UNSUPPORTED, "device %d cannot access peer %d (no NVLink / P2P path)", device, peer);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return QMC_OK;
+    }
+    QMC_CUDA_TRY(e);
     return QMC_OK;
 }

@@ -117,6 +117,18 @@ class ShardHandle:
         _lib.check(_lib.lib().qmc_shard_op(self.handle, _OPCODE[kind], int(k), int(pre), int(layout), state.data_ptr(),
                                            _device.current_stream_ptr(self.device)))
 
+    def set_peers(self, which: int, pointers: Sequence[int]) -> None:
+        """Device-accessible addresses of buffer ``which`` of every rank (own buffer included)."""
+        arr = (C.c_void_p * len(pointers))(*[C.c_void_p(int(p_)) for p_ in pointers])
+        _lib.check(_lib.lib().qmc_shard_set_peers(self.handle, int(which), arr))
+
+    def op_exchange(self, kind: str, k: int, pre: int, layout: int, state, dst_which: int) -> None:
+        """The pass ``kind`` fused with the qubit-swap exchange: its stores land in buffer ``dst_which`` of the
+        ranks that own the amplitudes after the swap."""
+        _lib.check(_lib.lib().qmc_shard_op_exchange(self.handle, _OPCODE[kind], int(k), int(pre), int(layout),
+                                                    state.data_ptr(), int(dst_which),
+                                                    _device.current_stream_ptr(self.device)))
+
     def norm(self, total) -> None:
         _lib.check(_lib.lib().qmc_shard_norm(self.handle, total.data_ptr(), _device.current_stream_ptr(self.device)))
 
@@ -146,11 +158,14 @@ class ShardedProposer:
     """One process per GPU (torchrun); every rank calls :meth:`propose` with the same arguments and gets the same
     measured bitstring back."""
 
-    def __init__(self, model, mixer, device: int = 0, group=None):
+    def __init__(self, model, mixer, device: int = 0, group=None, fused: bool = True):
+        """``fused``: the pass before every exchange stores straight into the peers' buffers over NVLink (CUDA IPC
+        mappings of the two state buffers of every rank) and the exchange shrinks to a barrier; ``False`` keeps the
+        pass local and calls NCCL ``all_to_all_single``."""
         import torch
         import torch.distributed as dist
 
-        self.dist, self.group = dist, group
+        self.dist, self.group, self._torch = dist, group, torch
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         g = self.world.bit_length() - 1
         if self.world < 2 or (1 << g) != self.world:
@@ -164,19 +179,87 @@ class ShardedProposer:
         self.layout = 0
         self.total = torch.zeros(1, dtype=torch.float64, device=dev)
         self.index = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.exchanges = 0
+        self.timeline = None        # set to a list to collect (label, start_event, end_event) per op
+        self.fused = bool(fused)
+        if self.fused:
+            self._map_peer_buffers(device)
+
+    def _map_peer_buffers(self, device: int) -> None:
+        """all-gather CUDA IPC handles of both state buffers, map the peers' buffers into this device's context
+        (qmc_ipc_export / qmc_ipc_open) and hand the address tables to the library."""
+        dist, L = self.dist, _lib.lib()
+        mine = []
+        for b in self.buf:
+            hb = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+            off = C.c_uint64(0)
+            _lib.check(L.qmc_ipc_export(int(device), C.c_void_p(b.data_ptr()), hb, C.byref(off)))
+            mine.append((hb.raw, int(off.value)))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (int(device), mine), group=self.group)
+        for which in (0, 1):
+            ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(self.buf[which].data_ptr())
+                    continue
+                peer_dev, handles = gathered[r]
+                raw, off = handles[which]
+                out = C.c_void_p()
+                _lib.check(L.qmc_ipc_open(int(device), raw, C.c_uint64(off), C.byref(out)))
+                ptrs.append(int(out.value))
+            self.handle.set_peers(which, ptrs)
+        dist.barrier(group=self.group)
+
+    def close(self) -> None:
+        """Unmap the peers' buffers (every rank, before any rank frees its state buffers) and free the handle."""
+        if self.fused:
+            self._torch.cuda.synchronize(self.dev)
+            self.dist.barrier(group=self.group)
+            _lib.lib().qmc_ipc_close_all()
+            self.dist.barrier(group=self.group)
+            self.fused = False
+        self.handle.close()
+
+    def _timed(self, label: str, fn) -> None:
+        """Run one op; with ``self.timeline`` set to a list, bracket it with CUDA events (label, start, end)."""
+        if self.timeline is None:
+            fn()
+            return
+        torch = _device._torch()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.timeline.append((label, e0, e1))
 
     def propose(self, s: int, gamma: float, r: int, u: float, delta_time: float = 0.8, group_id: int = 0) -> int:
         torch, dist, h = _device._torch(), self.dist, self.handle
         h.begin(s, gamma, r, delta_time, group_id)
-        for kind, k, pre in sharded_plan(r, h.n_groups, h.g):
+        ops = sharded_plan(r, h.n_groups, h.g)
+        i = 0
+        while i < len(ops):
+            kind, k, pre = ops[i]
+            if self.fused and i + 1 < len(ops) and ops[i + 1][0] == EXCHANGE:
+                def fused_step(kind=kind, k=k, pre=pre):
+                    h.op_exchange(kind, k, pre, self.layout, self.buf[self.cur], 1 - self.cur)
+                    dist.all_reduce(self._flag, group=self.group)   # barrier in stream order: every rank's stores have landed
+                self._timed("pass+exchange", fused_step)
+                self.cur ^= 1
+                self.layout ^= 1
+                self.exchanges += 1
+                i += 2
+                continue
             if kind == EXCHANGE:
-                dist.all_to_all_single(self.buf[1 - self.cur], self.buf[self.cur], group=self.group)
+                self._timed("exchange", lambda: dist.all_to_all_single(self.buf[1 - self.cur], self.buf[self.cur],
+                                                                       group=self.group))
                 self.cur ^= 1
                 self.layout ^= 1
                 self.exchanges += 1
             else:
-                h.op(kind, k, pre, self.layout, self.buf[self.cur])
+                self._timed("pass", lambda: h.op(kind, k, pre, self.layout, self.buf[self.cur]))
+            i += 1
         h.norm(self.total)
         totals = [torch.empty_like(self.total) for _ in range(self.world)]
         dist.all_gather(totals, self.total, group=self.group)

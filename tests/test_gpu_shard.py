@@ -15,7 +15,7 @@ from tests.shard_sim import logical_indices
 pytestmark = pytest.mark.gpu
 
 
-def _emulated_proposal(n, g, r, s, gamma, seed=11, us=()):
+def _emulated_proposal(n, g, r, s, gamma, seed=11, us=(), fused=False):
     import torch
     import qumcmc_b200 as q
     from qumcmc_b200.sharded import EXCHANGE, ShardHandle, pick_owner, sharded_plan
@@ -29,7 +29,28 @@ def _emulated_proposal(n, g, r, s, gamma, seed=11, us=()):
     for hd in hs:
         hd.begin(s, gamma, r, 0.8)
     layout = 0
-    for kind, k, pre in sharded_plan(r, hs[0].n_groups, g):
+    ops = sharded_plan(r, hs[0].n_groups, g)
+    if fused:   # the pass before every exchange stores straight into the owning "rank"'s other buffer (same device here)
+        both = [bufs, [torch.zeros(1 << nl, dtype=torch.complex64, device=dev) for _ in range(W)]]
+        for hd in hs:
+            for which in (0, 1):
+                hd.set_peers(which, [b.data_ptr() for b in both[which]])
+        cur, i = 0, 0
+        while i < len(ops):
+            kind, k, pre = ops[i]
+            if i + 1 < len(ops) and ops[i + 1][0] == EXCHANGE:
+                for R, hd in enumerate(hs):
+                    hd.op_exchange(kind, k, pre, layout, both[cur][R], 1 - cur)
+                cur ^= 1
+                layout ^= 1
+                i += 2
+                continue
+            assert kind != EXCHANGE
+            for R, hd in enumerate(hs):
+                hd.op(kind, k, pre, layout, both[cur][R])
+            i += 1
+        bufs, ops = both[cur], []
+    for kind, k, pre in ops:
         if kind == EXCHANGE:
             stacked = torch.stack([b.view(W, -1) for b in bufs])                  # [rank][chunk][...]
             bufs = [stacked[:, R, :].contiguous().view(-1) for R in range(W)]
@@ -79,6 +100,21 @@ def test_shard_ops_match_oracle(n, g, r):
             assert abs(cdf[hi - 1] - u * cdf[-1]) < 1e-6 * cdf[-1] or abs(cdf[lo] - u * cdf[-1]) < 1e-6 * cdf[-1], (u, got, want)
 
 
+@pytest.mark.parametrize("n,g,r", [(19, 1, 2), (20, 2, 4), (21, 1, 5), (22, 3, 6), (25, 2, 3)])
+def test_shard_fused_exchange_matches_staged(n, g, r):
+    """qmc_shard_op_exchange (pass + all-to-all in one kernel, stores into the peers' buffers) gives bit-identical
+    amplitudes to pass-then-exchange: same arithmetic, only the store addresses differ."""
+    rng = np.random.default_rng(77 * n + g + r)
+    s = int(rng.integers(0, 1 << n))
+    gamma = float(rng.uniform(0.25, 0.6))
+    us = [0.1, 0.6, 0.93]
+    _, _, p0, t0, l0, k0 = _emulated_proposal(n, g, r, s, gamma, us=us)
+    _, _, p1, t1, l1, k1 = _emulated_proposal(n, g, r, s, gamma, us=us, fused=True)
+    assert l0 == l1 == 0
+    assert np.array_equal(p0, p1) and k0 == k1
+    assert np.allclose(t0, t1, rtol=1e-12, atol=0)       # the norm reduction uses atomics: summation order varies
+
+
 def test_shard_rejects_bad_configurations():
     import qumcmc_b200 as q
     from qumcmc_b200 import _lib
@@ -91,7 +127,7 @@ def test_shard_rejects_bad_configurations():
         ShardHandle(q.IsingEnergyFunction(J, h), q.GenericMixer.OneBodyMixer(19), 2, 1, 0)   # rank outside the world
 
 
-def _nccl_worker(rank, world, port, n, cases, q):
+def _nccl_worker(rank, world, port, n, cases, q, fused):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -101,14 +137,15 @@ def _nccl_worker(rank, world, port, n, cases, q):
         import qumcmc_b200 as qq
         from qumcmc_b200.sharded import ShardedProposer
         J, h = models.packaged_random_model(n, 11)
-        prop = ShardedProposer(qq.IsingEnergyFunction(J, h), qq.GenericMixer.OneBodyMixer(n), device=rank)
+        prop = ShardedProposer(qq.IsingEnergyFunction(J, h), qq.GenericMixer.OneBodyMixer(n), device=rank, fused=fused)
         out = [prop.propose(s, gamma, r, u) for (s, gamma, r, u) in cases]
         q.put((rank, out, prop.exchanges))
     finally:
         dist.destroy_process_group()
 
 
-def test_shard_nccl_world2_matches_emulation():
+@pytest.mark.parametrize("fused", [False, True])
+def test_shard_nccl_world2_matches_emulation(fused):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
@@ -122,7 +159,7 @@ def test_shard_nccl_world2_matches_emulation():
         port = sk.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_nccl_worker, args=(rk, world, port, n, cases, q)) for rk in range(world)]
+    procs = [ctx.Process(target=_nccl_worker, args=(rk, world, port, n, cases, q, fused)) for rk in range(world)]
     for p_ in procs:
         p_.start()
     res = sorted((q.get(timeout=600) for _ in range(world)), key=lambda t: t[0])
