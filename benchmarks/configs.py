@@ -75,7 +75,7 @@ def c4():
     print(json.dumps({"config": "C4 n=28 single chain x %d hops (2 GiB complex64 statevector)" % H, "seconds": dt,
                       "proposals_per_s": H / dt, "layers": rs, "algorithmic_GB": alg / 1e9,
                       "algorithmic_GBps": alg / 1e9 / dt, "frac_of_measured_hbm": alg / 1e9 / dt / 6547.8,
-                      "path": "generic sweeps: LO(12) + HI6 groups, ~3 passes per layer"}))
+                      "path": "generic sweeps: LO(12) + HI8 + HI8 qubit groups, 2 passes per layer (B_alg counts 1)"}))
 
 
 def exact():

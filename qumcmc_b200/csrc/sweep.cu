@@ -679,24 +679,97 @@ struct Hi6Args {
     double fx_scale;        // 2^k_fx
 };
 
+// Phase exponent fields of a thread whose six register qubits are p..p+5, evaluated in fp64 from the couplings
+// (Jq[nt*nt], hq[nt] in global memory, L2-resident; no table, any n).  The fixed qubits split into the seven that
+// differ between the threads of a CTA (positions tpos(0..6): lane and warp bits) and the rest, which are CTA-uniform:
+//     A   = A_C + sum_a z_a g_a + sum_{a<a'} Jq[a][a'] z_a z_a'       F_b = f_b + sum_a Jq[a][p+b] z_a
+// with A_C (pair + field sum over the uniform qubits), g_a = hq[a] + sum_c Jq[a][c] z_c and f_b = hq[p+b] +
+// sum_c Jq[c][p+b] z_c computed once per CTA by 77 threads (O(n) each) while the other threads copy the 63
+// thread-level couplings into shared memory; every thread then adds its own 70 terms instead of running the O(n^2)
+// double loop.  Contains a barrier: call from uniform control flow.
+constexpr int AF_SCR = 16 + 64;
+struct IdPos { __device__ __forceinline__ int operator()(int a) const { return a; } };
+__device__ __forceinline__ double jsym(const double *__restrict__ Jq, int nt, int q1, int q2) {
+    return q1 < q2 ? __ldg(Jq + q1 * nt + q2) : __ldg(Jq + q2 * nt + q1);
+}
+template <typename TPOS>
+__device__ __forceinline__ PhaseAF af_factored(const double *__restrict__ Jq, const double *__restrict__ hq, int nt, int p,
+                                               unsigned long long full, TPOS tpos, double fx_scale, int tid, double *scr,
+                                               int active) {
+    unsigned long long tmask = 0ULL;
+#pragma unroll
+    for (int a = 0; a < 7; ++a) tmask |= 1ULL << tpos(a);
+    const unsigned long long cmask = (nt >= 64 ? ~0ULL : ((1ULL << nt) - 1ULL)) & ~(63ULL << p) & ~tmask;
+    if (tid < 64) {  // rows of A_C (qubit tid), reduced per warp
+        double row = 0.0;
+        const int q = tid;
+        if (q < nt && ((cmask >> q) & 1ULL)) {
+            double acc = __ldg(hq + q);
+            for (int q2 = q + 1; q2 < nt; ++q2)
+                if ((cmask >> q2) & 1ULL) acc += ((full >> q2) & 1ULL) ? -__ldg(Jq + q * nt + q2) : __ldg(Jq + q * nt + q2);
+            row = ((full >> q) & 1ULL) ? -acc : acc;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) row += __shfl_xor_sync(0xffffffffu, row, off);
+        if ((tid & 31) == 0) scr[tid >> 5] = row;
+    } else if (tid < 64 + 13) {  // g_a (k < 7), f_b (k >= 7)
+        const int k = tid - 64;
+        const int tq = k < 7 ? tpos(k) : p + (k - 7);
+        double val = __ldg(hq + tq);
+        for (int c = 0; c < nt; ++c)
+            if ((cmask >> c) & 1ULL) val += ((full >> c) & 1ULL) ? -jsym(Jq, nt, c, tq) : jsym(Jq, nt, c, tq);
+        scr[2 + k] = val;
+    } else {  // thread-level couplings: [16 + a(a-1)/2 + a2] = Jq[t_a2][t_a] (a2 < a), [16 + 21 + 6a + b] = Jq[t_a][p+b]
+        for (int e = tid - 77; e < 63; e += NT - 77) {
+            double x;
+            if (e < 21) {
+                int a = 1;
+                while ((a + 1) * a / 2 <= e) ++a;
+                x = jsym(Jq, nt, tpos(e - a * (a - 1) / 2), tpos(a));
+            } else {
+                x = jsym(Jq, nt, tpos((e - 21) / 6), p + (e - 21) % 6);
+            }
+            scr[16 + e] = x;
+        }
+    }
+    __syncthreads();
+    PhaseAF af;
+    af.a0 = make_int4(0, 0, 0, 0);
+    af.a1 = af.a0;
+    if (active) {
+        double A = scr[0] + scr[1], F[6], z[7];
+#pragma unroll
+        for (int b = 0; b < 6; ++b) F[b] = scr[9 + b];
+#pragma unroll
+        for (int a = 0; a < 7; ++a) {
+            z[a] = ((full >> tpos(a)) & 1ULL) ? -1.0 : 1.0;
+            double acc = scr[2 + a];
+#pragma unroll
+            for (int a2 = 0; a2 < a; ++a2) acc += scr[16 + a * (a - 1) / 2 + a2] * z[a2];
+            A += z[a] * acc;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) F[b] += scr[16 + 21 + 6 * a + b] * z[a];
+        }
+        af.a0 = make_int4((int)rint(A * fx_scale), (int)rint(F[0] * fx_scale), (int)rint(F[1] * fx_scale),
+                          (int)rint(F[2] * fx_scale));
+        af.a1 = make_int4((int)rint(F[3] * fx_scale), (int)rint(F[4] * fx_scale), (int)rint(F[5] * fx_scale), 0);
+    }
+    return af;
+}
+
 // PRE = active (top) register qubits of the half-layer before the phase, when it differs from ACT: the sharded path
 // mixes only the g qubits that the preceding all-to-all brought in, then all six after the phase.
 template <int ROLE, int ACT, int PRE = ACT>
 __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, const Hi6Args g, const int *__restrict__ order,
                                                           const int list_off) {
-    extern __shared__ __align__(16) double smd[];  // Jq[n*n], hq[n]
     __shared__ ChainParams cp_s;
     __shared__ __align__(16) int hs_s[64];
+    __shared__ double af_scr[AF_SCR];
     const int tid = threadIdx.x;
     const int n = a.n;
     const int64_t tile = blockIdx.x;
     const int64_t chain = order[list_off + blockIdx.y];
     if (ROLE != HI6_SINGLE) build_hs(hs_s, g.dr, a.params + chain, tid);
-    if (ROLE != HI6_SINGLE) {
-        const int nt_ = a.n_total;
-        for (int i = tid; i < nt_ * nt_; i += NT) smd[i] = g.Jq[i];
-        for (int i = tid; i < nt_; i += NT) smd[nt_ * nt_ + i] = g.hq[i];
-    }
     stage_params(cp_s, a.params + chain, tid);  // barrier inside
     const ChainParams &cp = cp_s;
     const int p = g.p;
@@ -711,42 +784,23 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
     const int nt = a.n_total;
     const int64_t stride = (int64_t)1 << p;
     const HiP qp{p};
-    // phase exponent fields first (fp64, registers still free): A = sum_{a<b fixed} Jq z z + sum_{a fixed} hq z,
-    // F_b = hq[p+b] + sum_{a fixed} Jq[a][p+b] z_a
-    PhaseAF af;
-    af.a0 = make_int4(0, 0, 0, 0);
-    af.a1 = af.a0;
-    if (ROLE != HI6_SINGLE && cp.active) {
-        const double *Jq = smd, *hq = smd + nt * nt;
-        double A = 0.0, F[6];
-#pragma unroll
-        for (int b = 0; b < 6; ++b) F[b] = hq[p + b];
-        for (int q = 0; q < nt; ++q) {
-            if (q >= p && q < p + 6) continue;
-            const double zq = ((full >> q) & 1ULL) ? -1.0 : 1.0;
-            double acc = hq[q];
-            for (int q2 = q + 1; q2 < nt; ++q2) {
-                if (q2 >= p && q2 < p + 6) continue;
-                acc += ((full >> q2) & 1ULL) ? -Jq[q * nt + q2] : Jq[q * nt + q2];
-            }
-            A += zq * acc;
-#pragma unroll
-            for (int b = 0; b < 6; ++b) F[b] += Jq[q * nt + p + b] * zq;
-        }
-        af.a0 = make_int4((int)rint(A * g.fx_scale), (int)rint(F[0] * g.fx_scale), (int)rint(F[1] * g.fx_scale),
-                          (int)rint(F[2] * g.fx_scale));
-        af.a1 = make_int4((int)rint(F[3] * g.fx_scale), (int)rint(F[4] * g.fx_scale), (int)rint(F[5] * g.fx_scale), 0);
-    }
     A64 v[64];
-    if (ROLE == HI6_FIRST) {
-        init_product(v, full, nt, cp, qp);
-    } else {
+    if (ROLE != HI6_FIRST) {  // in flight while the phase exponent fields are evaluated
         const A64 *src = state;
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
             v[j] = *src;
             src += stride;
         }
+    }
+    // phase exponent fields (fp64): A = sum_{a<b fixed} Jq z z + sum_{a fixed} hq z,  F_b = hq[p+b] + sum_{a fixed} Jq[a][p+b] z_a
+    PhaseAF af;
+    af.a0 = make_int4(0, 0, 0, 0);
+    af.a1 = af.a0;
+    if (ROLE != HI6_SINGLE) af = af_factored(g.Jq, g.hq, nt, p, full, IdPos(), g.fx_scale, tid, af_scr, cp.active);
+    if (ROLE == HI6_FIRST) {
+        init_product(v, full, nt, cp, qp);
+    } else {
         bfly6<ACTIVE_PRE>(v, cp, qp);
     }
     if (ROLE != HI6_SINGLE) {
@@ -762,6 +816,107 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
         for (int j = 0; j < 64; ++j) {
             *dst = v[j];
             dst += stride;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// HI8 sweeps: eight qubits [p, p+8) per pass (tile = index bits [0,5) u [p,p+8), 2^13 amplitudes, the geometry of
+// hi_sweep_kernel<8> with a run-time window position), so that a large statevector needs ceil((n-12)/8) + 1 qubit
+// groups instead of ceil((n-12)/6) + 1.
+//   A' layout: regs = qubits p+2..p+7; lane = bits 0..4; warp = qubits (p, p+1)        (HBM loads / stores)
+//   B' layout: regs = qubits p..p+5;   lane = bits 0..4; warp = qubits (p+6, p+7)      (phase + qubits p, p+1)
+// ACT = 7 / 8 active (top) qubits of the window; PRE = qubits mixed before the phase of a MID pass (ACT, or the 1..6
+// top qubits an exchange brought in).  Phase exponent fields as in the HI6 kernels (af_factored, B' layout).
+// ------------------------------------------------------------------------------------------
+enum { HI8_FIRST = 0, HI8_MID = 1, HI8_SINGLE = 2 };
+struct Hi8QA { int p; __device__ __forceinline__ int operator()(int b) const { return p + 2 + b; } };
+struct Hi8QB { int p; __device__ __forceinline__ int operator()(int b) const { return p + b; } };
+struct Hi8TposB { int p; __device__ __forceinline__ int operator()(int a) const { return a < 5 ? a : p + 1 + a; } };
+
+template <int ROLE, int ACT, int PRE>
+__global__ void __launch_bounds__(NT, 3) hi8_sweep_kernel(const SweepArgs a, const Hi6Args g, const int *__restrict__ order,
+                                                          const int list_off) {
+    extern __shared__ __align__(16) float2 sm[];
+    __shared__ ChainParams cp_s;
+    __shared__ __align__(16) int hs_s[64];
+    __shared__ double af_scr[AF_SCR];
+    static_assert(ACT == 7 || ACT == 8, "HI8 windows carry 7 or 8 active qubits");
+    constexpr int MASK_B = ACT == 8 ? 3 : 2;
+    constexpr int PRE_A = PRE >= 6 ? 63 : (63 & ~((1 << (6 - PRE)) - 1));
+    constexpr int PRE_B = PRE == 8 ? 3 : (PRE == 7 ? 2 : 0);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int n = a.n, nt = a.n_total, p = g.p;
+    const int64_t tile = blockIdx.x;
+    const int64_t chain = order[list_off + blockIdx.y];
+    const int low_bits = p - 5;
+    const int64_t base_tile = ((tile & (((int64_t)1 << low_bits) - 1)) << 5) | ((tile >> low_bits) << (p + 8));
+    const int64_t base_a = (int64_t)lane | ((int64_t)(w & 1) << p) | ((int64_t)(w >> 1) << (p + 1)) | base_tile;
+    const int64_t base_b = (int64_t)lane | ((int64_t)(w & 1) << (p + 6)) | ((int64_t)(w >> 1) << (p + 7)) | base_tile;
+    const int64_t stride_a = (int64_t)1 << (p + 2), stride_b = (int64_t)1 << p;
+    A64 *state = reinterpret_cast<A64 *>(a.state + (chain << n));
+    A64 *smv = reinterpret_cast<A64 *>(sm);
+    A64 v[64];
+    if (ROLE != HI8_FIRST) {  // in flight while the parameters and the phase exponent fields are prepared
+        const A64 *src = state + base_a;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            v[j] = *src;
+            src += stride_a;
+        }
+    }
+    if (ROLE != HI8_SINGLE) build_hs(hs_s, g.dr, a.params + chain, tid);
+    stage_params(cp_s, a.params + chain, tid);  // barrier inside
+    const ChainParams &cp = cp_s;
+    const Hi8QA qa{p};
+    const Hi8QB qb{p};
+    const unsigned long long full_b = (unsigned long long)base_b | a.gbits;  // incl. the global (sharded) qubits
+    PhaseAF af;
+    af.a0 = make_int4(0, 0, 0, 0);
+    af.a1 = af.a0;
+    if (ROLE != HI8_SINGLE) af = af_factored(g.Jq, g.hq, nt, p, full_b, Hi8TposB{p}, g.fx_scale, tid, af_scr, cp.active);
+    if (ROLE == HI8_FIRST) {
+        init_product(v, full_b, nt, cp, qb);
+    } else {
+        bfly6 < ROLE == HI8_SINGLE ? 63 : PRE_A > (v, cp, qa);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) smv[hi_loc_a(tid, j)] = v[j];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] = smv[hi_loc_b(tid, j)];
+        bfly6 < ROLE == HI8_SINGLE ? MASK_B : PRE_B > (v, cp, qb);
+    }
+    if (ROLE == HI8_SINGLE) {  // B' keeps the lanes on the 32 lowest amplitudes: store from here
+        if (a.xchg_peers) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) *xchg_addr(a, base_b + j * stride_b) = v[j];
+        } else {
+            A64 *dst = state + base_b;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                *dst = v[j];
+                dst += stride_b;
+            }
+        }
+        return;
+    }
+    phase_gray<false>(v, af, hs_s, g.dr[0], cp);
+    bfly6<MASK_B>(v, cp, qb);
+#pragma unroll
+    for (int j = 0; j < 64; ++j) smv[hi_loc_b(tid, j)] = v[j];  // each thread rewrites exactly the slots it read
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = smv[hi_loc_a(tid, j)];
+    bfly6<63>(v, cp, qa);
+    if (a.xchg_peers) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) *xchg_addr(a, base_a + j * stride_a) = v[j];
+    } else {
+        A64 *dst = state + base_a;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            *dst = v[j];
+            dst += stride_a;
         }
     }
 }
@@ -882,7 +1037,83 @@ __global__ void hop_prepare_kernel(const HopArgs h, ChainParams *params) {
 }
 
 // K3 + K4: one CTA per chain
-__global__ void __launch_bounds__(NT) sample_accept_kernel(const SweepArgs a, const HopArgs h) {
+// Block-cooperative inverse-CDF step: the entry of arr[0..cnt) at which the running sum (fp64, index order) passes the
+// target -- `target` itself, or target * total when `relative` (then target is the uniform in [0,1)).  Thread t owns
+// the contiguous chunk [t * per, (t + 1) * per); results in *s_sel (entry) and *s_rem (target minus the sum before
+// that entry).  Ends with a barrier.
+template <typename T>
+__device__ __forceinline__ void block_pick(const T *__restrict__ arr, int64_t cnt, double target, bool relative, int tid,
+                                           double *s_incl, double *s_warp, long long *s_sel, double *s_rem) {
+    const int64_t per = (cnt + NT - 1) / NT;
+    const int64_t i0 = tid * per < cnt ? tid * per : cnt, i1 = i0 + per < cnt ? i0 + per : cnt;
+    const int last_owner = (int)((cnt - 1) / per);
+    double local = 0.0;
+    for (int64_t i = i0; i < i1; ++i) local += (double)arr[i];
+    double incl = local;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double x = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += x;
+    }
+    __syncthreads();  // previous users of the scratch are done
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    double base = 0.0;
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    incl += base;
+    s_incl[tid] = incl;
+    __syncthreads();
+    if (relative) target *= s_incl[NT - 1];
+    const double lo = tid == 0 ? 0.0 : s_incl[tid - 1];
+    if (tid <= last_owner && target >= lo && (target < incl || tid == last_owner)) {
+        double c = lo;  // cumulative sum before entry i
+        int64_t sel = -1;
+        double before = 0.0;
+        for (int64_t i = i0; i < i1; ++i) {
+            const double x = (double)arr[i];
+            if (target < c + x) {
+                sel = i;
+                before = c;
+                break;
+            }
+            c += x;
+        }
+        if (sel < 0) {  // rounding tail: last entry of this thread
+            sel = i1 - 1;
+            before = c - (double)arr[sel];
+        }
+        *s_sel = sel;
+        *s_rem = target - before;
+    }
+    __syncthreads();
+}
+
+// Large n: sums of COARSE consecutive segment sums, so that the sampler's scan touches 2^(n-18) + 2^12 entries
+// instead of 2^(n-6).  grid = (2^(n-6) / COARSE, chains).
+constexpr int COARSE_BITS = 12, COARSE = 1 << COARSE_BITS;
+__global__ void __launch_bounds__(256) coarse_sums_kernel(const float *__restrict__ segsum, int n, double *__restrict__ coarse) {
+    __shared__ double red[8];
+    const int64_t chain = blockIdx.y;
+    const float4 *src = reinterpret_cast<const float4 *>(segsum + (chain << (n - 6)) + ((int64_t)blockIdx.x << COARSE_BITS));
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < COARSE / 4 / 256; ++i) {
+        const float4 x = src[i * 256 + threadIdx.x];
+        s += ((double)x.x + (double)x.y) + ((double)x.z + (double)x.w);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        coarse[(chain << (n - 6 - COARSE_BITS)) + blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(NT) sample_accept_kernel(const SweepArgs a, const HopArgs h, const double *__restrict__ coarse) {
     extern __shared__ __align__(16) float2 sm[];
     __shared__ ChainParams cp_s;
     __shared__ double s_incl[NT];
@@ -901,46 +1132,16 @@ __global__ void __launch_bounds__(NT) sample_accept_kernel(const SweepArgs a, co
     __syncthreads();
     const ChainParams &cp = cp_s;
     const int64_t nseg = 1LL << (n - 6);
-    const int64_t per = nseg / NT;  // >= 2 for n >= 14
     const float *seg = a.segsum + (chain << (n - 6));
-    double local = 0.0;
-    for (int64_t i = 0; i < per; ++i) local += (double)seg[tid * per + i];
-    double incl = local;
-    const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const double x = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += x;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    double base = 0.0;
-    for (int w = 0; w < warp; ++w) base += s_warp[w];
-    incl += base;
-    s_incl[tid] = incl;
-    __syncthreads();
-    const double total = s_incl[NT - 1];
-    const double target = cp.u_meas * total;
-    const double lo = tid == 0 ? 0.0 : s_incl[tid - 1];
-    if (target >= lo && (target < incl || tid == NT - 1)) {
-        double c = lo;  // cumulative sum before segment i
-        int64_t sel = -1;
-        double before = 0.0;
-        for (int64_t i = 0; i < per; ++i) {
-            const double x = (double)seg[tid * per + i];
-            if (target < c + x) {
-                sel = tid * per + i;
-                before = c;
-                break;
-            }
-            c += x;
-        }
-        if (sel < 0) {  // rounding tail: last segment of this thread
-            sel = tid * per + per - 1;
-            before = c - (double)seg[sel];
-        }
-        s_seg = sel;
-        s_rem = target - before;
+    if (coarse) {  // two levels: coarse block, then the segment inside it
+        block_pick(coarse + (chain << (n - 6 - COARSE_BITS)), nseg >> COARSE_BITS, cp.u_meas, true, tid, s_incl, s_warp,
+                   &s_seg, &s_rem);
+        const int64_t blk = s_seg;
+        const double rem = s_rem;
+        block_pick(seg + (blk << COARSE_BITS), (int64_t)COARSE, rem, false, tid, s_incl, s_warp, &s_seg, &s_rem);
+        if (tid == 0) s_seg += blk << COARSE_BITS;
+    } else {
+        block_pick(seg, nseg, cp.u_meas, true, tid, s_incl, s_warp, &s_seg, &s_rem);
     }
     __syncthreads();
     const int64_t sg = s_seg;
@@ -1060,6 +1261,7 @@ struct SweepWorkspace {
     float2 *state = nullptr;
     ChainParams *params = nullptr;
     float *segsum = nullptr;
+    double *coarse = nullptr;     // n > 20: sums of COARSE consecutive segment sums, [chains][2^(n-18)]
     int *hist = nullptr;
     int *order = nullptr;
     float *tan_sorted = nullptr;  // fast path: per-position mixer multiplier, copied into c_tan[] every hop
@@ -1079,6 +1281,7 @@ void qmc_sweep_free(qmc_model *m) {
     cudaFree(w->state);
     cudaFree(w->params);
     cudaFree(w->segsum);
+    cudaFree(w->coarse);
     cudaFree(w->hist);
     cudaFree(w->order);
     cudaFree(w->tan_sorted);
@@ -1184,12 +1387,13 @@ static int ensure_workspace(qmc_model *m, int64_t chains, cudaStream_t st) {
     }
     if (chains > w->cap_chains) {
         QMC_CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(w->state); cudaFree(w->params); cudaFree(w->segsum); cudaFree(w->hist); cudaFree(w->order); cudaFree(w->tan_sorted);
-        w->state = nullptr; w->params = nullptr; w->segsum = nullptr; w->hist = nullptr; w->order = nullptr; w->tan_sorted = nullptr;
+        cudaFree(w->state); cudaFree(w->params); cudaFree(w->segsum); cudaFree(w->coarse); cudaFree(w->hist); cudaFree(w->order); cudaFree(w->tan_sorted);
+        w->state = nullptr; w->params = nullptr; w->segsum = nullptr; w->coarse = nullptr; w->hist = nullptr; w->order = nullptr; w->tan_sorted = nullptr;
         w->cap_chains = 0;
         QMC_CUDA_TRY(cudaMalloc(&w->state, sizeof(float2) * (size_t)N * chains));
         QMC_CUDA_TRY(cudaMalloc(&w->params, sizeof(ChainParams) * chains));
         QMC_CUDA_TRY(cudaMalloc(&w->segsum, sizeof(float) * (size_t)(N >> 6) * chains));
+        if (n > 20) QMC_CUDA_TRY(cudaMalloc(&w->coarse, sizeof(double) * (size_t)(N >> (6 + COARSE_BITS)) * chains));
         QMC_CUDA_TRY(cudaMalloc(&w->hist, sizeof(int) * (size_t)(n + 1) * chains));
         QMC_CUDA_TRY(cudaMalloc(&w->order, sizeof(int) * (size_t)chains));
         QMC_CUDA_TRY(cudaMalloc(&w->tan_sorted, sizeof(float) * (size_t)chains));
@@ -1279,8 +1483,7 @@ static int launch_hi(const SweepTune &tu, int n, const SweepArgs &a, const int *
 template <int ROLE, int ACT>
 static int launch_hi6_ra(const SweepArgs &a, const Hi6Args &g, const int *order, int off, int64_t tiles, int count,
                          cudaStream_t st) {
-    const size_t smem = ROLE == HI6_SINGLE ? 0 : sizeof(double) * (size_t)(a.n_total * a.n_total + a.n_total);
-    hi6_sweep_kernel<ROLE, ACT><<<dim3((unsigned)tiles, (unsigned)count), NT, smem, st>>>(a, g, order, off);
+    hi6_sweep_kernel<ROLE, ACT><<<dim3((unsigned)tiles, (unsigned)count), NT, 0, st>>>(a, g, order, off);
     return QMC_OK;
 }
 template <int ROLE>
@@ -1301,7 +1504,7 @@ static int launch_hi6(int act, const SweepArgs &a, const Hi6Args &g, const int *
 // MID on the top group of a shard: before the phase only the `pre` swapped-in (top) qubits are mixed
 static int launch_hi6_pre(int pre, const SweepArgs &a, const Hi6Args &g, const int *order, int off, int64_t tiles, int count,
                           cudaStream_t st) {
-    const size_t smem = sizeof(double) * (size_t)(a.n_total * a.n_total + a.n_total);
+    const size_t smem = 0;
     switch (pre) {
         case 1: hi6_sweep_kernel<HI6_MID, 6, 1><<<dim3((unsigned)tiles, (unsigned)count), NT, smem, st>>>(a, g, order, off); return QMC_OK;
         case 2: hi6_sweep_kernel<HI6_MID, 6, 2><<<dim3((unsigned)tiles, (unsigned)count), NT, smem, st>>>(a, g, order, off); return QMC_OK;
@@ -1314,19 +1517,91 @@ static int launch_hi6_pre(int pre, const SweepArgs &a, const Hi6Args &g, const i
     return QMC_ERR_BADARG;
 }
 
-// Sweep list of one proposal with r mixer layers on the generic path (LO group + K >= 2 HI6 groups):
-//   HI6_FIRST(g0); per middle layer: LO_SINGLE, HI6_SINGLE for the other groups, HI6_MID on the next
-//   group (which carries its M into the following layer); last layer: HI6_SINGLE..., LO_FINAL.
-static int run_generic_schedule(int n, int r, const SweepArgs &a, const std::vector<Hi6Args> &groups,
-                                const std::vector<int> &acts, const int *order, int off, int count, int64_t tiles,
-                                cudaStream_t st, int &launched) {
+template <int ROLE, int ACT, int PRE>
+static int launch_hi8_rap(const SweepArgs &a, const Hi6Args &g, const int *order, int off, int64_t tiles, int count,
+                          cudaStream_t st) {
+    static bool done = false;
+    int rc = set_smem_once(hi8_sweep_kernel<ROLE, ACT, PRE>, done);
+    if (rc != QMC_OK) return rc;
+    hi8_sweep_kernel<ROLE, ACT, PRE><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, g, order, off);
+    return QMC_OK;
+}
+template <int ACT>
+static int launch_hi8_mid_pre(int pre, const SweepArgs &a, const Hi6Args &g, const int *order, int off, int64_t tiles,
+                              int count, cudaStream_t st) {
+    switch (pre) {
+        case 1: return launch_hi8_rap<HI8_MID, ACT, 1>(a, g, order, off, tiles, count, st);
+        case 2: return launch_hi8_rap<HI8_MID, ACT, 2>(a, g, order, off, tiles, count, st);
+        case 3: return launch_hi8_rap<HI8_MID, ACT, 3>(a, g, order, off, tiles, count, st);
+        case 4: return launch_hi8_rap<HI8_MID, ACT, 4>(a, g, order, off, tiles, count, st);
+        case 5: return launch_hi8_rap<HI8_MID, ACT, 5>(a, g, order, off, tiles, count, st);
+        case 6: return launch_hi8_rap<HI8_MID, ACT, 6>(a, g, order, off, tiles, count, st);
+    }
+    qmc_set_error("hi8 sweep: %d swapped-in qubits", pre);
+    return QMC_ERR_BADARG;
+}
+
+// One register group above the LO qubits: kind 6 = HI6 window [p, p+6) (register-only pass), kind 8 = HI8 window
+// [p, p+8) (one shared-memory transposition each way); the top `act` qubits of the window are the group's own.
+struct HiGroup {
+    int kind = 6, act = 6;
+    Hi6Args args;
+};
+
+// Geometry for `nl` local qubits, top group first: full HI8 groups stack down from the top; the remainder (1..7
+// qubits) is the lowest group -- an HI8 window with 7 active qubits or an HI6 window with 1..6.
+static void hi_group_geometry(int nl, std::vector<int> &kind, std::vector<int> &pos, std::vector<int> &act) {
+    const int hi = nl - LO_BITS, full8 = hi / 8, rem = hi % 8;
+    for (int k = 0; k < full8; ++k) {
+        kind.push_back(8); pos.push_back(nl - 8 * (k + 1)); act.push_back(8);
+    }
+    if (rem == 7) {
+        kind.push_back(8); pos.push_back(LO_BITS + 7 - 8); act.push_back(7);
+    } else if (rem > 0) {
+        kind.push_back(6); pos.push_back(LO_BITS + rem - 6); act.push_back(rem);
+    }
+}
+
+// ROLE: 0 FIRST | 1 MID | 2 SINGLE (HI6_* == HI8_*).  pre > 0: MID mixes only the top `pre` qubits before the phase;
+// SINGLE mixes only the top `pre` qubits (the ones an exchange brought in).
+template <int ROLE>
+static int launch_group(const HiGroup &G, int pre, const SweepArgs &a, const int *order, int off, int64_t tiles, int count,
+                        cudaStream_t st) {
+    if (G.kind == 6) {
+        if (ROLE == HI6_MID && pre > 0 && pre != G.act) {
+            if (G.act != 6) {
+                qmc_set_error("restricted MID needs a full top group");
+                return QMC_ERR_BADARG;
+            }
+            return launch_hi6_pre(pre, a, G.args, order, off, tiles, count, st);
+        }
+        return launch_hi6<ROLE>(ROLE == HI6_SINGLE && pre > 0 ? pre : G.act, a, G.args, order, off, tiles, count, st);
+    }
+    if (ROLE == HI8_SINGLE && pre > 0) {  // the top `pre` (<= 6) qubits of the window: a register-only pass reaches them
+        Hi6Args g6 = G.args;
+        g6.p = G.args.p + 2;
+        return launch_hi6<HI6_SINGLE>(pre, a, g6, order, off, tiles, count, st);
+    }
+    if (G.act == 8) {
+        if (ROLE == HI8_MID && pre > 0 && pre != 8) return launch_hi8_mid_pre<8>(pre, a, G.args, order, off, tiles, count, st);
+        return launch_hi8_rap<ROLE, 8, 8>(a, G.args, order, off, tiles, count, st);
+    }
+    if (ROLE == HI8_MID && pre > 0 && pre != 7) return launch_hi8_mid_pre<7>(pre, a, G.args, order, off, tiles, count, st);
+    return launch_hi8_rap<ROLE, 7, 7>(a, G.args, order, off, tiles, count, st);
+}
+
+// Sweep list of one proposal with r mixer layers on the generic path (LO group + K >= 2 register groups):
+//   FIRST(g0); per middle layer: LO_SINGLE, SINGLE for the other groups, MID on the next group (which carries
+//   its M into the following layer); last layer: SINGLE..., LO_FINAL.  K passes per layer for K + 1 qubit groups.
+static int run_generic_schedule(int n, int r, const SweepArgs &a, const std::vector<HiGroup> &groups, const int *order,
+                                int off, int count, int64_t tiles, cudaStream_t st, int &launched) {
     int rc = QMC_OK;
     const int K = (int)groups.size();
     if (r <= 1) {
         ++launched;
         return launch_lo<LO_FINAL1>(SweepTune(), a, order, off, tiles, count, st);
     }
-    rc = launch_hi6<HI6_FIRST>(acts[0], a, groups[0], order, off, tiles, count, st);
+    rc = launch_group<HI6_FIRST>(groups[0], 0, a, order, off, tiles, count, st);
     ++launched;
     int carried = 0;
     for (int layer = 2; layer <= r && rc == QMC_OK; ++layer) {
@@ -1338,12 +1613,12 @@ static int run_generic_schedule(int n, int r, const SweepArgs &a, const std::vec
         }
         for (int k = 0; k < K && rc == QMC_OK; ++k) {
             if (k == carried || (!last && k == mid)) continue;
-            rc = launch_hi6<HI6_SINGLE>(acts[k], a, groups[k], order, off, tiles, count, st);
+            rc = launch_group<HI6_SINGLE>(groups[k], 0, a, order, off, tiles, count, st);
             ++launched;
         }
         if (rc != QMC_OK) break;
         if (!last) {
-            rc = launch_hi6<HI6_MID>(acts[mid], a, groups[mid], order, off, tiles, count, st);
+            rc = launch_group<HI6_MID>(groups[mid], 0, a, order, off, tiles, count, st);
             carried = mid;
         } else {
             rc = launch_lo<LO_FINAL>(SweepTune(), a, order, off, tiles, count, st);
@@ -1389,22 +1664,21 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     int rc = ensure_workspace(m, batch, st);
     if (rc != QMC_OK) return rc;
     SweepWorkspace *w = m->sweep;
-    std::vector<Hi6Args> groups;
-    std::vector<int> acts;
+    std::vector<HiGroup> groups;
     if (generic) {
-        const int hi_qubits = n - LO_BITS;
-        const int K = (hi_qubits + 5) / 6;
-        for (int k = 0; k < K; ++k) {
-            Hi6Args g;
-            const bool last = (k == K - 1);
-            g.p = last ? n - 6 : LO_BITS + 6 * k;
-            acts.push_back(last ? hi_qubits - 6 * (K - 1) : 6);
-            const int pos[6] = {g.p, g.p + 1, g.p + 2, g.p + 3, g.p + 4, g.p + 5};
-            gray_increments(w->Jq, n, w->fx_scale, pos, g.dr);
-            g.Jq = w->dJq;
-            g.hq = w->dhq;
-            g.fx_scale = w->fx_scale;
-            groups.push_back(g);
+        std::vector<int> kind, pos, act;
+        hi_group_geometry(n, kind, pos, act);
+        for (size_t k = 0; k < kind.size(); ++k) {
+            HiGroup G;
+            G.kind = kind[k];
+            G.act = act[k];
+            G.args.p = pos[k];
+            const int rp[6] = {pos[k], pos[k] + 1, pos[k] + 2, pos[k] + 3, pos[k] + 4, pos[k] + 5};
+            gray_increments(w->Jq, n, w->fx_scale, rp, G.args.dr);
+            G.args.Jq = w->dJq;
+            G.args.hq = w->dhq;
+            G.args.fx_scale = w->fx_scale;
+            groups.push_back(G);
         }
     }
 
@@ -1535,7 +1809,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                 int off = 0;
                 for (int r = r_max; r >= 1; --r) {
                     if (rhist[r] == 0) continue;
-                    rc = run_generic_schedule(n, r, a, groups, acts, w->order, off, rhist[r], tiles, st, launched);
+                    rc = run_generic_schedule(n, r, a, groups, w->order, off, rhist[r], tiles, st, launched);
                     if (rc != QMC_OK) return rc;
                     off += rhist[r];
                 }
@@ -1583,7 +1857,11 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                 probs_normalize_kernel<<<148 * 4, 256, 0, st>>>(n, w->segsum, a.probs_out, a.amps_out);
                 m->launches++;
             } else {
-                sample_accept_kernel<<<(unsigned)nc, NT, TILE * 8, st>>>(a, h);
+                if (generic) {
+                    coarse_sums_kernel<<<dim3((unsigned)(N >> (6 + COARSE_BITS)), (unsigned)nc), 256, 0, st>>>(w->segsum, n, w->coarse);
+                    ++m->launches;
+                }
+                sample_accept_kernel<<<(unsigned)nc, NT, TILE * 8, st>>>(a, h, generic ? w->coarse : nullptr);
                 m->launches++;
             }
             QMC_CUDA_TRY(cudaGetLastError());
@@ -1629,7 +1907,7 @@ struct qmc_shard {
     double *dJq[2] = {nullptr, nullptr}, *dhq[2] = {nullptr, nullptr};
     std::vector<double> Jq[2], hq[2];
     std::vector<int> perm[2];       // perm[layout][position] = logical qubit
-    std::vector<Hi6Args> groups[2];
+    std::vector<HiGroup> groups[2];
     std::vector<int> acts;
     double fx_scale = 1.0;
     int k_fx = 0;
@@ -1797,15 +2075,11 @@ extern "C" int qmc_shard_create(qmc_shard **out, qmc_model *m, int rank, int log
     sh->k_fx = (int)floor(log2(2147483647.0 / (dmax * 1.0000001))) - 1;
     if (sh->k_fx > 30) sh->k_fx = 30;
     sh->fx_scale = ldexp(1.0, sh->k_fx);
-    // group geometry (positions): top group full, the partial group lowest; LO = positions 0..11
-    const int hi_qubits = nl - LO_BITS, K = (hi_qubits + 5) / 6;
-    std::vector<int> ps;
-    for (int k = 0; k < K; ++k) {  // k = 0 is the top group
-        const bool lowest = (k == K - 1);
-        const int act = lowest ? hi_qubits - 6 * (K - 1) : 6;
-        ps.push_back(lowest ? LO_BITS + act - 6 : nl - 6 * (k + 1));
-        sh->acts.push_back(act);
-    }
+    // group geometry (positions): full HI8 groups from the top, the partial group lowest; LO = positions 0..11
+    std::vector<int> kinds, ps;
+    hi_group_geometry(nl, kinds, ps, sh->acts);
+    const int K = (int)kinds.size();
+    QMC_REQUIRE(g <= sh->acts[0] && g <= 6, QMC_ERR_UNSUPPORTED, "sharded statevector: 2^%d ranks need a top group of >= %d qubits", g, g);
     for (int L = 0; L < 2; ++L) {
         sh->perm[L].resize(n);
         for (int a = 0; a < n; ++a) sh->perm[L][a] = a;
@@ -1822,14 +2096,17 @@ extern "C" int qmc_shard_create(qmc_shard **out, qmc_model *m, int rank, int log
         QMC_CUDA_TRY(cudaMemcpy(sh->dJq[L], sh->Jq[L].data(), sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
         QMC_CUDA_TRY(cudaMemcpy(sh->dhq[L], sh->hq[L].data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
         for (int k = 0; k < K; ++k) {
-            Hi6Args ga;
+            HiGroup G;
+            G.kind = kinds[k];
+            G.act = sh->acts[k];
+            Hi6Args &ga = G.args;
             ga.p = ps[k];
             const int pos[6] = {ga.p, ga.p + 1, ga.p + 2, ga.p + 3, ga.p + 4, ga.p + 5};
             gray_increments(sh->Jq[L], n, sh->fx_scale, pos, ga.dr);
             ga.Jq = sh->dJq[L];
             ga.hq = sh->dhq[L];
             ga.fx_scale = sh->fx_scale;
-            sh->groups[L].push_back(ga);
+            sh->groups[L].push_back(G);
         }
     }
     QMC_CUDA_TRY(cudaMalloc(&sh->params, sizeof(ChainParams)));
@@ -1892,19 +2169,19 @@ static int shard_op_impl(qmc_shard *sh, int op, int k, int pre, int layout, void
         a.xchg_rank = sh->rank;
     }
     const int64_t tiles = (int64_t)1 << (sh->nl - TILE_BITS);
-    const Hi6Args &ga = sh->groups[layout][k];
+    const HiGroup &G = sh->groups[layout][k];
     int rc = QMC_OK;
     switch (op) {
         case 0:
             QMC_REQUIRE(k == 0, QMC_ERR_BADARG, "qmc_shard_op: FIRST runs on the top group");
-            rc = launch_hi6<HI6_FIRST>(6, a, ga, sh->order, 0, tiles, 1, st);
+            rc = launch_group<HI6_FIRST>(G, 0, a, sh->order, 0, tiles, 1, st);
             break;
         case 1:
             QMC_REQUIRE(k == 0 && pre == sh->g, QMC_ERR_BADARG, "qmc_shard_op: MID runs on the top group with pre = log2(world)");
-            rc = launch_hi6_pre(pre, a, ga, sh->order, 0, tiles, 1, st);
+            rc = launch_group<HI6_MID>(G, pre, a, sh->order, 0, tiles, 1, st);
             break;
         case 2:
-            rc = launch_hi6<HI6_SINGLE>(k == 0 && pre > 0 ? pre : sh->acts[k], a, ga, sh->order, 0, tiles, 1, st);
+            rc = launch_group<HI6_SINGLE>(G, k == 0 ? pre : 0, a, sh->order, 0, tiles, 1, st);
             break;
         case 3:
             rc = launch_lo<LO_SINGLE>(SweepTune(), a, sh->order, 0, tiles, 1, st);

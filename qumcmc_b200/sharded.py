@@ -28,7 +28,7 @@ _OPCODE = {FIRST: _lib.SHARD_OP_FIRST, MID: _lib.SHARD_OP_MID, SINGLE: _lib.SHAR
 def sharded_plan(r: int, n_groups: int, log2_world: int) -> List[Tuple[str, int, int]]:
     """Op list ``(kind, group, pre)`` of one proposal with ``r`` mixer layers.
 
-    Positions 0..11 are the LO group; ``n_groups`` register groups of 6 cover the remaining local positions, group 0
+    Positions 0..11 are the LO group; ``n_groups`` register groups of up to 8 cover the remaining local positions, group 0
     on top (it contains the ``g`` positions an exchange swaps with the rank bits).  Layer 1 is analytic (FIRST builds
     M|s> over all n qubits).  Every later layer j: the top group was mixed by the preceding FIRST/MID pass (after
     its phase), the other groups by SINGLE passes, the g global qubits after the exchange brought them in -- as the
@@ -55,16 +55,13 @@ def sharded_plan(r: int, n_groups: int, log2_world: int) -> List[Tuple[str, int,
 
 
 def shard_geometry(n_local: int) -> List[Tuple[int, int]]:
-    """Active position range [lo, hi) of every register group, top group first (mirrors qmc_shard_create):
-    positions 0..11 belong to the LO passes, full groups of 6 stack down from the top, the partial group is lowest."""
+    """Active position range [lo, hi) of every register group, top group first (mirrors hi_group_geometry in
+    csrc/sweep.cu): positions 0..11 belong to the LO passes, full groups of 8 (HI8 passes) stack down from the top,
+    the remaining 1..7 positions form the lowest group."""
     hi_qubits = n_local - 12
-    K = (hi_qubits + 5) // 6
-    out = []
-    for k in range(K):
-        if k == K - 1:
-            out.append((12, 12 + hi_qubits - 6 * (K - 1)))
-        else:
-            out.append((n_local - 6 * (k + 1), n_local - 6 * k))
+    out = [(n_local - 8 * (k + 1), n_local - 8 * k) for k in range(hi_qubits // 8)]
+    if hi_qubits % 8:
+        out.append((12, 12 + hi_qubits % 8))
     return out
 
 

@@ -59,7 +59,7 @@ def test_sweep_gamma_extremes_and_skip_rule():
     assert np.abs(p - ref).max() < 1e-6
 
 
-@pytest.mark.parametrize("n,C", [(14, 96), (16, 64), (20, 24)])
+@pytest.mark.parametrize("n,C", [(14, 96), (16, 64), (20, 24), (22, 8), (25, 3)])   # n > 20: two-level (coarse) scan
 def test_sweep_propose_indices(n, C):
     """qmc_propose with explicit (s, gamma, r, u): the sampled index equals the oracle's sequential
     inverse CDF except where u sits within fp32 rounding of a CDF boundary."""
@@ -169,8 +169,8 @@ def test_unsupported_configurations_fail_loudly():
 
 @pytest.mark.parametrize("n,rs", [(21, (1, 2, 3, 6)), (22, (2, 5)), (23, (3, 4)), (24, (2, 7)), (25, (3,)), (26, (4,))])
 def test_generic_path_transition_probabilities(n, rs):
-    """n >= 21: LO group + K >= 2 register-only HI6 groups (every ACT / group-count combination up to
-    n = 26), vs the oracle's fused simulator."""
+    """n >= 21: LO group + an HI8 group + a partial HI6 group with 1..6 active qubits (n = 21..26), vs the
+    oracle's fused simulator.  (HI8 windows with 7 active qubits: tests/test_gpu_shard.py, 19 local qubits.)"""
     q, J, h, m, mx, masks, w = _setup(n, seed=2)
     al = oracle.alpha(J, h)
     rng = np.random.default_rng(n)

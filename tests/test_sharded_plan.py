@@ -59,7 +59,8 @@ def test_geometry_covers_every_local_position_once():
         for lo, hi in shard_geometry(nl):
             covered += list(range(lo, hi))
         assert sorted(covered) == list(range(nl))
-        assert shard_geometry(nl)[0] == (nl - 6, nl)
+        top = shard_geometry(nl)[0]
+        assert top[1] == nl and top[1] - top[0] >= 6                     # the top group holds the exchanged positions
 
 
 def test_pick_owner_is_the_sequential_cdf():
