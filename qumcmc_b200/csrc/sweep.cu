@@ -677,84 +677,90 @@ struct Hi6Args {
     int dr[64];     // Gray-order increments of R(j) for this group
     const double *Jq, *hq;  // circuit couplings in qubit order
     double fx_scale;        // 2^k_fx
+    const double *cta_tab;  // [tiles][AF_CTA_STRIDE] tile-uniform phase exponent fields (af_cta_table_kernel)
+    const double *thr_tab;  // [NT][AF_THR_STRIDE] thread-level sums
 };
 
-// Phase exponent fields of a thread whose six register qubits are p..p+5, evaluated in fp64 from the couplings
-// (Jq[nt*nt], hq[nt] in global memory, L2-resident; no table, any n).  The fixed qubits split into the seven that
-// differ between the threads of a CTA (positions tpos(0..6): lane and warp bits) and the rest, which are CTA-uniform:
+// Phase exponent fields of a thread whose six register qubits are p..p+5 (no per-thread table, any n).  The fixed
+// qubits split into the seven that differ between the threads of a CTA (positions tpos(0..6): lane and warp bits)
+// and the rest, which are uniform over the CTA (= the tile):
 //     A   = A_C + sum_a z_a g_a + sum_{a<a'} Jq[a][a'] z_a z_a'       F_b = f_b + sum_a Jq[a][p+b] z_a
 // with A_C (pair + field sum over the uniform qubits), g_a = hq[a] + sum_c Jq[a][c] z_c and f_b = hq[p+b] +
-// sum_c Jq[c][p+b] z_c computed once per CTA by 77 threads (O(n) each) while the other threads copy the 63
-// thread-level couplings into shared memory; every thread then adds its own 70 terms instead of running the O(n^2)
-// double loop.  Contains a barrier: call from uniform control flow.
-constexpr int AF_SCR = 16 + 64;
-struct IdPos { __device__ __forceinline__ int operator()(int a) const { return a; } };
-__device__ __forceinline__ double jsym(const double *__restrict__ Jq, int nt, int q1, int q2) {
-    return q1 < q2 ? __ldg(Jq + q1 * nt + q2) : __ldg(Jq + q2 * nt + q1);
+// sum_c Jq[c][p+b] z_c.  The 14 per-tile values depend on the couplings and the geometry only, so they are tabulated
+// once per (group, layout) by af_cta_table_kernel (16 doubles per tile, 1/512 of the state's size).
+constexpr int AF_SCR = 16;
+constexpr int AF_CTA_STRIDE = 16;  // doubles per tile: g_a[7], f_b[6], A_C, pad
+constexpr int AF_THR_STRIDE = 8;   // doubles per thread: P (pair sum over the thread bits), Q_b[6], pad
+// The thread-level sums depend on the thread index only: P(tid) = sum_{a<a'} Jq[a][a'] z_a z_a' and Q_b(tid) =
+// sum_a Jq[a][p+b] z_a are a static [128][8] table per group, so a thread adds 7 + 6 fp64 terms:
+//     A = A_C + P(tid) + sum_a z_a g_a        F_b = f_b + Q_b(tid)
+// af_fetch (before the staging barrier): tile row -> scr, the thread's own table row -> its slot of thr_s.
+__device__ __forceinline__ void af_fetch(double *scr, double *thr_s, const double *__restrict__ cta_tab,
+                                         const double *__restrict__ thr_tab, int64_t tile, int tid) {
+    if (tid < 14) scr[tid] = __ldg(cta_tab + tile * AF_CTA_STRIDE + tid);
+    const double2 *src = reinterpret_cast<const double2 *>(thr_tab + tid * AF_THR_STRIDE);
+    double2 *dst = reinterpret_cast<double2 *>(thr_s + tid * AF_THR_STRIDE);
+#pragma unroll
+    for (int i = 0; i < AF_THR_STRIDE / 2; ++i) dst[i] = __ldg(src + i);
 }
-template <typename TPOS>
-__device__ __forceinline__ PhaseAF af_factored(const double *__restrict__ Jq, const double *__restrict__ hq, int nt, int p,
-                                               unsigned long long full, TPOS tpos, double fx_scale, int tid, double *scr,
-                                               int active) {
-    unsigned long long tmask = 0ULL;
-#pragma unroll
-    for (int a = 0; a < 7; ++a) tmask |= 1ULL << tpos(a);
-    const unsigned long long cmask = (nt >= 64 ? ~0ULL : ((1ULL << nt) - 1ULL)) & ~(63ULL << p) & ~tmask;
-    if (tid < 64) {  // rows of A_C (qubit tid), reduced per warp
-        double row = 0.0;
-        const int q = tid;
-        if (q < nt && ((cmask >> q) & 1ULL)) {
-            double acc = __ldg(hq + q);
-            for (int q2 = q + 1; q2 < nt; ++q2)
-                if ((cmask >> q2) & 1ULL) acc += ((full >> q2) & 1ULL) ? -__ldg(Jq + q * nt + q2) : __ldg(Jq + q * nt + q2);
-            row = ((full >> q) & 1ULL) ? -acc : acc;
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) row += __shfl_xor_sync(0xffffffffu, row, off);
-        if ((tid & 31) == 0) scr[tid >> 5] = row;
-    } else if (tid < 64 + 13) {  // g_a (k < 7), f_b (k >= 7)
-        const int k = tid - 64;
-        const int tq = k < 7 ? tpos(k) : p + (k - 7);
-        double val = __ldg(hq + tq);
-        for (int c = 0; c < nt; ++c)
-            if ((cmask >> c) & 1ULL) val += ((full >> c) & 1ULL) ? -jsym(Jq, nt, c, tq) : jsym(Jq, nt, c, tq);
-        scr[2 + k] = val;
-    } else {  // thread-level couplings: [16 + a(a-1)/2 + a2] = Jq[t_a2][t_a] (a2 < a), [16 + 21 + 6a + b] = Jq[t_a][p+b]
-        for (int e = tid - 77; e < 63; e += NT - 77) {
-            double x;
-            if (e < 21) {
-                int a = 1;
-                while ((a + 1) * a / 2 <= e) ++a;
-                x = jsym(Jq, nt, tpos(e - a * (a - 1) / 2), tpos(a));
-            } else {
-                x = jsym(Jq, nt, tpos((e - 21) / 6), p + (e - 21) % 6);
-            }
-            scr[16 + e] = x;
-        }
-    }
-    __syncthreads();
+__device__ __forceinline__ PhaseAF af_thread(const double *scr, const double *thr_s, int tid, double fx_scale, int active) {
     PhaseAF af;
     af.a0 = make_int4(0, 0, 0, 0);
     af.a1 = af.a0;
     if (active) {
-        double A = scr[0] + scr[1], F[6], z[7];
+        const double2 *row = reinterpret_cast<const double2 *>(thr_s + tid * AF_THR_STRIDE);
+        const double2 r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3];  // P Q0 | Q1 Q2 | Q3 Q4 | Q5 -
+        double A = scr[13] + r0.x;
 #pragma unroll
-        for (int b = 0; b < 6; ++b) F[b] = scr[9 + b];
-#pragma unroll
-        for (int a = 0; a < 7; ++a) {
-            z[a] = ((full >> tpos(a)) & 1ULL) ? -1.0 : 1.0;
-            double acc = scr[2 + a];
-#pragma unroll
-            for (int a2 = 0; a2 < a; ++a2) acc += scr[16 + a * (a - 1) / 2 + a2] * z[a2];
-            A += z[a] * acc;
-#pragma unroll
-            for (int b = 0; b < 6; ++b) F[b] += scr[16 + 21 + 6 * a + b] * z[a];
-        }
-        af.a0 = make_int4((int)rint(A * fx_scale), (int)rint(F[0] * fx_scale), (int)rint(F[1] * fx_scale),
-                          (int)rint(F[2] * fx_scale));
-        af.a1 = make_int4((int)rint(F[3] * fx_scale), (int)rint(F[4] * fx_scale), (int)rint(F[5] * fx_scale), 0);
+        for (int a = 0; a < 7; ++a) A += ((tid >> a) & 1) ? -scr[a] : scr[a];
+        af.a0 = make_int4((int)rint(A * fx_scale), (int)rint((scr[7] + r0.y) * fx_scale), (int)rint((scr[8] + r1.x) * fx_scale),
+                          (int)rint((scr[9] + r1.y) * fx_scale));
+        af.a1 = make_int4((int)rint((scr[10] + r2.x) * fx_scale), (int)rint((scr[11] + r2.y) * fx_scale),
+                          (int)rint((scr[12] + r3.x) * fx_scale), 0);
     }
     return af;
+}
+
+// Index bits that are uniform over the CTA of `tile`: kind 6 = HI6 geometry (thread bits 0..6, register window
+// [p, p+6)), kind 8 = HI8 geometry (thread bits 0..4 and p+6, p+7; window [p, p+8)).
+__host__ __device__ __forceinline__ unsigned long long hi_tile_base(int kind, int p, int64_t tile) {
+    const int low_bits = kind == 6 ? p - 7 : p - 5;
+    const unsigned long long t = (unsigned long long)tile;
+    return ((t & ((1ULL << low_bits) - 1ULL)) << (kind == 6 ? 7 : 5)) | ((t >> low_bits) << (kind == 6 ? p + 6 : p + 8));
+}
+__host__ __device__ __forceinline__ int hi_thread_pos(int kind, int p, int a) { return (kind == 6 || a < 5) ? a : p + 1 + a; }
+
+// One thread per tile: the 14 tile-uniform fields (fp64, fixed summation order).
+__global__ void af_cta_table_kernel(int kind, int p, int nt, unsigned long long gbits, const double *__restrict__ Jq,
+                                    const double *__restrict__ hq, int64_t tiles, double *__restrict__ out) {
+    const int64_t tile = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (tile >= tiles) return;
+    const unsigned long long full = hi_tile_base(kind, p, tile) | gbits;
+    unsigned long long tmask = 0ULL;
+    for (int a = 0; a < 7; ++a) tmask |= 1ULL << hi_thread_pos(kind, p, a);
+    const unsigned long long cmask = (nt >= 64 ? ~0ULL : ((1ULL << nt) - 1ULL)) & ~(63ULL << p) & ~tmask;
+    double AC = 0.0;
+    for (int q = 0; q < nt; ++q) {
+        if (!((cmask >> q) & 1ULL)) continue;
+        double acc = hq[q];
+        for (int q2 = q + 1; q2 < nt; ++q2)
+            if ((cmask >> q2) & 1ULL) acc += ((full >> q2) & 1ULL) ? -Jq[q * nt + q2] : Jq[q * nt + q2];
+        AC += ((full >> q) & 1ULL) ? -acc : acc;
+    }
+    double *o = out + tile * AF_CTA_STRIDE;
+    for (int k = 0; k < 13; ++k) {
+        const int tq = k < 7 ? hi_thread_pos(kind, p, k) : p + (k - 7);
+        double val = hq[tq];
+        for (int c = 0; c < nt; ++c) {
+            if (!((cmask >> c) & 1ULL)) continue;
+            const double j = c < tq ? Jq[c * nt + tq] : Jq[tq * nt + c];
+            val += ((full >> c) & 1ULL) ? -j : j;
+        }
+        o[k] = val;
+    }
+    o[13] = AC;
+    o[14] = 0.0;
+    o[15] = 0.0;
 }
 
 // PRE = active (top) register qubits of the half-layer before the phase, when it differs from ACT: the sharded path
@@ -765,11 +771,13 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
     __shared__ ChainParams cp_s;
     __shared__ __align__(16) int hs_s[64];
     __shared__ double af_scr[AF_SCR];
+    __shared__ __align__(16) double thr_s[ROLE != HI6_SINGLE ? NT * AF_THR_STRIDE : 2];
     const int tid = threadIdx.x;
     const int n = a.n;
     const int64_t tile = blockIdx.x;
     const int64_t chain = order[list_off + blockIdx.y];
     if (ROLE != HI6_SINGLE) build_hs(hs_s, g.dr, a.params + chain, tid);
+    if (ROLE != HI6_SINGLE) af_fetch(af_scr, thr_s, g.cta_tab, g.thr_tab, tile, tid);
     stage_params(cp_s, a.params + chain, tid);  // barrier inside
     const ChainParams &cp = cp_s;
     const int p = g.p;
@@ -797,7 +805,7 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
     PhaseAF af;
     af.a0 = make_int4(0, 0, 0, 0);
     af.a1 = af.a0;
-    if (ROLE != HI6_SINGLE) af = af_factored(g.Jq, g.hq, nt, p, full, IdPos(), g.fx_scale, tid, af_scr, cp.active);
+    if (ROLE != HI6_SINGLE) af = af_thread(af_scr, thr_s, tid, g.fx_scale, cp.active);
     if (ROLE == HI6_FIRST) {
         init_product(v, full, nt, cp, qp);
     } else {
@@ -827,12 +835,11 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
 //   A' layout: regs = qubits p+2..p+7; lane = bits 0..4; warp = qubits (p, p+1)        (HBM loads / stores)
 //   B' layout: regs = qubits p..p+5;   lane = bits 0..4; warp = qubits (p+6, p+7)      (phase + qubits p, p+1)
 // ACT = 7 / 8 active (top) qubits of the window; PRE = qubits mixed before the phase of a MID pass (ACT, or the 1..6
-// top qubits an exchange brought in).  Phase exponent fields as in the HI6 kernels (af_factored, B' layout).
+// top qubits an exchange brought in).  Phase exponent fields as in the HI6 kernels (af_thread, B' layout).
 // ------------------------------------------------------------------------------------------
 enum { HI8_FIRST = 0, HI8_MID = 1, HI8_SINGLE = 2 };
 struct Hi8QA { int p; __device__ __forceinline__ int operator()(int b) const { return p + 2 + b; } };
 struct Hi8QB { int p; __device__ __forceinline__ int operator()(int b) const { return p + b; } };
-struct Hi8TposB { int p; __device__ __forceinline__ int operator()(int a) const { return a < 5 ? a : p + 1 + a; } };
 
 template <int ROLE, int ACT, int PRE>
 __global__ void __launch_bounds__(NT, 3) hi8_sweep_kernel(const SweepArgs a, const Hi6Args g, const int *__restrict__ order,
@@ -841,6 +848,7 @@ __global__ void __launch_bounds__(NT, 3) hi8_sweep_kernel(const SweepArgs a, con
     __shared__ ChainParams cp_s;
     __shared__ __align__(16) int hs_s[64];
     __shared__ double af_scr[AF_SCR];
+    __shared__ __align__(16) double thr_s[ROLE != HI8_SINGLE ? NT * AF_THR_STRIDE : 2];
     static_assert(ACT == 7 || ACT == 8, "HI8 windows carry 7 or 8 active qubits");
     constexpr int MASK_B = ACT == 8 ? 3 : 2;
     constexpr int PRE_A = PRE >= 6 ? 63 : (63 & ~((1 << (6 - PRE)) - 1));
@@ -865,7 +873,15 @@ __global__ void __launch_bounds__(NT, 3) hi8_sweep_kernel(const SweepArgs a, con
             src += stride_a;
         }
     }
+    if (ROLE != HI8_FIRST) {  // L2 prefetch of the tile a later CTA will read: 2^8 rows of 32 contiguous amplitudes
+        int64_t pc, pt;
+        if (pf_target(a, order, list_off, pc, pt)) {
+            const float2 *src = a.state + (pc << n) + (int64_t)hi_tile_base(8, p, pt);
+            for (int r = tid; r < 256; r += NT) l2_prefetch_bulk(src + ((int64_t)r << p), 256);
+        }
+    }
     if (ROLE != HI8_SINGLE) build_hs(hs_s, g.dr, a.params + chain, tid);
+    if (ROLE != HI8_SINGLE) af_fetch(af_scr, thr_s, g.cta_tab, g.thr_tab, tile, tid);
     stage_params(cp_s, a.params + chain, tid);  // barrier inside
     const ChainParams &cp = cp_s;
     const Hi8QA qa{p};
@@ -874,7 +890,7 @@ __global__ void __launch_bounds__(NT, 3) hi8_sweep_kernel(const SweepArgs a, con
     PhaseAF af;
     af.a0 = make_int4(0, 0, 0, 0);
     af.a1 = af.a0;
-    if (ROLE != HI8_SINGLE) af = af_factored(g.Jq, g.hq, nt, p, full_b, Hi8TposB{p}, g.fx_scale, tid, af_scr, cp.active);
+    if (ROLE != HI8_SINGLE) af = af_thread(af_scr, thr_s, tid, g.fx_scale, cp.active);
     if (ROLE == HI8_FIRST) {
         init_product(v, full_b, nt, cp, qb);
     } else {
@@ -1256,6 +1272,65 @@ __global__ void af_table_kernel(int n, const double *__restrict__ Jq, const doub
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+// One register group above the LO qubits: kind 6 = HI6 window [p, p+6) (register-only pass), kind 8 = HI8 window
+// [p, p+8) (one shared-memory transposition each way); the top `act` qubits of the window are the group's own.
+struct HiGroup {
+    int kind = 6, act = 6;
+    Hi6Args args;
+};
+
+// Geometry for `nl` local qubits, top group first: full HI8 groups stack down from the top; the remainder (1..7
+// qubits) is the lowest group -- an HI8 window with 7 active qubits or an HI6 window with 1..6.
+static void hi_group_geometry(int nl, std::vector<int> &kind, std::vector<int> &pos, std::vector<int> &act) {
+    const int hi = nl - LO_BITS, full8 = hi / 8, rem = hi % 8;
+    for (int k = 0; k < full8; ++k) {
+        kind.push_back(8); pos.push_back(nl - 8 * (k + 1)); act.push_back(8);
+    }
+    if (rem == 7) {
+        kind.push_back(8); pos.push_back(LO_BITS + 7 - 8); act.push_back(7);
+    } else if (rem > 0) {
+        kind.push_back(6); pos.push_back(LO_BITS + rem - 6); act.push_back(rem);
+    }
+}
+
+// Tables of one group (see af_thread): tile-uniform fields on the device, thread-level couplings from the host copy.
+static int build_group_tables(HiGroup &G, int nl, int nt, unsigned long long gbits, const std::vector<double> &Jq_host,
+                              cudaStream_t st) {
+    const int64_t tiles = (int64_t)1 << (nl - TILE_BITS);
+    double *cta = nullptr, *thr = nullptr;
+    QMC_CUDA_TRY(cudaMalloc(&cta, sizeof(double) * AF_CTA_STRIDE * (size_t)tiles));
+    QMC_CUDA_TRY(cudaMalloc(&thr, sizeof(double) * NT * AF_THR_STRIDE));
+    G.args.cta_tab = cta;
+    G.args.thr_tab = thr;
+    const int p = G.args.p;
+    af_cta_table_kernel<<<(unsigned)((tiles + 127) / 128), 128, 0, st>>>(G.kind, p, nt, gbits, G.args.Jq, G.args.hq, tiles, cta);
+    QMC_CUDA_TRY(cudaGetLastError());
+    std::vector<double> h((size_t)NT * AF_THR_STRIDE, 0.0);
+    auto J = [&](int q1, int q2) { return q1 < q2 ? Jq_host[(size_t)q1 * nt + q2] : Jq_host[(size_t)q2 * nt + q1]; };
+    for (int t = 0; t < NT; ++t) {  // thread bit a <-> index position hi_thread_pos(kind, p, a)
+        double z[7];
+        for (int a = 0; a < 7; ++a) z[a] = ((t >> a) & 1) ? -1.0 : 1.0;
+        double P = 0.0;
+        for (int a = 1; a < 7; ++a)
+            for (int a2 = 0; a2 < a; ++a2) P += J(hi_thread_pos(G.kind, p, a2), hi_thread_pos(G.kind, p, a)) * z[a2] * z[a];
+        h[(size_t)t * AF_THR_STRIDE] = P;
+        for (int b2 = 0; b2 < 6; ++b2) {
+            double Q = 0.0;
+            for (int a = 0; a < 7; ++a) Q += J(hi_thread_pos(G.kind, p, a), p + b2) * z[a];
+            h[(size_t)t * AF_THR_STRIDE + 1 + b2] = Q;
+        }
+    }
+    QMC_CUDA_TRY(cudaMemcpyAsync(thr, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, st));
+    QMC_CUDA_TRY(cudaStreamSynchronize(st));  // h lives on this frame
+    return QMC_OK;
+}
+static void free_group_tables(HiGroup &G) {
+    cudaFree(const_cast<double *>(G.args.cta_tab));
+    cudaFree(const_cast<double *>(G.args.thr_tab));
+    G.args.cta_tab = nullptr;
+    G.args.thr_tab = nullptr;
+}
+
 struct SweepWorkspace {
     int64_t cap_chains = 0;
     float2 *state = nullptr;
@@ -1272,6 +1347,7 @@ struct SweepWorkspace {
     double *dJq = nullptr, *dhq = nullptr;
     double fx_scale = 1.0;
     int k_fx = 0;
+    std::vector<HiGroup> groups;  // n > 20: register groups above the LO qubits, with their phase tables
     std::vector<cudaEvent_t> ev;
 };
 
@@ -1290,6 +1366,7 @@ void qmc_sweep_free(qmc_model *m) {
     cudaFree(w->af_hib);
     cudaFree(w->dJq);
     cudaFree(w->dhq);
+    for (auto &G : w->groups) free_group_tables(G);
     for (auto e : w->ev) cudaEventDestroy(e);
     delete w;
     m->sweep = nullptr;
@@ -1541,27 +1618,6 @@ static int launch_hi8_mid_pre(int pre, const SweepArgs &a, const Hi6Args &g, con
     return QMC_ERR_BADARG;
 }
 
-// One register group above the LO qubits: kind 6 = HI6 window [p, p+6) (register-only pass), kind 8 = HI8 window
-// [p, p+8) (one shared-memory transposition each way); the top `act` qubits of the window are the group's own.
-struct HiGroup {
-    int kind = 6, act = 6;
-    Hi6Args args;
-};
-
-// Geometry for `nl` local qubits, top group first: full HI8 groups stack down from the top; the remainder (1..7
-// qubits) is the lowest group -- an HI8 window with 7 active qubits or an HI6 window with 1..6.
-static void hi_group_geometry(int nl, std::vector<int> &kind, std::vector<int> &pos, std::vector<int> &act) {
-    const int hi = nl - LO_BITS, full8 = hi / 8, rem = hi % 8;
-    for (int k = 0; k < full8; ++k) {
-        kind.push_back(8); pos.push_back(nl - 8 * (k + 1)); act.push_back(8);
-    }
-    if (rem == 7) {
-        kind.push_back(8); pos.push_back(LO_BITS + 7 - 8); act.push_back(7);
-    } else if (rem > 0) {
-        kind.push_back(6); pos.push_back(LO_BITS + rem - 6); act.push_back(rem);
-    }
-}
-
 // ROLE: 0 FIRST | 1 MID | 2 SINGLE (HI6_* == HI8_*).  pre > 0: MID mixes only the top `pre` qubits before the phase;
 // SINGLE mixes only the top `pre` qubits (the ones an exchange brought in).
 template <int ROLE>
@@ -1664,8 +1720,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     int rc = ensure_workspace(m, batch, st);
     if (rc != QMC_OK) return rc;
     SweepWorkspace *w = m->sweep;
-    std::vector<HiGroup> groups;
-    if (generic) {
+    if (generic && w->groups.empty()) {  // register groups above the LO qubits, built once per model
         std::vector<int> kind, pos, act;
         hi_group_geometry(n, kind, pos, act);
         for (size_t k = 0; k < kind.size(); ++k) {
@@ -1678,9 +1733,13 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
             G.args.Jq = w->dJq;
             G.args.hq = w->dhq;
             G.args.fx_scale = w->fx_scale;
-            groups.push_back(G);
+            rc = build_group_tables(G, n, n, 0ULL, w->Jq, st);
+            w->groups.push_back(G);  // owns the tables from here on
+            m->launches++;
+            if (rc != QMC_OK) return rc;
         }
     }
+    const std::vector<HiGroup> &groups = w->groups;
 
     // tuning knobs (defaults = measured best on B200; the env overrides exist for A/B runs and profiling)
     const char *pf_env = getenv("QUMCMC_SWEEP_PF");
@@ -2106,7 +2165,16 @@ extern "C" int qmc_shard_create(qmc_shard **out, qmc_model *m, int rank, int log
             ga.Jq = sh->dJq[L];
             ga.hq = sh->dhq[L];
             ga.fx_scale = sh->fx_scale;
+            ga.cta_tab = nullptr;
+            ga.thr_tab = nullptr;
+            int rc = QMC_OK;
+            if (k == 0)  // the plan runs FIRST / MID (the passes with a phase layer) on the top group only
+                rc = build_group_tables(G, nl, n, (unsigned long long)rank << nl, sh->Jq[L], 0);
             sh->groups[L].push_back(G);
+            if (rc != QMC_OK) {
+                qmc_shard_destroy(sh);
+                return rc;
+            }
         }
     }
     QMC_CUDA_TRY(cudaMalloc(&sh->params, sizeof(ChainParams)));
@@ -2126,7 +2194,10 @@ extern "C" int qmc_shard_create(qmc_shard **out, qmc_model *m, int rank, int log
 extern "C" int qmc_shard_destroy(qmc_shard *sh) {
     if (!sh) return QMC_OK;
     cudaFree(sh->params); cudaFree(sh->order); cudaFree(sh->segsum); cudaFree(sh->total);
-    for (int L = 0; L < 2; ++L) { cudaFree(sh->dJq[L]); cudaFree(sh->dhq[L]); cudaFree(sh->d_peers[L]); }
+    for (int L = 0; L < 2; ++L) {
+        cudaFree(sh->dJq[L]); cudaFree(sh->dhq[L]); cudaFree(sh->d_peers[L]);
+        for (auto &G : sh->groups[L]) free_group_tables(G);
+    }
     delete sh;
     return QMC_OK;
 }
