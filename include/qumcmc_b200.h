@@ -23,6 +23,10 @@
  *   slot 0: w0,w1 -> u_gamma (53 bit), w2 -> t = 2 + floor(w2*10/2^32), w3 -> u_group = w3/2^32
  *   slot 1: w0,w1 -> u_measure, w2,w3 -> u_accept        u53(a,b) = ((a>>5)*2^26 + (b>>6)) / 2^53
  *   initial state (when s0 is NULL): hop = 0xFFFFFFFF, slot 0: (w1<<32 | w0) & (2^n - 1)
+ *   classical draws (qmc_classical_chains): slot 2: w0,w1 -> u_method, w2,w3 -> u_accept;
+ *     slot 3: UniformProposals state = (w1<<32 | w0) & (2^n - 1); FixedWeightProposals(k): partial Fisher-Yates over the
+ *     string positions 0..n-1, step i < k uses word (i & 3) of slot 3 + (i >> 2): j = i + floor(w * (n - i) / 2^32),
+ *     swap(pos[i], pos[j]), flip index bit n-1-pos[i].
  *   gamma = g_lo + (g_hi-g_lo)*u_gamma;  r = max(1, floor(t/delta_time)).
  *   `chain` is the GLOBAL chain id, so results do not depend on how chains are sharded over GPUs.
  */
@@ -128,6 +132,26 @@ int qmc_run_chains_host(qmc_model *m, int64_t n_chains, int64_t n_hops, const ui
                         uint64_t *proposals_host, uint8_t *accepted_host,
                         uint64_t *final_state_host, int64_t *acc_count_host,
                         int64_t *hamming_hist_host);
+
+/* classical_mcmc (qumcmc/classical_mcmc_routines.py:44-99) for n_chains independent chains x n_hops hops with the
+ * proposal rules of qumcmc/classical_mixers.py:27-101.  The proposal method is a mixture (CombineProposals, :76-101)
+ * of n_methods rules: kinds[i] UNIFORM (get_random_state), FIXED_WEIGHT (params[i] = bodyness: xor with k random
+ * ones, basic_utils.py:383-388) or CUSTOM (params[i] = flip mask over index bits); probs NULL = equal weights.
+ * kinds / params / probs are HOST arrays; the remaining arguments as in qmc_run_chains. */
+#define QMC_MAX_CLASSICAL_METHODS 16
+#define QMC_CLASSICAL_UNIFORM 0
+#define QMC_CLASSICAL_FIXED_WEIGHT 1
+#define QMC_CLASSICAL_CUSTOM 2
+int qmc_classical_chains(qmc_model *m, int64_t n_chains, int64_t n_hops, const uint64_t *s0_dev,
+                         uint64_t chain_id0, uint32_t hop0, double temperature, int n_methods,
+                         const int *kinds, const uint64_t *params, const double *probs, uint64_t seed,
+                         uint64_t *proposals_dev, uint8_t *accepted_dev, uint64_t *final_state_dev,
+                         int64_t *acc_count_dev, int64_t *hamming_hist_dev, void *stream);
+int qmc_classical_chains_host(qmc_model *m, int64_t n_chains, int64_t n_hops, const uint64_t *s0_host,
+                              uint64_t chain_id0, uint32_t hop0, double temperature, int n_methods,
+                              const int *kinds, const uint64_t *params, const double *probs, uint64_t seed,
+                              uint64_t *proposals_host, uint8_t *accepted_host, uint64_t *final_state_host,
+                              int64_t *acc_count_host, int64_t *hamming_hist_host);
 
 /* ---- Sharded statevector: n > 34, or any n with 18 <= n - log2(world) <= 34 ------------------------------
  * Replaces run_qmcmc_quantum_ckt (qumcmc/quantum_mcmc_routines.py:110-156) when 2^n amplitudes do not fit one GPU:

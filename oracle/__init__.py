@@ -71,6 +71,10 @@ def lib() -> C.CDLL:
             C.c_uint64, C.c_int64, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_double,
             C.c_uint64, C.c_uint64, C.c_int, u64p, C.POINTER(C.c_uint8)]
         L.orc_run_chain.restype = C.c_int64
+        L.orc_classical_chain.argtypes = [C.c_int, dp, dp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64), dp,
+                                          C.c_uint64, C.c_int64, C.c_uint32, C.c_double, C.c_uint64, C.c_uint64,
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)]
+        L.orc_classical_chain.restype = C.c_int64
         L.orc_exact_boltzmann.argtypes = [C.c_int, dp, dp, C.c_double, dp, dp]
         L.orc_exact_boltzmann.restype = C.c_double
         L.orc_set_num_threads.argtypes = [C.c_int]
@@ -212,6 +216,26 @@ def run_chain(J, h, masks, weights, s0: int, n_hops: int, temperature: float, ga
                         float(temperature), float(g_lo), float(g_hi), float(delta_time), int(seed),
                         int(chain_id), int(bool(gatewise)), _u64p(props),
                         acc.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return props, acc
+
+
+def classical_chain(J, h, kinds, params, probs, s0: int, n_hops: int, temperature: float, seed: int,
+                    chain_id: int = 0, hop0: int = 0):
+    """One classical_mcmc chain (classical_mcmc_routines.py:44-99) under the classical draw contract.
+    kinds: 0 uniform / 1 fixed weight (param k) / 2 custom (param mask); returns (proposals u64[H], accepted u8[H])."""
+    J, h = _d(J), _d(h)
+    n = len(h)
+    k = np.ascontiguousarray(kinds, dtype=np.int32)
+    p = np.ascontiguousarray(params, dtype=np.uint64)
+    pr = np.full(len(k), 1.0 / len(k)) if probs is None else np.asarray(probs, dtype=np.float64)
+    cum = np.cumsum(pr / pr.sum())
+    cum[-1] = 1.0
+    cum = _d(cum)
+    props = np.empty(n_hops, dtype=np.uint64)
+    acc = np.empty(n_hops, dtype=np.uint8)
+    lib().orc_classical_chain(n, _dp(J), _dp(h), len(k), k.ctypes.data_as(C.POINTER(C.c_int)), _u64p(p), _dp(cum),
+                              int(s0), int(n_hops), int(hop0), float(temperature), int(seed), int(chain_id),
+                              _u64p(props), acc.ctypes.data_as(C.POINTER(C.c_uint8)))
     return props, acc
 
 

@@ -434,3 +434,59 @@ ORC_API int orc_num_threads(void) {
     return 1;
 #endif
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * classical_mcmc (qumcmc/classical_mcmc_routines.py:44-99) with the proposal rules of
+ * qumcmc/classical_mixers.py:27-101, under the classical draw contract of include/qumcmc_b200.h:
+ *   slot 2: w0,w1 -> u_method (CombineProposals' np.random.choice(p), :99), w2,w3 -> u_accept (:41)
+ *   slot 3..: UniformProposals (:38-40, get_random_state): (w1<<32|w0) & (2^n-1);
+ *             FixedWeightProposals (:56-59, random_bstr basic_utils.py:383-388): k distinct string positions by a
+ *             partial Fisher-Yates shuffle, step i uses word (i&3) of slot 3+(i>>2); string position p <-> bit n-1-p;
+ *             CustomProposals (:72-78): xor with the fixed mask.
+ * kind: 0 uniform, 1 fixed weight (param = k), 2 custom (param = mask over index bits).  cum = cumulative
+ * probabilities.  Returns the number of accepted proposals. */
+static uint64_t classical_propose(int n, int n_methods, const int *kind, const uint64_t *param, const double *cum,
+                                  uint64_t cur, uint64_t seed, uint64_t chain, uint32_t hop, double u_method) {
+    int m = n_methods - 1;
+    for (int i = 0; i < n_methods; ++i)
+        if (u_method < cum[i]) { m = i; break; }
+    uint32_t w[4];
+    if (kind[m] == 0) {
+        orc_philox4x32(seed, chain, hop, 3, w);
+        const uint64_t v = ((uint64_t)w[1] << 32) | w[0];
+        return n >= 64 ? v : (v & ((1ULL << n) - 1ULL));
+    }
+    if (kind[m] == 2) return cur ^ param[m];
+    int pos[64];
+    for (int i = 0; i < n; ++i) pos[i] = i;
+    uint64_t flips = 0;
+    const int k = (int)param[m];
+    for (int i = 0; i < k; ++i) {
+        if ((i & 3) == 0) orc_philox4x32(seed, chain, hop, 3 + (uint32_t)(i >> 2), w);
+        const int j = i + (int)(((uint64_t)w[i & 3] * (uint64_t)(n - i)) >> 32);
+        const int t = pos[i]; pos[i] = pos[j]; pos[j] = t;
+        flips |= 1ULL << (n - 1 - pos[i]);
+    }
+    return cur ^ flips;
+}
+
+ORC_API int64_t orc_classical_chain(int n, const double *J, const double *h, int n_methods, const int *kind,
+                                    const uint64_t *param, const double *cum, uint64_t s0, int64_t H,
+                                    uint32_t hop0, double temperature, uint64_t seed, uint64_t chain_id,
+                                    uint64_t *proposals, uint8_t *accepted) {
+    uint64_t cur = s0;
+    double e_cur = orc_energy(n, J, h, cur);
+    int64_t nacc = 0;
+    for (int64_t hop = 0; hop < H; ++hop) {
+        uint32_t w[4];
+        orc_philox4x32(seed, chain_id, hop0 + (uint32_t)hop, 2, w);
+        const uint64_t sp = classical_propose(n, n_methods, kind, param, cum, cur, seed, chain_id,
+                                              hop0 + (uint32_t)hop, u53(w[0], w[1]));
+        const double e_sp = orc_energy(n, J, h, sp);
+        const int acc = orc_test_accept(e_cur, e_sp, temperature, u53(w[2], w[3]));
+        proposals[hop] = sp;
+        accepted[hop] = (uint8_t)acc;
+        if (acc) { cur = sp; e_cur = e_sp; ++nacc; }
+    }
+    return nacc;
+}

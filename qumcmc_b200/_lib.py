@@ -27,6 +27,8 @@ SMEM_MAX_SPINS_F64 = 12
 MAX_SPINS = 40          # model limit; one GPU holds a statevector up to MAX_LOCAL_SPINS qubits
 MAX_LOCAL_SPINS = 34
 IPC_HANDLE_BYTES = 64
+CLASSICAL_UNIFORM, CLASSICAL_FIXED_WEIGHT, CLASSICAL_CUSTOM = range(3)
+MAX_CLASSICAL_METHODS = 16
 SHARD_OP_FIRST, SHARD_OP_MID, SHARD_OP_SINGLE, SHARD_OP_LO_SINGLE, SHARD_OP_LO_FINAL = range(5)
 
 # every symbol include/qumcmc_b200.h declares (tests check the library exports all of them)
@@ -39,6 +41,7 @@ EXPORTS = [
     "qmc_shard_create", "qmc_shard_destroy", "qmc_shard_num_groups", "qmc_shard_begin", "qmc_shard_op",
     "qmc_shard_norm", "qmc_shard_select", "qmc_shard_final_probs", "qmc_shard_set_peers", "qmc_shard_op_exchange",
     "qmc_enable_peer_access", "qmc_ipc_export", "qmc_ipc_open", "qmc_ipc_close_all",
+    "qmc_classical_chains", "qmc_classical_chains_host",
 ]
 
 
@@ -112,6 +115,10 @@ def lib() -> C.CDLL:
     L.qmc_ipc_export.argtypes = [C.c_int, vp, vp, u64p]
     L.qmc_ipc_open.argtypes = [C.c_int, vp, C.c_uint64, C.POINTER(C.c_void_p)]
     L.qmc_ipc_close_all.argtypes = []
+    L.qmc_classical_chains.argtypes = [C.c_void_p, C.c_int64, C.c_int64, u64p, C.c_uint64, C.c_uint32, C.c_double, C.c_int,
+                                       vp, vp, vp, C.c_uint64, u64p, vp, u64p, i64p, i64p, vp]
+    L.qmc_classical_chains_host.argtypes = [C.c_void_p, C.c_int64, C.c_int64, u64p, C.c_uint64, C.c_uint32, C.c_double,
+                                            C.c_int, vp, vp, vp, C.c_uint64, u64p, vp, u64p, i64p, i64p]
     L.qmc_shard_op_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -1,16 +1,18 @@
 """``classical_mcmc`` and ``test_accept`` (/root/reference/qumcmc/classical_mcmc_routines.py).
 
-Classical proposals are string flips on the host (not the quantum hot path); the
-energies still come from the CUDA energy kernel (one batched table for n <= 20)."""
+The built-in proposal rules run on the device, all chains and hops in one launch (``qmc_classical_chains``, SURVEY
+section 8 row f2): Philox draws, fixed-order fp64 energies and the Metropolis rule are shared with the quantum path."""
 from __future__ import annotations
 
 from typing import Optional
 
 import numpy as np
 
+from . import _device, _lib
 from .basic_utils import MCMCChain, MCMCState, get_random_state
 from .classical_mixers import ClassicalMixer, UniformProposals
 from .energy_models import IsingEnergyFunction
+from .quantum_mcmc_routines import ChainBatch
 
 
 def test_accept(energy_s: float, energy_sprime: float, temperature: float = 1.0) -> bool:
@@ -23,14 +25,88 @@ def test_accept(energy_s: float, energy_sprime: float, temperature: float = 1.0)
 test_accept.__test__ = False  # not a pytest test
 
 
+def lower_proposals(proposition_method: ClassicalMixer):
+    """(kinds int32[M], params uint64[M], probs float64[M]) of a built-in proposal rule, or None for host-only rules."""
+    spec = proposition_method.lower()
+    if spec is None:
+        return None
+    if len(spec) > _lib.MAX_CLASSICAL_METHODS:
+        raise ValueError(f"CombineProposals with {len(spec)} leaf rules (device limit {_lib.MAX_CLASSICAL_METHODS})")
+    kinds = np.array([k for k, _, _ in spec], dtype=np.int32)
+    params = np.array([p for _, p, _ in spec], dtype=np.uint64)
+    probs = np.array([q for _, _, q in spec], dtype=np.float64)
+    return kinds, params, probs
+
+
+def run_classical_chains(model: IsingEnergyFunction, proposition_method: ClassicalMixer, n_hops: int, n_chains: int,
+                         initial_states: Optional[np.ndarray], temperature: float, seed: int, device: int = 0,
+                         chain_id0: int = 0, hop0: int = 0, name: str = "cl-mcmc", record: bool = True) -> ChainBatch:
+    """Batched driver over qmc_classical_chains (device buffers are torch tensors): every chain, every hop, one launch."""
+    spec = lower_proposals(proposition_method)
+    if spec is None:
+        raise _lib.QmcUnsupported(f"{proposition_method!r} has no device lowering (host-only proposal rule)")
+    kinds, params, probs = spec
+    torch = _device._torch()
+    dm = model.device_model(device)
+    n = model.num_spins
+    dev = _device.require_cuda(device)
+    C_, H = int(n_chains), int(n_hops)
+    s0 = None
+    if initial_states is not None:
+        s0 = torch.from_numpy(np.ascontiguousarray(initial_states, dtype=np.uint64).view(np.int64)).to(dev)
+    props = torch.empty((C_, H), dtype=torch.int64, device=dev) if record else None
+    acc = torch.empty((C_, H), dtype=torch.uint8, device=dev) if record else None
+    fin = torch.empty(C_, dtype=torch.int64, device=dev)
+    cnt = torch.empty(C_, dtype=torch.int64, device=dev)
+    hist = torch.empty((C_, n + 1), dtype=torch.int64, device=dev)
+    ptr = lambda t: None if t is None else t.data_ptr()
+    _lib.check(_lib.lib().qmc_classical_chains(
+        dm.handle, C_, H, ptr(s0), int(chain_id0), int(hop0) & 0xFFFFFFFF, float(temperature), len(kinds),
+        kinds.ctypes.data, params.ctypes.data, probs.ctypes.data, int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(props), ptr(acc),
+        ptr(fin), ptr(cnt), ptr(hist), _device.current_stream_ptr(device)))
+    torch.cuda.synchronize(device)
+    to_u64 = lambda t: t.cpu().numpy().view(np.uint64)
+    if initial_states is None:
+        from .rng import initial_states_philox
+        init = initial_states_philox(int(seed), int(chain_id0), C_, n)
+    else:
+        init = np.ascontiguousarray(initial_states, dtype=np.uint64)
+    return ChainBatch(n, init, to_u64(props) if record else None, acc.cpu().numpy() if record else None,
+                      to_u64(fin), cnt.cpu().numpy(), hist.cpu().numpy(), name)
+
+
 def classical_mcmc(n_hops: int, model: IsingEnergyFunction, proposition_method: Optional[ClassicalMixer] = None,
                    initial_state: Optional[str] = None, temperature: float = 1.0, verbose: bool = False,
-                   name="cl-mcmc", *, device: int = 0):
+                   name="cl-mcmc", *, n_chains: Optional[int] = None, seed: Optional[int] = None, device: int = 0,
+                   chain_id0: int = 0, hop0: int = 0):
     """Metropolis chain with classical proposals.  ``proposition_method`` defaults to
-    ``UniformProposals`` (the README call shape passes none)."""
+    ``UniformProposals`` (the README call shape passes none).  The built-in proposal rules run on the device
+    (``qmc_classical_chains``: returns an ``MCMCChain``, or a ``ChainBatch`` when ``n_chains`` is given); a user
+    subclass of ``ClassicalMixer`` keeps the reference's host loop around its ``propose_transition`` with energies
+    from the CUDA energy kernel."""
     n = model.num_spins
     if proposition_method is None:
         proposition_method = UniformProposals(n)
+    if proposition_method.lower() is not None:
+        if seed is None:  # stays under the control of np.random.seed, like the reference's global RNG use
+            seed = int(np.random.randint(0, 2 ** 62))
+        single = n_chains is None
+        C_ = 1 if single else int(n_chains)
+        if initial_state is None:
+            init = np.array([int(get_random_state(n), 2)], dtype=np.uint64) if single else None
+        elif isinstance(initial_state, str):
+            init = np.full(C_, int(initial_state, 2), dtype=np.uint64)
+        else:
+            init = np.array([int(s, 2) if isinstance(s, str) else int(s) for s in initial_state], dtype=np.uint64)
+            if len(init) != C_:
+                raise ValueError("one initial state per chain expected")
+        if verbose and init is not None:
+            print("starting with: ", f"{int(init[0]):0{n}b}", "with energy:", model.get_energy(f"{int(init[0]):0{n}b}"))
+        batch = run_classical_chains(model, proposition_method, n_hops, C_, init, temperature, seed, device=device,
+                                     chain_id0=chain_id0, hop0=hop0, name=name)
+        return batch[0] if single else batch
+    if n_chains is not None:
+        raise _lib.QmcUnsupported(f"{proposition_method!r} has no device lowering: n_chains needs a built-in proposal rule")
     start = get_random_state(n) if initial_state is None else initial_state
     table = model.get_energies(np.arange(1 << n, dtype=np.uint64), device=device) if n <= 20 else None
     energy_of = (lambda s: float(table[int(s, 2)])) if table is not None else model.get_energy

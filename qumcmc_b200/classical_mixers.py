@@ -1,6 +1,7 @@
 """Classical proposal rules of the reference's ``qumcmc.classical_mixers``
-(/root/reference/qumcmc/classical_mixers.py).  These are host-side string operations: not part of
-the quantum-proposal hot path, kept so ``classical_mcmc`` has the same surface."""
+(/root/reference/qumcmc/classical_mixers.py).  ``propose_transition`` keeps the reference's host-side string
+semantics (user subclasses plug in there); the four built-in rules also ``lower()`` to the
+``(kinds, params, probabilities)`` mixture that ``qmc_classical_chains`` runs on the device."""
 from __future__ import annotations
 
 from abc import ABC, abstractmethod
@@ -8,6 +9,7 @@ from typing import List
 
 import numpy as np
 
+from . import _lib
 from .basic_utils import get_random_state, random_bstr, xor_strings
 
 
@@ -25,6 +27,11 @@ class ClassicalMixer(ABC):
     def _check(self, current_state: str) -> None:
         assert len(current_state) == self.num_spins, "Wrong 'current_state' "
 
+    def lower(self):
+        """``[(kind, param, probability), ...]`` for the device kernel, or ``None`` when the rule only exists as
+        host code (a user subclass)."""
+        return None
+
 
 class UniformProposals(ClassicalMixer):
     def __repr__(self):
@@ -33,6 +40,9 @@ class UniformProposals(ClassicalMixer):
     def propose_transition(self, current_state=None):
         self._check(current_state)
         return get_random_state(self.num_spins)
+
+    def lower(self):
+        return [(_lib.CLASSICAL_UNIFORM, 0, 1.0)]
 
 
 class FixedWeightProposals(ClassicalMixer):
@@ -48,6 +58,9 @@ class FixedWeightProposals(ClassicalMixer):
         self._check(current_state)
         return xor_strings(current_state, random_bstr(self.num_spins, self.bodyness))
 
+    def lower(self):
+        return [(_lib.CLASSICAL_FIXED_WEIGHT, int(self.bodyness), 1.0)]
+
 
 class CustomProposals(ClassicalMixer):
     def __init__(self, num_spins: int, flip_pattern: List[int]) -> None:
@@ -61,6 +74,13 @@ class CustomProposals(ClassicalMixer):
         self._check(current_state)
         flips = "".join("1" if i in self.flip_pattern else "0" for i in range(self.num_spins))
         return xor_strings(current_state, flips)
+
+    def lower(self):
+        mask = 0
+        for i in set(self.flip_pattern):  # string position i (MSB first) <-> index bit n-1-i
+            if 0 <= i < self.num_spins:
+                mask |= 1 << (self.num_spins - 1 - i)
+        return [(_lib.CLASSICAL_CUSTOM, mask, 1.0)]
 
 
 class CombineProposals(ClassicalMixer):
@@ -80,3 +100,12 @@ class CombineProposals(ClassicalMixer):
         self._check(current_state)
         method = np.random.choice(self.proposal_methods, p=self.probabilities)
         return method.propose_transition(current_state)
+
+    def lower(self):
+        out = []
+        for method, p in zip(self.proposal_methods, self.probabilities):
+            sub = method.lower()
+            if sub is None:
+                return None
+            out.extend((kind, param, float(p) * q) for kind, param, q in sub)
+        return out

@@ -77,6 +77,7 @@ struct SweepArgs {
     // index bits with the rank bits, done by the sweep's own stores over NVLink peer mappings (no staging copy).
     float2 *const *xchg_peers;
     int xchg_shift, xchg_rank;
+    int xchg_g, xchg_tile_bits;  // log2(ranks), log2(tiles of the local shard)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -408,6 +409,15 @@ __device__ __forceinline__ int64_t hi_base_b(int tid, int64_t tile) {
 __device__ __forceinline__ int hi_loc_a(int tid, int j) { return (tid & 31) | ((tid >> 5) << 5) | (j << 7); }
 __device__ __forceinline__ int hi_loc_b(int tid, int j) { return (tid & 31) | (j << 5) | ((tid >> 5) << 11); }
 
+// Tile of CTA b.  Fused exchange: the top g bits of the tile index select the destination rank of a lower-group
+// pass, so the CTAs are renumbered with those bits fastest (and rotated by the rank): at any moment the stores of a
+// GPU fan out over all peers instead of every GPU writing to the same peer at the same time.
+__device__ __forceinline__ int64_t sweep_tile(const SweepArgs &a, unsigned b) {
+    if (!a.xchg_peers) return (int64_t)b;
+    const unsigned W1 = (1u << a.xchg_g) - 1u;
+    return ((int64_t)((b + (unsigned)a.xchg_rank) & W1) << (a.xchg_tile_bits - a.xchg_g)) | (int64_t)(b >> a.xchg_g);
+}
+
 __device__ __forceinline__ A64 *xchg_addr(const SweepArgs &a, int64_t local_idx) {
     const int64_t low = local_idx & (((int64_t)1 << a.xchg_shift) - 1);
     return reinterpret_cast<A64 *>(a.xchg_peers[local_idx >> a.xchg_shift]) + (low | ((int64_t)a.xchg_rank << a.xchg_shift));
@@ -458,7 +468,7 @@ __global__ void __launch_bounds__(NTH, 384 / NTH) lo_sweep_kernel(const SweepArg
     __shared__ ChainParams cp_s;
     __shared__ __align__(16) int hs_s[64];
     const int tid = threadIdx.x;
-    const int64_t tile = blockIdx.x;
+    const int64_t tile = sweep_tile(a, blockIdx.x);
     const int64_t chain = order[list_off + blockIdx.y];
     // ct_off == list_off: passed separately so that this index stays pure uniform-datapath arithmetic (LDCU -> UR)
     const float tu = FAST ? c_tan[ct_off + blockIdx.y] : 0.f;
@@ -774,7 +784,7 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
     __shared__ __align__(16) double thr_s[ROLE != HI6_SINGLE ? NT * AF_THR_STRIDE : 2];
     const int tid = threadIdx.x;
     const int n = a.n;
-    const int64_t tile = blockIdx.x;
+    const int64_t tile = sweep_tile(a, blockIdx.x);
     const int64_t chain = order[list_off + blockIdx.y];
     if (ROLE != HI6_SINGLE) build_hs(hs_s, g.dr, a.params + chain, tid);
     if (ROLE != HI6_SINGLE) af_fetch(af_scr, thr_s, g.cta_tab, g.thr_tab, tile, tid);
@@ -855,7 +865,7 @@ __global__ void __launch_bounds__(NT, 3) hi8_sweep_kernel(const SweepArgs a, con
     constexpr int PRE_B = PRE == 8 ? 3 : (PRE == 7 ? 2 : 0);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int n = a.n, nt = a.n_total, p = g.p;
-    const int64_t tile = blockIdx.x;
+    const int64_t tile = sweep_tile(a, blockIdx.x);
     const int64_t chain = order[list_off + blockIdx.y];
     const int low_bits = p - 5;
     const int64_t base_tile = ((tile & (((int64_t)1 << low_bits) - 1)) << 5) | ((tile >> low_bits) << (p + 8));
@@ -1824,7 +1834,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         memcpy(a.dr_lo, w->dr_lo, sizeof(a.dr_lo)); memcpy(a.dr_hia, w->dr_hia, sizeof(a.dr_hia)); memcpy(a.dr_hib, w->dr_hib, sizeof(a.dr_hib));
         a.segsum = w->segsum;
         a.pf_dist = pf_dist;
-        a.xchg_peers = nullptr; a.xchg_shift = 0; a.xchg_rank = 0;
+        a.xchg_peers = nullptr; a.xchg_shift = 0; a.xchg_rank = 0; a.xchg_g = 0; a.xchg_tile_bits = 0;
         a.probs_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float *>(probs_out) : nullptr;
         a.amps_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float2 *>(amps_out) : nullptr;
         // PROBS with amps only: still need a probs-free normalisation; handled by the normalise kernel
@@ -2238,6 +2248,8 @@ static int shard_op_impl(qmc_shard *sh, int op, int k, int pre, int layout, void
         a.xchg_peers = sh->d_peers[dst_which];
         a.xchg_shift = sh->nl - sh->g;
         a.xchg_rank = sh->rank;
+        a.xchg_g = sh->g;
+        a.xchg_tile_bits = sh->nl - TILE_BITS;
     }
     const int64_t tiles = (int64_t)1 << (sh->nl - TILE_BITS);
     const HiGroup &G = sh->groups[layout][k];

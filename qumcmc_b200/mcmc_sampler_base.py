@@ -33,8 +33,9 @@ class MCMCSampler(ABC):
 class ClassicalMCMCSampler(MCMCSampler):
     def __init__(self, n_hops: int, model: IsingEnergyFunction, proposition_method: ClassicalMixer,
                  initial_state: Optional[str] = None, temperature: float = 1, verbose: bool = False,
-                 name: str = "Cl-MCMC") -> None:
+                 name: str = "Cl-MCMC", **device_kwargs) -> None:
         self.proposition_method = proposition_method
+        self.device_kwargs = device_kwargs  # n_chains / seed / device
         super().__init__(n_hops, model, initial_state, temperature, verbose, name)
 
     def __repr__(self):
@@ -45,7 +46,7 @@ class ClassicalMCMCSampler(MCMCSampler):
     def run(self):
         return classical_mcmc(n_hops=self.n_hops, model=self.model, proposition_method=self.proposition_method,
                               initial_state=self.initial_state, temperature=self.temperature,
-                              verbose=self.verbose, name=self.name)
+                              verbose=self.verbose, name=self.name, **self.device_kwargs)
 
 
 class QuantumMCMCSampler(MCMCSampler):
