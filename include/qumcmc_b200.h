@@ -153,6 +153,20 @@ int qmc_classical_chains_host(qmc_model *m, int64_t n_chains, int64_t n_hops, co
                               uint64_t *proposals_host, uint8_t *accepted_host, uint64_t *final_state_host,
                               int64_t *acc_count_host, int64_t *hamming_hist_host);
 
+/* Trajectory statistics of recorded chains (qumcmc/trajectory_processing.py:114-153,183-210,213-321), one pass per
+ * chain on the device.  Inputs: s0_dev[C], proposals_dev / accepted_dev [C*H] as written by qmc_run_chains /
+ * qmc_classical_chains.  Outputs, all nullable:
+ *   markov_chain_dev [C*(H+1)]   state after every hop, entry 0 = initial state (basic_utils.py:84-115)
+ *   energy_diff_dev  [C*H]       E(proposal) - E(current state) per hop ("energy" statistic, :235-263)
+ *   running_mag_dev  [C*H]       mean magnetisation (#1 - #0) of markov_chain[0:k], k = 1..H (:183-210)
+ *   hamming_acc_rej_dev [C*(n+1)*2]  proposals per Hamming distance to the current state: accepted, rejected (:279-301)
+ *   running_kl_dev   [C*(H+1)]   vectoried_KL(boltzmann, counts of markov_chain[0:k+1] / (k+1)) (:137-151, natural log,
+ *                                EPS = 1e-8, mask p > 1e-10); needs boltz_probs_dev[2^n] (index order) and H < 1e8. */
+int qmc_trajectory_stats(qmc_model *m, int64_t n_chains, int64_t n_hops, const uint64_t *s0_dev,
+                         const uint64_t *proposals_dev, const uint8_t *accepted_dev, const double *boltz_probs_dev,
+                         uint64_t *markov_chain_dev, double *energy_diff_dev, double *running_mag_dev,
+                         int64_t *hamming_acc_rej_dev, double *running_kl_dev, void *stream);
+
 /* ---- Sharded statevector: n > 34, or any n with 18 <= n - log2(world) <= 34 ------------------------------
  * Replaces run_qmcmc_quantum_ckt (qumcmc/quantum_mcmc_routines.py:110-156) when 2^n amplitudes do not fit one GPU:
  * rank R of 2^g holds the amplitudes whose top g index bits equal R (2^(n-g) complex64, caller-owned buffer).

@@ -170,3 +170,29 @@ def markov_chain_from(s0: int, proposals: np.ndarray, accepted: np.ndarray) -> n
             cur = p
         out[k + 1] = cur
     return out
+
+
+def running_magnetisation(markov_chain_idx: np.ndarray, n: int) -> np.ndarray:
+    """calculate_runnning_magnetisation (trajectory_processing.py:183-210): for k = 1..H the expectation of
+    magnetization_of_state (#'1' - #'0', basic_utils.py:174-186) over get_accepted_dict(normalize=True, until_index=k),
+    i.e. over markov_chain[0:k]."""
+    mags = np.array([2 * bin(int(s)).count("1") - n for s in markov_chain_idx], dtype=np.float64)
+    H = len(markov_chain_idx) - 1
+    return np.array([mags[:k].sum() / k for k in range(1, H + 1)])
+
+
+def trajectory_statistics(J, h, s0: int, proposals: np.ndarray, accepted: np.ndarray):
+    """get_trajectory_statistics (trajectory_processing.py:213-321): per hop E(proposal) - E(current) (:235-263) and
+    the Hamming-distance table of accepted / rejected proposals w.r.t. the current state (:279-301)."""
+    n = len(h)
+    ediff = np.empty(len(proposals))
+    ham = np.zeros((n + 1, 2), dtype=np.int64)
+    cur = int(s0)
+    e_cur = float(_energies(J, h, np.array([cur], dtype=np.uint64))[0])
+    for k, (p, a) in enumerate(zip(proposals, accepted)):
+        e_p = float(_energies(J, h, np.array([int(p)], dtype=np.uint64))[0])
+        ediff[k] = e_p - e_cur
+        ham[bin(int(p) ^ cur).count("1"), 0 if a else 1] += 1
+        if a:
+            cur, e_cur = int(p), e_p
+    return ediff, ham
