@@ -167,6 +167,13 @@ int qmc_trajectory_stats(qmc_model *m, int64_t n_chains, int64_t n_hops, const u
                          uint64_t *markov_chain_dev, double *energy_diff_dev, double *running_mag_dev,
                          int64_t *hamming_acc_rej_dev, double *running_kl_dev, void *stream);
 
+/* Spin moments of `count` states (the model side of the contrastive-divergence gradient, qumcmc/training.py:70-99):
+ * exact counts over the states with mask_dev[k] != 0 (mask_dev NULL = all): n_used_dev[1], ones_dev[n] = #states with
+ * s_i = +1, agree_dev[n*n] = #states with s_i == s_j (spin i <-> index bit n-1-i).
+ * <s_i> = (2 ones_i - N)/N, <s_i s_j> = (2 agree_ij - N)/N. */
+int qmc_state_moments(qmc_model *m, int64_t count, const uint64_t *states_dev, const uint8_t *mask_dev,
+                      int64_t *n_used_dev, int64_t *ones_dev, int64_t *agree_dev, void *stream);
+
 /* ---- Sharded statevector: n > 34, or any n with 18 <= n - log2(world) <= 34 ------------------------------
  * Replaces run_qmcmc_quantum_ckt (qumcmc/quantum_mcmc_routines.py:110-156) when 2^n amplitudes do not fit one GPU:
  * rank R of 2^g holds the amplitudes whose top g index bits equal R (2^(n-g) complex64, caller-owned buffer).

@@ -10,7 +10,7 @@ import qumcmc_b200 as _impl
 from qumcmc_b200 import *  # noqa: F401,F403
 
 for _name in ("basic_utils", "energy_models", "mixers", "classical_mixers", "classical_mcmc_routines",
-              "quantum_mcmc_routines", "mcmc_sampler_base", "prob_dist", "trajectory_processing"):
+              "quantum_mcmc_routines", "mcmc_sampler_base", "prob_dist", "trajectory_processing", "training"):
     _mod = importlib.import_module(f"qumcmc_b200.{_name}")
     sys.modules[f"{__name__}.{_name}"] = _mod
     globals()[_name] = _mod

@@ -221,3 +221,80 @@ extern "C" int qmc_trajectory_stats(qmc_model *m, int64_t n_chains, int64_t n_ho
     }
     return rc;
 }
+
+// ------------------------------------------------------------------------------------------
+// Spin moments of a set of states: the model expectations of the contrastive-divergence
+// gradient, cd_J / cd_h of qumcmc/training.py:70-99 (<s_i s_j>, <s_i> over mcmc_chain.accepted_states), as exact
+// integer counts:  ones[i] = #states with s_i = +1,  agree[i][j] = #states with s_i == s_j   (spin i <-> index bit
+// n-1-i), so that <s_i> = (2 ones_i - N) / N and <s_i s_j> = (2 agree_ij - N) / N.
+// grid = (state chunks, n + 1 rows): row i < n fixes spin i, row n counts the ones.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) state_moments_kernel(int n, int64_t count, const uint64_t *__restrict__ states,
+                                                            const uint8_t *__restrict__ mask,
+                                                            unsigned long long *__restrict__ used,
+                                                            unsigned long long *__restrict__ ones,
+                                                            unsigned long long *__restrict__ agree) {
+    const int row = blockIdx.y;
+    unsigned cnt[QMC_MAX_SPINS];
+#pragma unroll
+    for (int j = 0; j < QMC_MAX_SPINS; ++j) cnt[j] = 0u;
+    unsigned nused = 0u;
+    // chunks of at most 2^31 states per thread keep the 32-bit counters exact
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x) {
+        if (mask && !mask[k]) continue;
+        const uint64_t x = states[k];
+        // bit b of y is 1 iff the spin at bit b agrees with spin `row` (row n: iff the spin is +1)
+        const uint64_t y = (row < n && !((x >> (n - 1 - row)) & 1ULL)) ? ~x : x;
+#pragma unroll
+        for (int j = 0; j < QMC_MAX_SPINS; ++j) cnt[j] += (unsigned)((y >> j) & 1ULL);
+        ++nused;
+    }
+    __shared__ unsigned long long red[QMC_MAX_SPINS + 1];
+    if (threadIdx.x <= QMC_MAX_SPINS) red[threadIdx.x] = 0ULL;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < QMC_MAX_SPINS; ++j) {
+        unsigned v = cnt[j];
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0 && j < n) atomicAdd(&red[j], (unsigned long long)v);
+    }
+    {
+        unsigned v = nused;
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&red[QMC_MAX_SPINS], (unsigned long long)v);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < n) {  // bit j <-> spin n-1-j
+        const int spin = n - 1 - (int)threadIdx.x;
+        if (row < n) atomicAdd(&agree[row * n + spin], red[threadIdx.x]);
+        else atomicAdd(&ones[spin], red[threadIdx.x]);
+    }
+    if (threadIdx.x == 0 && row == n) atomicAdd(used, red[QMC_MAX_SPINS]);
+}
+
+}  // namespace
+
+extern "C" int qmc_state_moments(qmc_model *m, int64_t count, const uint64_t *states_dev, const uint8_t *mask_dev,
+                                 int64_t *n_used_dev, int64_t *ones_dev, int64_t *agree_dev, void *stream) {
+    QMC_REQUIRE(m && n_used_dev && ones_dev && agree_dev && (count == 0 || states_dev), QMC_ERR_BADARG,
+                "qmc_state_moments: null argument");
+    QMC_REQUIRE(count >= 0, QMC_ERR_BADARG, "negative state count");
+    QMC_CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = m->n;
+    QMC_CUDA_TRY(cudaMemsetAsync(n_used_dev, 0, sizeof(int64_t), st));
+    QMC_CUDA_TRY(cudaMemsetAsync(ones_dev, 0, sizeof(int64_t) * n, st));
+    QMC_CUDA_TRY(cudaMemsetAsync(agree_dev, 0, sizeof(int64_t) * n * n, st));
+    if (count == 0) return QMC_OK;
+    int64_t blocks = (count + 256 * 64 - 1) / (256 * 64);  // ~64 states per thread
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    state_moments_kernel<<<dim3((unsigned)blocks, (unsigned)(n + 1)), 256, 0, st>>>(
+        n, count, states_dev, mask_dev, reinterpret_cast<unsigned long long *>(n_used_dev),
+        reinterpret_cast<unsigned long long *>(ones_dev), reinterpret_cast<unsigned long long *>(agree_dev));
+    m->launches++;
+    QMC_CUDA_TRY(cudaGetLastError());
+    return QMC_OK;
+}
