@@ -13,6 +13,7 @@ from .prob_dist import DiscreteProbabilityDistribution, js_divergence, kl_diverg
 from .trajectory_processing import (batch_trajectory_statistics, calculate_running_kl_divergence,
                                     calculate_runnning_magnetisation, get_trajectory_statistics)
 from .training import CDTraining
+from .io import load_chains, load_legacy_pickle, save_chains
 from .quantum_mcmc_routines import (ChainBatch, quantum_enhanced_mcmc, run_chains, run_qmcmc_quantum_ckt,
                                     transition_probabilities)
 
