@@ -81,6 +81,19 @@ def c4():
                       "path": "generic sweeps: LO(12) + HI8 + HI8 qubit groups, 2 passes per layer (B_alg counts 1)"}))
 
 
+def general():
+    """General path (tiled passes, any X-string mixer / complex128): proposals/s and the pass count."""
+    for n, mixer_name, dtype, chains, H in [(16, "two", "fp32", 512, 8), (16, "two", "fp64", 512, 8), (20, "one", "fp64", 256, 8),
+                                            (20, "two", "fp32", 256, 4)]:
+        m = q.random_ising_model(n, 1)
+        mx = q.GenericMixer.OneBodyMixer(n) if mixer_name == "one" else q.GenericMixer.TwoBodyMixer(n)
+        q.quantum_enhanced_mcmc(1, m, mx, (0.25, 0.6), temperature=1.0, n_chains=chains, seed=3, dtype=dtype)  # warm + alloc
+        dt, b = timed(lambda: q.quantum_enhanced_mcmc(H, m, mx, (0.25, 0.6), temperature=1.0, n_chains=chains, seed=4, dtype=dtype))
+        print(json.dumps({"config": "general path n=%d, %s-body mixer, %s, %d chains x %d hops" % (n, mixer_name, dtype, chains, H),
+                          "seconds": dt, "proposals_per_s": chains * H / dt, "acceptance": b.acceptance_rate(),
+                          "reference_cost": "one statevector pass per gate: %d passes per layer" % (n * (n - 1) // 2 + n + (n if mixer_name == "one" else n * (n - 1) // 2))}))
+
+
 def exact():
     for n in (20, 24, 28):
         m = q.random_ising_model(n, 1)
@@ -97,6 +110,6 @@ def exact():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c1", "c2", "c4", "exact"]
+    which = sys.argv[1:] or ["c1", "c2", "c4", "exact", "general"]
     for w in which:
-        {"c1": c1, "c2": c2, "c4": c4, "exact": exact}[w]()
+        {"c1": c1, "c2": c2, "c4": c4, "exact": exact, "general": general}[w]()

@@ -50,6 +50,7 @@ extern "C" {
 
 #define QMC_MAX_SPINS 40       /* model limit; one GPU holds a statevector up to n = 34 (2^34 complex64 = 128 GiB) */
 #define QMC_MAX_LOCAL_SPINS 34
+#define QMC_GENERAL_MAX_SPINS 24 /* general path (k-body / custom mixers, complex128): 2^n fp64 phase table */
 #define QMC_SMEM_MAX_SPINS_F32 13 /* whole statevector in shared memory, one CTA per chain */
 #define QMC_SMEM_MAX_SPINS_F64 12
 

@@ -25,9 +25,15 @@ static int dispatch(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, co
         return qmc_small_run(m, mode, n_chains, n_hops, s_in, chain_id0, hop0, temperature, g_lo, g_hi, dt, seed,
                              dtype, gamma_arr, r_arr, u_arr, group_arr, proposals, accepted, final_state,
                              acc_count, hamming_hist, probs_out, amps_out, st);
-    return qmc_sweep_run(m, mode, n_chains, n_hops, s_in, chain_id0, hop0, temperature, g_lo, g_hi, dt, seed, dtype,
-                         gamma_arr, r_arr, u_arr, group_arr, proposals, accepted, final_state, acc_count,
-                         hamming_hist, probs_out, amps_out, st);
+    // specialised sweeps: complex64 + one-body X mixers (every qubit at most once per group)
+    if (dtype == QMC_DTYPE_F32 && m->all_one_body && m->n >= 14)
+        return qmc_sweep_run(m, mode, n_chains, n_hops, s_in, chain_id0, hop0, temperature, g_lo, g_hi, dt, seed, dtype,
+                             gamma_arr, r_arr, u_arr, group_arr, proposals, accepted, final_state, acc_count,
+                             hamming_hist, probs_out, amps_out, st);
+    // everything else: tiled general path (k-body / custom / summed mixers, complex128)
+    return qmc_general_run(m, mode, n_chains, n_hops, s_in, chain_id0, hop0, temperature, g_lo, g_hi, dt, seed, dtype,
+                           gamma_arr, r_arr, u_arr, group_arr, proposals, accepted, final_state, acc_count,
+                           hamming_hist, probs_out, amps_out, st);
 }
 
 // single-element device staging for the transition_probs hook

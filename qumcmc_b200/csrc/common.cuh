@@ -106,7 +106,8 @@ __host__ __device__ __forceinline__ int qmc_pick_group(int n_groups, const doubl
 // ---------------------------------------------------------------------------------------------
 // model handle
 // ---------------------------------------------------------------------------------------------
-struct SweepWorkspace;  // sweep.cu
+struct SweepWorkspace;    // sweep.cu
+struct GeneralWorkspace;  // general.cu
 
 struct qmc_model {
     int n = 0;
@@ -137,6 +138,9 @@ struct qmc_model {
     double fast_e0 = 0.0;
     // large-n path
     SweepWorkspace *sweep = nullptr;
+    // general path (arbitrary mixers / complex128 in HBM)
+    GeneralWorkspace *general = nullptr;
+    int mixer_epoch = 0;  // bumped by qmc_mixer_set
     // stats
     int64_t launches = 0;
     int profile = 0;
@@ -160,6 +164,15 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                   uint64_t *final_state, int64_t *acc_count, int64_t *hamming_hist, void *probs_out,
                   void *amps_out, cudaStream_t st);
 void qmc_sweep_free(qmc_model *m);
+
+int qmc_general_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, const uint64_t *s_in,
+                    uint64_t chain_id0, uint32_t hop0, double temperature, double g_lo, double g_hi,
+                    double dt, uint64_t seed, int dtype, const double *gamma_arr, const int *r_arr,
+                    const double *u_arr, const int *group_arr, uint64_t *proposals, uint8_t *accepted,
+                    uint64_t *final_state, int64_t *acc_count, int64_t *hamming_hist, void *probs_out,
+                    void *amps_out, cudaStream_t st);
+void qmc_general_free(qmc_model *m);
+int qmc_general_num_passes(qmc_model *m, int group);
 
 enum { QMC_MODE_CHAIN = 0, QMC_MODE_PROPOSE = 1, QMC_MODE_PROBS = 2 };
 

@@ -388,6 +388,7 @@ extern "C" int qmc_model_destroy(qmc_model *m) {
     if (!m) return QMC_OK;
     cudaSetDevice(m->device);
     qmc_sweep_free(m);
+    qmc_general_free(m);
     cudaFree(m->dJ);
     cudaFree(m->dh);
     cudaFree(m->dD);
@@ -455,6 +456,7 @@ extern "C" int qmc_mixer_set(qmc_model *m, int n_groups, const int *group_offset
     }
     m->max_terms_in_group = max_terms;
     m->all_one_body = one_body;
+    m->mixer_epoch++;
     cudaFree(m->d_group_off);
     cudaFree(m->d_masks);
     cudaFree(m->d_weights);

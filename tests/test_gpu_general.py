@@ -1,0 +1,114 @@
+"""General HBM path (general.cu): arbitrary X-string mixers above the shared-memory limit and complex128 statevectors
+above n = 12, against the oracle's fused simulator.  Tolerances: 1e-6 (fp32) / 1e-10 (fp64), the north-star figures."""
+import numpy as np
+import pytest
+
+import oracle
+from tests import models
+
+pytestmark = pytest.mark.gpu
+
+
+def _lowered(mixer):
+    offs, masks, w, probs = mixer.lower()
+    return offs, masks, w, probs
+
+
+def _check(q, n, mixer, dtype, rs, seed=3, group=0):
+    J, h = models.packaged_random_model(n, seed)
+    m = q.IsingEnergyFunction(J, h)
+    offs, masks, w, _ = _lowered(mixer)
+    gm, gw = masks[offs[group]:offs[group + 1]], w[offs[group]:offs[group + 1]]
+    al = oracle.alpha(J, h)
+    rng = np.random.default_rng(n + len(gm))
+    tol_p, tol_a = (1e-10, 1e-9) if dtype == "fp64" else (1e-6, 5e-5)
+    for r in rs:
+        s = int(rng.integers(0, 1 << n))
+        gamma = float(rng.uniform(0.25, 0.6))
+        p, a = q.transition_probabilities(m, mixer, s, gamma, r, dtype=dtype, return_amplitudes=True, group=group)
+        ref = oracle.evolve(J, h, al, gamma, 0.8, r, gm, gw, s, gatewise=False)
+        assert abs(p.sum() - 1.0) < 1e-5
+        assert np.abs(p - np.abs(ref) ** 2).max() < tol_p, (n, r, dtype)
+        assert np.linalg.norm(a - ref) < tol_a, (n, r, np.linalg.norm(a - ref))
+
+
+@pytest.mark.parametrize("n,dtype", [(13, "fp64"), (14, "fp64"), (16, "fp64"), (18, "fp64"), (20, "fp64")])
+def test_one_body_complex128_above_the_shared_memory_limit(n, dtype):
+    import qumcmc_b200 as q
+    _check(q, n, q.GenericMixer.OneBodyMixer(n), dtype, (1, 2, 5) if n < 20 else (3,))
+
+
+@pytest.mark.parametrize("n,dtype", [(14, "fp32"), (14, "fp64"), (16, "fp32"), (17, "fp64"), (20, "fp32")])
+def test_two_body_mixer(n, dtype):
+    import qumcmc_b200 as q
+    _check(q, n, q.GenericMixer.TwoBodyMixer(n), dtype, (1, 2, 4) if n < 20 else (2,))
+
+
+def test_three_body_custom_and_coherent_sum_mixers():
+    import qumcmc_b200 as q
+    n = 15
+    _check(q, n, q.GenericMixer.ThreeBodyMixer(n), "fp32", (2, 3))
+    custom = q.CustomMixer(n, [[0, 14], [3, 7, 11], [1], [2, 5, 8, 13], [4, 9], [6, 10, 12, 14]])
+    _check(q, n, custom, "fp64", (1, 3, 6))
+    coh = q.CoherentMixerSum([q.GenericMixer.OneBodyMixer(n), q.GenericMixer.TwoBodyMixer(n)], [0.7, 0.3])
+    _check(q, n, coh, "fp32", (2, 5))
+    _check(q, n, coh, "fp64", (3,))
+
+
+def test_single_tile_mixer_runs_in_one_pass():
+    """Every term inside one 12-qubit tile: the whole proposal M (P M)^(r-1) is one pass per tile instance."""
+    import qumcmc_b200 as q
+    n = 16
+    mixer = q.CustomMixer(n, [[0, 1], [2, 3], [4, 5, 6], [7], [8, 9, 10, 11], [1, 11]])
+    _check(q, n, mixer, "fp64", (1, 4, 9))
+
+
+def test_incoherent_sum_uses_the_chosen_group():
+    import qumcmc_b200 as q
+    n = 14
+    inc = q.IncoherentMixerSum([q.GenericMixer.OneBodyMixer(n), q.GenericMixer.TwoBodyMixer(n)], [0.5, 0.5])
+    _check(q, n, inc, "fp64", (2,), group=0)
+    _check(q, n, inc, "fp64", (3,), group=1)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "fp64"])
+def test_general_path_chains_follow_the_oracle(dtype):
+    """quantum_enhanced_mcmc on the general path (two-body mixer, n = 14): proposals equal the oracle's sequential
+    inverse CDF (up to CDF-boundary ties in fp32), accept flags / counts / final states follow bit-exactly from the
+    device's proposals."""
+    import qumcmc_b200 as q
+    n, C, H, seed = 14, 6, 5, 19
+    J, h = models.packaged_random_model(n, 8)
+    m = q.IsingEnergyFunction(J, h)
+    mixer = q.GenericMixer.TwoBodyMixer(n)
+    offs, masks, w, _ = _lowered(mixer)
+    b = q.quantum_enhanced_mcmc(H, m, mixer, (0.25, 0.6), temperature=1.0, n_chains=C, seed=seed, dtype=dtype)
+    al = oracle.alpha(J, h)
+    mismatched = 0
+    for c in range(C):
+        cur = oracle.initial_state(seed, c, n)
+        assert int(b.initial[c]) == cur
+        e_cur = oracle.energy(J, h, cur)
+        hist = np.zeros(n + 1, dtype=np.int64)
+        nacc = 0
+        for hop in range(H):
+            ug, t, _, um, ua = oracle.hop_draws(seed, c, hop)
+            gamma = 0.25 + (0.6 - 0.25) * ug
+            r = oracle.trotter_steps(t, 0.8)
+            st = oracle.evolve(J, h, al, gamma, 0.8, r, masks, w, cur, gatewise=False)
+            want = oracle.sample_index(st, um)
+            sp = int(b.proposals[c, hop])
+            if sp != want:
+                cdf = np.cumsum(np.abs(st) ** 2)
+                lo = cdf[sp - 1] if sp > 0 else 0.0
+                assert dtype == "fp32" and lo - 5e-6 <= um <= cdf[sp] + 5e-6, (c, hop, sp, want)
+                mismatched += 1
+            e_sp = oracle.energy(J, h, sp)
+            acc = oracle.test_accept(e_cur, e_sp, 1.0, ua)
+            assert bool(b.accepted[c, hop]) == acc
+            hist[bin(cur ^ sp).count("1")] += 1
+            if acc:
+                cur, e_cur, nacc = sp, e_sp, nacc + 1
+        assert int(b.final_state[c]) == cur and int(b.acc_count[c]) == nacc
+        assert np.array_equal(b.hamming_hist[c], hist)
+    assert mismatched <= 2
