@@ -2148,7 +2148,11 @@ extern "C" int qmc_shard_create(qmc_shard **out, qmc_model *m, int rank, int log
     std::vector<int> kinds, ps;
     hi_group_geometry(nl, kinds, ps, sh->acts);
     const int K = (int)kinds.size();
-    QMC_REQUIRE(g <= sh->acts[0] && g <= 6, QMC_ERR_UNSUPPORTED, "sharded statevector: 2^%d ranks need a top group of >= %d qubits", g, g);
+    if (g > sh->acts[0] || g > 6) {
+        delete sh;
+        qmc_set_error("sharded statevector: 2^%d ranks need a top group of >= %d qubits", g, g);
+        return QMC_ERR_UNSUPPORTED;
+    }
     for (int L = 0; L < 2; ++L) {
         sh->perm[L].resize(n);
         for (int a = 0; a < n; ++a) sh->perm[L][a] = a;
