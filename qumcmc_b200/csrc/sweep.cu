@@ -72,6 +72,7 @@ struct SweepArgs {
     float *probs_out;         // PROBS mode: unnormalised |a|^2 (index order) or null
     float2 *amps_out;
     int pf_dist;              // > 0: each CTA L2-prefetches the tile of the CTA launched pf_dist later (in launch order)
+    int pf_lines;             // strided tiles: 1 = per-thread prefetch.global.L2 of 128-byte lines, 0 = bulk prefetch per row
     // Fused exchange (sharded statevector): when xchg_peers != null the pass stores amplitude L of this rank to
     // xchg_peers[L >> xchg_shift][(L & low) | (xchg_rank << xchg_shift)] -- the all-to-all that swaps the top local
     // index bits with the rank bits, done by the sweep's own stores over NVLink peer mappings (no staging copy).
@@ -429,6 +430,20 @@ __device__ __forceinline__ A64 *xchg_addr(const SweepArgs &a, int64_t local_idx)
 __device__ __forceinline__ void l2_prefetch_bulk(const void *p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// Per-lane variant for strided tiles: cp.async.bulk.prefetch takes a uniform address, so issuing one per row from
+// every lane makes the compiler serialise the warp (a 32-trip R2UR / UBLKPF / BRA.U.ANY loop, ~19 % of the stall
+// samples of the HI sweep); prefetch.global.L2 is an ordinary per-lane LSU instruction.
+__device__ __forceinline__ void l2_prefetch_line(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory"); }
+// A strided tile = `rows` rows of row_bytes contiguous bytes (64 KiB in total = 512 lines): 4 lines per thread.
+__device__ __forceinline__ void l2_prefetch_rows(const char *src, int64_t row_stride_bytes, int row_bytes, int tid) {
+    const int lines_per_row = row_bytes >> 7;
+#pragma unroll
+    for (int i = 0; i < (TILE * 8 / 128) / NT; ++i) {
+        const int l = tid + NT * i;
+        const int row = l / lines_per_row, within = l - row * lines_per_row;
+        l2_prefetch_line(src + row * row_stride_bytes + ((int64_t)within << 7));
+    }
+}
 __device__ __forceinline__ bool pf_target(const SweepArgs &a, const int *__restrict__ order, int list_off, int64_t &chain,
                                           int64_t &tile) {
     if (a.pf_dist <= 0) return false;
@@ -622,7 +637,8 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
             // tile rows: 2^W rows of 2^Lc contiguous amplitudes, row stride 2^12 amplitudes
             constexpr int ROWS = 1 << W, ROW_BYTES = (1 << G::Lc) * 8;
             const float2 *src = a.state + (pc << n) + (pt << G::Lc);
-            for (int r = tid; r < ROWS; r += NT) l2_prefetch_bulk(src + ((int64_t)r << 12), ROW_BYTES);
+            if (a.pf_lines && ROW_BYTES >= 128) l2_prefetch_rows(reinterpret_cast<const char *>(src), (int64_t)8 << 12, ROW_BYTES, tid);
+            else for (int r = tid; r < ROWS; r += NT) l2_prefetch_bulk(src + ((int64_t)r << 12), ROW_BYTES);
         }
     }
     build_hs(hs_s, G::two_rounds ? a.dr_hib : a.dr_hia, a.params + chain, tid);
@@ -887,7 +903,8 @@ __global__ void __launch_bounds__(NT, 3) hi8_sweep_kernel(const SweepArgs a, con
         int64_t pc, pt;
         if (pf_target(a, order, list_off, pc, pt)) {
             const float2 *src = a.state + (pc << n) + (int64_t)hi_tile_base(8, p, pt);
-            for (int r = tid; r < 256; r += NT) l2_prefetch_bulk(src + ((int64_t)r << p), 256);
+            if (a.pf_lines) l2_prefetch_rows(reinterpret_cast<const char *>(src), (int64_t)8 << p, 256, tid);
+            else for (int r = tid; r < 256; r += NT) l2_prefetch_bulk(src + ((int64_t)r << p), 256);
         }
     }
     if (ROLE != HI8_SINGLE) build_hs(hs_s, g.dr, a.params + chain, tid);
@@ -1754,6 +1771,8 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     // tuning knobs (defaults = measured best on B200; the env overrides exist for A/B runs and profiling)
     const char *pf_env = getenv("QUMCMC_SWEEP_PF");
     const int pf_dist = pf_env ? atoi(pf_env) : 222;
+    const char *pfl_env = getenv("QUMCMC_SWEEP_PFLINES");
+    const int pf_lines = pfl_env ? atoi(pfl_env) : 1;
     const char *fast_env = getenv("QUMCMC_SWEEP_FAST");
     const int r_cap = qmc_trotter_steps(11, dt);
     int r_max = r_cap;
@@ -1834,6 +1853,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         memcpy(a.dr_lo, w->dr_lo, sizeof(a.dr_lo)); memcpy(a.dr_hia, w->dr_hia, sizeof(a.dr_hia)); memcpy(a.dr_hib, w->dr_hib, sizeof(a.dr_hib));
         a.segsum = w->segsum;
         a.pf_dist = pf_dist;
+        a.pf_lines = pf_lines;
         a.xchg_peers = nullptr; a.xchg_shift = 0; a.xchg_rank = 0; a.xchg_g = 0; a.xchg_tile_bits = 0;
         a.probs_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float *>(probs_out) : nullptr;
         a.amps_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float2 *>(amps_out) : nullptr;
