@@ -126,3 +126,44 @@ def test_classical_mcmc_api_shapes_and_resume():
     assert all(s.bitstring in ("11010000", "00001011") for s in ch.states)
     with pytest.raises(q._lib.QmcUnsupported):
         q.classical_mcmc(20, m, Reverse(8), temperature=1.0, n_chains=4)
+
+
+@pytest.mark.gpu
+def test_classical_and_trajectory_edge_cases():
+    """Zero chains / zero hops are no-ops; malformed proposal specs and missing inputs fail loudly (no fallback)."""
+    import torch
+    import qumcmc_b200 as q
+    from qumcmc_b200 import _lib
+    from qumcmc_b200.classical_mcmc_routines import run_classical_chains
+    from qumcmc_b200.classical_mixers import CustomProposals, FixedWeightProposals, UniformProposals
+    J, h = models.packaged_random_model(7, 2)
+    m = q.IsingEnergyFunction(J, h)
+    b = run_classical_chains(m, UniformProposals(7), 0, 3, np.array([1, 2, 3], dtype=np.uint64), 1.0, 5)
+    assert b.proposals.shape == (3, 0) and b.final_state.tolist() == [1, 2, 3] and b.acc_count.tolist() == [0, 0, 0]
+    dm = m.device_model(0)
+    L = _lib.lib()
+    fin = torch.zeros(4, dtype=torch.int64, device="cuda")
+    kinds = np.array([7], dtype=np.int32)
+    params = np.array([0], dtype=np.uint64)
+    with pytest.raises(_lib.QmcError):                                        # unknown proposal kind
+        _lib.check(L.qmc_classical_chains(dm.handle, 4, 2, None, 0, 0, 1.0, 1, kinds.ctypes.data, params.ctypes.data, None,
+                                          1, None, None, fin.data_ptr(), None, None, None))
+    kinds[0], params[0] = _lib.CLASSICAL_FIXED_WEIGHT, 9
+    with pytest.raises(_lib.QmcError):                                        # bodyness > num_spins
+        _lib.check(L.qmc_classical_chains(dm.handle, 4, 2, None, 0, 0, 1.0, 1, kinds.ctypes.data, params.ctypes.data, None,
+                                          1, None, None, fin.data_ptr(), None, None, None))
+    kinds[0], params[0] = _lib.CLASSICAL_CUSTOM, 1 << 9
+    with pytest.raises(_lib.QmcError):                                        # flip mask outside the model
+        _lib.check(L.qmc_classical_chains(dm.handle, 4, 2, None, 0, 0, 1.0, 1, kinds.ctypes.data, params.ctypes.data, None,
+                                          1, None, None, fin.data_ptr(), None, None, None))
+    with pytest.raises(_lib.QmcError):                                        # non-positive temperature
+        run_classical_chains(m, FixedWeightProposals(7, 1), 5, 2, None, 0.0, 1)
+    with pytest.raises(ValueError):                                           # running KL without the target distribution
+        q.batch_trajectory_statistics(m, np.zeros(1, np.uint64), np.zeros((1, 3), np.uint64), np.zeros((1, 3), np.uint8),
+                                      None, to_observe=("kldiv",))
+    res = q.batch_trajectory_statistics(m, np.array([5], np.uint64), np.zeros((1, 0), np.uint64), np.zeros((1, 0), np.uint8),
+                                        np.full(128, 1 / 128), to_observe=("markov_chain", "kldiv"))
+    assert res["markov_chain"].tolist() == [[5]] and res["kldiv"].shape == (1, 1)
+    assert abs(res["kldiv"][0, 0] - (np.log(1 / 128) - (1 / 128) * np.log(1.0) - (127 / 128) * np.log(1e-8))) < 1e-9
+    ch = q.classical_mcmc(30, m, CustomProposals(7, [0, 6]), initial_state="0000000", temperature=1e9, seed=1)
+    assert set(ch.markov_chain) <= {"0000000", "1000001"}                     # one fixed flip pattern, always accepted
