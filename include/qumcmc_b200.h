@@ -212,6 +212,11 @@ int qmc_ipc_export(int device, void *dev_ptr, void *handle_out /* 64 bytes */, u
 int qmc_ipc_open(int device, const void *handle, uint64_t offset, void **ptr_out);
 int qmc_ipc_close_all(void);
 int qmc_shard_op_exchange(qmc_shard *sh, int op, int k, int pre, int layout, void *state_dev, int dst_which, void *stream);
+/* One chunk (the chunk-th of 2^chunk_bits contiguous sub-blocks of the shard) of a SINGLE (group k >= 1) or LO_SINGLE
+ * pass: local when dst_which < 0, fused with the exchange when dst_which = 0 / 1 (then chunk_bits >= log2(world): one
+ * destination rank per chunk).  Lets the caller overlap the local passes of chunk i+1 with the NVLink stores of chunk i. */
+int qmc_shard_op_chunk(qmc_shard *sh, int op, int k, int pre, int layout, void *state_dev, int dst_which,
+                       int chunk_bits, int64_t chunk, void *stream);
 int qmc_shard_norm(qmc_shard *sh, double *total_dev, void *stream);
 int qmc_shard_select(qmc_shard *sh, void *state_dev, double target, int layout, uint64_t *index_dev, void *stream);
 /* Test hook: LO_FINAL that also writes |a|^2 of the local shard (2^(n-g) floats, local index order). */

@@ -41,7 +41,7 @@ EXPORTS = [
     "qmc_shard_create", "qmc_shard_destroy", "qmc_shard_num_groups", "qmc_shard_begin", "qmc_shard_op",
     "qmc_shard_norm", "qmc_shard_select", "qmc_shard_final_probs", "qmc_shard_set_peers", "qmc_shard_op_exchange",
     "qmc_enable_peer_access", "qmc_ipc_export", "qmc_ipc_open", "qmc_ipc_close_all",
-    "qmc_classical_chains", "qmc_classical_chains_host", "qmc_trajectory_stats", "qmc_state_moments",
+    "qmc_classical_chains", "qmc_classical_chains_host", "qmc_trajectory_stats", "qmc_state_moments", "qmc_shard_op_chunk",
 ]
 
 
@@ -121,6 +121,7 @@ def lib() -> C.CDLL:
     L.qmc_state_moments.argtypes = [C.c_void_p, C.c_int64, u64p, vp, i64p, i64p, i64p, vp]
     L.qmc_classical_chains_host.argtypes = [C.c_void_p, C.c_int64, C.c_int64, u64p, C.c_uint64, C.c_uint32, C.c_double,
                                             C.c_int, vp, vp, vp, C.c_uint64, u64p, vp, u64p, i64p, i64p]
+    L.qmc_shard_op_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int64, vp]
     L.qmc_shard_op_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -79,6 +79,7 @@ struct SweepArgs {
     float2 *const *xchg_peers;
     int xchg_shift, xchg_rank;
     int xchg_g, xchg_tile_bits;  // log2(ranks), log2(tiles of the local shard)
+    int64_t xchg_idx0;           // chunked pass: index of the chunk's first amplitude inside the shard (else 0)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -415,11 +416,13 @@ __device__ __forceinline__ int hi_loc_b(int tid, int j) { return (tid & 31) | (j
 // GPU fan out over all peers instead of every GPU writing to the same peer at the same time.
 __device__ __forceinline__ int64_t sweep_tile(const SweepArgs &a, unsigned b) {
     if (!a.xchg_peers) return (int64_t)b;
+    if (a.xchg_tile_bits < a.xchg_g) return (int64_t)b;  // a chunk inside one destination: the caller orders the chunks
     const unsigned W1 = (1u << a.xchg_g) - 1u;
     return ((int64_t)((b + (unsigned)a.xchg_rank) & W1) << (a.xchg_tile_bits - a.xchg_g)) | (int64_t)(b >> a.xchg_g);
 }
 
 __device__ __forceinline__ A64 *xchg_addr(const SweepArgs &a, int64_t local_idx) {
+    local_idx += a.xchg_idx0;
     const int64_t low = local_idx & (((int64_t)1 << a.xchg_shift) - 1);
     return reinterpret_cast<A64 *>(a.xchg_peers[local_idx >> a.xchg_shift]) + (low | ((int64_t)a.xchg_rank << a.xchg_shift));
 }
@@ -1854,7 +1857,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         a.segsum = w->segsum;
         a.pf_dist = pf_dist;
         a.pf_lines = pf_lines;
-        a.xchg_peers = nullptr; a.xchg_shift = 0; a.xchg_rank = 0; a.xchg_g = 0; a.xchg_tile_bits = 0;
+        a.xchg_peers = nullptr; a.xchg_shift = 0; a.xchg_rank = 0; a.xchg_g = 0; a.xchg_tile_bits = 0; a.xchg_idx0 = 0;
         a.probs_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float *>(probs_out) : nullptr;
         a.amps_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float2 *>(amps_out) : nullptr;
         // PROBS with amps only: still need a probs-free normalisation; handled by the normalise kernel
@@ -2250,7 +2253,8 @@ extern "C" int qmc_shard_begin(qmc_shard *sh, uint64_t s, double gamma, int r, d
 // One local pass.  op: 0 FIRST(top group: analytic M|s>, P, M_top) | 1 MID(top group: M_top restricted to the
 // `pre` swapped-in qubits, P, M_top) | 2 SINGLE(group k, its active qubits; k == 0 with pre > 0: only the `pre`
 // swapped-in qubits) | 3 LO_SINGLE | 4 LO_FINAL (segment sums; r == 1: of the analytic product state).
-static int shard_op_impl(qmc_shard *sh, int op, int k, int pre, int layout, void *state_dev, int dst_which, void *stream) {
+static int shard_op_impl(qmc_shard *sh, int op, int k, int pre, int layout, void *state_dev, int dst_which, void *stream,
+                         int chunk_bits = 0, int64_t chunk = 0) {
     QMC_REQUIRE(sh && state_dev, QMC_ERR_BADARG, "qmc_shard_op: null argument");
     QMC_REQUIRE(dst_which < 0 || (dst_which < 2 && sh->d_peers[dst_which]), QMC_ERR_BADARG,
                 "qmc_shard_op_exchange: peer table %d not set (qmc_shard_set_peers)", dst_which);
@@ -2268,14 +2272,34 @@ static int shard_op_impl(qmc_shard *sh, int op, int k, int pre, int layout, void
     a.params = sh->params;
     a.segsum = sh->segsum;
     a.pf_dist = 0;
+    if (chunk_bits > 0) {
+        // A pass that leaves the top chunk_bits local positions alone (LO_SINGLE, SINGLE on a group below them) is the
+        // same pass on each of the 2^chunk_bits contiguous sub-blocks: the chunk becomes a smaller "shard" whose fixed
+        // top bits join the global bits.  Lets the caller pipeline local passes against the exchange chunk by chunk.
+        QMC_REQUIRE(op == 2 || op == 3, QMC_ERR_BADARG, "chunked passes: SINGLE / LO_SINGLE only");
+        const int top = op == 3 ? TILE_BITS : sh->groups[layout][k].args.p + (sh->groups[layout][k].kind == 8 ? 8 : 6);
+        QMC_REQUIRE(k > 0 || op == 3, QMC_ERR_BADARG, "chunked passes: not on the top group");
+        QMC_REQUIRE(sh->nl - chunk_bits >= top && sh->nl - chunk_bits >= TILE_BITS, QMC_ERR_BADARG,
+                    "chunked pass: %d chunk bits reach into the pass's qubits", chunk_bits);
+        QMC_REQUIRE(chunk >= 0 && chunk < ((int64_t)1 << chunk_bits), QMC_ERR_BADARG, "chunk %lld of 2^%d", (long long)chunk, chunk_bits);
+        a.n = sh->nl - chunk_bits;
+        a.state += chunk << a.n;
+        a.gbits |= (unsigned long long)chunk << a.n;
+    }
     if (dst_which >= 0) {
         a.xchg_peers = sh->d_peers[dst_which];
         a.xchg_shift = sh->nl - sh->g;
         a.xchg_rank = sh->rank;
         a.xchg_g = sh->g;
-        a.xchg_tile_bits = sh->nl - TILE_BITS;
+        a.xchg_tile_bits = a.n - TILE_BITS;
+        a.xchg_idx0 = chunk_bits > 0 ? chunk << a.n : 0;
+        if (chunk_bits > 0 && chunk_bits < sh->g) {
+            qmc_set_error("chunked exchange pass: chunk_bits >= log2(world) required");
+            return QMC_ERR_BADARG;
+        }
+        if (chunk_bits > 0) a.xchg_tile_bits = 0;  // one destination per chunk: no renumbering
     }
-    const int64_t tiles = (int64_t)1 << (sh->nl - TILE_BITS);
+    const int64_t tiles = (int64_t)1 << (a.n - TILE_BITS);
     const HiGroup &G = sh->groups[layout][k];
     int rc = QMC_OK;
     switch (op) {
@@ -2330,6 +2354,16 @@ extern "C" int qmc_shard_op_exchange(qmc_shard *sh, int op, int k, int pre, int 
                                      void *stream) {
     QMC_REQUIRE(dst_which == 0 || dst_which == 1, QMC_ERR_BADARG, "qmc_shard_op_exchange: dst_which %d", dst_which);
     return shard_op_impl(sh, op, k, pre, layout, state_dev, dst_which, stream);
+}
+
+// One chunk (the `chunk`-th of 2^chunk_bits contiguous sub-blocks of the shard) of a SINGLE / LO_SINGLE pass, local
+// (dst_which < 0) or fused with the exchange (dst_which = 0 / 1; needs chunk_bits >= log2(world), i.e. one destination
+// rank per chunk).  The caller orders the chunks (destinations rotated by rank) and overlaps streams.
+extern "C" int qmc_shard_op_chunk(qmc_shard *sh, int op, int k, int pre, int layout, void *state_dev, int dst_which,
+                                  int chunk_bits, int64_t chunk, void *stream) {
+    QMC_REQUIRE(dst_which >= -1 && dst_which <= 1, QMC_ERR_BADARG, "qmc_shard_op_chunk: dst_which %d", dst_which);
+    QMC_REQUIRE(chunk_bits >= 1, QMC_ERR_BADARG, "qmc_shard_op_chunk: chunk_bits %d", chunk_bits);
+    return shard_op_impl(sh, op, k, pre, layout, state_dev, dst_which, stream, chunk_bits, chunk);
 }
 
 // sum of |a|^2 over the local shard (after LO_FINAL) -> total_dev[0]

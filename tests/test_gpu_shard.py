@@ -15,7 +15,7 @@ from tests.shard_sim import logical_indices
 pytestmark = pytest.mark.gpu
 
 
-def _emulated_proposal(n, g, r, s, gamma, seed=11, us=(), fused=False):
+def _emulated_proposal(n, g, r, s, gamma, seed=11, us=(), fused=False, chunk_bits=0):
     import torch
     import qumcmc_b200 as q
     from qumcmc_b200.sharded import EXCHANGE, ShardHandle, pick_owner, sharded_plan
@@ -35,9 +35,24 @@ def _emulated_proposal(n, g, r, s, gamma, seed=11, us=(), fused=False):
         for hd in hs:
             for which in (0, 1):
                 hd.set_peers(which, [b.data_ptr() for b in both[which]])
+        from qumcmc_b200.sharded import LO_SINGLE, SINGLE, chunk_order
         cur, i = 0, 0
         while i < len(ops):
             kind, k, pre = ops[i]
+            j = i
+            while chunk_bits and j < len(ops) and (ops[j][0] == LO_SINGLE or (ops[j][0] == SINGLE and ops[j][1] > 0)):
+                j += 1
+            if chunk_bits and j > i and j < len(ops) and ops[j][0] == EXCHANGE:   # pipelined run, chunk by chunk
+                for R, hd in enumerate(hs):
+                    for c in chunk_order(chunk_bits, g, R):
+                        for kind2, k2, pre2 in ops[i:j - 1]:
+                            hd.op_chunk(kind2, k2, pre2, layout, both[cur][R], -1, chunk_bits, c)
+                        kind2, k2, pre2 = ops[j - 1]
+                        hd.op_chunk(kind2, k2, pre2, layout, both[cur][R], 1 - cur, chunk_bits, c)
+                cur ^= 1
+                layout ^= 1
+                i = j + 1
+                continue
             if i + 1 < len(ops) and ops[i + 1][0] == EXCHANGE:
                 for R, hd in enumerate(hs):
                     hd.op_exchange(kind, k, pre, layout, both[cur][R], 1 - cur)
@@ -115,6 +130,23 @@ def test_shard_fused_exchange_matches_staged(n, g, r):
     assert np.allclose(t0, t1, rtol=1e-12, atol=0)       # the norm reduction uses atomics: summation order varies
 
 
+@pytest.mark.parametrize("n,g,r,cb", [(19, 1, 3, 1), (20, 2, 4, 3), (22, 3, 4, 3), (24, 1, 3, 2), (25, 2, 5, 4), (25, 2, 2, 2)])
+def test_shard_chunked_exchange_matches_staged(n, g, r, cb):
+    """qmc_shard_op_chunk: the passes before an exchange run chunk by chunk (the last one storing into the peers'
+    buffers) -- bit-identical amplitudes to pass-then-exchange on the whole shard."""
+    from qumcmc_b200.sharded import max_chunk_bits
+    assert g <= cb <= max_chunk_bits(n - g)
+    rng = np.random.default_rng(31 * n + g + r)
+    s = int(rng.integers(0, 1 << n))
+    gamma = float(rng.uniform(0.25, 0.6))
+    us = [0.2, 0.71]
+    _, _, p0, t0, l0, k0 = _emulated_proposal(n, g, r, s, gamma, us=us)
+    _, _, p1, t1, l1, k1 = _emulated_proposal(n, g, r, s, gamma, us=us, fused=True, chunk_bits=cb)
+    assert l0 == l1 == 0
+    assert np.array_equal(p0, p1) and k0 == k1
+    assert np.allclose(t0, t1, rtol=1e-12, atol=0)
+
+
 def test_shard_rejects_bad_configurations():
     import qumcmc_b200 as q
     from qumcmc_b200 import _lib
@@ -137,14 +169,15 @@ def _nccl_worker(rank, world, port, n, cases, q, fused):
         import qumcmc_b200 as qq
         from qumcmc_b200.sharded import ShardedProposer
         J, h = models.packaged_random_model(n, 11)
-        prop = ShardedProposer(qq.IsingEnergyFunction(J, h), qq.GenericMixer.OneBodyMixer(n), device=rank, fused=fused)
+        prop = ShardedProposer(qq.IsingEnergyFunction(J, h), qq.GenericMixer.OneBodyMixer(n), device=rank, fused=bool(fused),
+                               chunk_bits=(2 if fused == "chunked" else 0))
         out = [prop.propose(s, gamma, r, u) for (s, gamma, r, u) in cases]
         q.put((rank, out, prop.exchanges))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("fused", [False, True, "chunked"])
 def test_shard_nccl_world2_matches_emulation(fused):
     import torch
     if torch.cuda.device_count() < 2:
