@@ -6,7 +6,7 @@ static bool use_small_path(const qmc_model *m, int dtype) {
     const int lim = dtype == QMC_DTYPE_F64 ? QMC_SMEM_MAX_SPINS_F64 : QMC_SMEM_MAX_SPINS_F32;
     if (m->n > lim) return false;
     const size_t esz = dtype == QMC_DTYPE_F64 ? 16 : 8;
-    const size_t smem = (2 * ((size_t)1 << m->n) + (size_t)m->max_terms_in_group) * esz;
+    const size_t smem = (2 * ((size_t)1 << m->n) + (size_t)m->max_terms_in_group) * esz + sizeof(int) * (size_t)m->max_terms_in_group;
     return smem <= 227 * 1024;
 }
 

@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(SMALL_NT) smem_chain_kernel(const SmallParams 
     T2 *st = reinterpret_cast<T2 *>(smraw);
     T2 *ph = st + N;
     T2 *cs = ph + N;
+    int *tm = reinterpret_cast<int *>(cs + p.max_terms);  // term masks of the current group
     __shared__ double s_incl[SMALL_NT];
     __shared__ double s_warp[SMALL_NT / 32];
     __shared__ unsigned long long s_sel;
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(SMALL_NT) smem_chain_kernel(const SmallParams 
         const int t0 = p.group_off[grp], t1 = p.group_off[grp + 1];
         const int nterms = t1 - t0;
 
-        // ---- per-term rotation constants: exp(-i gamma w dt X_S) -> (cos, sin)
+        // ---- per-term rotation constants: exp(-i gamma w dt X_S) -> (cos, sin); masks staged next to them
         for (int k = tid; k < nterms; k += NT) {
             double s, c;
             sincos(gamma * p.weights[t0 + k] * p.dt, &s, &c);
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(SMALL_NT) smem_chain_kernel(const SmallParams 
             v.x = (T)c;
             v.y = (T)s;
             cs[k] = v;
+            tm[k] = (int)p.masks[t0 + k];
         }
         // ---- K1: phase table for this proposal (same c for all r-1 layers)
         const bool phase = p.phase_active && r > 1;
@@ -139,14 +141,52 @@ __global__ void __launch_bounds__(SMALL_NT) smem_chain_kernel(const SmallParams 
                 }
                 __syncthreads();
             }
-            for (int k = 0; k < nterms; ++k) {
-                const uint64_t mask = p.masks[t0 + k];
-                const int tb = 63 - __clzll((long long)mask);
+            // Terms two at a time: X_S1, X_S2 (S1 != S2) act on orbits {i, i^S1, i^S2, i^S1^S2}; a thread owns whole
+            // orbits, so both rotations run in registers between one load and one store of the four amplitudes --
+            // half the shared-memory traffic and half the barriers, the same arithmetic per amplitude in the same order.
+            int k = 0;
+            while (k < nterms) {
+                const int m1 = tm[k];
+                const int m2 = (k + 1 < nterms) ? tm[k + 1] : m1;
+                if (m2 != m1) {
+                    const int p1 = 31 - __clz(m1);
+                    const int m2r = ((m2 >> p1) & 1) ? (m2 ^ m1) : m2;
+                    const int p2 = 31 - __clz(m2r);
+                    const int lo_b = p1 < p2 ? p1 : p2, hi_b = p1 < p2 ? p2 : p1;
+                    const int lo_m = (1 << lo_b) - 1, hi_m = (1 << hi_b) - 1;
+                    const T c1 = cs[k].x, s1 = cs[k].y, c2 = cs[k + 1].x, s2 = cs[k + 1].y;
+                    for (int q = tid; q < (N >> 2); q += NT) {
+                        int i = ((q >> lo_b) << (lo_b + 1)) | (q & lo_m);   // orbit representative: bits p1, p2 clear
+                        i = ((i >> hi_b) << (hi_b + 1)) | (i & hi_m);
+                        const int i1 = i ^ m1, i2 = i ^ m2, i3 = i1 ^ m2;
+                        T2 a0 = st[i], a1 = st[i1], a2 = st[i2], a3 = st[i3];
+                        T2 t0_, t1_;
+                        // term k on (a0, a1) and (a2, a3)
+                        t0_.x = c1 * a0.x + s1 * a1.y; t0_.y = c1 * a0.y - s1 * a1.x;
+                        t1_.x = c1 * a1.x + s1 * a0.y; t1_.y = c1 * a1.y - s1 * a0.x;
+                        a0 = t0_; a1 = t1_;
+                        t0_.x = c1 * a2.x + s1 * a3.y; t0_.y = c1 * a2.y - s1 * a3.x;
+                        t1_.x = c1 * a3.x + s1 * a2.y; t1_.y = c1 * a3.y - s1 * a2.x;
+                        a2 = t0_; a3 = t1_;
+                        // term k+1 on (a0, a2) and (a1, a3)
+                        t0_.x = c2 * a0.x + s2 * a2.y; t0_.y = c2 * a0.y - s2 * a2.x;
+                        t1_.x = c2 * a2.x + s2 * a0.y; t1_.y = c2 * a2.y - s2 * a0.x;
+                        a0 = t0_; a2 = t1_;
+                        t0_.x = c2 * a1.x + s2 * a3.y; t0_.y = c2 * a1.y - s2 * a3.x;
+                        t1_.x = c2 * a3.x + s2 * a1.y; t1_.y = c2 * a3.y - s2 * a1.x;
+                        a1 = t0_; a3 = t1_;
+                        st[i] = a0; st[i1] = a1; st[i2] = a2; st[i3] = a3;
+                    }
+                    __syncthreads();
+                    k += 2;
+                    continue;
+                }
+                const int tb = 31 - __clz(m1);
                 const int lowmask = (1 << tb) - 1;
                 const T c = cs[k].x, s = cs[k].y;
                 for (int q = tid; q < (N >> 1); q += NT) {
                     const int i = ((q >> tb) << (tb + 1)) | (q & lowmask);
-                    const int j = i ^ (int)mask;
+                    const int j = i ^ m1;
                     const T2 a = st[i], b = st[j];
                     T2 oa, ob;
                     oa.x = c * a.x + s * b.y;
@@ -157,6 +197,7 @@ __global__ void __launch_bounds__(SMALL_NT) smem_chain_kernel(const SmallParams 
                     st[j] = ob;
                 }
                 __syncthreads();
+                k += 1;
             }
         }
 
@@ -292,7 +333,7 @@ int qmc_small_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
 
     const size_t N = (size_t)1 << m->n;
     const size_t esz = dtype == QMC_DTYPE_F64 ? sizeof(double2) : sizeof(float2);
-    const size_t smem = (2 * N + (size_t)m->max_terms_in_group) * esz;
+    const size_t smem = (2 * N + (size_t)m->max_terms_in_group) * esz + sizeof(int) * (size_t)m->max_terms_in_group;
     QMC_REQUIRE(smem <= 227 * 1024, QMC_ERR_UNSUPPORTED,
                 "shared-memory path: n=%d with %d mixer terms needs %zu B of shared memory (> 227 KiB)", m->n,
                 m->max_terms_in_group, smem);
