@@ -38,7 +38,7 @@ struct GenChain {  // per chain, rewritten every hop
 };
 
 struct GenArgs {
-    int n, n_groups, phase_active, mode;
+    int n, n_groups, phase_active, mode, max_terms;
     double alpha, dt, temperature, g_lo, g_hi;
     const GenPass *passes;
     const int *group_pass_off;       // [n_groups + 1]
@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(GTH) gen_pass_kernel(const GenArgs a, const in
     extern __shared__ __align__(16) unsigned char smraw[];
     T2 *st = reinterpret_cast<T2 *>(smraw);           // [GN]
     T2 *cs = st + GN;                                 // [terms of this pass]
+    int *tm = reinterpret_cast<int *>(cs + a.max_terms);  // their tile-local masks
     __shared__ unsigned long long hoff[GN >> GFORCED];  // index offset of the local bits 4..11
     __shared__ GenChain ch_s;
     const int tid = threadIdx.x;
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(GTH) gen_pass_kernel(const GenArgs a, const in
         v.x = (T)cc;
         v.y = (T)s;
         cs[k] = v;
+        tm[k] = a.lmask[P.term0 + k];
     }
     __syncthreads();
     T2 *state = reinterpret_cast<T2 *>(a.state) + ((size_t)c << n);
@@ -227,15 +229,51 @@ __global__ void __launch_bounds__(GTH) gen_pass_kernel(const GenArgs a, const in
             }
             __syncthreads();
         }
-        for (int k = 0; k < nterms; ++k) {
-            const int mask = a.lmask[P.term0 + k];
-            const int tb = 31 - __clz(mask);
+        // Terms two at a time on orbits {i, i^S1, i^S2, i^S1^S2} held in registers (as in small_n.cu): half the
+        // shared-memory traffic and half the barriers, same arithmetic per amplitude in the same order.
+        int k = 0;
+        while (k < nterms) {
+            const int m1 = tm[k];
+            const int m2 = (k + 1 < nterms) ? tm[k + 1] : m1;
+            if (m2 != m1) {
+                const int p1 = 31 - __clz(m1);
+                const int m2r = ((m2 >> p1) & 1) ? (m2 ^ m1) : m2;
+                const int p2 = 31 - __clz(m2r);
+                const int lo_b = p1 < p2 ? p1 : p2, hi_b = p1 < p2 ? p2 : p1;
+                const int lo_m = (1 << lo_b) - 1, hi_m = (1 << hi_b) - 1;
+                const T c1 = cs[k].x, s1 = cs[k].y, c2 = cs[k + 1].x, s2 = cs[k + 1].y;
+#pragma unroll 2
+                for (int q = tid; q < (GN >> 2); q += GTH) {
+                    int i = ((q >> lo_b) << (lo_b + 1)) | (q & lo_m);  // orbit representative: bits p1, p2 clear
+                    i = ((i >> hi_b) << (hi_b + 1)) | (i & hi_m);
+                    const int i1 = i ^ m1, i2 = i ^ m2, i3 = i1 ^ m2;
+                    T2 a0 = st[i], a1 = st[i1], a2 = st[i2], a3 = st[i3];
+                    T2 u0, u1;
+                    u0.x = c1 * a0.x + s1 * a1.y; u0.y = c1 * a0.y - s1 * a1.x;
+                    u1.x = c1 * a1.x + s1 * a0.y; u1.y = c1 * a1.y - s1 * a0.x;
+                    a0 = u0; a1 = u1;
+                    u0.x = c1 * a2.x + s1 * a3.y; u0.y = c1 * a2.y - s1 * a3.x;
+                    u1.x = c1 * a3.x + s1 * a2.y; u1.y = c1 * a3.y - s1 * a2.x;
+                    a2 = u0; a3 = u1;
+                    u0.x = c2 * a0.x + s2 * a2.y; u0.y = c2 * a0.y - s2 * a2.x;
+                    u1.x = c2 * a2.x + s2 * a0.y; u1.y = c2 * a2.y - s2 * a0.x;
+                    a0 = u0; a2 = u1;
+                    u0.x = c2 * a1.x + s2 * a3.y; u0.y = c2 * a1.y - s2 * a3.x;
+                    u1.x = c2 * a3.x + s2 * a1.y; u1.y = c2 * a3.y - s2 * a1.x;
+                    a1 = u0; a3 = u1;
+                    st[i] = a0; st[i1] = a1; st[i2] = a2; st[i3] = a3;
+                }
+                __syncthreads();
+                k += 2;
+                continue;
+            }
+            const int tb = 31 - __clz(m1);
             const int lowmask = (1 << tb) - 1;
             const T cc = cs[k].x, s = cs[k].y;
 #pragma unroll 4
             for (int q = tid; q < (GN >> 1); q += GTH) {
                 const int i = ((q >> tb) << (tb + 1)) | (q & lowmask);
-                const int j = i ^ mask;
+                const int j = i ^ m1;
                 const T2 x = st[i], y = st[j];
                 T2 ox, oy;
                 ox.x = cc * x.x + s * y.y;
@@ -246,6 +284,7 @@ __global__ void __launch_bounds__(GTH) gen_pass_kernel(const GenArgs a, const in
                 st[j] = oy;
             }
             __syncthreads();
+            k += 1;
         }
     }
 #pragma unroll 4
@@ -543,7 +582,7 @@ static int general_run_t(qmc_model *m, GeneralWorkspace *w, GenArgs a, int64_t n
     using T2 = typename V2<T>::type;
     const int n = m->n;
     const int64_t N = 1LL << n;
-    const size_t smem = sizeof(T2) * (size_t)(GN + w->max_terms_per_pass);
+    const size_t smem = sizeof(T2) * (size_t)(GN + w->max_terms_per_pass) + sizeof(int) * (size_t)w->max_terms_per_pass;
     QMC_REQUIRE(smem <= 200 * 1024, QMC_ERR_UNSUPPORTED, "general path: %d mixer terms in one tile", w->max_terms_per_pass);
     QMC_CUDA_TRY(cudaFuncSetAttribute(gen_pass_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     size_t free_b = 0, total_b = 0;
@@ -623,7 +662,7 @@ int qmc_general_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, co
     }
     GenArgs a;
     memset(&a, 0, sizeof(a));
-    a.n = n; a.n_groups = m->n_groups; a.phase_active = m->phase_active; a.mode = mode;
+    a.n = n; a.n_groups = m->n_groups; a.phase_active = m->phase_active; a.mode = mode; a.max_terms = w->max_terms_per_pass;
     a.alpha = m->alpha; a.dt = dt; a.temperature = temperature; a.g_lo = g_lo; a.g_hi = g_hi;
     a.passes = w->d_passes; a.group_pass_off = w->d_group_pass_off; a.lmask = w->d_lmask; a.weight = w->d_weight;
     a.D = w->dD; a.J = m->dJ; a.h = m->dh; a.group_cum = m->d_group_cum;
