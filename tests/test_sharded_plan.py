@@ -141,3 +141,22 @@ def test_sharded_schedule_gloo_world2():
         p[logical_indices(rank, n - 1, 1, layout)] = probs
         assert abs(sum(totals) - 1.0) < 1e-10
     assert np.abs(p - ref).max() < 1e-12
+
+
+def test_chunk_order_rotates_destinations_and_covers_every_chunk():
+    from qumcmc_b200.sharded import chunk_order, max_chunk_bits
+    for g in (1, 2, 3):
+        W = 1 << g
+        for cb in range(g, g + 3):
+            orders = [chunk_order(cb, g, rank) for rank in range(W)]
+            for rank, order in enumerate(orders):
+                assert sorted(order) == list(range(1 << cb))                    # every chunk exactly once
+            for step in range(1 << cb):
+                dests = [orders[rank][step] >> (cb - g) for rank in range(W)]  # destination = top g bits of the chunk
+                assert sorted(dests) == list(range(W))                          # all ranks store to different peers
+    # a chunk must keep the LO tile (13 positions) and the windows of the groups below the top one
+    for nl in range(18, 35):
+        geo = shard_geometry(nl)
+        cb = max_chunk_bits(nl)
+        assert nl - cb >= 13 and all(hi <= nl - cb for _, hi in geo[1:])
+        assert cb >= 0
