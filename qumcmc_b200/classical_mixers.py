@@ -1,51 +1,73 @@
-"""Classical proposal rules of the reference's ``qumcmc.classical_mixers``
-(/root/reference/qumcmc/classical_mixers.py).  ``propose_transition`` keeps the reference's host-side string
-semantics (user subclasses plug in there); the four built-in rules also ``lower()`` to the
-``(kinds, params, probabilities)`` mixture that ``qmc_classical_chains`` runs on the device."""
+"""Classical proposal rules with the surface of the reference's ``qumcmc.classical_mixers``
+(/root/reference/qumcmc/classical_mixers.py:27-101).
+
+Every built-in rule is described by what it does to the current state -- replace it (uniform) or xor it with a flip
+pattern -- and ``lower()`` turns that description into the ``(kind, param, probability)`` mixture that
+``qmc_classical_chains`` runs on the device.  ``propose_transition`` is the host-side
+entry point the reference's callers use; user subclasses only need to override it (they then run in the reference's
+host loop, see ``classical_mcmc``)."""
 from __future__ import annotations
 
 from abc import ABC, abstractmethod
-from typing import List
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
 from . import _lib
 from .basic_utils import get_random_state, random_bstr, xor_strings
 
+Lowered = List[Tuple[int, int, float]]
+
 
 class ClassicalMixer(ABC):
+    """A rule ``current bitstring -> proposed bitstring`` over ``num_spins`` spins."""
+
     def __init__(self, num_spins: int) -> None:
         self.num_spins = num_spins
         self._precompute_properties()
 
+    def _precompute_properties(self):
+        """Hook kept for subclasses written against the reference."""
+
+    def _require_width(self, state: str) -> None:
+        assert len(state) == self.num_spins, "Wrong 'current_state' "
+
     @abstractmethod
     def propose_transition(self, current_state: str) -> str: ...
 
-    def _precompute_properties(self):
-        pass
-
-    def _check(self, current_state: str) -> None:
-        assert len(current_state) == self.num_spins, "Wrong 'current_state' "
-
-    def lower(self):
-        """``[(kind, param, probability), ...]`` for the device kernel, or ``None`` when the rule only exists as
-        host code (a user subclass)."""
+    def lower(self) -> Optional[Lowered]:
+        """Device form ``[(kind, param, probability), ...]``; ``None`` = host-only rule (the default for subclasses)."""
         return None
 
 
+class _XorRule(ClassicalMixer):
+    """Built-in rules of the form ``state xor pattern``; subclasses supply the pattern."""
+
+    def _pattern(self) -> str:
+        raise NotImplementedError
+
+    def propose_transition(self, current_state: str) -> str:
+        self._require_width(current_state)
+        return xor_strings(current_state, self._pattern())
+
+
 class UniformProposals(ClassicalMixer):
+    """Independent uniform draw over all 2^n states (reference :27-40)."""
+
     def __repr__(self):
         return f"UniformProposals({self.num_spins})"
 
-    def propose_transition(self, current_state=None):
-        self._check(current_state)
+    def propose_transition(self, current_state=None) -> str:
+        self._require_width(current_state)
         return get_random_state(self.num_spins)
 
-    def lower(self):
+    def lower(self) -> Lowered:
         return [(_lib.CLASSICAL_UNIFORM, 0, 1.0)]
 
 
-class FixedWeightProposals(ClassicalMixer):
+class FixedWeightProposals(_XorRule):
+    """Flip ``bodyness`` spins chosen uniformly at random (reference :43-59, ``random_bstr``)."""
+
     def __init__(self, num_spins: int, bodyness: int) -> None:
         assert bodyness <= num_spins, "Incorrect"
         self.bodyness = bodyness
@@ -54,15 +76,16 @@ class FixedWeightProposals(ClassicalMixer):
     def __repr__(self):
         return f"FixedWeightProposals({self.num_spins}, ({self.bodyness}))"
 
-    def propose_transition(self, current_state: str):
-        self._check(current_state)
-        return xor_strings(current_state, random_bstr(self.num_spins, self.bodyness))
+    def _pattern(self) -> str:
+        return random_bstr(self.num_spins, self.bodyness)
 
-    def lower(self):
+    def lower(self) -> Lowered:
         return [(_lib.CLASSICAL_FIXED_WEIGHT, int(self.bodyness), 1.0)]
 
 
-class CustomProposals(ClassicalMixer):
+class CustomProposals(_XorRule):
+    """Flip a fixed set of string positions (reference :62-78)."""
+
     def __init__(self, num_spins: int, flip_pattern: List[int]) -> None:
         self.flip_pattern = flip_pattern
         super().__init__(num_spins)
@@ -70,42 +93,44 @@ class CustomProposals(ClassicalMixer):
     def __repr__(self):
         return f"CustomProposals({self.num_spins}, pattern: {self.flip_pattern})"
 
-    def propose_transition(self, current_state: str):
-        self._check(current_state)
-        flips = "".join("1" if i in self.flip_pattern else "0" for i in range(self.num_spins))
-        return xor_strings(current_state, flips)
+    def _positions(self) -> Sequence[int]:
+        return sorted(i for i in set(self.flip_pattern) if 0 <= i < self.num_spins)
 
-    def lower(self):
-        mask = 0
-        for i in set(self.flip_pattern):  # string position i (MSB first) <-> index bit n-1-i
-            if 0 <= i < self.num_spins:
-                mask |= 1 << (self.num_spins - 1 - i)
-        return [(_lib.CLASSICAL_CUSTOM, mask, 1.0)]
+    def _pattern(self) -> str:
+        marks = ["0"] * self.num_spins
+        for i in self._positions():
+            marks[i] = "1"
+        return "".join(marks)
+
+    def lower(self) -> Lowered:
+        n = self.num_spins  # string position i (MSB first) <-> index bit n-1-i
+        return [(_lib.CLASSICAL_CUSTOM, sum(1 << (n - 1 - i) for i in self._positions()), 1.0)]
 
 
 class CombineProposals(ClassicalMixer):
+    """Mixture: pick one of ``proposal_methods`` with the given probabilities, then apply it (reference :81-101)."""
+
     def __init__(self, proposal_methods: List[ClassicalMixer], probabilities: List[float]) -> None:
-        self.num_spins = proposal_methods[0].num_spins
-        assert all(self.num_spins == pm.num_spins for pm in proposal_methods), \
-            "Mixers don't have the same number of qubits"
-        assert len(probabilities) == len(proposal_methods), \
-            "Length of list of mixers and probabilities is not equal"
-        self.probabilities = np.array(probabilities) / sum(probabilities)
+        widths = {pm.num_spins for pm in proposal_methods}
+        assert len(widths) == 1, "Mixers don't have the same number of qubits"
+        assert len(probabilities) == len(proposal_methods), "Length of list of mixers and probabilities is not equal"
+        self.num_spins = widths.pop()
         self.proposal_methods = proposal_methods
+        self.probabilities = np.array(probabilities) / sum(probabilities)
 
     def __repr__(self):
         return f"CombinedProposals( num-proposal-methods = {len(self.proposal_methods)} , p = {self.probabilities})"
 
-    def propose_transition(self, current_state: str):
-        self._check(current_state)
-        method = np.random.choice(self.proposal_methods, p=self.probabilities)
-        return method.propose_transition(current_state)
+    def propose_transition(self, current_state: str) -> str:
+        self._require_width(current_state)
+        chosen = np.random.choice(len(self.proposal_methods), p=self.probabilities)
+        return self.proposal_methods[int(chosen)].propose_transition(current_state)
 
-    def lower(self):
-        out = []
-        for method, p in zip(self.proposal_methods, self.probabilities):
-            sub = method.lower()
-            if sub is None:
+    def lower(self) -> Optional[Lowered]:
+        flat: Lowered = []
+        for weight, method in zip(self.probabilities, self.proposal_methods):
+            leaves = method.lower()
+            if leaves is None:
                 return None
-            out.extend((kind, param, float(p) * q) for kind, param, q in sub)
-        return out
+            flat += [(kind, param, float(weight) * q) for kind, param, q in leaves]
+        return flat
