@@ -9,6 +9,9 @@
 //   K3     -> block prefix-sum of |a|^2 + inverse CDF                 (QuantumState.sampling :153)
 //   K4     -> energy lookup + Metropolis accept                       (test_accept, classical_mcmc_routines.py:28-41)
 #include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -339,12 +342,19 @@ int qmc_small_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                 m->max_terms_in_group, smem);
     QMC_REQUIRE(n_chains <= 0x7fffffffLL, QMC_ERR_BADARG, "too many chains for one launch");
     if (n_chains == 0) return QMC_OK;
+    // threads per chain: one 4-amplitude orbit per thread keeps every lane busy in the term loop (2^n / 4), within
+    // [64, 256]; QUMCMC_SMALL_NT overrides for A/B runs
+    int threads = (int)std::min<size_t>(SMALL_NT, std::max<size_t>(64, N >> 2));
+    if (const char *e = getenv("QUMCMC_SMALL_NT")) {
+        const int v = atoi(e);
+        if (v == 64 || v == 128 || v == 256) threads = v;
+    }
     if (dtype == QMC_DTYPE_F64) {
         QMC_CUDA_TRY(cudaFuncSetAttribute(smem_chain_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_chain_kernel<double><<<(unsigned)n_chains, SMALL_NT, smem, st>>>(p);
+        smem_chain_kernel<double><<<(unsigned)n_chains, threads, smem, st>>>(p);
     } else {
         QMC_CUDA_TRY(cudaFuncSetAttribute(smem_chain_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_chain_kernel<float><<<(unsigned)n_chains, SMALL_NT, smem, st>>>(p);
+        smem_chain_kernel<float><<<(unsigned)n_chains, threads, smem, st>>>(p);
     }
     m->launches++;
     QMC_CUDA_TRY(cudaGetLastError());
