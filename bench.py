@@ -271,7 +271,7 @@ def run_ours(args, rank, local_rank, world):
         except Exception:
             traffic = None
     roofline = {
-        "bound": "hbm", "kernel": "sweep_kernel<8> (fused phase + butterfly sweep)", "achieved": achieved, "peak": peak,
+        "bound": "hbm", "kernel": "hi_sweep_kernel<8> / lo_sweep_kernel (fused phase + butterfly sweeps; all sweep launches of the step)", "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": None if achieved is None else achieved / peak, "traffic": traffic,
         "peak_source": peak_src, "sweep_ms_per_step": c_ms.value / max(1, K),
         "algorithmic_bytes_per_step": c_by.value / max(1, K), "launches_per_step": c_ln.value / max(1, K),
