@@ -99,6 +99,9 @@ class ClockSampler(threading.Thread):
 # CPU arm: the reference's algorithm (one pass over the complex128 state per gate) restated in
 # oracle/qmc_oracle.c, OpenMP over the host cores.  qulacs is not installable in this image.
 # ---------------------------------------------------------------------------------------------
+REF_HOPS_PER_STEP = 4
+
+
 def cpu_reference_rate(hops, warm=0):
     import oracle
     from qumcmc_b200.energy_models import random_ising_model
@@ -121,14 +124,16 @@ def cpu_reference_rate(hops, warm=0):
 def run_reference(args, rank):
     if rank != 0:
         return
-    rate, dt, threads = cpu_reference_rate(args.steps, warm=args.warmup)
+    # one step = REF_HOPS_PER_STEP hops of one chain (a bounded sample of the workload: the full step is one hop of
+    # 4096 chains); several hops per step average over the Trotter depth r, which varies 1..13 from hop to hop
+    rate, dt, threads = cpu_reference_rate(args.steps * REF_HOPS_PER_STEP, warm=args.warmup * REF_HOPS_PER_STEP)
     sample = "1 chain x %d hops (+%d warm-up), gate-at-a-time complex128 (n(n-1)/2+n diagonal + n X gates per layer)" % (
-        args.steps, args.warmup)
+        args.steps * REF_HOPS_PER_STEP, args.warmup * REF_HOPS_PER_STEP)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-        "config": workload_config(args.chains, args.gpus, {"reference_step": "one hop of one chain on the host CPU"}),
+        "config": workload_config(args.chains, args.gpus, {"reference_step": "%d hops of one chain on the host CPU" % REF_HOPS_PER_STEP}),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "note": "oracle/qmc_oracle.c restatement of the qulacs circuit; qulacs itself is not installable here"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
