@@ -13,13 +13,10 @@ def pytest_configure(config):
 
 
 def pytest_sessionstart(session):
-    """A fresh checkout has no built artefacts (they are git-ignored): compile the CUDA extension once (nvcc
-    cross-compiles sm_100a without a GPU; `make` is a no-op when the library is current).  The oracle builds itself."""
+    """A fresh checkout has no built artefacts (they are git-ignored): compile the CUDA extension once if the library
+    is missing (nvcc cross-compiles sm_100a without a GPU).  The oracle builds itself on first use."""
     from qumcmc_b200 import _lib
-    csrc = os.path.dirname(_lib.LIB_PATH)
-    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))]
-    srcs.append(os.path.join(ROOT, "include", "qumcmc_b200.h"))
-    if not os.path.exists(_lib.LIB_PATH) or os.path.getmtime(_lib.LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
+    if not os.path.exists(_lib.LIB_PATH):
         _lib.build(verbose=False)
 
 
