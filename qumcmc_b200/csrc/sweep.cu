@@ -66,8 +66,9 @@ struct SweepArgs {
     ChainParams *params;      // [chains]
     // on-the-fly phase exponent: D_fx(idx) = A + sum_b z_b F_b + R(j) per register layout;
     // af_*[tile*128 + thread] = {A, F0, F1, F2}, {F3, F4, F5, -}; dr_*[i] = Gray-order increments of R
-    const int4 *af_lo, *af_hia, *af_hib;
-    int dr_lo[64], dr_hia[64], dr_hib[64];
+    const int4 *af_lo, *af_hia, *af_hib, *af_hic;
+    int dr_lo[64], dr_hia[64], dr_hib[64], dr_hic[64];
+    int hiq;                  // n = 20: HI MID sweeps with amplitude pairs in the registers (hiq_sweep_kernel)
     float *segsum;            // [chains][2^n / 64]
     float *probs_out;         // PROBS mode: unnormalised |a|^2 (index order) or null
     float2 *amps_out;
@@ -686,6 +687,92 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
 }
 
 // ------------------------------------------------------------------------------------------
+// HI MID sweep for W = 8 (n = 20) with amplitude PAIRS in the registers: index bit 0 (a LO qubit, never mixed here) is
+// register bit 0, so every HBM access is a 128-bit LDG / STG (32 instead of 64 per thread and direction) and the
+// transpositions move 128-bit shared-memory words (half the LDS / STS count; the HI sweep is MIO-throttled).
+// Tile: local bits 0..4 <-> qubits 0..4, local 5..12 <-> qubits 12..19 (as HiGeom<8>).
+//   A'' layout: regs = local {0, 8..12}; lanes = local 1..5; warps = local (6, 7)      active: qubits 15..19
+//   B'' layout: regs = local {0, 5, 6, 7, 8, 9}; lanes = local {1..4, 10}; warps = local (11, 12)
+//                                                                                      active: qubits 12..14; phase
+// ------------------------------------------------------------------------------------------
+typedef ulonglong2 P128;
+__device__ __forceinline__ int64_t hiq_base_a(int tid, int64_t tile) {
+    const int lane = tid & 31, w = tid >> 5;
+    return (int64_t)((lane & 15) << 1) | ((int64_t)(lane >> 4) << 12) | ((int64_t)(w & 1) << 13) | ((int64_t)(w >> 1) << 14) |
+           (tile << 5);
+}
+__host__ __device__ __forceinline__ int64_t hiq_base_b(int tid, int64_t tile) {
+    const int lane = tid & 31, w = tid >> 5;
+    return (int64_t)((lane & 15) << 1) | ((int64_t)(lane >> 4) << 17) | ((int64_t)(w & 1) << 18) | ((int64_t)(w >> 1) << 19) |
+           (tile << 5);
+}
+__host__ __device__ __forceinline__ int hiq_pos_b(int b) { return b == 0 ? 0 : 11 + b; }  // register bit -> qubit, B''
+struct HiqQA { __device__ __forceinline__ int operator()(int b) const { return b == 0 ? 0 : 14 + b; } };
+struct HiqQB { __device__ __forceinline__ int operator()(int b) const { return hiq_pos_b(b); } };
+// shared-memory slot (in 128-bit words) of register pair jp
+__device__ __forceinline__ int hiq_loc_a(int tid, int jp) { return (tid & 31) | ((tid >> 5) << 5) | (jp << 7); }
+__device__ __forceinline__ int hiq_loc_b(int tid, int jp) {
+    return (tid & 15) | ((jp & 7) << 4) | ((jp >> 3) << 7) | (((tid >> 4) & 1) << 9) | ((tid >> 5) << 10);
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(NT, 3) hiq_sweep_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off,
+                                                          const int ct_off) {
+    extern __shared__ __align__(16) float2 sm[];
+    __shared__ ChainParams cp_s;
+    __shared__ __align__(16) int hs_s[64];
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int64_t chain = order[list_off + blockIdx.y];
+    const float tu = FAST ? c_tan[ct_off + blockIdx.y] : 0.f;
+    const int n = a.n;
+    A64 *state = reinterpret_cast<A64 *>(a.state + (chain << n)) + hiq_base_a(tid, tile);
+    P128 *smq = reinterpret_cast<P128 *>(sm);
+    A64 v[64];
+#pragma unroll
+    for (int jp = 0; jp < 32; ++jp) {  // in flight while the parameters are staged
+        const P128 x = *reinterpret_cast<const P128 *>(state + ((int64_t)jp << 15));
+        v[2 * jp] = x.x;
+        v[2 * jp + 1] = x.y;
+    }
+    {
+        int64_t pc, pt;
+        if (pf_target(a, order, list_off, pc, pt))
+            l2_prefetch_rows(reinterpret_cast<const char *>(a.state + (pc << n) + (pt << 5)), (int64_t)8 << 12, 256, tid);
+    }
+    build_hs(hs_s, a.dr_hic, a.params + chain, tid);
+    stage_params(cp_s, a.params + chain, tid);
+    const ChainParams &cp = cp_s;
+    const PhaseAF af = load_af(a.af_hic, tile * NT + tid);
+    bfly6<62, FAST>(v, cp, HiqQA(), tu);
+#pragma unroll
+    for (int jp = 0; jp < 32; ++jp) smq[hiq_loc_a(tid, jp)] = make_ulonglong2(v[2 * jp], v[2 * jp + 1]);
+    __syncthreads();
+#pragma unroll
+    for (int jp = 0; jp < 32; ++jp) {
+        const P128 x = smq[hiq_loc_b(tid, jp)];
+        v[2 * jp] = x.x;
+        v[2 * jp + 1] = x.y;
+    }
+    bfly6<14, FAST>(v, cp, HiqQB(), tu);
+    phase_gray<FAST>(v, af, hs_s, a.dr_hic[0], cp);
+    bfly6<14, FAST>(v, cp, HiqQB(), tu);
+#pragma unroll
+    for (int jp = 0; jp < 32; ++jp) smq[hiq_loc_b(tid, jp)] = make_ulonglong2(v[2 * jp], v[2 * jp + 1]);  // own slots
+    __syncthreads();
+#pragma unroll
+    for (int jp = 0; jp < 32; ++jp) {
+        const P128 x = smq[hiq_loc_a(tid, jp)];
+        v[2 * jp] = x.x;
+        v[2 * jp + 1] = x.y;
+    }
+    bfly6<62, FAST>(v, cp, HiqQA(), tu);
+#pragma unroll
+    for (int jp = 0; jp < 32; ++jp)
+        *reinterpret_cast<P128 *>(state + ((int64_t)jp << 15)) = make_ulonglong2(v[2 * jp], v[2 * jp + 1]);
+}
+
+// ------------------------------------------------------------------------------------------
 // Generic large-n path (n >= 21: three or more qubit groups).  LO group = qubits 0..11 (kernels
 // above, roles SINGLE / FINAL); the remaining qubits are covered by register-only HI6 sweeps:
 // a thread owns the 64 amplitudes over qubits [p, p+6), lanes sit on qubits 0..4, so every access is
@@ -1273,10 +1360,12 @@ __global__ void af_table_kernel(int n, const double *__restrict__ Jq, const doub
         const int tid = (int)(f & 127);
         uint64_t base;
         int p[6];
-        for (int b = 0; b < 6; ++b) p[b] = LAYOUT == 0 ? b : (LAYOUT == 1 ? HiGeom<W>::gpos(7 + b) : HiGeom<W>::gpos(5 + b));
+        for (int b = 0; b < 6; ++b)
+            p[b] = LAYOUT == 0 ? b : (LAYOUT == 1 ? HiGeom<W>::gpos(7 + b) : (LAYOUT == 2 ? HiGeom<W>::gpos(5 + b) : hiq_pos_b(b)));
         if (LAYOUT == 0) base = ((uint64_t)tile << TILE_BITS) | ((uint64_t)tid << 6);
         else if (LAYOUT == 1) base = (uint64_t)hi_base_a<W>(tid, tile);
-        else base = (uint64_t)hi_base_b<W>(tid, tile);
+        else if (LAYOUT == 2) base = (uint64_t)hi_base_b<W>(tid, tile);
+        else base = (uint64_t)hiq_base_b(tid, tile);
         uint64_t regmask = 0;
         for (int b = 0; b < 6; ++b) regmask |= 1ULL << p[b];
         double A = 0.0, F[6];
@@ -1370,8 +1459,8 @@ struct SweepWorkspace {
     int *hist = nullptr;
     int *order = nullptr;
     float *tan_sorted = nullptr;  // fast path: per-position mixer multiplier, copied into c_tan[] every hop
-    int4 *af_lo = nullptr, *af_hia = nullptr, *af_hib = nullptr;
-    int dr_lo[64], dr_hia[64], dr_hib[64];
+    int4 *af_lo = nullptr, *af_hia = nullptr, *af_hib = nullptr, *af_hic = nullptr;
+    int dr_lo[64], dr_hia[64], dr_hib[64], dr_hic[64];
     bool tables_ready = false;
     std::vector<double> Jq, hq;   // circuit couplings in qubit order (host)
     double *dJq = nullptr, *dhq = nullptr;
@@ -1394,6 +1483,7 @@ void qmc_sweep_free(qmc_model *m) {
     cudaFree(w->af_lo);
     cudaFree(w->af_hia);
     cudaFree(w->af_hib);
+    cudaFree(w->af_hic);
     cudaFree(w->dJq);
     cudaFree(w->dhq);
     for (auto &G : w->groups) free_group_tables(G);
@@ -1483,6 +1573,14 @@ static int ensure_workspace(qmc_model *m, int64_t chains, cudaStream_t st) {
             QMC_CUDA_TRY(cudaMalloc(&w->af_hia, af_bytes));
             QMC_CUDA_TRY(cudaMalloc(&w->af_hib, af_bytes));
             int pos[3][6];
+            if (n == 20) {  // pair-register HI layout (hiq_sweep_kernel)
+                QMC_CUDA_TRY(cudaMalloc(&w->af_hic, af_bytes));
+                const int grid = (int)std::min<int64_t>(148 * 8, (((int64_t)1 << (n - 6)) + 127) / 128);
+                af_table_kernel<8, 3><<<grid, 128, 0, st>>>(n, w->dJq, w->dhq, w->fx_scale, w->af_hic);
+                m->launches++;
+                const int pc[6] = {hiq_pos_b(0), hiq_pos_b(1), hiq_pos_b(2), hiq_pos_b(3), hiq_pos_b(4), hiq_pos_b(5)};
+                gray_increments(w->Jq, n, w->fx_scale, pc, w->dr_hic);
+            }
             int rc = build_af_tables(n, w->dJq, w->dhq, w->fx_scale, w->af_lo, w->af_hia, w->af_hib, pos, st);
             if (rc != QMC_OK) return rc;
             m->launches += 3;
@@ -1559,6 +1657,13 @@ static int launch_lo(const SweepTune &tu, const SweepArgs &a, const int *order, 
 
 template <int W, bool FIRST, bool FAST>
 static int launch_hi_w(const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
+    if (W == 8 && !FIRST && a.hiq) {
+        static bool doneq = false;
+        int rcq = set_smem_once(hiq_sweep_kernel<FAST>, doneq);
+        if (rcq != QMC_OK) return rcq;
+        hiq_sweep_kernel<FAST><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off, off);
+        return QMC_OK;
+    }
     static bool done = false;
     int rc = set_smem_once(hi_sweep_kernel<W, FIRST, FAST>, done);
     if (rc != QMC_OK) return rc;
@@ -1774,6 +1879,8 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     // tuning knobs (defaults = measured best on B200; the env overrides exist for A/B runs and profiling)
     const char *pf_env = getenv("QUMCMC_SWEEP_PF");
     const int pf_dist = pf_env ? atoi(pf_env) : 222;
+    const char *hiq_env = getenv("QUMCMC_SWEEP_HIQ");
+    const bool hiq_on = hiq_env ? atoi(hiq_env) != 0 : true;
     const char *pfl_env = getenv("QUMCMC_SWEEP_PFLINES");
     const int pf_lines = pfl_env ? atoi(pfl_env) : 1;
     const char *fast_env = getenv("QUMCMC_SWEEP_FAST");
@@ -1852,8 +1959,10 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         h.hamming_hist = hamming_hist ? hamming_hist + c0 * (n + 1) : nullptr;
         h.hist = w->hist;
         SweepArgs a;
-        a.n = n; a.n_total = n; a.gbits = 0ULL; a.state = w->state; a.params = w->params; a.af_lo = w->af_lo; a.af_hia = w->af_hia; a.af_hib = w->af_hib;
+        a.n = n; a.n_total = n; a.gbits = 0ULL; a.state = w->state; a.params = w->params; a.af_lo = w->af_lo; a.af_hia = w->af_hia; a.af_hib = w->af_hib; a.af_hic = w->af_hic;
         memcpy(a.dr_lo, w->dr_lo, sizeof(a.dr_lo)); memcpy(a.dr_hia, w->dr_hia, sizeof(a.dr_hia)); memcpy(a.dr_hib, w->dr_hib, sizeof(a.dr_hib));
+        if (w->af_hic) memcpy(a.dr_hic, w->dr_hic, sizeof(a.dr_hic));
+        a.hiq = (w->af_hic && hiq_on) ? 1 : 0;
         a.segsum = w->segsum;
         a.pf_dist = pf_dist;
         a.pf_lines = pf_lines;
