@@ -228,8 +228,11 @@ def run_ours(args, rank, local_rank, world):
     c_ms, c_ln, c_by = Ct.c_double(), Ct.c_int64(), Ct.c_double()
     _lib.check(L.qmc_profile_read(dm.handle, Ct.byref(c_ms), Ct.byref(c_ln), Ct.byref(c_by)))
     _lib.check(L.qmc_profile_enable(dm.handle, 0))
+    c_mv = Ct.c_double()
+    _lib.check(L.qmc_profile_read_moved(dm.handle, Ct.byref(c_mv)))
     value = world * C * K / (ms * 1e-3)
-    acc_rate = float(cnt.sum().item()) / (C * K)
+    # acceptance over ALL ranks' chains (the gathered counts when N > 1)
+    acc_rate = float(g_acc.sum()) / (C * world * K) if g_acc is not None else float(cnt.sum().item()) / (C * K)
 
     # ---- end to end through the host-buffer C-ABI: every step copies its inputs H2D and results D2H
     pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
@@ -261,12 +264,133 @@ def run_ours(args, rank, local_rank, world):
     bi = C * 8
     bo = C * (8 + 1 + 8 + 8 + n1 * 8)
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+    # ---- secondary measurements (never allowed to lose the headline line: guarded, with a watchdog)
+    secondary = {}
+    state = {"line": None}
+    watchdog = start_watchdog(args.secondary_timeout, rank, state)
+    if world > 1 and not args.no_secondary:
+        try:   # strong scaling: the metric's 4096 chains IN TOTAL over the N GPUs (same global chain ids as one GPU)
+            secondary["strong"] = strong_scaling_block(args, L, dm, rank, world, dev, stream, barrier, max_over_ranks)
+        except Exception as e:  # noqa: BLE001
+            secondary["strong"] = {"error": repr(e)[:300]}
 
+    if rank == 0:
+        state["line"] = build_line(args, world, C, K, W, ms, value, acc_rate, clocks, launches, c_ms.value, c_ln.value,
+                                   c_by.value, c_mv.value, e2e_value, Ke, bi, bo, e2e_consistent, g_acc, secondary)
+    if world >= 2 and (world & (world - 1)) == 0 and not args.no_secondary and not args.no_c5:
+        try:   # C5: statevector sharded by global qubits, 33 local qubits per GPU (n = 36 on 8 GPUs)
+            del props_buf, acc_buf
+            dm = None
+            from qumcmc_b200 import _device as _dv
+            _dv._cache.clear()           # frees the 32 GiB C3 workspace: C5 needs 2 x 64 GiB per GPU
+            torch.cuda.empty_cache()
+            secondary["c5"] = c5_block(args, rank, local_rank, world)
+        except Exception as e:  # noqa: BLE001
+            secondary["c5"] = {"error": repr(e)[:300]}
+    if watchdog is not None:
+        watchdog.cancel()
+    if rank == 0:
+        state["line"]["secondary"] = secondary
+        print(json.dumps(state["line"]), flush=True)
+    if dist is not None:
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def start_watchdog(seconds, rank, state):
+    """If a secondary block hangs (a collective that never completes), rank 0 still prints the headline line."""
+    if seconds <= 0:
+        return None
+
+    def fire():
+        if rank == 0 and state.get("line") is not None:
+            state["line"]["secondary"] = {"error": "secondary measurements timed out after %d s" % seconds}
+            print(json.dumps(state["line"]), flush=True)
+        os._exit(0 if state.get("line") is not None or rank != 0 else 1)
+
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
+def strong_scaling_block(args, L, dm, rank, world, dev, stream, barrier, max_over_ranks):
+    """BASELINE's metric reads "4096 chains": the same 4096 global chain ids split over the N GPUs (strong scaling).
+    Results do not depend on the split (Philox is keyed by the global chain id)."""
+    import torch
+    from qumcmc_b200 import _lib
+    from qumcmc_b200.distributed import shard_range
+    total = args.chains
+    a, b = shard_range(total, rank, world)
+    Cl, K, W = b - a, args.steps, args.warmup
+    props = torch.empty(Cl * max(K, 1), dtype=torch.int64, device=dev)
+    accb = torch.empty(Cl * max(K, 1), dtype=torch.uint8, device=dev)
+    fin = torch.empty(Cl, dtype=torch.int64, device=dev)
+    cnt = torch.empty(Cl, dtype=torch.int64, device=dev)
+    hist = torch.empty((Cl, N_SPINS + 1), dtype=torch.int64, device=dev)
+
+    def run(n_hops, s0, hop0):
+        _lib.check(L.qmc_run_chains(dm.handle, Cl, n_hops, None if s0 is None else s0.data_ptr(), a, hop0, 1.0 / BETA,
+                                    GAMMA[0], GAMMA[1], DELTA_T, PHILOX_SEED, _lib.DTYPE_F32, props.data_ptr(),
+                                    accb.data_ptr(), fin.data_ptr(), cnt.data_ptr(), hist.data_ptr(), stream))
+
+    run(max(W, 1), None, 0)
+    torch.cuda.synchronize()
+    s0 = fin.clone()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(K, s0, max(W, 1))
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    return {"value": total * K / (ms * 1e-3), "unit": UNIT, "chains_total": total, "chains_per_gpu": Cl, "steps": K,
+            "ms_per_step": ms / max(1, K), "scaling": "strong"}
+
+
+def c5_block(args, rank, local_rank, world):
+    """BASELINE config C5 scaled to the world size: 33 local qubits per GPU (n = 36 on 8 GPUs, 2 x 64 GiB of state
+    buffers each), fused pass + exchange over NVLink peer mappings; plus the same 64 GiB statevector on ONE GPU (n = 33,
+    rank 0) as the weak-scaling reference."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+    import sharded_bench as sb
+    import qumcmc_b200 as q
+    from qumcmc_b200.sharded import ShardedProposer
+    g = world.bit_length() - 1
+    n_local = args.c5_local_spins
+    n = n_local + g
+    model = q.random_ising_model(n, 1)
+    prop = ShardedProposer(model, q.GenericMixer.OneBodyMixer(n), device=local_rank, fused=True)
+    rows = sb.measure_proposals(prop, 0x5EED5EED5 & ((1 << n) - 1), [2, 5], 2, world, rank)
+    prop.close()
+    del prop
+    torch.cuda.empty_cache()
+    out = {"n": n, "n_local": n_local, "world": world, "proposals": rows}
+    if rank == 0:
+        ref = {}
+        for row in rows:
+            r = row["layers"]
+            ref[r] = sb.single_gpu_reference(n_local, r, 2, local_rank)
+            row["single_gpu_same_shard_seconds"] = ref[r]
+            row["weak_scaling_efficiency"] = ref[r] / row["seconds_per_proposal"]
+    dist.barrier()
+    return out
+
+
+def build_line(args, world, C, K, W, ms, value, acc_rate, clocks, launches, sweep_ms, sweep_launches, alg_bytes, moved_bytes,
+               e2e_value, Ke, bi, bo, e2e_consistent, g_acc, secondary):
     peak, peak_src = measured_peak_gbs()
+    class _V:  # the three profile counters, named as below
+        pass
+    c_ms, c_ln, c_by = _V(), _V(), _V()
+    c_ms.value, c_ln.value, c_by.value = sweep_ms, sweep_launches, alg_bytes
     achieved = (c_by.value / 1e9) / (c_ms.value * 1e-3) if c_ms.value > 0 else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
@@ -275,16 +399,24 @@ def run_ours(args, rank, local_rank, world):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    moved = (moved_bytes / 1e9) / (c_ms.value * 1e-3) if c_ms.value > 0 else None
     roofline = {
-        "bound": "hbm", "kernel": "hi_sweep_kernel<8> / lo_sweep_kernel (fused phase + butterfly sweeps; all sweep launches of the step)", "achieved": achieved, "peak": peak,
+        "bound": "hbm",
+        "kernel": "lo_sweep_kernel<MID> + hiq_sweep_kernel (HI MID) + their FIRST / FINAL roles: all sweep launches of the step "
+                  "(fused phase + butterfly sweeps)",
+        "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": None if achieved is None else achieved / peak, "traffic": traffic,
+        "dram_achieved": moved, "dram_frac": None if moved is None else moved / peak,
+        "dram_definition": "bytes the sweep launches actually move: 16 B * 2^n * (r - 1) per proposal (first sweep write-only, "
+                           "last read-only) / the same device time",
         "peak_source": peak_src, "sweep_ms_per_step": c_ms.value / max(1, K),
         "algorithmic_bytes_per_step": c_by.value / max(1, K), "launches_per_step": c_ln.value / max(1, K),
         "share_of_step": c_ms.value / ms if ms > 0 else None,
         "definition": "B_alg = 2 * 2^n * 8 B * r per proposal (SURVEY 8d); achieved = sum B_alg / device time of the sweep launches (CUDA events)",
     }
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    world_is_one = world == 1
+    if world_is_one and not args.no_cpu_baseline:
         rate, dt, threads = cpu_reference_rate(args.cpu_hops)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "1 chain x %d hops of the same workload, gate-at-a-time complex128 (reference cost structure), %.1f s"
@@ -305,9 +437,7 @@ def run_ours(args, rank, local_rank, world):
     }
     if g_acc is not None:
         line["config"]["gathered_chains"] = int(len(g_acc))
-    print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    return line
 
 
 def main():
@@ -320,6 +450,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-hops", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary blocks (strong scaling, C5)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the sharded-statevector block")
+    ap.add_argument("--c5-local-spins", type=int, default=33, help="local qubits per GPU of the C5 block (33 = 64 GiB per buffer)")
+    ap.add_argument("--secondary-timeout", type=int, default=420, help="watchdog for the secondary blocks, seconds")
     ap.add_argument("--model-scale", type=float, default=1.0, help="diagnostics only: scales J,h (1e-6 disables the phase layer)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -134,6 +134,16 @@ int qmc_run_chains_host(qmc_model *m, int64_t n_chains, int64_t n_hops, const ui
                         uint64_t *final_state_host, int64_t *acc_count_host,
                         int64_t *hamming_hist_host);
 
+/* Visit histogram of the Markov chains on the device: Counter(markov_chain) of MCMCChain.get_accepted_dict
+ * (qumcmc/basic_utils.py:117-131), summed over chains, as a dense int64[2^n] in index order (n <= 30).  While a
+ * histogram is attached, every qmc_run_chains / qmc_classical_chains call (and their _host variants) on this handle adds
+ * one count per chain and hop at the state after the hop, plus one at the initial state when hop0 == 0 (entry 0 of
+ * markov_chain), so resumed runs (hop0 > 0) and repeated calls add up to the histogram of the whole run.  The buffer is
+ * caller-owned and caller-zeroed; NULL detaches.  Ranks of a chain-sharded run sum their histograms with one
+ * all-reduce (qumcmc_b200/distributed.py: gather_statistics). */
+#define QMC_VISIT_HIST_MAX_SPINS 30
+int qmc_set_visit_histogram(qmc_model *m, int64_t *visit_hist_dev);
+
 /* classical_mcmc (qumcmc/classical_mcmc_routines.py:44-99) for n_chains independent chains x n_hops hops with the
  * proposal rules of qumcmc/classical_mixers.py:27-101.  The proposal method is a mixture (CombineProposals, :76-101)
  * of n_methods rules: kinds[i] UNIFORM (get_random_state), FIXED_WEIGHT (params[i] = bodyness: xor with k random
@@ -231,6 +241,9 @@ int64_t qmc_model_launch_count(const qmc_model *m);
 int qmc_profile_enable(qmc_model *m, int on);
 int qmc_profile_read(qmc_model *m, double *sweep_ms, int64_t *sweep_launches,
                      double *algorithmic_bytes);
+/* Bytes the timed sweep launches actually read + wrote: 16 B * 2^n * K * (r - 1) per proposal with K passes per layer
+ * (the first sweep of a proposal is write-only, the last read-only), against algorithmic_bytes = 16 B * 2^n * r. */
+int qmc_profile_read_moved(qmc_model *m, double *moved_bytes);
 
 #ifdef __cplusplus
 }

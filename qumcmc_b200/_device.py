@@ -61,6 +61,14 @@ class DeviceModel:
         _lib.check(_lib.lib().qmc_mixer_set(self.handle, len(offs) - 1, _hp(offs), _hp(masks), _hp(weights), _hp(probs)))
         self._mixer_key = key
 
+    def attach_visit_histogram(self, hist) -> None:
+        """Attach (torch int64[2^n] CUDA tensor, zeroed by the caller) or detach (None) the visit-histogram accumulator:
+        while attached every chain call on this handle counts the states of its Markov chains into it."""
+        if hist is not None and (hist.numel() != (1 << self.n) or str(hist.dtype) != "torch.int64" or not hist.is_cuda):
+            raise ValueError("visit histogram must be a CUDA int64 tensor of 2^n entries")
+        _lib.check(_lib.lib().qmc_set_visit_histogram(self.handle, None if hist is None else hist.data_ptr()))
+        self._visit = hist  # keeps the tensor alive while attached
+
     def launch_count(self) -> int:
         return int(_lib.lib().qmc_model_launch_count(self.handle))
 

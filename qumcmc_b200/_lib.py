@@ -27,6 +27,7 @@ SMEM_MAX_SPINS_F64 = 12
 MAX_SPINS = 40          # model limit; one GPU holds a statevector up to MAX_LOCAL_SPINS qubits
 MAX_LOCAL_SPINS = 34
 IPC_HANDLE_BYTES = 64
+VISIT_HIST_MAX_SPINS = 30
 CLASSICAL_UNIFORM, CLASSICAL_FIXED_WEIGHT, CLASSICAL_CUSTOM = range(3)
 MAX_CLASSICAL_METHODS = 16
 SHARD_OP_FIRST, SHARD_OP_MID, SHARD_OP_SINGLE, SHARD_OP_LO_SINGLE, SHARD_OP_LO_FINAL = range(5)
@@ -42,6 +43,7 @@ EXPORTS = [
     "qmc_shard_norm", "qmc_shard_select", "qmc_shard_final_probs", "qmc_shard_set_peers", "qmc_shard_op_exchange",
     "qmc_enable_peer_access", "qmc_ipc_export", "qmc_ipc_open", "qmc_ipc_close_all",
     "qmc_classical_chains", "qmc_classical_chains_host", "qmc_trajectory_stats", "qmc_state_moments", "qmc_shard_op_chunk",
+    "qmc_set_visit_histogram", "qmc_profile_read_moved",
 ]
 
 
@@ -56,14 +58,48 @@ class QmcUnsupported(QmcError, NotImplementedError):
 _lib: Optional[C.CDLL] = None
 
 
-def build(verbose: bool = False) -> str:
-    """Compile the CUDA extension for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
-    res = subprocess.run(["make", "-C", CSRC, "-j4"], capture_output=True, text=True)
+STAMP_PATH = os.path.join(CSRC, ".build_stamp")
+
+
+def source_digest() -> str:
+    """sha256 over every input of the build (sources, headers, Makefile): staleness is decided by content, not by
+    mtimes (a snapshot copied to another box does not keep them)."""
+    import hashlib
+    h = hashlib.sha256()
+    inc = os.path.join(os.path.dirname(_HERE), "include")
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh")) or f == "Makefile"]
+    files += [os.path.join(inc, f) for f in sorted(os.listdir(inc)) if f.endswith(".h")]
+    for path in files:
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB_PATH) or not os.path.exists(STAMP_PATH):
+        return True
+    with open(STAMP_PATH) as f:
+        return f.read().strip() != source_digest()
+
+
+def build(verbose: bool = False, force: bool = False) -> str:
+    """Compile the CUDA extension for sm_100a in-tree (nvcc cross-compiles without a GPU).  A no-op when the library
+    was built from exactly the present sources (content digest in csrc/.build_stamp)."""
+    if not force and not is_stale():
+        return LIB_PATH
+    digest = source_digest()
+    cmd = ["make", "-C", CSRC, "-j8"]
+    if os.environ.get("GRAFT_REPO_ROOT"):  # a snapshot on another box: file times say nothing, rebuild everything
+        cmd.append("-B")
+    res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout[-4000:])
         print(res.stderr[-4000:])
     if res.returncode != 0:
         raise RuntimeError("building libqumcmc_b200.so failed")
+    with open(STAMP_PATH, "w") as f:
+        f.write(digest + "\n")
     return LIB_PATH
 
 
@@ -122,6 +158,8 @@ def lib() -> C.CDLL:
     L.qmc_classical_chains_host.argtypes = [C.c_void_p, C.c_int64, C.c_int64, u64p, C.c_uint64, C.c_uint32, C.c_double,
                                             C.c_int, vp, vp, vp, C.c_uint64, u64p, vp, u64p, i64p, i64p]
     L.qmc_shard_op_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int64, vp]
+    L.qmc_set_visit_histogram.argtypes = [C.c_void_p, i64p]
+    L.qmc_profile_read_moved.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.qmc_shard_op_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

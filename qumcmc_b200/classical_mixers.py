@@ -39,6 +39,17 @@ class ClassicalMixer(ABC):
         """Device form ``[(kind, param, probability), ...]``; ``None`` = host-only rule (the default for subclasses)."""
         return None
 
+    def device_lowering(self) -> Optional[Lowered]:
+        """``lower()`` -- unless a user subclass of a built-in rule overrides ``propose_transition`` (or the flip
+        pattern behind it): the device rule would silently ignore the override, whereas the reference always calls
+        ``propose_transition`` (classical_mcmc_routines.py:44-99).  Such rules run in the host loop."""
+        for attr in ("propose_transition", "_pattern", "_positions"):
+            mine = getattr(type(self), attr, None)
+            owner = next((k for k in type(self).__mro__ if attr in k.__dict__), None)
+            if mine is not None and owner is not None and owner.__module__ != __name__:
+                return None
+        return self.lower()
+
 
 class _XorRule(ClassicalMixer):
     """Built-in rules of the form ``state xor pattern``; subclasses supply the pattern."""
@@ -129,7 +140,7 @@ class CombineProposals(ClassicalMixer):
     def lower(self) -> Optional[Lowered]:
         flat: Lowered = []
         for weight, method in zip(self.probabilities, self.proposal_methods):
-            leaves = method.lower()
+            leaves = method.device_lowering()
             if leaves is None:
                 return None
             flat += [(kind, param, float(weight) * q) for kind, param, q in leaves]

@@ -84,6 +84,9 @@ extern "C" int qmc_run_chains(qmc_model *m, int64_t n_chains, int64_t n_hops, co
                     final_state_dev, acc_count_dev, hamming_hist_dev, nullptr, nullptr, stream);
 }
 
+// Host-buffer variant.  Steady state (same or smaller shapes than an earlier call): no allocation, no device-wide
+// synchronisation -- one cudaMemcpyAsync per buffer on the handle's own stream around the device-pointer call, one
+// stream synchronise.  Pinned host buffers make the copies truly asynchronous; pageable ones are staged by the runtime.
 extern "C" int qmc_run_chains_host(qmc_model *m, int64_t n_chains, int64_t n_hops, const uint64_t *s0_host,
                                    uint64_t chain_id0, uint32_t hop0, double temperature, double gamma_lo,
                                    double gamma_hi, double delta_time, uint64_t seed, int dtype,
@@ -93,39 +96,24 @@ extern "C" int qmc_run_chains_host(qmc_model *m, int64_t n_chains, int64_t n_hop
     QMC_REQUIRE(n_chains >= 0 && n_hops >= 0, QMC_ERR_BADARG, "negative chain or hop count");
     if (n_chains == 0) return QMC_OK;
     QMC_CUDA_TRY(cudaSetDevice(m->device));
-    const size_t CH = (size_t)n_chains * (size_t)n_hops;
-    const size_t hb = (size_t)n_chains * (size_t)(m->n + 1);
-    uint64_t *d_s0 = nullptr, *d_prop = nullptr, *d_fin = nullptr;
-    uint8_t *d_acc = nullptr;
-    int64_t *d_cnt = nullptr, *d_hist = nullptr;
-    cudaError_t e = cudaSuccess;
-    int rc = QMC_OK;
-    auto A = [&](void **p, size_t bytes) {
-        if (e == cudaSuccess && bytes) e = cudaMalloc(p, bytes);
-    };
-    if (s0_host) A((void **)&d_s0, sizeof(uint64_t) * n_chains);
-    if (proposals_host) A((void **)&d_prop, sizeof(uint64_t) * CH);
-    if (accepted_host) A((void **)&d_acc, CH);
-    A((void **)&d_fin, sizeof(uint64_t) * n_chains);
-    if (acc_count_host) A((void **)&d_cnt, sizeof(int64_t) * n_chains);
-    if (hamming_hist_host) A((void **)&d_hist, sizeof(int64_t) * hb);
-    if (e == cudaSuccess && d_s0) e = cudaMemcpy(d_s0, s0_host, sizeof(uint64_t) * n_chains, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess)
-        rc = qmc_run_chains(m, n_chains, n_hops, d_s0, chain_id0, hop0, temperature, gamma_lo, gamma_hi, delta_time,
-                            seed, dtype, d_prop, d_acc, d_fin, d_cnt, d_hist, nullptr);
-    if (e == cudaSuccess && rc == QMC_OK) e = cudaDeviceSynchronize();
-    auto D2H = [&](void *dst, const void *src, size_t bytes) {
-        if (e == cudaSuccess && rc == QMC_OK && dst && src && bytes) e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
-    };
-    D2H(proposals_host, d_prop, sizeof(uint64_t) * CH);
-    D2H(accepted_host, d_acc, CH);
-    D2H(final_state_host, d_fin, sizeof(uint64_t) * n_chains);
-    D2H(acc_count_host, d_cnt, sizeof(int64_t) * n_chains);
-    D2H(hamming_hist_host, d_hist, sizeof(int64_t) * hb);
-    cudaFree(d_s0); cudaFree(d_prop); cudaFree(d_acc); cudaFree(d_fin); cudaFree(d_cnt); cudaFree(d_hist);
-    if (e != cudaSuccess) {
-        qmc_set_error("qmc_run_chains_host: %s", cudaGetErrorString(e));
-        return QMC_ERR_CUDA;
+    const size_t C = (size_t)n_chains, CH = C * (size_t)n_hops, hb = C * (size_t)(m->n + 1);
+    ChainIoDev d;
+    cudaStream_t st = nullptr;
+    int rc = qmc_stage_chain_io(m, n_chains, n_hops, s0_host != nullptr, proposals_host != nullptr, accepted_host != nullptr,
+                                acc_count_host != nullptr, hamming_hist_host != nullptr, &d, &st);
+    if (rc != QMC_OK) return rc;
+    if (d.s0) QMC_CUDA_TRY(cudaMemcpyAsync(d.s0, s0_host, 8 * C, cudaMemcpyHostToDevice, st));
+    rc = qmc_run_chains(m, n_chains, n_hops, d.s0, chain_id0, hop0, temperature, gamma_lo, gamma_hi, delta_time, seed,
+                        dtype, d.prop, d.acc, d.fin, d.cnt, d.hist, st);
+    if (rc != QMC_OK) {
+        cudaStreamSynchronize(st);
+        return rc;
     }
-    return rc;
+    if (d.prop && CH) QMC_CUDA_TRY(cudaMemcpyAsync(proposals_host, d.prop, 8 * CH, cudaMemcpyDeviceToHost, st));
+    if (d.acc && CH) QMC_CUDA_TRY(cudaMemcpyAsync(accepted_host, d.acc, CH, cudaMemcpyDeviceToHost, st));
+    QMC_CUDA_TRY(cudaMemcpyAsync(final_state_host, d.fin, 8 * C, cudaMemcpyDeviceToHost, st));
+    if (d.cnt) QMC_CUDA_TRY(cudaMemcpyAsync(acc_count_host, d.cnt, 8 * C, cudaMemcpyDeviceToHost, st));
+    if (d.hist) QMC_CUDA_TRY(cudaMemcpyAsync(hamming_hist_host, d.hist, 8 * hb, cudaMemcpyDeviceToHost, st));
+    QMC_CUDA_TRY(cudaStreamSynchronize(st));
+    return QMC_OK;
 }

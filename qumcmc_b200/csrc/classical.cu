@@ -28,6 +28,7 @@ struct ClassicalArgs {
     uint8_t *accepted;
     uint64_t *final_state;
     int64_t *acc_count, *hist;
+    unsigned long long *visit;  // visit histogram accumulator or null
 };
 
 // proposal of one hop; string position i <-> index bit n-1-i (bitstrings are MSB first)
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(128) classical_chain_kernel(const ClassicalArg
     uint64_t cur = a.s0 ? a.s0[c] : qmc_initial_state(a.seed, chain, n);
     double e_cur = qmc_energy_dev(n, J, h, cur);
     int64_t nacc = 0;
+    if (a.hop0 == 0) qmc_visit(a.visit, cur);  // entry 0 of markov_chain
     for (int64_t k = 0; k < a.n_hops; ++k) {
         const uint32_t hop = a.hop0 + (uint32_t)k;
         const Philox4 d = philox4x32_10(a.seed, chain, hop, 2);
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(128) classical_chain_kernel(const ClassicalArg
             e_cur = e_sp;
             ++nacc;
         }
+        qmc_visit(a.visit, cur);
     }
     a.final_state[c] = cur;
     if (a.acc_count) a.acc_count[c] = nacc;
@@ -150,6 +153,7 @@ extern "C" int qmc_classical_chains(qmc_model *m, int64_t n_chains, int64_t n_ho
     a.final_state = final_state_dev;
     a.acc_count = acc_count_dev;
     a.hist = hamming_hist_dev;
+    a.visit = m->visit_hist;
     if (hamming_hist_dev)
         QMC_CUDA_TRY(cudaMemsetAsync(hamming_hist_dev, 0, sizeof(int64_t) * (size_t)n_chains * (size_t)(m->n + 1), st));
     const size_t smem = sizeof(double) * (size_t)(m->n * m->n + m->n);
@@ -170,39 +174,24 @@ extern "C" int qmc_classical_chains_host(qmc_model *m, int64_t n_chains, int64_t
     QMC_REQUIRE(n_chains >= 0 && n_hops >= 0, QMC_ERR_BADARG, "negative chain or hop count");
     if (n_chains == 0) return QMC_OK;
     QMC_CUDA_TRY(cudaSetDevice(m->device));
-    const size_t CH = (size_t)n_chains * (size_t)n_hops;
-    const size_t hb = (size_t)n_chains * (size_t)(m->n + 1);
-    uint64_t *d_s0 = nullptr, *d_prop = nullptr, *d_fin = nullptr;
-    uint8_t *d_acc = nullptr;
-    int64_t *d_cnt = nullptr, *d_hist = nullptr;
-    cudaError_t e = cudaSuccess;
-    int rc = QMC_OK;
-    auto A = [&](void **p, size_t bytes) {
-        if (e == cudaSuccess && bytes) e = cudaMalloc(p, bytes);
-    };
-    if (s0_host) A((void **)&d_s0, sizeof(uint64_t) * n_chains);
-    if (proposals_host) A((void **)&d_prop, sizeof(uint64_t) * CH);
-    if (accepted_host) A((void **)&d_acc, CH);
-    A((void **)&d_fin, sizeof(uint64_t) * n_chains);
-    if (acc_count_host) A((void **)&d_cnt, sizeof(int64_t) * n_chains);
-    if (hamming_hist_host) A((void **)&d_hist, sizeof(int64_t) * hb);
-    if (e == cudaSuccess && d_s0) e = cudaMemcpy(d_s0, s0_host, sizeof(uint64_t) * n_chains, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess)
-        rc = qmc_classical_chains(m, n_chains, n_hops, d_s0, chain_id0, hop0, temperature, n_methods, kinds, params, probs,
-                                  seed, d_prop, d_acc, d_fin, d_cnt, d_hist, nullptr);
-    if (e == cudaSuccess && rc == QMC_OK) e = cudaDeviceSynchronize();
-    auto D2H = [&](void *dst, const void *src, size_t bytes) {
-        if (e == cudaSuccess && rc == QMC_OK && dst && src && bytes) e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
-    };
-    D2H(proposals_host, d_prop, sizeof(uint64_t) * CH);
-    D2H(accepted_host, d_acc, CH);
-    D2H(final_state_host, d_fin, sizeof(uint64_t) * n_chains);
-    D2H(acc_count_host, d_cnt, sizeof(int64_t) * n_chains);
-    D2H(hamming_hist_host, d_hist, sizeof(int64_t) * hb);
-    cudaFree(d_s0); cudaFree(d_prop); cudaFree(d_acc); cudaFree(d_fin); cudaFree(d_cnt); cudaFree(d_hist);
-    if (e != cudaSuccess) {
-        qmc_set_error("qmc_classical_chains_host: %s", cudaGetErrorString(e));
-        return QMC_ERR_CUDA;
+    const size_t C = (size_t)n_chains, CH = C * (size_t)n_hops, hb = C * (size_t)(m->n + 1);
+    ChainIoDev d;
+    cudaStream_t st = nullptr;
+    int rc = qmc_stage_chain_io(m, n_chains, n_hops, s0_host != nullptr, proposals_host != nullptr, accepted_host != nullptr,
+                                acc_count_host != nullptr, hamming_hist_host != nullptr, &d, &st);
+    if (rc != QMC_OK) return rc;
+    if (d.s0) QMC_CUDA_TRY(cudaMemcpyAsync(d.s0, s0_host, 8 * C, cudaMemcpyHostToDevice, st));
+    rc = qmc_classical_chains(m, n_chains, n_hops, d.s0, chain_id0, hop0, temperature, n_methods, kinds, params, probs, seed,
+                              d.prop, d.acc, d.fin, d.cnt, d.hist, st);
+    if (rc != QMC_OK) {
+        cudaStreamSynchronize(st);
+        return rc;
     }
-    return rc;
+    if (d.prop && CH) QMC_CUDA_TRY(cudaMemcpyAsync(proposals_host, d.prop, 8 * CH, cudaMemcpyDeviceToHost, st));
+    if (d.acc && CH) QMC_CUDA_TRY(cudaMemcpyAsync(accepted_host, d.acc, CH, cudaMemcpyDeviceToHost, st));
+    QMC_CUDA_TRY(cudaMemcpyAsync(final_state_host, d.fin, 8 * C, cudaMemcpyDeviceToHost, st));
+    if (d.cnt) QMC_CUDA_TRY(cudaMemcpyAsync(acc_count_host, d.cnt, 8 * C, cudaMemcpyDeviceToHost, st));
+    if (d.hist) QMC_CUDA_TRY(cudaMemcpyAsync(hamming_hist_host, d.hist, 8 * hb, cudaMemcpyDeviceToHost, st));
+    QMC_CUDA_TRY(cudaStreamSynchronize(st));
+    return QMC_OK;
 }

@@ -131,7 +131,10 @@ struct qmc_model {
     double *d_weights = nullptr;
     double *d_group_cum = nullptr;
     int max_terms_in_group = 0;
-    bool all_one_body = false;        // every term has popcount 1 and each qubit appears at most once per group
+    bool all_one_body = false;        // every term is a single-qubit X (a qubit may carry several terms of a group:
+                                      // exp(-i a X) exp(-i b X) = exp(-i (a + b) X), their weights add up)
+    std::vector<double> qweight;      // all_one_body: summed weight per (group, qubit), [n_groups][n]
+    double *d_qweight = nullptr;
     std::vector<double> host_J, host_h, host_cJ, host_ch;
     // fast exact enumerator: symmetrised couplings / fields in qubit order, constant 0.5 * trace(J)
     double *dJp = nullptr, *dhq_e = nullptr;
@@ -141,12 +144,20 @@ struct qmc_model {
     // general path (arbitrary mixers / complex128 in HBM)
     GeneralWorkspace *general = nullptr;
     int mixer_epoch = 0;  // bumped by qmc_mixer_set
+    // *_host entry points: one device arena (grows, never shrinks) and one non-blocking stream owned by the handle, so
+    // that the steady state of a host-buffer call is cudaMemcpyAsync + launches + one stream synchronise
+    void *stage_dev = nullptr;
+    size_t stage_cap = 0;
+    cudaStream_t stage_stream = nullptr;
+    // visit histogram accumulator (qmc_set_visit_histogram): int64[2^n], caller-owned, or null
+    unsigned long long *visit_hist = nullptr;
     // stats
     int64_t launches = 0;
     int profile = 0;
     double prof_ms = 0.0;
     int64_t prof_launches = 0;
     double prof_bytes = 0.0;
+    double prof_moved = 0.0;  // bytes the sweep launches actually read + wrote (first sweep write-only, last read-only)
 };
 
 // implemented in the respective .cu files
@@ -175,6 +186,20 @@ void qmc_general_free(qmc_model *m);
 int qmc_general_num_passes(qmc_model *m, int group);
 
 enum { QMC_MODE_CHAIN = 0, QMC_MODE_PROPOSE = 1, QMC_MODE_PROBS = 2 };
+
+// Host-buffer staging (model.cu): carve the six chain-I/O device buffers out of the handle's arena.
+struct ChainIoDev {
+    uint64_t *s0 = nullptr, *prop = nullptr, *fin = nullptr;
+    uint8_t *acc = nullptr;
+    int64_t *cnt = nullptr, *hist = nullptr;
+};
+int qmc_stage_chain_io(qmc_model *m, int64_t n_chains, int64_t n_hops, bool want_s0, bool want_prop, bool want_acc,
+                       bool want_cnt, bool want_hist, ChainIoDev *out, cudaStream_t *stream_out);
+
+// One count per visit of the Markov chain (MCMCChain.get_accepted_dict, qumcmc/basic_utils.py:117-131)
+__device__ __forceinline__ void qmc_visit(unsigned long long *visit_hist, uint64_t state) {
+    if (visit_hist) atomicAdd(visit_hist + state, 1ULL);
+}
 
 // energy kernels (model.cu)
 int qmc_launch_energies(qmc_model *m, const uint64_t *idx_dev, int64_t count, double *E_dev, cudaStream_t st);

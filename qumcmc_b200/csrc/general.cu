@@ -61,6 +61,7 @@ struct GenArgs {
     uint64_t *final_state;
     int64_t *acc_count, *hist;
     void *probs_out, *amps_out;
+    unsigned long long *visit;  // visit histogram accumulator or null
 };
 
 template <typename T> struct V2;
@@ -119,6 +120,7 @@ __global__ void gen_prepare_kernel(const GenArgs a, int64_t nc, int first_hop) {
             ch.cur = a.s_in ? a.s_in[gc] : qmc_initial_state(a.seed, gchain, a.n);
             ch.e_cur = qmc_energy_dev(a.n, a.J, a.h, ch.cur);
             ch.n_acc = 0;
+            if (a.hop == 0) qmc_visit(a.visit, ch.cur);  // entry 0 of markov_chain
         }
         const HopDraws d = qmc_hop_draws(a.seed, gchain, a.hop);
         ch.gamma = a.g_lo + (a.g_hi - a.g_lo) * d.u_gamma;
@@ -396,6 +398,7 @@ __global__ void __launch_bounds__(GSEL) gen_sample_kernel(const GenArgs a) {
         ch.e_cur = e_sp;
         ch.n_acc += 1;
     }
+    qmc_visit(a.visit, ch.cur);
 }
 
 __global__ void gen_finish_kernel(const GenArgs a, int64_t nc) {
@@ -670,6 +673,7 @@ int qmc_general_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, co
     a.s_in = s_in; a.gamma_arr = gamma_arr; a.u_arr = u_arr; a.r_arr = r_arr; a.group_arr = group_arr;
     a.proposals = proposals; a.accepted = accepted; a.final_state = final_state; a.acc_count = acc_count;
     a.hist = hamming_hist; a.probs_out = probs_out; a.amps_out = amps_out;
+    a.visit = mode == QMC_MODE_CHAIN ? m->visit_hist : nullptr;
     if (mode == QMC_MODE_CHAIN && hamming_hist)
         QMC_CUDA_TRY(cudaMemsetAsync(hamming_hist, 0, sizeof(int64_t) * (size_t)n_chains * (size_t)(n + 1), st));
     if (dtype == QMC_DTYPE_F64) return general_run_t<double>(m, w, a, n_chains, n_hops, hop0, r_cap, st);

@@ -399,7 +399,48 @@ extern "C" int qmc_model_destroy(qmc_model *m) {
     cudaFree(m->d_masks);
     cudaFree(m->d_weights);
     cudaFree(m->d_group_cum);
+    cudaFree(m->d_qweight);
+    cudaFree(m->stage_dev);
+    if (m->stage_stream) cudaStreamDestroy(m->stage_stream);
     delete m;
+    return QMC_OK;
+}
+
+// Device arena of the *_host entry points: [s0 | proposals | final | acc_count | hamming_hist | accepted], every part
+// 256-byte aligned; reallocated only when a call needs more than any call before it.
+int qmc_stage_chain_io(qmc_model *m, int64_t n_chains, int64_t n_hops, bool want_s0, bool want_prop, bool want_acc,
+                       bool want_cnt, bool want_hist, ChainIoDev *out, cudaStream_t *stream_out) {
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t C = (size_t)n_chains, CH = C * (size_t)n_hops, hb = C * (size_t)(m->n + 1);
+    const size_t b_s0 = want_s0 ? up(8 * C) : 0, b_prop = want_prop ? up(8 * CH) : 0, b_fin = up(8 * C);
+    const size_t b_cnt = want_cnt ? up(8 * C) : 0, b_hist = want_hist ? up(8 * hb) : 0, b_acc = want_acc ? up(CH) : 0;
+    const size_t need = b_s0 + b_prop + b_fin + b_cnt + b_hist + b_acc;
+    if (!m->stage_stream) QMC_CUDA_TRY(cudaStreamCreateWithFlags(&m->stage_stream, cudaStreamNonBlocking));
+    if (need > m->stage_cap) {
+        QMC_CUDA_TRY(cudaStreamSynchronize(m->stage_stream));
+        cudaFree(m->stage_dev);
+        m->stage_dev = nullptr;
+        m->stage_cap = 0;
+        QMC_CUDA_TRY(cudaMalloc(&m->stage_dev, need));
+        m->stage_cap = need;
+    }
+    char *p = static_cast<char *>(m->stage_dev);
+    auto take = [&](size_t b) { char *q = b ? p : nullptr; p += b; return q; };
+    out->s0 = reinterpret_cast<uint64_t *>(take(b_s0));
+    out->prop = reinterpret_cast<uint64_t *>(take(b_prop));
+    out->fin = reinterpret_cast<uint64_t *>(take(b_fin));
+    out->cnt = reinterpret_cast<int64_t *>(take(b_cnt));
+    out->hist = reinterpret_cast<int64_t *>(take(b_hist));
+    out->acc = reinterpret_cast<uint8_t *>(take(b_acc));
+    *stream_out = m->stage_stream;
+    return QMC_OK;
+}
+
+extern "C" int qmc_set_visit_histogram(qmc_model *m, int64_t *visit_hist_dev) {
+    QMC_REQUIRE(m, QMC_ERR_BADARG, "qmc_set_visit_histogram: null model handle");
+    QMC_REQUIRE(!visit_hist_dev || m->n <= QMC_VISIT_HIST_MAX_SPINS, QMC_ERR_UNSUPPORTED,
+                "visit histogram: 2^%d counters (n <= %d)", m->n, QMC_VISIT_HIST_MAX_SPINS);
+    m->visit_hist = reinterpret_cast<unsigned long long *>(visit_hist_dev);
     return QMC_OK;
 }
 
@@ -421,15 +462,6 @@ extern "C" int qmc_mixer_set(qmc_model *m, int n_groups, const int *group_offset
         QMC_REQUIRE(masks[k] != 0 && (masks[k] & ~full) == 0, QMC_ERR_BADARG,
                     "qmc_mixer_set: term %d has an empty mask or a qubit >= n", k);
         if (__builtin_popcountll(masks[k]) != 1) one_body = false;
-    }
-    if (one_body) {  // each qubit at most once per group
-        for (int g = 0; g < n_groups && one_body; ++g) {
-            uint64_t seen = 0;
-            for (int k = group_offsets[g]; k < group_offsets[g + 1]; ++k) {
-                if (seen & masks[k]) one_body = false;
-                seen |= masks[k];
-            }
-        }
     }
     QMC_CUDA_TRY(cudaSetDevice(m->device));
     m->n_groups = n_groups;
@@ -456,6 +488,17 @@ extern "C" int qmc_mixer_set(qmc_model *m, int n_groups, const int *group_offset
     }
     m->max_terms_in_group = max_terms;
     m->all_one_body = one_body;
+    m->qweight.clear();
+    cudaFree(m->d_qweight);
+    m->d_qweight = nullptr;
+    if (one_body) {  // per-qubit rotation weights of the sweep kernels: terms on the same qubit add up
+        m->qweight.assign((size_t)n_groups * m->n, 0.0);
+        for (int g = 0; g < n_groups; ++g)
+            for (int k = group_offsets[g]; k < group_offsets[g + 1]; ++k)
+                m->qweight[(size_t)g * m->n + (__builtin_ffsll((long long)masks[k]) - 1)] += weights[k];
+        QMC_CUDA_TRY(cudaMalloc(&m->d_qweight, sizeof(double) * m->qweight.size()));
+        QMC_CUDA_TRY(cudaMemcpy(m->d_qweight, m->qweight.data(), sizeof(double) * m->qweight.size(), cudaMemcpyHostToDevice));
+    }
     m->mixer_epoch++;
     cudaFree(m->d_group_off);
     cudaFree(m->d_masks);
@@ -618,6 +661,7 @@ extern "C" int qmc_profile_enable(qmc_model *m, int on) {
     m->prof_ms = 0.0;
     m->prof_launches = 0;
     m->prof_bytes = 0.0;
+    m->prof_moved = 0.0;
     return QMC_OK;
 }
 extern "C" int qmc_profile_read(qmc_model *m, double *sweep_ms, int64_t *sweep_launches, double *algorithmic_bytes) {
@@ -625,5 +669,10 @@ extern "C" int qmc_profile_read(qmc_model *m, double *sweep_ms, int64_t *sweep_l
     if (sweep_ms) *sweep_ms = m->prof_ms;
     if (sweep_launches) *sweep_launches = m->prof_launches;
     if (algorithmic_bytes) *algorithmic_bytes = m->prof_bytes;
+    return QMC_OK;
+}
+extern "C" int qmc_profile_read_moved(qmc_model *m, double *moved_bytes) {
+    QMC_REQUIRE(m && moved_bytes, QMC_ERR_BADARG, "qmc_profile_read_moved: null argument");
+    *moved_bytes = m->prof_moved;
     return QMC_OK;
 }

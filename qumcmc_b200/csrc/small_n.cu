@@ -35,6 +35,7 @@ struct SmallParams {
     uint64_t *final_state;
     int64_t *acc_count, *hamming_hist;
     void *probs_out, *amps_out;
+    unsigned long long *visit;  // visit histogram accumulator or null
 };
 
 template <typename T> struct Vec2;
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(SMALL_NT) smem_chain_kernel(const SmallParams 
     double e_cur = (p.mode == QMC_MODE_CHAIN) ? p.E[cur] : 0.0;
     long long n_acc = 0;
     for (int i = tid; i < n + 1; i += NT) s_hist[i] = 0;
+    if (p.mode == QMC_MODE_CHAIN && p.hop0 == 0 && tid == 0) qmc_visit(p.visit, cur);  // entry 0 of markov_chain
 
     const int64_t hops = (p.mode == QMC_MODE_CHAIN) ? p.n_hops : 1;
     for (int64_t hop = 0; hop < hops; ++hop) {
@@ -283,6 +285,7 @@ __global__ void __launch_bounds__(SMALL_NT) smem_chain_kernel(const SmallParams 
             e_cur = e_sp;
             ++n_acc;
         }
+        if (tid == 0) qmc_visit(p.visit, cur);
         __syncthreads();  // st / s_sel reuse in the next hop
     }
 
@@ -333,6 +336,7 @@ int qmc_small_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     p.hamming_hist = hamming_hist;
     p.probs_out = probs_out;
     p.amps_out = amps_out;
+    p.visit = mode == QMC_MODE_CHAIN ? m->visit_hist : nullptr;
 
     const size_t N = (size_t)1 << m->n;
     const size_t esz = dtype == QMC_DTYPE_F64 ? sizeof(double2) : sizeof(float2);

@@ -1100,6 +1100,7 @@ struct HopArgs {
     const int *group_off;
     const uint64_t *masks;
     const double *weights, *group_cum;
+    const double *qweight;  // [n_groups][n] summed mixer weight per qubit
     const uint64_t *s_in;
     const double *gamma_arr;
     const int *r_arr;
@@ -1110,6 +1111,7 @@ struct HopArgs {
     uint64_t *final_state;
     int64_t *acc_count, *hamming_hist;
     int *hist;  // [chains][n+1] running histogram
+    unsigned long long *visit;  // visit histogram accumulator or null
 };
 
 __device__ void fill_proposal_params(ChainParams &cp, const HopArgs &h, double gamma, int r, int grp) {
@@ -1117,10 +1119,11 @@ __device__ void fill_proposal_params(ChainParams &cp, const HopArgs &h, double g
     cp.group = grp;
     for (int q = 0; q < QMC_MAX_SPINS; ++q) cp.tq[q] = 0.f;
     double scale = 1.0;
-    for (int k = h.group_off[grp]; k < h.group_off[grp + 1]; ++k) {
-        const int q = __ffsll((long long)h.masks[k]) - 1;
+    for (int q = 0; q < h.n; ++q) {  // theta_q = gamma * (summed weight of the group's terms on qubit q) * dt
+        const double wq = h.qweight[grp * h.n + q];
+        if (wq == 0.0) continue;
         double s, c;
-        sincos(gamma * h.weights[k] * h.dt, &s, &c);
+        sincos(gamma * wq * h.dt, &s, &c);
         cp.tq[q] = (float)(s / c);
         scale *= c;
     }
@@ -1149,6 +1152,7 @@ __global__ void chains_init_kernel(const HopArgs h, ChainParams *params) {
     cp.cur = cur;
     cp.e_cur = (h.mode == QMC_MODE_CHAIN) ? qmc_energy_dev(h.n, h.J, h.h, cur) : 0.0;
     cp.n_acc = 0;
+    if (h.mode == QMC_MODE_CHAIN && h.hop0 == 0) qmc_visit(h.visit, cur);  // entry 0 of markov_chain
     for (int i = 0; i <= h.n; ++i) h.hist[c * (h.n + 1) + i] = 0;
 }
 
@@ -1311,6 +1315,7 @@ __global__ void __launch_bounds__(NT) sample_accept_kernel(const SweepArgs a, co
                 out.e_cur = e_sp;
                 out.n_acc = cp.n_acc + 1;
             }
+            qmc_visit(h.visit, acc ? sp : cp.cur);
         }
     }
 }
@@ -1400,7 +1405,36 @@ struct HiGroup {
 
 // Geometry for `nl` local qubits, top group first: full HI8 groups stack down from the top; the remainder (1..7
 // qubits) is the lowest group -- an HI8 window with 7 active qubits or an HI6 window with 1..6.
-static void hi_group_geometry(int nl, std::vector<int> &kind, std::vector<int> &pos, std::vector<int> &act) {
+// Test hook: QUMCMC_HI_GROUPS="kind:act,kind:act,..." (top group first, kind 6 | 8) replaces the default cover, so that
+// schedules with three or four register groups and stacked HI8 windows can be checked against the oracle at sizes it
+// still finishes (tests/test_gpu_sweep.py, tests/test_gpu_shard.py).  A window [p, p + kind) owns its top `act` qubits;
+// the ones below belong to the next group (or to the LO qubits) and only ride along.  An override that does not
+// cover exactly the nl - 12 upper qubits, or that a kernel cannot run, is an error.
+static int hi_group_geometry(int nl, std::vector<int> &kind, std::vector<int> &pos, std::vector<int> &act) {
+    if (const char *e = getenv("QUMCMC_HI_GROUPS")) {
+        if (*e) {
+            int top = nl;
+            const char *c = e;
+            while (*c) {
+                char *end = nullptr;
+                const int k = (int)strtol(c, &end, 10);
+                QMC_REQUIRE(end != c && *end == ':', QMC_ERR_BADARG, "QUMCMC_HI_GROUPS=%s: expected kind:act[,kind:act...]", e);
+                c = end + 1;
+                const int a = (int)strtol(c, &end, 10);
+                QMC_REQUIRE(end != c && (*end == ',' || *end == 0), QMC_ERR_BADARG, "QUMCMC_HI_GROUPS=%s: expected kind:act[,kind:act...]", e);
+                c = *end ? end + 1 : end;
+                const int p = top - k;
+                const bool ok6 = k == 6 && a >= 1 && a <= 6 && p >= 7;
+                const bool ok8 = k == 8 && (a == 7 || a == 8) && p >= 5;
+                QMC_REQUIRE(ok6 || ok8, QMC_ERR_BADARG, "QUMCMC_HI_GROUPS=%s: group %d:%d at position %d has no kernel", e, k, a, p);
+                kind.push_back(k); pos.push_back(p); act.push_back(a);
+                top -= a;
+            }
+            QMC_REQUIRE(top == LO_BITS, QMC_ERR_BADARG, "QUMCMC_HI_GROUPS=%s covers qubits %d..%d of %d local qubits (LO group = 0..%d)", e, top,
+                        nl - 1, nl, LO_BITS - 1);
+            return QMC_OK;
+        }
+    }
     const int hi = nl - LO_BITS, full8 = hi / 8, rem = hi % 8;
     for (int k = 0; k < full8; ++k) {
         kind.push_back(8); pos.push_back(nl - 8 * (k + 1)); act.push_back(8);
@@ -1410,6 +1444,7 @@ static void hi_group_geometry(int nl, std::vector<int> &kind, std::vector<int> &
     } else if (rem > 0) {
         kind.push_back(6); pos.push_back(LO_BITS + rem - 6); act.push_back(rem);
     }
+    return QMC_OK;
 }
 
 // Tables of one group (see af_thread): tile-uniform fields on the device, thread-level couplings from the host copy.
@@ -1607,11 +1642,17 @@ static int ensure_workspace(qmc_model *m, int64_t chains, cudaStream_t st) {
     return QMC_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: `done` is a bit mask indexed by
+// the current device, so a process that drives several GPUs opts in on each of them.
+typedef unsigned long long DevMask;
 template <typename K>
-static int set_smem_once(K kernel, bool &done, int bytes = TILE * 8) {
-    if (!done) {
+static int set_smem_once(K kernel, DevMask &done, int bytes = TILE * 8) {
+    int dev = 0;
+    QMC_CUDA_TRY(cudaGetDevice(&dev));
+    const DevMask bit = 1ULL << (dev & 63);
+    if (!(done & bit)) {
         QMC_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        done = true;
+        done |= bit;
     }
     return QMC_OK;
 }
@@ -1624,7 +1665,7 @@ struct SweepTune {
 
 template <int ROLE, bool FAST>
 static int launch_lo_v(const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
-    static bool done = false;
+    static DevMask done = 0;
     int rc = set_smem_once(lo_sweep_kernel<ROLE, NT, FAST>, done);
     if (rc != QMC_OK) return rc;
     lo_sweep_kernel<ROLE, NT, FAST><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off, off);
@@ -1637,7 +1678,7 @@ static int launch_lo(const SweepTune &tu, const SweepArgs &a, const int *order, 
     if (ROLE == LO_MID) {
         const char *pe = getenv("QUMCMC_SWEEP_PROBE");
         const int mode = pe ? atoi(pe) : 0;
-        static bool done1 = false, done2 = false;
+        static DevMask done1 = 0, done2 = 0;
         if (mode == 1) {
             set_smem_once(lo_probe_kernel<9, 3>, done1);
             lo_probe_kernel<9, 3><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off);
@@ -1658,13 +1699,13 @@ static int launch_lo(const SweepTune &tu, const SweepArgs &a, const int *order, 
 template <int W, bool FIRST, bool FAST>
 static int launch_hi_w(const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
     if (W == 8 && !FIRST && a.hiq) {
-        static bool doneq = false;
+        static DevMask doneq = 0;
         int rcq = set_smem_once(hiq_sweep_kernel<FAST>, doneq);
         if (rcq != QMC_OK) return rcq;
         hiq_sweep_kernel<FAST><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off, off);
         return QMC_OK;
     }
-    static bool done = false;
+    static DevMask done = 0;
     int rc = set_smem_once(hi_sweep_kernel<W, FIRST, FAST>, done);
     if (rc != QMC_OK) return rc;
     hi_sweep_kernel<W, FIRST, FAST><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off, off);
@@ -1732,7 +1773,7 @@ static int launch_hi6_pre(int pre, const SweepArgs &a, const Hi6Args &g, const i
 template <int ROLE, int ACT, int PRE>
 static int launch_hi8_rap(const SweepArgs &a, const Hi6Args &g, const int *order, int off, int64_t tiles, int count,
                           cudaStream_t st) {
-    static bool done = false;
+    static DevMask done = 0;
     int rc = set_smem_once(hi8_sweep_kernel<ROLE, ACT, PRE>, done);
     if (rc != QMC_OK) return rc;
     hi8_sweep_kernel<ROLE, ACT, PRE><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, g, order, off);
@@ -1834,30 +1875,36 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                 "n=%d > %d: only one-body X mixers have an HBM sweep path (k-body/custom mixers: shared-memory path)", n,
                 QMC_SMEM_MAX_SPINS_F32);
     if (n_chains == 0) return QMC_OK;
-    static bool smem_attr = false;
-    if (!smem_attr) {
-        QMC_CUDA_TRY(cudaFuncSetAttribute(sample_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 8));
-        smem_attr = true;
+    {
+        static DevMask smem_attr = 0;
+        int rca = set_smem_once(sample_accept_kernel, smem_attr);
+        if (rca != QMC_OK) return rca;
     }
     const int64_t N = 1LL << n;
     const int64_t tiles = N >> TILE_BITS;
     // chains per batch: bounded by free memory (state dominates)
-    size_t free_b = 0, total_b = 0;
-    QMC_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    const size_t per_chain = sizeof(float2) * (size_t)N + sizeof(float) * (size_t)(N >> 6) + sizeof(ChainParams) + 256;
     SweepWorkspace *w0 = m->sweep;
-    const size_t have = w0 ? (size_t)w0->cap_chains * per_chain : 0;
-    int64_t cap = (int64_t)(((double)(free_b + have) * 0.85) / (double)per_chain);
-    if (cap > 65535) cap = 65535;  // gridDim.y
-    if (!generic && cap > CTAN_MAX) cap = CTAN_MAX;  // one c_tan[] entry per chain of a batch (fast path)
-    QMC_REQUIRE(cap >= 1, QMC_ERR_CUDA, "not enough device memory for one 2^%d statevector", n);
+    int64_t cap;
+    if (w0 && w0->cap_chains >= n_chains) {
+        cap = w0->cap_chains;  // steady state: the workspace of an earlier call holds every chain of this one
+    } else {
+        size_t free_b = 0, total_b = 0;
+        QMC_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_chain = sizeof(float2) * (size_t)N + sizeof(float) * (size_t)(N >> 6) + sizeof(ChainParams) + 256;
+        const size_t have = w0 ? (size_t)w0->cap_chains * per_chain : 0;
+        cap = (int64_t)(((double)(free_b + have) * 0.85) / (double)per_chain);
+        if (cap > 65535) cap = 65535;  // gridDim.y
+        if (!generic && cap > CTAN_MAX) cap = CTAN_MAX;  // one c_tan[] entry per chain of a batch (fast path)
+        QMC_REQUIRE(cap >= 1, QMC_ERR_CUDA, "not enough device memory for one 2^%d statevector", n);
+    }
     const int64_t batch = std::min<int64_t>(cap, n_chains);
     int rc = ensure_workspace(m, batch, st);
     if (rc != QMC_OK) return rc;
     SweepWorkspace *w = m->sweep;
     if (generic && w->groups.empty()) {  // register groups above the LO qubits, built once per model
         std::vector<int> kind, pos, act;
-        hi_group_geometry(n, kind, pos, act);
+        rc = hi_group_geometry(n, kind, pos, act);
+        if (rc != QMC_OK) return rc;
         for (size_t k = 0; k < kind.size(); ++k) {
             HiGroup G;
             G.kind = kind[k];
@@ -1904,14 +1951,14 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         double log_min = 0.0;  // min over proposals of r * sum_q log|cos(gamma w_q dt)|
         auto log_scale = [&](double gamma, int grp) {
             double ls = 0.0;
-            for (int k = m->group_off[grp]; k < m->group_off[grp + 1]; ++k) ls += log(std::max(1e-300, fabs(cos(gamma * m->weights[k] * dt))));
+            for (int q = 0; q < n; ++q) ls += log(std::max(1e-300, fabs(cos(gamma * m->qweight[(size_t)grp * n + q] * dt))));
             return ls;
         };
         if (mode == QMC_MODE_CHAIN) {
             for (int grp = 0; grp < m->n_groups; ++grp) {
                 bool monotone = true;  // |cos| is monotone on [g_lo w dt, g_hi w dt] when the angles stay below pi/2
-                for (int k = m->group_off[grp]; k < m->group_off[grp + 1]; ++k)
-                    monotone = monotone && fabs(std::max(fabs(g_lo), fabs(g_hi)) * m->weights[k] * dt) < 1.5;
+                for (int q = 0; q < n; ++q)
+                    monotone = monotone && fabs(std::max(fabs(g_lo), fabs(g_hi)) * m->qweight[(size_t)grp * n + q] * dt) < 1.5;
                 if (!monotone) { log_min = -1e300; break; }
                 log_min = std::min(log_min, r_max * std::min(log_scale(g_lo, grp), log_scale(g_hi, grp)));
             }
@@ -1928,9 +1975,9 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         // weight on all n qubits (GenericMixer.OneBodyMixer and sums of it), and the batch must fit c_tan[].
         bool uniform_w = true;
         for (int grp = 0; grp < m->n_groups && uniform_w; ++grp) {
-            const int k0 = m->group_off[grp], k1 = m->group_off[grp + 1];
-            uniform_w = (k1 - k0 == n);
-            for (int k = k0; k < k1 && uniform_w; ++k) uniform_w = m->weights[k] == m->weights[k0];
+            const double *qw = m->qweight.data() + (size_t)grp * n;
+            uniform_w = qw[0] != 0.0;
+            for (int q = 0; q < n && uniform_w; ++q) uniform_w = qw[q] == qw[0];
         }
         tune.fast = !generic && log_min > log(1e-24) && uniform_w && batch <= CTAN_MAX;
         if (fast_env) tune.fast = tune.fast && fast_env[0] == '1';
@@ -1946,7 +1993,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         h.chain_id0 = chain_id0 + (uint64_t)c0; h.seed = seed; h.hop0 = hop0;
         h.temperature = temperature; h.g_lo = g_lo; h.g_hi = g_hi; h.dt = dt; h.alpha = m->alpha;
         h.J = m->dJ; h.h = m->dh;
-        h.group_off = m->d_group_off; h.masks = m->d_masks; h.weights = m->d_weights; h.group_cum = m->d_group_cum;
+        h.group_off = m->d_group_off; h.masks = m->d_masks; h.weights = m->d_weights; h.group_cum = m->d_group_cum; h.qweight = m->d_qweight;
         h.s_in = s_in ? s_in + c0 : nullptr;
         h.gamma_arr = gamma_arr ? gamma_arr + c0 : nullptr;
         h.r_arr = r_arr ? r_arr + c0 : nullptr;
@@ -1958,6 +2005,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         h.acc_count = acc_count ? acc_count + c0 : nullptr;
         h.hamming_hist = hamming_hist ? hamming_hist + c0 * (n + 1) : nullptr;
         h.hist = w->hist;
+        h.visit = mode == QMC_MODE_CHAIN ? m->visit_hist : nullptr;
         SweepArgs a;
         a.n = n; a.n_total = n; a.gbits = 0ULL; a.state = w->state; a.params = w->params; a.af_lo = w->af_lo; a.af_hia = w->af_hia; a.af_hib = w->af_hib; a.af_hic = w->af_hic;
         memcpy(a.dr_lo, w->dr_lo, sizeof(a.dr_lo)); memcpy(a.dr_hia, w->dr_hia, sizeof(a.dr_hia)); memcpy(a.dr_hib, w->dr_hib, sizeof(a.dr_hib));
@@ -2052,6 +2100,9 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                 w->ev.push_back(e1);
                 // algorithmic bytes of this hop: 2 * 2^n * 8 B * r per chain
                 m->prof_bytes += 2.0 * (double)N * 8.0 * sum_r;
+                // bytes actually moved: K = groups.size() (1 on the two-group path) passes per layer, the first sweep of a
+                // proposal write-only, the last read-only => 16 B * 2^n * K * (r - 1) per proposal
+                m->prof_moved += 16.0 * (double)N * (double)(generic ? groups.size() : 1) * (sum_r - (double)nc);
                 m->prof_launches += launched;
             }
             if (mode == QMC_MODE_PROBS) {
@@ -2215,10 +2266,10 @@ static void shard_fill_params(qmc_shard *sh, uint64_t s, double gamma, int r, do
     double tq[QMC_MAX_SPINS];
     for (int q = 0; q < QMC_MAX_SPINS; ++q) tq[q] = 0.0;
     double scale = 1.0;
-    for (int k = m->group_off[grp]; k < m->group_off[grp + 1]; ++k) {
-        int q = 0;
-        while (!((m->masks[k] >> q) & 1ULL)) ++q;
-        const double th = gamma * m->weights[k] * dt;
+    for (int q = 0; q < n; ++q) {  // theta_q = gamma * (summed weight of the group's terms on qubit q) * dt
+        const double wq = m->qweight[(size_t)grp * n + q];
+        if (wq == 0.0) continue;
+        const double th = gamma * wq * dt;
         tq[q] = sin(th) / cos(th);
         scale *= cos(th);
     }
@@ -2278,7 +2329,13 @@ extern "C" int qmc_shard_create(qmc_shard **out, qmc_model *m, int rank, int log
     sh->fx_scale = ldexp(1.0, sh->k_fx);
     // group geometry (positions): full HI8 groups from the top, the partial group lowest; LO = positions 0..11
     std::vector<int> kinds, ps;
-    hi_group_geometry(nl, kinds, ps, sh->acts);
+    {
+        const int rcg = hi_group_geometry(nl, kinds, ps, sh->acts);
+        if (rcg != QMC_OK) {
+            delete sh;
+            return rcg;
+        }
+    }
     const int K = (int)kinds.size();
     if (g > sh->acts[0] || g > 6) {
         delete sh;
@@ -2328,10 +2385,13 @@ extern "C" int qmc_shard_create(qmc_shard **out, qmc_model *m, int rank, int log
     QMC_CUDA_TRY(cudaMemset(sh->order, 0, sizeof(int)));
     QMC_CUDA_TRY(cudaMalloc(&sh->segsum, sizeof(float) * ((size_t)1 << (nl - 6))));
     QMC_CUDA_TRY(cudaMalloc(&sh->total, sizeof(double) * (SEL_BLOCKS + 4)));
-    static bool attr = false;
-    if (!attr) {
-        QMC_CUDA_TRY(cudaFuncSetAttribute(shard_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 8));
-        attr = true;
+    {
+        static DevMask attr = 0;
+        int rca = set_smem_once(shard_resolve_kernel, attr);
+        if (rca != QMC_OK) {
+            qmc_shard_destroy(sh);
+            return rca;
+        }
     }
     *out = sh;
     return QMC_OK;

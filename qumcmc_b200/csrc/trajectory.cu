@@ -11,6 +11,10 @@
 // (sums over p_i > 1e-10, vectoried_KL's mask; c_i / k >= 1/k > EPS for k < 1e8), so one visit changes V, W by O(1)
 // terms; the counts live in a per-chain open-addressing hash table keyed by the state (<= H + 1 distinct keys).
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -61,7 +65,7 @@ __global__ void kl_constants_final(const double *__restrict__ part, int nblk, do
 
 struct TrajArgs {
     int n;
-    int64_t n_chains, n_hops, chain0;
+    int64_t n_chains, n_hops, chain0, batch_chains;  // this launch covers chains [chain0, chain0 + batch_chains)
     const double *J, *h;
     const uint64_t *s0, *proposals;
     const uint8_t *accepted;
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(64) trajectory_kernel(const TrajArgs a) {
     }
     const int64_t lc = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // chain inside the batch
     const int64_t c = a.chain0 + lc;
-    if (c >= a.n_chains) return;
+    if (lc >= a.batch_chains || c >= a.n_chains) return;  // threads past the batch must not touch the next batch's chains
     const int64_t H = a.n_hops;
     unsigned long long *keys = a.keys ? a.keys + lc * ((size_t)a.cap_mask + 1) : nullptr;
     unsigned *cnts = a.counts ? a.counts + lc * ((size_t)a.cap_mask + 1) : nullptr;
@@ -191,7 +195,8 @@ extern "C" int qmc_trajectory_stats(qmc_model *m, int64_t n_chains, int64_t n_ho
             size_t cap = 64;
             while (cap < 2 * (size_t)(n_hops + 1)) cap <<= 1;
             const size_t per_chain = cap * (sizeof(unsigned long long) + sizeof(unsigned));
-            const size_t budget = (size_t)4 << 30;  // hash tables of one batch of chains
+            size_t budget = (size_t)4 << 30;  // hash tables of one batch of chains
+            if (const char *be = getenv("QUMCMC_TRAJ_BUDGET_BYTES")) budget = (size_t)strtoull(be, nullptr, 10);  // tests: force several batches
             batch = (int64_t)std::max<size_t>(1, std::min<size_t>((size_t)n_chains, budget / per_chain));
             e = cudaMalloc(&keys, sizeof(unsigned long long) * cap * (size_t)batch);
             if (e == cudaSuccess) e = cudaMalloc(&counts, sizeof(unsigned) * cap * (size_t)batch);
@@ -207,6 +212,7 @@ extern "C" int qmc_trajectory_stats(qmc_model *m, int64_t n_chains, int64_t n_ho
         if (keys) e = cudaMemsetAsync(keys, 0xFF, sizeof(unsigned long long) * ((size_t)a.cap_mask + 1) * (size_t)nc, st);
         if (e != cudaSuccess) break;
         a.chain0 = c0;
+        a.batch_chains = nc;
         trajectory_kernel<<<(unsigned)((nc + 63) / 64), 64, smem, st>>>(a);
         m->launches++;
         e = cudaGetLastError();

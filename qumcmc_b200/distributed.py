@@ -21,9 +21,31 @@ def shard_range(n_chains: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
-def gather_statistics(acc_count: np.ndarray, hamming_hist: np.ndarray, n_chains: int, group=None):
+def reduce_visit_histogram(visit_hist, group=None):
+    """Sum of the ranks' visit histograms (``visit_hist(2^n)``, ncclAllReduce).  ``visit_hist`` is
+    this rank's int64[2^n] -- a CUDA tensor straight from the device accumulator (nccl: reduced in place over NVLink,
+    no host copy) or a numpy array / CPU tensor (gloo).  Returns the same kind of object."""
+    import torch
+    import torch.distributed as dist
+
+    backend = dist.get_backend(group)
+    if isinstance(visit_hist, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(visit_hist, dtype=np.int64))
+        if backend == "nccl":
+            t = t.to(torch.device("cuda", torch.cuda.current_device()))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t.cpu().numpy()
+    t = visit_hist
+    if backend == "nccl" and not t.is_cuda:
+        t = t.to(torch.device("cuda", torch.cuda.current_device()))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def gather_statistics(acc_count: np.ndarray, hamming_hist: np.ndarray, n_chains: int, group=None, visit_hist=None):
     """All-gather the per-chain acceptance counts [C_local] and Hamming histograms [C_local, n+1]
-    into global arrays ordered by chain id.  Works on CPU tensors (gloo) and CUDA tensors (nccl)."""
+    into global arrays ordered by chain id.  Works on CPU tensors (gloo) and CUDA tensors (nccl).
+    With ``visit_hist`` (this rank's int64[2^n]) a third result is returned: its sum over the ranks (one all-reduce)."""
     import torch
     import torch.distributed as dist
 
@@ -45,6 +67,8 @@ def gather_statistics(acc_count: np.ndarray, hamming_hist: np.ndarray, n_chains:
         blk = out[r].cpu().numpy()
         acc[a:b] = blk[: b - a, 0]
         hist[a:b] = blk[: b - a, 1:]
+    if visit_hist is not None:
+        return acc, hist, reduce_visit_histogram(visit_hist, group)
     return acc, hist
 
 

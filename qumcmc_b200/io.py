@@ -38,6 +38,7 @@ def load_legacy_pickle(path: str):
 
 def _as_batch(chains: Union[ChainBatch, MCMCChain, Sequence[MCMCChain]]):
     if isinstance(chains, ChainBatch):
+        chains.require_recorded("save_chains")
         return chains.num_spins, chains.initial, chains.proposals, chains.accepted, [chains.name] * len(chains.initial)
     if isinstance(chains, MCMCChain):
         chains = [chains]

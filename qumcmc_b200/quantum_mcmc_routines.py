@@ -20,6 +20,30 @@ from .mixers import GenericMixer, Mixer
 
 GammaType = Union[float, Tuple[float, float]]
 
+
+def initial_state_indices(initial_state, num_spins: int, n_chains: int) -> np.ndarray:
+    """uint64[n_chains] basis indices of the caller's initial state(s).  The reference asserts
+    ``len(bitstring) == num_spins`` inside get_energy (qumcmc/energy_models.py:124-144); here an out-of-range index
+    would reach the device unchecked, so it is rejected on the host."""
+    n = int(num_spins)
+
+    def one(s) -> int:
+        if isinstance(s, str):
+            if len(s) != n or any(ch not in "01" for ch in s):
+                raise ValueError(f"initial state {s!r} is not a bitstring of {n} spins")
+            return int(s, 2)
+        v = int(s)
+        if v < 0 or (n < 64 and v >= (1 << n)):
+            raise ValueError(f"initial state index {v} outside [0, 2^{n})")
+        return v
+
+    if isinstance(initial_state, str) or np.isscalar(initial_state):
+        return np.full(n_chains, one(initial_state), dtype=np.uint64)
+    init = np.array([one(s) for s in initial_state], dtype=np.uint64)
+    if len(init) != n_chains:
+        raise ValueError("one initial state per chain expected")
+    return init
+
 # README-era call shape quantum_enhanced_mcmc(n_hops, model, temperature) (README.md:62-66):
 # single-qubit X mixer and gamma ~ U(0.25, 0.6) (fossil in qumcmc/restricted_samplng.py:124-127).
 DEFAULT_GAMMA = (0.25, 0.6)
@@ -45,15 +69,27 @@ def _gamma_range(gamma: GammaType) -> Tuple[float, float]:
 class ChainBatch(Sequence):
     """Result of a multi-chain call: arrays plus a lazy ``MCMCChain`` view per chain."""
 
-    def __init__(self, num_spins, initial, proposals, accepted, final_state, acc_count, hamming_hist, name):
+    def __init__(self, num_spins, initial, proposals, accepted, final_state, acc_count, hamming_hist, name,
+                 n_hops=None, visit_hist=None):
         self.num_spins = num_spins
         self.initial = initial              # uint64[C]
-        self.proposals = proposals          # uint64[C, H]
-        self.accepted = accepted            # uint8[C, H]
+        self.proposals = proposals          # uint64[C, H]; None when the run was not recorded (record=False)
+        self.accepted = accepted            # uint8[C, H];  None when the run was not recorded
         self.final_state = final_state      # uint64[C]
         self.acc_count = acc_count          # int64[C]
         self.hamming_hist = hamming_hist    # int64[C, n+1]
         self.name = name
+        self.n_hops = int(n_hops) if n_hops is not None else (0 if proposals is None else int(proposals.shape[1]))
+        self.visit_hist = visit_hist        # int64[2^n] visits of the Markov chains (device histogram) or None
+
+    @property
+    def recorded(self) -> bool:
+        return self.proposals is not None and self.accepted is not None
+
+    def require_recorded(self, what: str) -> None:
+        if not self.recorded:
+            raise ValueError(f"{what} needs the per-hop record, but this batch was run with record=False "
+                             "(only final states, acceptance counts and histograms were kept)")
 
     def __len__(self):
         return len(self.initial)
@@ -61,18 +97,22 @@ class ChainBatch(Sequence):
     def __getitem__(self, c) -> MCMCChain:
         if isinstance(c, slice):
             return [self[i] for i in range(*c.indices(len(self)))]
+        self.require_recorded("ChainBatch[c] (an MCMCChain view)")
         return MCMCChain.from_arrays(self.num_spins, int(self.initial[c]), self.proposals[c], self.accepted[c],
                                      name=self.name)
 
     def acceptance_rate(self) -> float:
-        return float(self.acc_count.sum()) / float(self.proposals.size)
+        total = len(self.initial) * self.n_hops
+        return float(self.acc_count.sum()) / float(total) if total else float("nan")
 
 
 def run_chains(model: IsingEnergyFunction, mixer: Mixer, gamma: GammaType, n_hops: int, n_chains: int,
                initial_states: Optional[np.ndarray], temperature: float, delta_time: float, seed: int,
                dtype=None, device: int = 0, chain_id0: int = 0, hop0: int = 0, name: str = "Q-MCMC",
-               record: bool = True) -> ChainBatch:
-    """Batched driver over qmc_run_chains (device buffers are torch tensors)."""
+               record: bool = True, visit_histogram: bool = False) -> ChainBatch:
+    """Batched driver over qmc_run_chains (device buffers are torch tensors).  ``visit_histogram=True`` also returns
+    the dense visit counts of the Markov chains (``ChainBatch.visit_hist``: int64[2^n], summed over the chains of the
+    call, accumulated on the device -- MCMCChain.get_accepted_dict without materialising the chains)."""
     torch = _device._torch()
     dm = model.device_model(device)
     dm.set_mixer(mixer)
@@ -90,11 +130,18 @@ def run_chains(model: IsingEnergyFunction, mixer: Mixer, gamma: GammaType, n_hop
     cnt = torch.empty(C_, dtype=torch.int64, device=dev)
     hist = torch.empty((C_, n + 1), dtype=torch.int64, device=dev)
     ptr = lambda t: None if t is None else t.data_ptr()
-    _lib.check(_lib.lib().qmc_run_chains(
-        dm.handle, C_, H, ptr(s0), int(chain_id0), int(hop0) & 0xFFFFFFFF, float(temperature), g_lo, g_hi,
-        float(delta_time), int(seed) & 0xFFFFFFFFFFFFFFFF, dt, ptr(props), ptr(acc), ptr(fin), ptr(cnt), ptr(hist),
-        _device.current_stream_ptr(device)))
-    torch.cuda.synchronize(device)
+    visits = torch.zeros(1 << n, dtype=torch.int64, device=dev) if visit_histogram else None
+    if visits is not None:
+        dm.attach_visit_histogram(visits)
+    try:
+        _lib.check(_lib.lib().qmc_run_chains(
+            dm.handle, C_, H, ptr(s0), int(chain_id0), int(hop0) & 0xFFFFFFFF, float(temperature), g_lo, g_hi,
+            float(delta_time), int(seed) & 0xFFFFFFFFFFFFFFFF, dt, ptr(props), ptr(acc), ptr(fin), ptr(cnt), ptr(hist),
+            _device.current_stream_ptr(device)))
+        torch.cuda.synchronize(device)
+    finally:
+        if visits is not None:
+            dm.attach_visit_histogram(None)
     to_u64 = lambda t: t.cpu().numpy().view(np.uint64)
     if initial_states is None:
         from .rng import initial_states_philox
@@ -102,7 +149,8 @@ def run_chains(model: IsingEnergyFunction, mixer: Mixer, gamma: GammaType, n_hop
     else:
         init = np.ascontiguousarray(initial_states, dtype=np.uint64)
     return ChainBatch(n, init, to_u64(props) if record else None, acc.cpu().numpy() if record else None,
-                      to_u64(fin), cnt.cpu().numpy(), hist.cpu().numpy(), name)
+                      to_u64(fin), cnt.cpu().numpy(), hist.cpu().numpy(), name, n_hops=H,
+                      visit_hist=None if visits is None else visits.cpu().numpy())
 
 
 def quantum_enhanced_mcmc(
@@ -122,6 +170,8 @@ def quantum_enhanced_mcmc(
     device: int = 0,
     chain_id0: int = 0,
     hop0: int = 0,
+    record: bool = True,
+    visit_histogram: bool = False,
 ):
     """Quantum-enhanced MCMC.  Returns an ``MCMCChain`` (or a ``ChainBatch`` when ``n_chains`` is
     given).  ``mixer``/``gamma`` default to the README-era sampler when omitted."""
@@ -137,17 +187,14 @@ def quantum_enhanced_mcmc(
     C_ = 1 if single else int(n_chains)
     if initial_state is None:
         init = np.array([int(get_random_state(n), 2)], dtype=np.uint64) if single else None
-    elif isinstance(initial_state, str):
-        init = np.full(C_, int(initial_state, 2), dtype=np.uint64)
     else:
-        init = np.array([int(s, 2) if isinstance(s, str) else int(s) for s in initial_state], dtype=np.uint64)
-        if len(init) != C_:
-            raise ValueError("one initial state per chain expected")
+        init = initial_state_indices(initial_state, n, C_)
     if verbose and init is not None:
         e0 = model.get_energy(int_to_binary(int(init[0]), n))
         print("starting with: ", int_to_binary(int(init[0]), n), "with energy:", e0)
     batch = run_chains(model, mixer, gamma, n_hops, C_, init, temperature, delta_time, seed, dtype=dtype,
-                       device=device, chain_id0=chain_id0, hop0=hop0, name=chain_name)
+                       device=device, chain_id0=chain_id0, hop0=hop0, name=chain_name,
+                       record=record or single, visit_histogram=visit_histogram)
     return batch[0] if single else batch
 
 

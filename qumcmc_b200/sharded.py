@@ -58,6 +58,17 @@ def shard_geometry(n_local: int) -> List[Tuple[int, int]]:
     """Active position range [lo, hi) of every register group, top group first (mirrors hi_group_geometry in
     csrc/sweep.cu): positions 0..11 belong to the LO passes, full groups of 8 (HI8 passes) stack down from the top,
     the remaining 1..7 positions form the lowest group."""
+    import os
+    override = os.environ.get("QUMCMC_HI_GROUPS", "")
+    if override:  # test hook, see hi_group_geometry: "kind:act,..." from the top; a group owns the top `act` of its window
+        out, top = [], n_local
+        for item in override.split(","):
+            _, act = (int(x) for x in item.split(":"))
+            out.append((top - act, top))
+            top -= act
+        if top != 12:
+            raise ValueError(f"QUMCMC_HI_GROUPS={override} does not cover the {n_local - 12} upper local qubits")
+        return out
     hi_qubits = n_local - 12
     out = [(n_local - 8 * (k + 1), n_local - 8 * k) for k in range(hi_qubits // 8)]
     if hi_qubits % 8:

@@ -70,6 +70,7 @@ def spin_moments(model: IsingEnergyFunction, states: np.ndarray, mask: Optional[
 def chain_moments(model: IsingEnergyFunction, chains: Union[MCMCChain, ChainBatch], device: int = 0):
     """Moments over the accepted states of one chain or of every chain of a batch (pooled)."""
     if isinstance(chains, ChainBatch):
+        chains.require_recorded("chain_moments")
         states = np.concatenate([chains.initial.reshape(-1), chains.proposals.reshape(-1)])
         mask = np.concatenate([np.ones(len(chains.initial), dtype=np.uint8), chains.accepted.reshape(-1)])
     else:

@@ -15,7 +15,7 @@ from tests.shard_sim import logical_indices
 pytestmark = pytest.mark.gpu
 
 
-def _emulated_proposal(n, g, r, s, gamma, seed=11, us=(), fused=False, chunk_bits=0):
+def _emulated_proposal(n, g, r, s, gamma, seed=11, us=(), fused=False, chunk_bits=0, on_device=False):
     import torch
     import qumcmc_b200 as q
     from qumcmc_b200.sharded import EXCHANGE, ShardHandle, pick_owner, sharded_plan
@@ -78,8 +78,17 @@ def _emulated_proposal(n, g, r, s, gamma, seed=11, us=(), fused=False, chunk_bit
         t = torch.zeros(1, dtype=torch.float64, device=dev)
         hd.norm(t)
         totals.append(float(t.item()))
-    p = np.zeros(1 << n)
+    if on_device:  # large n: per-rank probabilities stay on the device (the caller compares them there)
+        p = []
+        for R, hd in enumerate(hs):
+            pr = torch.empty(1 << nl, dtype=torch.float32, device=dev)
+            hd.final_probabilities(bufs[R], layout, pr)
+            p.append(pr)
+    else:
+        p = np.zeros(1 << n)
     for R, hd in enumerate(hs):
+        if on_device:
+            break
         pr = torch.empty(1 << nl, dtype=torch.float32, device=dev)
         hd.final_probabilities(bufs[R], layout, pr)
         p[logical_indices(R, nl, g, layout)] = pr.cpu().numpy().astype(np.float64)
@@ -203,3 +212,65 @@ def test_shard_nccl_world2_matches_emulation(fused):
     for (s, gamma, r, u), got in zip(cases, res[0][1]):
         _, _, _, _, _, picks = _emulated_proposal(n, 1, r, s, gamma, us=[u])
         assert got == picks[0]
+
+
+@pytest.mark.parametrize("n,g,groups,r", [(27, 3, "8:8,6:2,6:2", 3), (25, 2, "8:8,6:3", 4), (24, 1, "6:6,6:3,6:2", 5)])
+def test_shard_ops_with_three_register_groups(monkeypatch, n, g, groups, r):
+    """C5's local shard (33 qubits) has K = 3 register groups; QUMCMC_HI_GROUPS gives an emulated shard
+    the same structure (HI8 top group + two lower groups, SINGLE passes on both before every exchange) at a size the
+    oracle finishes."""
+    from qumcmc_b200 import _device
+    monkeypatch.setenv("QUMCMC_HI_GROUPS", groups)
+    _device._cache.clear()
+    rng = np.random.default_rng(n * 7 + r)
+    s = int(rng.integers(0, 1 << n))
+    gamma = float(rng.uniform(0.25, 0.6))
+    try:
+        J, h, p, totals, layout, picks = _emulated_proposal(n, g, r, s, gamma, us=[0.3, 0.9], fused=(g == 3))
+    finally:
+        _device._cache.clear()
+    assert layout == 0
+    masks, w = models.one_body(n)
+    ref = oracle.transition_probs(J, h, oracle.alpha(J, h), gamma, 0.8, r, masks, w, s, gatewise=False)
+    assert abs(sum(totals) - 1.0) < 1e-5
+    assert np.abs(p - ref).max() < 1e-6
+    assert np.linalg.norm(p - ref) < 1e-4 * np.linalg.norm(ref)     # relative: probabilities are ~2^-n at this size
+
+
+@pytest.mark.slow
+def test_shard_eight_way_split_n30_matches_single_gpu():
+    """an (emulated) 8-way split of n = 30 (g = 3, 27 local qubits, fused pass + exchange) against
+    the single-GPU n = 30 path -- whose geometry class (K = 3) is checked against the oracle at n = 29.  Everything is
+    compared on the device: 2^30 probabilities."""
+    import torch
+    import qumcmc_b200 as q
+    from qumcmc_b200 import _device, _lib
+    n, g, r, s, gamma = 30, 3, 3, 0x2F00F00D & ((1 << 30) - 1), 0.43
+    nl = n - g
+    out = _emulated_proposal(n, g, r, s, gamma, seed=11, us=[0.37], fused=True, on_device=True)
+    J, h, parts, totals, layout, picks = out
+    assert layout == 0 and abs(sum(totals) - 1.0) < 1e-5
+    model = q.IsingEnergyFunction(J, h)
+    dm = model.device_model(0)
+    dm.set_mixer(q.GenericMixer.OneBodyMixer(n))
+    dev = torch.device("cuda", 0)
+    single = torch.empty(1 << n, dtype=torch.float32, device=dev)
+    _lib.check(_lib.lib().qmc_transition_probs(dm.handle, s, gamma, r, 0.8, 0, _lib.DTYPE_F32, single.data_ptr(), None, None))
+    torch.cuda.synchronize()
+    num = den = 0.0
+    worst = 0.0
+    for R, pr in enumerate(parts):     # layout 0: logical index = (R << nl) | local index
+        ref = single[R << nl:(R + 1) << nl]
+        d = (pr.double() - ref.double())
+        num += float((d * d).sum())
+        den += float((ref.double() ** 2).sum())
+        worst = max(worst, float(d.abs().max()))
+    assert worst < 1e-6                                   # north-star tolerance (fp32), trivial at 2^-30 per state ...
+    assert (num / den) ** 0.5 < 2e-4                      # ... so also relative L2 over all 2^30 probabilities
+    # measurement through the sharded selector = sequential inverse CDF over the single-GPU probabilities
+    cdf_at = float(single[: picks[0]].double().sum())
+    p_at = float(single[picks[0]])
+    assert cdf_at - 2e-5 <= 0.37 <= cdf_at + p_at + 2e-5
+    del parts, single
+    _device._cache.clear()
+    torch.cuda.empty_cache()

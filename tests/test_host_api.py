@@ -183,7 +183,14 @@ def _gloo_worker(rank, world, port, C, width, q):
         return ids * 3, np.stack([ids * 10 + k for k in range(width)], axis=1).reshape(count, width), (chain_id0, count)
 
     acc, hist, payload = run_chains_sharded(run_local, C, None)
-    q.put((rank, acc.tolist(), hist.tolist(), payload))
+    # visit histogram of this rank's chains (here: chain id mod 8) -> one all-reduce, as numpy and as a tensor
+    from qumcmc_b200.distributed import gather_statistics, reduce_visit_histogram, shard_range
+    a, b = shard_range(C, rank, world)
+    mine = np.bincount(np.arange(a, b) % 8, minlength=8).astype(np.int64)
+    import torch
+    total_t = reduce_visit_histogram(torch.from_numpy(mine.copy()), None)
+    _, _, total_np = gather_statistics(np.arange(a, b) * 3, np.zeros((b - a, width), dtype=np.int64), C, None, visit_hist=mine)
+    q.put((rank, acc.tolist(), hist.tolist(), payload, total_np.tolist(), total_t.tolist()))
     dist.destroy_process_group()
 
 
@@ -201,9 +208,10 @@ def test_chain_sharding_gather_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     ids = np.arange(C)
-    for rank, acc, hist, payload in outs:
+    for rank, acc, hist, payload, visits_np, visits_t in outs:
         assert acc == (ids * 3).tolist()
         assert hist == np.stack([ids * 10 + k for k in range(width)], axis=1).tolist()
+        assert visits_np == visits_t == np.bincount(ids % 8, minlength=8).tolist()   # K7: all-reduced visit histogram
     assert sorted(p[3] for p in outs) == [(0, 6), (6, 5)]
 
 
@@ -252,3 +260,51 @@ def test_combine_logsumexp_edge_cases():
     assert combine_logsumexp([[0.0, 1.0], [0.0, 1.0]]) == pytest.approx(np.log(2.0))
     assert combine_logsumexp([[1000.0, 1.0], [-1000.0, 5.0]]) == pytest.approx(1000.0)
     assert combine_logsumexp([[float("-inf"), 0.0], [2.0, 3.0]]) == pytest.approx(2.0 + np.log(3.0))
+
+
+def test_initial_states_are_validated_on_the_host():
+    """the reference asserts len(bitstring) == num_spins; an out-of-range index must not reach the device."""
+    from qumcmc_b200.quantum_mcmc_routines import initial_state_indices
+    assert initial_state_indices("0101", 4, 3).tolist() == [5, 5, 5]
+    assert initial_state_indices(["0001", 7], 4, 2).tolist() == [1, 7]
+    for bad in ("01010", "012", 16, -1, ["0000", "00000"]):
+        with pytest.raises(ValueError):
+            initial_state_indices(bad, 4, 2 if isinstance(bad, list) else 1)
+    with pytest.raises(ValueError):
+        initial_state_indices(["0000"], 4, 2)   # one state per chain
+
+
+def test_chain_batch_without_a_record():
+    """record=False batches keep acceptance counts / final states; views that need the record say so."""
+    from qumcmc_b200.quantum_mcmc_routines import ChainBatch
+    b = ChainBatch(4, np.array([1, 2], dtype=np.uint64), None, None, np.array([3, 4], dtype=np.uint64),
+                   np.array([5, 7], dtype=np.int64), np.zeros((2, 5), dtype=np.int64), "x", n_hops=10)
+    assert not b.recorded and b.acceptance_rate() == pytest.approx(12 / 20)
+    with pytest.raises(ValueError, match="record=False"):
+        b[0]
+    from qumcmc_b200 import io as qio
+    with pytest.raises(ValueError, match="record=False"):
+        qio.save_chains("/tmp/never_written.npz", b)
+    full = ChainBatch(4, np.array([1], dtype=np.uint64), np.array([[2, 3]], dtype=np.uint64),
+                      np.array([[1, 0]], dtype=np.uint8), np.array([2], dtype=np.uint64), np.array([1], dtype=np.int64),
+                      np.zeros((1, 5), dtype=np.int64), "y")
+    assert full.recorded and full.n_hops == 2 and full.acceptance_rate() == 0.5 and full[0].markov_chain[-1] == "0010"
+
+
+def test_overridden_builtin_proposal_rules_run_on_the_host():
+    """a user subclass of a built-in rule that overrides propose_transition must not be lowered to the
+    built-in device rule (the reference always calls propose_transition)."""
+    from qumcmc_b200.classical_mixers import CombineProposals, CustomProposals, FixedWeightProposals, UniformProposals
+
+    class Sticky(UniformProposals):
+        def propose_transition(self, current_state=None):
+            return current_state
+
+    class Plain(FixedWeightProposals):
+        pass
+
+    assert UniformProposals(5).device_lowering() is not None
+    assert Plain(5, 2).device_lowering() == FixedWeightProposals(5, 2).device_lowering()
+    assert Sticky(5).device_lowering() is None
+    assert CombineProposals([Sticky(5), CustomProposals(5, [0])], [0.5, 0.5]).device_lowering() is None
+    assert CombineProposals([UniformProposals(5), CustomProposals(5, [0])], [0.5, 0.5]).device_lowering() is not None

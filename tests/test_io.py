@@ -5,6 +5,7 @@ import pickle
 import pickletools
 
 import numpy as np
+import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LEGACY = os.path.join(HERE, "golden", "legacy_chains.pkl")
@@ -57,3 +58,25 @@ def test_compact_format_round_trip(tmp_path):
         assert a.name == b.name and a.markov_chain == b.markov_chain
     n, initial, proposals, accepted, names = load_chains(path, as_batch=True)
     assert n == 9 and proposals.shape == (2, 299) and accepted.shape == (2, 299) and initial.dtype == np.uint64
+
+
+REF_PICKLE = "/root/reference/gamma_variation/num_spins_8_Gamma_var_num_spins_8_beta_1.5_seed_1.pkl"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PICKLE), reason="reference checkout not present (GPU box)")
+def test_reference_written_pickle_loads():
+    """A pickle the reference itself wrote (gamma-variation experiment): a dict gamma-range -> MCMCChain of 10 001 states.
+    The acceptance rates must equal the ones tests/golden/make_golden.py extracted from the same file."""
+    import json
+    from qumcmc_b200.basic_utils import MCMCChain
+    from qumcmc_b200.io import load_chains, load_legacy_pickle, save_chains
+    d = load_legacy_pickle(REF_PICKLE)
+    with open(os.path.join(HERE, "golden", "chain_stats.json")) as f:
+        fx = json.load(f)["gamma_variation"]["n8_seed1"]["ranges"]
+    assert set(d) == set(fx)
+    for key, ch in d.items():
+        assert isinstance(ch, MCMCChain) and ch.num_spins == 8 and len(ch) == fx[key]["n_hops"] + 1
+        assert abs(ch.acceptance_rate() - fx[key]["acceptance"]) < 1e-12
+        assert int(ch.proposal_indices[0]) == fx[key]["initial"]
+        top = sorted(zip(*np.unique(ch.markov_chain_indices(), return_counts=True)), key=lambda kc: -kc[1])[:4]
+        assert [int(c) for _, c in top] == [c for _, c in fx[key]["visit_top"][:4]]

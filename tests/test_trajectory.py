@@ -95,3 +95,26 @@ def test_running_kl_of_quantum_chains_decreases_towards_zero():
     kl = q.batch_trajectory_statistics(m, b.initial, b.proposals, b.accepted, P, to_observe=("kldiv",))["kldiv"]
     assert kl.shape == (64, 4001)
     assert np.median(kl[:, -1]) < 0.05 * np.median(kl[:, 20]) and np.median(kl[:, -1]) < 0.5   # unvisited tail: p log(p/EPS)
+
+
+@pytest.mark.gpu
+def test_running_kl_batches_that_are_not_a_multiple_of_the_block_size(monkeypatch):
+    """with a hash-table budget that forces several batches of chains (batch = 5, CTA = 64 threads) every
+    output must equal the unbatched run -- threads past the batch must not touch the next batch's chains."""
+    import qumcmc_b200 as q
+    n, C, H = 8, 23, 120
+    J, h, init, props, acc = _recorded_chains(n, C, H, seed=3)
+    m = q.IsingEnergyFunction(J, h)
+    _, _, P = oracle.exact_boltzmann(J, h, 1.0)
+    full = q.batch_trajectory_statistics(m, init, props, acc, P)
+    cap = 256  # power of two >= 2 (H + 1)
+    monkeypatch.setenv("QUMCMC_TRAJ_BUDGET_BYTES", str(5 * cap * 12))
+    small = q.batch_trajectory_statistics(m, init, props, acc, P)
+    for key in ("markov_chain", "energy", "hamming", "magnetisation", "kldiv"):
+        assert np.array_equal(np.asarray(full[key]), np.asarray(small[key])), key
+    for c in range(C):
+        mc = np_oracle.markov_chain_from(int(init[c]), props[c], acc[c])
+        rk = np_oracle.running_kl(P, mc)
+        assert np.abs(small["kldiv"][c] - rk).max() < 1e-10 * max(1.0, np.abs(rk).max())
+        _, ham = np_oracle.trajectory_statistics(J, h, int(init[c]), props[c], acc[c])
+        assert np.array_equal(small["hamming"][c], ham)
