@@ -227,9 +227,9 @@ def run_ours(args, rank, local_rank, world):
     import ctypes as Ct
     c_ms, c_ln, c_by = Ct.c_double(), Ct.c_int64(), Ct.c_double()
     _lib.check(L.qmc_profile_read(dm.handle, Ct.byref(c_ms), Ct.byref(c_ln), Ct.byref(c_by)))
-    _lib.check(L.qmc_profile_enable(dm.handle, 0))
     c_mv = Ct.c_double()
     _lib.check(L.qmc_profile_read_moved(dm.handle, Ct.byref(c_mv)))
+    _lib.check(L.qmc_profile_enable(dm.handle, 0))   # also resets the counters
     value = world * C * K / (ms * 1e-3)
     # acceptance over ALL ranks' chains (the gathered counts when N > 1)
     acc_rate = float(g_acc.sum()) / (C * world * K) if g_acc is not None else float(cnt.sum().item()) / (C * K)

@@ -227,6 +227,12 @@ int qmc_shard_op_exchange(qmc_shard *sh, int op, int k, int pre, int layout, voi
  * destination rank per chunk).  Lets the caller overlap the local passes of chunk i+1 with the NVLink stores of chunk i. */
 int qmc_shard_op_chunk(qmc_shard *sh, int op, int k, int pre, int layout, void *state_dev, int dst_which,
                        int chunk_bits, int64_t chunk, void *stream);
+/* Overlap mode of the fused exchange: with ctas > 0 the exchange pass of a register-only (HI6) group runs as a persistent
+ * kernel on `ctas` CTAs instead of one CTA per tile, so that the HBM-bound local passes of the next chunk (issued on
+ * another stream) run beside the NVLink-bound stores instead of queueing behind them.  Same arithmetic, same results.
+ * qmc_shard_exchange_can_persist: 1 when this shard's pre-exchange pass has such a variant. */
+int qmc_shard_set_exchange_ctas(qmc_shard *sh, int ctas);
+int qmc_shard_exchange_can_persist(const qmc_shard *sh);
 int qmc_shard_norm(qmc_shard *sh, double *total_dev, void *stream);
 int qmc_shard_select(qmc_shard *sh, void *state_dev, double target, int layout, uint64_t *index_dev, void *stream);
 /* Test hook: LO_FINAL that also writes |a|^2 of the local shard (2^(n-g) floats, local index order). */

@@ -944,6 +944,44 @@ __global__ void __launch_bounds__(NT, 3) hi6_sweep_kernel(const SweepArgs a, con
     }
 }
 
+// Exchange pass as a PERSISTENT kernel on a bounded number of CTAs (sharded statevector, overlap mode): the SINGLE pass
+// of an HI6 group whose stores go to the peers' buffers over NVLink.  A full-grid launch of this NVLink-bound pass
+// occupies every CTA slot of the GPU with CTAs that wait on NVLink back-pressure, so the HBM-bound local passes of the
+// next chunk (another stream) cannot run beside it; gridDim.x << tiles keeps most slots free for them while a few dozen
+// CTAs keep enough stores in flight to fill the NVLink egress.  CTA b walks tiles b, b + gridDim.x, ...
+template <int ACT>
+__global__ void __launch_bounds__(NT, 3) hi6_xchg_kernel(const SweepArgs a, const Hi6Args g, const int *__restrict__ order,
+                                                         const int list_off, const unsigned n_tiles) {
+    __shared__ ChainParams cp_s;
+    const int tid = threadIdx.x;
+    const int n = a.n;
+    const int64_t chain = order[list_off + blockIdx.y];
+    stage_params(cp_s, a.params + chain, tid);  // barrier inside
+    const ChainParams &cp = cp_s;
+    const int p = g.p;
+    constexpr int ACTIVE = 63 & ~((1 << (6 - ACT)) - 1);
+    const int low_bits = p - 7;
+    const int64_t stride = (int64_t)1 << p;
+    const HiP qp{p};
+    const A64 *state = reinterpret_cast<const A64 *>(a.state + (chain << n));
+#pragma unroll 1
+    for (unsigned b = blockIdx.x; b < n_tiles; b += gridDim.x) {
+        const int64_t tile = sweep_tile(a, b);
+        const int64_t base = (int64_t)(tid & 31) | ((int64_t)(tid >> 5) << 5) | ((tile & (((int64_t)1 << low_bits) - 1)) << 7) |
+                             ((tile >> low_bits) << (p + 6));
+        A64 v[64];
+        const A64 *src = state + base;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            v[j] = *src;
+            src += stride;
+        }
+        bfly6<ACTIVE>(v, cp, qp);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) *xchg_addr(a, base + j * stride) = v[j];
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // HI8 sweeps: eight qubits [p, p+8) per pass (tile = index bits [0,5) u [p,p+8), 2^13 amplitudes, the geometry of
 // hi_sweep_kernel<8> with a run-time window position), so that a large statevector needs ceil((n-12)/8) + 1 qubit
@@ -1665,6 +1703,19 @@ struct SweepTune {
 
 template <int ROLE, bool FAST>
 static int launch_lo_v(const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
+    if (ROLE == LO_MID && FAST && !a.xchg_peers) {  // A/B knob: 64-thread CTAs on 2^12-amplitude tiles (6 resident CTAs per SM)
+        static const int nth = getenv("QUMCMC_LO_NTH") ? atoi(getenv("QUMCMC_LO_NTH")) : NT;
+        if (nth == 64) {
+            static DevMask done64 = 0;
+            int rc64 = set_smem_once(lo_sweep_kernel<LO_MID, 64, true>, done64, TILE * 4);
+            if (rc64 != QMC_OK) return rc64;
+            SweepArgs a64 = a;
+            static const int pf64 = getenv("QUMCMC_LO_PF") ? atoi(getenv("QUMCMC_LO_PF")) : 2 * a.pf_dist;
+            a64.pf_dist = pf64;
+            lo_sweep_kernel<LO_MID, 64, true><<<dim3((unsigned)(2 * tiles), (unsigned)count), 64, TILE * 4, st>>>(a64, order, off, off);
+            return QMC_OK;
+        }
+    }
     static DevMask done = 0;
     int rc = set_smem_once(lo_sweep_kernel<ROLE, NT, FAST>, done);
     if (rc != QMC_OK) return rc;
@@ -2165,6 +2216,7 @@ struct qmc_shard {
     int k_fx = 0;
     ChainParams host_cp[2];         // physical-coordinate parameters of the current proposal, per layout
     float2 **d_peers[2] = {nullptr, nullptr};  // device tables: pointer to buffer `which` of every rank
+    int xchg_ctas = 0;              // > 0: exchange passes of HI6 groups run as a persistent kernel on this many CTAs
     int r = 0;
 };
 
@@ -2410,6 +2462,19 @@ extern "C" int qmc_shard_destroy(qmc_shard *sh) {
 
 extern "C" int qmc_shard_num_groups(const qmc_shard *sh) { return sh ? (int)sh->acts.size() : 0; }
 
+// Overlap mode: exchange passes (qmc_shard_op_exchange / qmc_shard_op_chunk with dst_which >= 0) on register-only HI6
+// groups run as a persistent kernel on `ctas` CTAs (0 = one CTA per tile, the default).  Results are bit-identical.
+extern "C" int qmc_shard_set_exchange_ctas(qmc_shard *sh, int ctas) {
+    QMC_REQUIRE(sh && ctas >= 0, QMC_ERR_BADARG, "qmc_shard_set_exchange_ctas: bad argument");
+    sh->xchg_ctas = ctas;
+    return QMC_OK;
+}
+// 1 when the pass before the exchange (SINGLE on the lowest register group) has a persistent variant
+extern "C" int qmc_shard_exchange_can_persist(const qmc_shard *sh) {
+    if (!sh || sh->groups[0].size() < 2) return 0;
+    return sh->groups[0].back().kind == 6 ? 1 : 0;
+}
+
 extern "C" int qmc_shard_begin(qmc_shard *sh, uint64_t s, double gamma, int r, double delta_time, int group) {
     QMC_REQUIRE(sh, QMC_ERR_BADARG, "qmc_shard_begin: null handle");
     QMC_REQUIRE(group >= 0 && group < sh->m->n_groups, QMC_ERR_BADARG, "qmc_shard_begin: group %d of %d", group, sh->m->n_groups);
@@ -2481,6 +2546,18 @@ static int shard_op_impl(qmc_shard *sh, int op, int k, int pre, int layout, void
             rc = launch_group<HI6_MID>(G, pre, a, sh->order, 0, tiles, 1, st);
             break;
         case 2:
+            if (dst_which >= 0 && sh->xchg_ctas > 0 && G.kind == 6 && k > 0 && (int64_t)sh->xchg_ctas < tiles) {
+                const unsigned ctas = (unsigned)sh->xchg_ctas;
+                switch (G.act) {  // persistent exchange pass (overlap mode)
+                    case 1: hi6_xchg_kernel<1><<<dim3(ctas, 1), NT, 0, st>>>(a, G.args, sh->order, 0, (unsigned)tiles); break;
+                    case 2: hi6_xchg_kernel<2><<<dim3(ctas, 1), NT, 0, st>>>(a, G.args, sh->order, 0, (unsigned)tiles); break;
+                    case 3: hi6_xchg_kernel<3><<<dim3(ctas, 1), NT, 0, st>>>(a, G.args, sh->order, 0, (unsigned)tiles); break;
+                    case 4: hi6_xchg_kernel<4><<<dim3(ctas, 1), NT, 0, st>>>(a, G.args, sh->order, 0, (unsigned)tiles); break;
+                    case 5: hi6_xchg_kernel<5><<<dim3(ctas, 1), NT, 0, st>>>(a, G.args, sh->order, 0, (unsigned)tiles); break;
+                    default: hi6_xchg_kernel<6><<<dim3(ctas, 1), NT, 0, st>>>(a, G.args, sh->order, 0, (unsigned)tiles); break;
+                }
+                break;
+            }
             rc = launch_group<HI6_SINGLE>(G, k == 0 ? pre : 0, a, sh->order, 0, tiles, 1, st);
             break;
         case 3:

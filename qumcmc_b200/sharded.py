@@ -159,6 +159,13 @@ class ShardHandle:
                                                  state.data_ptr(), int(dst_which), int(chunk_bits), int(chunk),
                                                  _device.current_stream_ptr(self.device)))
 
+    def set_exchange_ctas(self, ctas: int) -> None:
+        """Overlap mode: exchange passes of register-only (HI6) groups as a persistent kernel on ``ctas`` CTAs (0 = off)."""
+        _lib.check(_lib.lib().qmc_shard_set_exchange_ctas(self.handle, int(ctas)))
+
+    def exchange_can_persist(self) -> bool:
+        return bool(_lib.lib().qmc_shard_exchange_can_persist(self.handle))
+
     def norm(self, total) -> None:
         _lib.check(_lib.lib().qmc_shard_norm(self.handle, total.data_ptr(), _device.current_stream_ptr(self.device)))
 
@@ -184,14 +191,36 @@ def pick_owner(totals: np.ndarray, u: float) -> Tuple[int, float]:
     return owner, target - cum[owner]
 
 
+# Schedule defaults of ShardedProposer (measured on 8 B200, n = 36: see DESIGN.md section 5 and profiles/)
+DEFAULT_MODE = "fused"
+DEFAULT_XCHG_CTAS = 64
+DEFAULT_OVERLAP_CHUNK_BITS = 5
+
+
 class ShardedProposer:
     """One process per GPU (torchrun); every rank calls :meth:`propose` with the same arguments and gets the same
     measured bitstring back."""
 
-    def __init__(self, model, mixer, device: int = 0, group=None, fused: bool = True, chunk_bits: Optional[int] = None):
+    def __init__(self, model, mixer, device: int = 0, group=None, fused: bool = True, chunk_bits: Optional[int] = None,
+                 mode: Optional[str] = None, xchg_ctas: Optional[int] = None):
         """``fused``: the pass before every exchange stores straight into the peers' buffers over NVLink (CUDA IPC
         mappings of the two state buffers of every rank) and the exchange shrinks to a barrier; ``False`` keeps the
-        pass local and calls NCCL ``all_to_all_single``."""
+        pass local and calls NCCL ``all_to_all_single``.
+
+        ``mode``: ``"fused"`` -- one kernel per pass over the whole shard, the exchange pass serial after the local ones;
+        ``"overlap"`` -- the passes before each exchange run chunk by chunk (``chunk_bits``), the local ones on a
+        high-priority stream and the NVLink-bound exchange pass as a persistent kernel on ``xchg_ctas`` CTAs on a second
+        stream, so that HBM-bound and NVLink-bound work proceed side by side; ``None`` = the measured default
+        (environment override QUMCMC_SHARD_MODE / QUMCMC_SHARD_CTAS / QUMCMC_SHARD_CHUNK_BITS for A/B runs)."""
+        import os
+        if mode is None:
+            mode = os.environ.get("QUMCMC_SHARD_MODE") or DEFAULT_MODE
+        if mode not in ("fused", "overlap"):
+            raise ValueError(f"unknown sharded mode {mode!r}")
+        if xchg_ctas is None:
+            xchg_ctas = int(os.environ.get("QUMCMC_SHARD_CTAS", DEFAULT_XCHG_CTAS))
+        if chunk_bits is None and os.environ.get("QUMCMC_SHARD_CHUNK_BITS"):
+            chunk_bits = int(os.environ["QUMCMC_SHARD_CHUNK_BITS"])
         import torch
         import torch.distributed as dist
 
@@ -218,12 +247,37 @@ class ShardedProposer:
         cmax = max_chunk_bits(self.handle.n_local)
         # default off: measured on 8 B200 (n=36, 5 layers) 0.653 s with 8 chunks vs 0.647 s unchunked -- per layer the
         # HBM traffic floor (98 ms) sits too close to the NVLink floor (87 ms + the MID pass) for the overlap to pay
+        if mode == "overlap" and (not self.fused or not self.handle.exchange_can_persist() or cmax < g):
+            mode = "fused"   # no persistent variant of this shard's exchange pass (or nothing to chunk): serial schedule
+        if mode == "overlap" and chunk_bits is None:
+            chunk_bits = max(g, min(DEFAULT_OVERLAP_CHUNK_BITS, cmax))
+        self.mode = mode
         want = 0 if chunk_bits is None else min(int(chunk_bits), cmax)
         self.chunk_bits = want if (self.fused and want >= g) else 0
+        if mode == "overlap":
+            self.handle.set_exchange_ctas(int(xchg_ctas))
+        self.xchg_ctas = int(xchg_ctas) if mode == "overlap" else 0
         self._xstream = torch.cuda.Stream(device=dev) if self.chunk_bits else None            # exchange passes
         self._cstream = torch.cuda.Stream(device=dev, priority=-1) if self.chunk_bits else None  # local passes: SM slots first
         if self.fused:
             self._map_peer_buffers(device)
+
+    def reconfigure(self, mode: str, chunk_bits: Optional[int] = None, xchg_ctas: Optional[int] = None) -> None:
+        """Switch the exchange schedule of an existing proposer (same buffers and peer mappings): A/B runs."""
+        torch, g = self._torch, self.handle.g
+        cmax = max_chunk_bits(self.handle.n_local)
+        if mode == "overlap" and (not self.fused or not self.handle.exchange_can_persist() or cmax < g):
+            mode = "fused"
+        if mode == "overlap" and chunk_bits is None:
+            chunk_bits = max(g, min(DEFAULT_OVERLAP_CHUNK_BITS, cmax))
+        want = 0 if chunk_bits is None else min(int(chunk_bits), cmax)
+        self.mode = mode
+        self.chunk_bits = want if (self.fused and want >= g) else 0
+        self.xchg_ctas = int(xchg_ctas if xchg_ctas is not None else DEFAULT_XCHG_CTAS) if mode == "overlap" else 0
+        self.handle.set_exchange_ctas(self.xchg_ctas)
+        if self.chunk_bits and self._xstream is None:
+            self._xstream = torch.cuda.Stream(device=self.dev)
+            self._cstream = torch.cuda.Stream(device=self.dev, priority=-1)
 
     def _map_peer_buffers(self, device: int) -> None:
         """all-gather CUDA IPC handles of both state buffers, map the peers' buffers into this device's context

@@ -15,7 +15,7 @@ from tests.shard_sim import logical_indices
 pytestmark = pytest.mark.gpu
 
 
-def _emulated_proposal(n, g, r, s, gamma, seed=11, us=(), fused=False, chunk_bits=0, on_device=False):
+def _emulated_proposal(n, g, r, s, gamma, seed=11, us=(), fused=False, chunk_bits=0, on_device=False, xchg_ctas=0):
     import torch
     import qumcmc_b200 as q
     from qumcmc_b200.sharded import EXCHANGE, ShardHandle, pick_owner, sharded_plan
@@ -28,6 +28,9 @@ def _emulated_proposal(n, g, r, s, gamma, seed=11, us=(), fused=False, chunk_bit
     bufs = [torch.zeros(1 << nl, dtype=torch.complex64, device=dev) for _ in range(W)]
     for hd in hs:
         hd.begin(s, gamma, r, 0.8)
+        if xchg_ctas:
+            assert hd.exchange_can_persist()
+            hd.set_exchange_ctas(xchg_ctas)
     layout = 0
     ops = sharded_plan(r, hs[0].n_groups, g)
     if fused:   # the pass before every exchange stores straight into the owning "rank"'s other buffer (same device here)
@@ -156,6 +159,31 @@ def test_shard_chunked_exchange_matches_staged(n, g, r, cb):
     assert np.allclose(t0, t1, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("n,g,r,cb,ctas,groups", [(22, 1, 3, 2, 7, ""), (24, 3, 4, 3, 5, ""), (25, 2, 5, 4, 16, ""), (26, 2, 2, 0, 3, ""),
+                                                  (24, 3, 3, 3, 6, "8:8,6:1"), (27, 3, 3, 4, 11, "8:8,6:2,6:2")])
+def test_shard_persistent_exchange_kernel_matches_staged(monkeypatch, n, g, r, cb, ctas, groups):
+    """Overlap mode: the exchange pass as a persistent kernel on a few CTAs (hi6_xchg_kernel), whole-shard (cb = 0) and
+    chunk by chunk -- bit-identical amplitudes to pass-then-exchange; also with C5's three-group shard structure."""
+    from qumcmc_b200 import _device
+    from qumcmc_b200.sharded import max_chunk_bits
+    if groups:
+        monkeypatch.setenv("QUMCMC_HI_GROUPS", groups)
+    _device._cache.clear()
+    try:
+        assert cb == 0 or g <= cb <= max_chunk_bits(n - g)
+        rng = np.random.default_rng(13 * n + g + r)
+        s = int(rng.integers(0, 1 << n))
+        gamma = float(rng.uniform(0.25, 0.6))
+        us = [0.15, 0.8]
+        _, _, p0, t0, l0, k0 = _emulated_proposal(n, g, r, s, gamma, us=us)
+        _, _, p1, t1, l1, k1 = _emulated_proposal(n, g, r, s, gamma, us=us, fused=True, chunk_bits=cb, xchg_ctas=ctas)
+    finally:
+        _device._cache.clear()
+    assert l0 == l1 == 0
+    assert np.array_equal(p0, p1) and k0 == k1
+    assert np.allclose(t0, t1, rtol=1e-12, atol=0)
+
+
 def test_shard_rejects_bad_configurations():
     import qumcmc_b200 as q
     from qumcmc_b200 import _lib
@@ -169,6 +197,8 @@ def test_shard_rejects_bad_configurations():
 
 
 def _nccl_worker(rank, world, port, n, cases, q, fused):
+    if fused == "overlap":
+        os.environ["QUMCMC_SHARD_CTAS"] = "9"
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -179,20 +209,22 @@ def _nccl_worker(rank, world, port, n, cases, q, fused):
         from qumcmc_b200.sharded import ShardedProposer
         J, h = models.packaged_random_model(n, 11)
         prop = ShardedProposer(qq.IsingEnergyFunction(J, h), qq.GenericMixer.OneBodyMixer(n), device=rank, fused=bool(fused),
-                               chunk_bits=(2 if fused == "chunked" else 0))
+                               chunk_bits=(2 if fused in ("chunked", "overlap") else 0),
+                               mode=("overlap" if fused == "overlap" else "fused"))
+        assert prop.mode == ("overlap" if fused == "overlap" else "fused")
         out = [prop.propose(s, gamma, r, u) for (s, gamma, r, u) in cases]
         q.put((rank, out, prop.exchanges))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("fused", [False, True, "chunked"])
+@pytest.mark.parametrize("fused", [False, True, "chunked", "overlap"])
 def test_shard_nccl_world2_matches_emulation(fused):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
-    n, world = 21, 2
+    n, world = (22 if fused == "overlap" else 21), 2   # 21 local qubits: HI8 + HI6 groups (persistent exchange pass)
     rng = np.random.default_rng(5)
     cases = [(int(rng.integers(0, 1 << n)), float(rng.uniform(0.25, 0.6)), int(r), float(rng.uniform(0, 1)))
              for r in (1, 2, 3, 6)]
