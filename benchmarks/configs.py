@@ -94,6 +94,28 @@ def general():
                           "reference_cost": "one statevector pass per gate: %d passes per layer" % (n * (n - 1) // 2 + n + (n if mixer_name == "one" else n * (n - 1) // 2))}))
 
 
+def c128():
+    """C3's model in the reference's own precision: n = 20, complex128 (16 MiB per chain), fp64 sweep kernels.
+    Roofline (SURVEY 8d with b = 16): 2 * 2^20 * 16 B * r per proposal."""
+    n = 20
+    m = q.random_ising_model(n, 1)
+    mx = q.GenericMixer.OneBodyMixer(n)
+    for chains, H in ((2048, 6),):
+        q.quantum_enhanced_mcmc(1, m, mx, (0.25, 0.6), temperature=1.0, n_chains=chains, seed=3, dtype="fp64", record=False)
+        dt, b = timed(lambda: q.quantum_enhanced_mcmc(H, m, mx, (0.25, 0.6), temperature=1.0, n_chains=chains, seed=4,
+                                                      dtype="fp64", record=False))
+        from qumcmc_b200.rng import philox4x32
+        sum_r = 0
+        for hop in range(H):
+            w2 = philox4x32(4, np.arange(chains, dtype=np.uint64), hop, 0)[:, 2].astype(np.uint64)
+            sum_r += int(np.maximum(1, np.floor((2 + ((w2 * np.uint64(10)) >> np.uint64(32))).astype(np.float64) / 0.8)).sum())
+        alg = 2.0 * (1 << n) * 16 * sum_r
+        print(json.dumps({"config": "C3 model in complex128: n=20, %d chains x %d hops (fp64 sweep kernels)" % (chains, H),
+                          "seconds": dt, "proposals_per_s": chains * H / dt, "acceptance": b.acceptance_rate(),
+                          "algorithmic_GBps": alg / 1e9 / dt, "frac_of_measured_hbm": alg / 1e9 / dt / 6547.8,
+                          "roofline_proposals_per_s": 6547.8e9 / (alg / (chains * H))}))
+
+
 def exact():
     for n in (20, 24, 28):
         m = q.random_ising_model(n, 1)
@@ -110,6 +132,6 @@ def exact():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c1", "c2", "c4", "exact", "general"]
+    which = sys.argv[1:] or ["c1", "c2", "c4", "exact", "general", "c128"]
     for w in which:
-        {"c1": c1, "c2": c2, "c4": c4, "exact": exact, "general": general}[w]()
+        {"c1": c1, "c2": c2, "c4": c4, "exact": exact, "general": general, "c128": c128}[w]()

@@ -51,6 +51,7 @@ extern "C" {
 #define QMC_MAX_SPINS 40       /* model limit; one GPU holds a statevector up to n = 34 (2^34 complex64 = 128 GiB) */
 #define QMC_MAX_LOCAL_SPINS 34
 #define QMC_GENERAL_MAX_SPINS 24 /* general path (k-body / custom mixers, complex128): 2^n fp64 phase table */
+#define QMC_SWEEP_F64_MAX_SPINS 20 /* complex128 sweep kernels (one-body mixers): 13 <= n <= 20 */
 #define QMC_SMEM_MAX_SPINS_F32 13 /* whole statevector in shared memory, one CTA per chain */
 #define QMC_SMEM_MAX_SPINS_F64 12
 
@@ -250,6 +251,13 @@ int qmc_profile_read(qmc_model *m, double *sweep_ms, int64_t *sweep_launches,
 /* Bytes the timed sweep launches actually read + wrote: 16 B * 2^n * K * (r - 1) per proposal with K passes per layer
  * (the first sweep of a proposal is write-only, the last read-only), against algorithmic_bytes = 16 B * 2^n * r. */
 int qmc_profile_read_moved(qmc_model *m, double *moved_bytes);
+
+/* Static-analysis hooks (CPU, no device needed; tests/test_smem_layouts.py): the shared-memory slot / statevector offset
+ * a thread touches in the register layouts of the sweep kernels, evaluated by the functions the kernels themselves use.
+ * They back the barrier-free "a thread rewrites exactly the slots it read" steps and the conflict-free swizzles with an
+ * exhaustive check (compute-sanitizer is not available on the GPU pool). */
+int qmc_debug_smem_slot(int layout, int tid, int j);
+int qmc_debug_layout128(int geometry, int layout, int tid, int j, long long *out4);
 
 #ifdef __cplusplus
 }

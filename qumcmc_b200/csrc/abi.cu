@@ -1,5 +1,7 @@
 // abi.cu -- extern "C" entry points of the proposal path; dispatch between the shared-memory
 // kernel (small n) and the HBM sweep kernels (large n).  See include/qumcmc_b200.h.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 static bool use_small_path(const qmc_model *m, int dtype) {
@@ -30,6 +32,11 @@ static int dispatch(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, co
         return qmc_sweep_run(m, mode, n_chains, n_hops, s_in, chain_id0, hop0, temperature, g_lo, g_hi, dt, seed, dtype,
                              gamma_arr, r_arr, u_arr, group_arr, proposals, accepted, final_state, acc_count,
                              hamming_hist, probs_out, amps_out, st);
+    // complex128 + one-body X mixers, 13 <= n <= 20: fp64 sweeps (sweep128.cu)
+    if (dtype == QMC_DTYPE_F64 && m->all_one_body && m->n >= 13 && m->n <= QMC_SWEEP_F64_MAX_SPINS && !getenv("QUMCMC_NO_SWEEP128"))
+        return qmc_sweep128_run(m, mode, n_chains, n_hops, s_in, chain_id0, hop0, temperature, g_lo, g_hi, dt, seed,
+                                gamma_arr, r_arr, u_arr, group_arr, proposals, accepted, final_state, acc_count,
+                                hamming_hist, probs_out, amps_out, st);
     // everything else: tiled general path (k-body / custom / summed mixers, complex128)
     return qmc_general_run(m, mode, n_chains, n_hops, s_in, chain_id0, hop0, temperature, g_lo, g_hi, dt, seed, dtype,
                            gamma_arr, r_arr, u_arr, group_arr, proposals, accepted, final_state, acc_count,

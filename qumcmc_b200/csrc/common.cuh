@@ -108,6 +108,7 @@ __host__ __device__ __forceinline__ int qmc_pick_group(int n_groups, const doubl
 // ---------------------------------------------------------------------------------------------
 struct SweepWorkspace;    // sweep.cu
 struct GeneralWorkspace;  // general.cu
+struct Sweep128Workspace; // sweep128.cu
 
 struct qmc_model {
     int n = 0;
@@ -143,6 +144,8 @@ struct qmc_model {
     SweepWorkspace *sweep = nullptr;
     // general path (arbitrary mixers / complex128 in HBM)
     GeneralWorkspace *general = nullptr;
+    // complex128 sweep path (one-body mixers, 13 <= n <= 20)
+    Sweep128Workspace *sweep128 = nullptr;
     int mixer_epoch = 0;  // bumped by qmc_mixer_set
     // *_host entry points: one device arena (grows, never shrinks) and one non-blocking stream owned by the handle, so
     // that the steady state of a host-buffer call is cudaMemcpyAsync + launches + one stream synchronise
@@ -183,6 +186,13 @@ int qmc_general_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, co
                     uint64_t *final_state, int64_t *acc_count, int64_t *hamming_hist, void *probs_out,
                     void *amps_out, cudaStream_t st);
 void qmc_general_free(qmc_model *m);
+
+int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, const uint64_t *s_in, uint64_t chain_id0,
+                     uint32_t hop0, double temperature, double g_lo, double g_hi, double dt, uint64_t seed,
+                     const double *gamma_arr, const int *r_arr, const double *u_arr, const int *group_arr,
+                     uint64_t *proposals, uint8_t *accepted, uint64_t *final_state, int64_t *acc_count,
+                     int64_t *hamming_hist, void *probs_out, void *amps_out, cudaStream_t st);
+void qmc_sweep128_free(qmc_model *m);
 int qmc_general_num_passes(qmc_model *m, int group);
 
 enum { QMC_MODE_CHAIN = 0, QMC_MODE_PROPOSE = 1, QMC_MODE_PROBS = 2 };

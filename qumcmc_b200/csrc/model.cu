@@ -389,6 +389,7 @@ extern "C" int qmc_model_destroy(qmc_model *m) {
     cudaSetDevice(m->device);
     qmc_sweep_free(m);
     qmc_general_free(m);
+    qmc_sweep128_free(m);
     cudaFree(m->dJ);
     cudaFree(m->dh);
     cudaFree(m->dD);

@@ -171,14 +171,14 @@ __device__ __forceinline__ float2 times_i_pow(float2 z, int k) {
 // 16 slots; B-layout accesses (lane stride 64 slots) hit 16 distinct 8-byte slots per half-warp: both
 // conflict-free with 64-bit accesses.  (128-bit B accesses would pin amplitude pairs (j, j+1) to aligned register
 // quads, which costs ~400 MOVs around the qubit-0 butterflies.)
-__device__ __forceinline__ int lo_swz(int local) { return local ^ ((local >> 6) & 15); }
+__host__ __device__ __forceinline__ int lo_swz(int local) { return local ^ ((local >> 6) & 15); }
 
 // ------------------------------------------------------------------------------------------
 // LO tile: 2^13 contiguous amplitudes, qubits 0..11 butterflied.
 //   A layout: regs = local bits 6..11; lane = bits 0..4; warp = bits (5, 12)   (coalesced HBM access)
 //   B layout: regs = local bits 0..5 (64 contiguous amplitudes); thread = bits 6..12
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int lo_base_a(int tid) {
+__host__ __device__ __forceinline__ int lo_base_a(int tid) {
     const int lane = tid & 31, w = tid >> 5;
     return lane | ((w & 1) << 5) | ((w >> 1) << 12);
 }
@@ -409,8 +409,8 @@ __device__ __forceinline__ int64_t hi_base_b(int tid, int64_t tile) {
     const int lane = tid & 31, w = tid >> 5;
     return (int64_t)lane | ((int64_t)(w & 1) << G::gpos(11)) | ((int64_t)(w >> 1) << G::gpos(12)) | (tile << G::Lc);
 }
-__device__ __forceinline__ int hi_loc_a(int tid, int j) { return (tid & 31) | ((tid >> 5) << 5) | (j << 7); }
-__device__ __forceinline__ int hi_loc_b(int tid, int j) { return (tid & 31) | (j << 5) | ((tid >> 5) << 11); }
+__host__ __device__ __forceinline__ int hi_loc_a(int tid, int j) { return (tid & 31) | ((tid >> 5) << 5) | (j << 7); }
+__host__ __device__ __forceinline__ int hi_loc_b(int tid, int j) { return (tid & 31) | (j << 5) | ((tid >> 5) << 11); }
 
 // Tile of CTA b.  Fused exchange: the top g bits of the tile index select the destination rank of a lower-group
 // pass, so the CTAs are renumbered with those bits fastest (and rotated by the rank): at any moment the stores of a
@@ -710,8 +710,8 @@ __host__ __device__ __forceinline__ int hiq_pos_b(int b) { return b == 0 ? 0 : 1
 struct HiqQA { __device__ __forceinline__ int operator()(int b) const { return b == 0 ? 0 : 14 + b; } };
 struct HiqQB { __device__ __forceinline__ int operator()(int b) const { return hiq_pos_b(b); } };
 // shared-memory slot (in 128-bit words) of register pair jp
-__device__ __forceinline__ int hiq_loc_a(int tid, int jp) { return (tid & 31) | ((tid >> 5) << 5) | (jp << 7); }
-__device__ __forceinline__ int hiq_loc_b(int tid, int jp) {
+__host__ __device__ __forceinline__ int hiq_loc_a(int tid, int jp) { return (tid & 31) | ((tid >> 5) << 5) | (jp << 7); }
+__host__ __device__ __forceinline__ int hiq_loc_b(int tid, int jp) {
     return (tid & 15) | ((jp & 7) << 4) | ((jp >> 3) << 7) | (((tid >> 4) & 1) << 9) | ((tid >> 5) << 10);
 }
 
@@ -1430,6 +1430,22 @@ __global__ void af_table_kernel(int n, const double *__restrict__ Jq, const doub
 }
 
 }  // namespace
+
+// Static-analysis hook (tests/test_smem_layouts.py, CPU): the shared-memory slot (in units of the access width) that
+// thread `tid` touches for register `j` in one of the transposition layouts of the sweep kernels, evaluated by the very
+// functions the kernels call.  layout: 0 LO A, 1 LO B (64-bit slots, j < 64); 2 HI A', 3 HI B' (64-bit, j < 64);
+// 4 HIQ A'', 5 HIQ B'' (128-bit slots, j < 32).  Returns -1 for an unknown layout.
+extern "C" int qmc_debug_smem_slot(int layout, int tid, int j) {
+    switch (layout) {
+        case 0: return (lo_base_a(tid) ^ (j & 15)) + (j << 6);                                  // lo_a_to_smem / lo_smem_to_a
+        case 1: return (tid << 6) + (((j & 15) ^ (tid & 15)) + (j & ~15));                  // lo_b_to_smem / lo_smem_to_b
+        case 2: return hi_loc_a(tid, j);
+        case 3: return hi_loc_b(tid, j);
+        case 4: return hiq_loc_a(tid, j);
+        case 5: return hiq_loc_b(tid, j);
+    }
+    return -1;
+}
 
 // ------------------------------------------------------------------------------------------
 // host side

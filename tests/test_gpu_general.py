@@ -33,8 +33,11 @@ def _check(q, n, mixer, dtype, rs, seed=3, group=0):
 
 
 @pytest.mark.parametrize("n,dtype", [(13, "fp64"), (14, "fp64"), (16, "fp64"), (18, "fp64"), (20, "fp64")])
-def test_one_body_complex128_above_the_shared_memory_limit(n, dtype):
+def test_one_body_complex128_above_the_shared_memory_limit(monkeypatch, n, dtype):
+    """The general tiled path with one-body mixers in complex128 (QUMCMC_NO_SWEEP128 keeps the dispatcher off the fp64
+    sweep kernels, which are tested in tests/test_gpu_sweep128.py)."""
     import qumcmc_b200 as q
+    monkeypatch.setenv("QUMCMC_NO_SWEEP128", "1")
     _check(q, n, q.GenericMixer.OneBodyMixer(n), dtype, (1, 2, 5) if n < 20 else (3,))
 
 
