@@ -1719,8 +1719,11 @@ struct SweepTune {
 
 template <int ROLE, bool FAST>
 static int launch_lo_v(const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
-    if (ROLE == LO_MID && FAST && !a.xchg_peers) {  // A/B knob: 64-thread CTAs on 2^12-amplitude tiles (6 resident CTAs per SM)
-        static const int nth = getenv("QUMCMC_LO_NTH") ? atoi(getenv("QUMCMC_LO_NTH")) : NT;
+    if (ROLE == LO_MID && FAST && !a.xchg_peers) {
+        // 64-thread CTAs on 2^12-amplitude tiles (6 resident CTAs per SM instead of 3 x 128 threads: the same 12 warps, but
+        // barriers span two warps and six tiles are in different phases): +1.5 % on C3, measured 3 x A/B on one box
+        // (43.78 k vs 43.12 k proposals/s, profiles/r2c_lo_nth_ab.txt).  QUMCMC_LO_NTH=128 restores the 128-thread CTAs.
+        static const int nth = getenv("QUMCMC_LO_NTH") ? atoi(getenv("QUMCMC_LO_NTH")) : 64;
         if (nth == 64) {
             static DevMask done64 = 0;
             int rc64 = set_smem_once(lo_sweep_kernel<LO_MID, 64, true>, done64, TILE * 4);
