@@ -50,7 +50,7 @@ extern "C" {
 
 #define QMC_MAX_SPINS 40       /* model limit; one GPU holds a statevector up to n = 34 (2^34 complex64 = 128 GiB) */
 #define QMC_MAX_LOCAL_SPINS 34
-#define QMC_GENERAL_MAX_SPINS 24 /* general path (k-body / custom mixers, complex128): 2^n fp64 phase table */
+#define QMC_GENERAL_MAX_SPINS 30 /* general path (any X-string mixer, complex64 / complex128): Hadamard-basis passes, no 2^n table */
 #define QMC_SWEEP_F64_MAX_SPINS 20 /* complex128 sweep kernels (one-body mixers): 13 <= n <= 20 */
 #define QMC_SMEM_MAX_SPINS_F32 13 /* whole statevector in shared memory, one CTA per chain */
 #define QMC_SMEM_MAX_SPINS_F64 12
@@ -258,6 +258,7 @@ int qmc_profile_read_moved(qmc_model *m, double *moved_bytes);
  * exhaustive check (compute-sanitizer is not available on the GPU pool). */
 int qmc_debug_smem_slot(int layout, int tid, int j);
 int qmc_debug_layout128(int geometry, int layout, int tid, int j, long long *out4);
+int qmc_debug_general_slot(int stage, int tid, int j, int *local_out);
 
 #ifdef __cplusplus
 }

@@ -1,34 +1,47 @@
 // general.cu -- HBM statevector path for everything the specialised kernels do not cover: arbitrary X-string mixers
 // (GenericMixer k-body, CustomMixer, CoherentMixerSum, IncoherentMixerSum: qumcmc/mixers.py:21-151) above the
-// shared-memory limit, and complex128 statevectors above n = 12.  13 <= n <= QMC_GENERAL_MAX_SPINS.
+// shared-memory limit, and complex128 statevectors the fp64 sweep kernels do not take.  13 <= n <= QMC_GENERAL_MAX_SPINS.
 //
-// The reference pays one pass over the statevector per gate (qumcmc/quantum_mcmc_routines.py:54-106).  Here the mixer
-// terms of a group are partitioned into TILE passes: a tile is a set of 12 qubit positions (always including qubits
-// 0..3, so that HBM accesses come in runs of 16 amplitudes); a CTA gathers the 2^12 amplitudes of one tile instance
-// into shared memory, applies every term whose support lies inside the tile, and scatters them back.  All X-string
-// rotations commute, so a layer M = prod_tiles M_tile in any order; consecutive layers walk the tiles in opposite
-// directions and the turn-around tile applies  M_tile(k) P M_tile(k+1)  in one pass, P being the diagonal phase
-// layer exp(+i c D(idx)) read from a 2^n fp64 table.  m tiles => r (m - 1) + 1 passes for r mixer layers (one pass in
-// total when a single tile holds every term).  The first pass starts from the basis ket analytically (no read).
+// The reference pays one pass over the statevector per gate (qumcmc/quantum_mcmc_routines.py:54-106): a two-body mixer
+// alone has n(n-1)/2 gates per Trotter layer.  All X-strings commute and are diagonal in the Hadamard basis:
+//     M = prod_S exp(-i gamma w_S dt X_S) = H^(x)n  diag( exp(-i gamma dt E_x(x)) )  H^(x)n,   E_x(x) = sum_S w_S chi_S(x),
+// chi_S(x) = (-1)^popcount(x & S).  The phase layer P = diag(exp(+i c D(idx))) has the same form in the computational basis
+// (D = sum_{j<k} J z_j z_k + sum_j h z_j, a Walsh polynomial of degree 2).  So U = M (P M)^{r-1} is an alternation of
+// Walsh-Hadamard transforms and two kinds of diagonals, independent of the NUMBER of mixer terms:
+//     U = H Dx H (P H Dx H)^{r-1}.
+// H factorises over qubit groups (G0 = qubits 0..11, then groups of 8 from the top); a pass over the tiles of one group
+// applies  H_g  diag  H_g  ("host" pass: the diagonal needs every group's H on either side, the host's own ones are fused
+// into the pass), the other groups run plain H passes in between.  Hosts alternate: G1 hosts Dx, G0 hosts P, so with two
+// groups (n <= 20) a Trotter layer costs TWO passes whatever the mixer is (a one-body layer costs one sweep in sweep.cu);
+// with K + 1 groups 2 K passes.  The first pass starts from H|s> analytically (write-only), the last one (always G0)
+// leaves the amplitudes in the computational basis and emits the |a|^2 segment sums.
+//
+// A tile = 12 index positions (always 0..3: HBM runs of 16 amplitudes) handled by a 256-thread CTA; each thread works
+// on 16 amplitudes in registers, in three register stages (local bits 8..11 / 4..7 / 0..3) joined by XOR-swizzled
+// shared-memory transpositions; the first and last stage read / write HBM directly.
+// Diagonals are evaluated without any 2^n table: for a tile with fixed outside bits B,
+//     E(l; B) = A(B) + sum_t z_t F_t(B) + R_T(l) [+ residual terms of weight >= 3 through a Walsh transform of their
+//     tile-local coefficients], A, F_t from O(n^2) fp64 work per CTA, R_T a 4096-entry table per (tile, diagonal).
 // Measurement: 64-amplitude segment sums (fp64) -> block inverse CDF -> the 64 amplitudes of the chosen segment.
 #include <math.h>
+#include <string.h>
 
 #include <algorithm>
+#include <map>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int GT = 12;          // tile qubits
-constexpr int GN = 1 << GT;     // amplitudes per tile
-constexpr int GTH = 256;        // threads per CTA
-constexpr int GFORCED = 4;      // qubits 0..3 belong to every tile
-constexpr int GSEL = 128;       // threads of the sampler
+constexpr int XT = 12;           // tile positions
+constexpr int XN = 1 << XT;      // amplitudes per tile
+constexpr int XTH = 256;         // threads per CTA
+constexpr int XR = 16;           // amplitudes per thread (4 register bits per stage)
+constexpr int XFORCED = 4;       // index positions 0..3 belong to every tile
+constexpr int GSEL = 128;        // threads of the sampler
+constexpr int XMAXG = 6;         // qubit groups: G0 (12 qubits) + up to 5 groups of 8
 
-struct GenPass {
-    unsigned char tpos[GT];  // ascending qubit positions of the tile
-    int term0, term1;        // range in the assigned-term arrays
-};
+enum { X_FIRST = 0, X_HOST = 1, X_HONLY = 2, X_FINAL = 3 };
 
 struct GenChain {  // per chain, rewritten every hop
     unsigned long long cur;
@@ -37,18 +50,37 @@ struct GenChain {  // per chain, rewritten every hop
     int r, grp;
 };
 
+struct XGroup {   // tile geometry of one qubit group
+    unsigned char tpos[XT];   // ascending index positions of the tile
+    unsigned short active;    // local bits that are the group's qubits
+    int n_active;
+    unsigned long long tmask; // union of the tile positions
+};
+
+// A diagonal exp(i theta E(idx)), E(idx) = sum_S w_S prod_{q in S} z_q, z_q = +1 / -1 for index bit q clear / set, as
+// hosted on one tile geometry: terms of weight <= 2 as a linear + symmetric pair form, the rest grouped by their
+// tile-local pattern.
+struct XDiag {
+    const double *lin;             // [n]
+    const double *quad;            // [n * n], symmetric, zero diagonal
+    const double *R;               // [4096] sum_{t < t'} quad[p_t][p_t'] z_t z_t' over the tile positions
+    int n_mu;                      // residual: distinct tile-local patterns
+    const int *mu_off;             // [n_mu + 1] term ranges
+    const unsigned short *mu;      // [n_mu] local pattern
+    const unsigned long long *omask;  // per term: positions outside the tile
+    const double *w;               // per term
+};
+
 struct GenArgs {
-    int n, n_groups, phase_active, mode, max_terms;
+    int n, n_groups, phase_active, mode, K;   // K = number of HI groups (qubit groups = K + 1)
     double alpha, dt, temperature, g_lo, g_hi;
-    const GenPass *passes;
-    const int *group_pass_off;       // [n_groups + 1]
-    const unsigned short *lmask;     // assigned terms: mask in tile-local bit coordinates
-    const double *weight;            // assigned terms: gamma multiplier
-    const double *D;                 // [2^n] phase exponent
+    XGroup groups[XMAXG];
+    const XDiag *diag_p;     // P hosted on G0
+    const XDiag *diag_x;     // [n_groups] Dx of every mixer group, hosted on G1
     const double *J, *h, *group_cum;
     GenChain *chains;
-    void *state;                     // [batch][2^n] complex
-    double *segsum;                  // [batch][2^n / 64]
+    void *state;             // [batch][2^n] complex
+    double *segsum;          // [batch][2^n / 64]
     // hop bookkeeping
     uint64_t seed, chain_id0;
     uint32_t hop;
@@ -68,6 +100,7 @@ template <typename T> struct V2;
 template <> struct V2<float> { using type = float2; };
 template <> struct V2<double> { using type = double2; };
 
+// exp(i x): argument formed and range-reduced in fp64, evaluated in T
 __device__ __forceinline__ float2 gen_phase(double x, float) {
     double t = x * 0.31830988618379067154;  // x / pi
     t -= 2.0 * rint(0.5 * t);
@@ -79,33 +112,6 @@ __device__ __forceinline__ double2 gen_phase(double x, double) {
     double s, c;
     sincos(x, &s, &c);
     return make_double2(c, s);
-}
-
-// Phase exponent D(idx) = sum_{j<k} J_jk z_j z_k + sum_j h_j z_j, z = -s (fn_qckt_problem_half, :54-91); same loop
-// order as the oracle's orc_phase_D.
-__global__ void __launch_bounds__(256) gen_phase_table_kernel(int n, const double *__restrict__ J, const double *__restrict__ h,
-                                                              double *__restrict__ D) {
-    extern __shared__ double sm[];
-    double *sJ = sm, *sh = sm + n * n;
-    for (int i = threadIdx.x; i < n * n; i += blockDim.x) sJ[i] = J[i];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = h[i];
-    __syncthreads();
-    const int64_t N = 1LL << n;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < N; idx += (int64_t)gridDim.x * blockDim.x) {
-        double d = 0.0;
-        for (int j = 0; j < n - 1; ++j) {
-            const double zj = ((idx >> (n - 1 - j)) & 1LL) ? -1.0 : 1.0;
-            for (int k = j + 1; k < n; ++k) {
-                const double zk = ((idx >> (n - 1 - k)) & 1LL) ? -1.0 : 1.0;
-                d = __dadd_rn(d, __dmul_rn(__dmul_rn(sJ[j * n + k], zj), zk));
-            }
-        }
-        for (int j = 0; j < n; ++j) {
-            const double zj = ((idx >> (n - 1 - j)) & 1LL) ? -1.0 : 1.0;
-            d = __dadd_rn(d, __dmul_rn(sh[j], zj));
-        }
-        D[idx] = d;
-    }
 }
 
 // Per-hop parameters of every chain of the batch (draws: common.cuh; explicit arrays in PROPOSE / PROBS mode).
@@ -140,44 +146,191 @@ __global__ void gen_prepare_kernel(const GenArgs a, int64_t nc, int first_hop) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// register stages: stage s holds local bits [4 s, 4 s + 4) in registers
+//   stage 2: l = tid | j << 8          stage 1: l = (tid & 15) | j << 4 | (tid >> 4) << 8          stage 0: l = tid << 4 | j
+// shared-memory slot of local index l: XOR the four low bits with bits 4..7 (conflict-free for all three stages, 64- and
+// 128-bit elements; checked exhaustively in tests/test_smem_layouts.py through qmc_debug_general_slot)
+// ---------------------------------------------------------------------------------------------
+template <int S>
+__host__ __device__ __forceinline__ int xl(int tid, int j) {
+    return S == 2 ? (tid | (j << 8)) : (S == 1 ? ((tid & 15) | (j << 4) | ((tid >> 4) << 8)) : ((tid << 4) | j));
+}
+__host__ __device__ __forceinline__ int xswz(int l) { return l ^ ((l >> 4) & 15); }
+
+template <typename T2>
+__device__ __forceinline__ void wht4(T2 (&v)[XR], int mask) {  // Walsh-Hadamard butterflies on the register bits in `mask`
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        if (!((mask >> b) & 1)) continue;  // uniform over the CTA
+#pragma unroll
+        for (int j = 0; j < XR; ++j) {
+            if (j & (1 << b)) continue;
+            const T2 u = v[j], w = v[j | (1 << b)];
+            v[j].x = u.x + w.x;
+            v[j].y = u.y + w.y;
+            v[j | (1 << b)].x = u.x - w.x;
+            v[j | (1 << b)].y = u.y - w.y;
+        }
+    }
+}
+template <int S, typename T2>
+__device__ __forceinline__ void x_to_smem(const T2 (&v)[XR], T2 *sm, int tid) {
+#pragma unroll
+    for (int j = 0; j < XR; ++j) sm[xswz(xl<S>(tid, j))] = v[j];
+}
+template <int S, typename T2>
+__device__ __forceinline__ void x_from_smem(T2 (&v)[XR], const T2 *sm, int tid) {
+#pragma unroll
+    for (int j = 0; j < XR; ++j) v[j] = sm[xswz(xl<S>(tid, j))];
+}
+
+// Shared scratch of the diagonal evaluation
+struct XDiagSmem {
+    double F[XT];
+    double rows[64];
+    double A;
+    double SL[64], SH[64];
+};
+
+// E(l) tables for the tile with outside bits `full` (index of the tile's element l = 0): A, F_t -> SL / SH.
+__device__ __forceinline__ void diag_prepare(XDiagSmem &d, const XDiag &D, const XGroup &G, int n, unsigned long long full,
+                                             int tid) {
+    if (tid < XT) {  // F_t = lin[p_t] + sum_{b outside} quad[p_t][b] z_b
+        const int p = G.tpos[tid];
+        double f = D.lin[p];
+        for (int b = 0; b < n; ++b)
+            if (!((G.tmask >> b) & 1ULL)) f += ((full >> b) & 1ULL) ? -D.quad[p * n + b] : D.quad[p * n + b];
+        d.F[tid] = f;
+    } else if (tid >= 32 && tid < 32 + n) {  // rows of A over the outside positions (n <= 64 - 12)
+        const int b = tid - 32;
+        double row = 0.0;
+        if (!((G.tmask >> b) & 1ULL)) {
+            row = D.lin[b];
+            for (int b2 = b + 1; b2 < n; ++b2)
+                if (!((G.tmask >> b2) & 1ULL)) row += ((full >> b2) & 1ULL) ? -D.quad[b * n + b2] : D.quad[b * n + b2];
+            if ((full >> b) & 1ULL) row = -row;
+        }
+        d.rows[b] = row;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double A = 0.0;
+        for (int b = 0; b < n; ++b) A += d.rows[b];  // fixed order
+        d.A = A;
+    }
+    if (tid >= 64 && tid < 192) {  // SL[x] = sum_{t < 6} z_t(x) F_t,  SH[x] = sum_{t >= 6} z_t(x) F_t
+        const int x = (tid - 64) & 63, hi = (tid - 64) >> 6;
+        double s = 0.0;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) s += ((x >> t) & 1) ? -d.F[6 * hi + t] : d.F[6 * hi + t];
+        (hi ? d.SH : d.SL)[x] = s;
+    }
+    __syncthreads();
+}
+
+// Residual terms (weight >= 3): coefficients by tile-local pattern, then a 12-bit real Walsh transform in shared memory:
+// c[l] <- sum_mu c_mu (-1)^popcount(l & mu).  Deterministic (one thread per pattern, terms in plan order).
+__device__ __forceinline__ void diag_residual(double *c, const XDiag &D, unsigned long long full, int tid) {
+    for (int i = tid; i < XN; i += XTH) c[i] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < D.n_mu; i += XTH) {
+        double s = 0.0;
+        for (int k = D.mu_off[i]; k < D.mu_off[i + 1]; ++k) s += (__popcll(full & D.omask[k]) & 1) ? -D.w[k] : D.w[k];
+        c[xswz(D.mu[i])] = s;
+    }
+    __syncthreads();
+    double v[XR];
+#pragma unroll
+    for (int j = 0; j < XR; ++j) v[j] = c[xswz(xl<2>(tid, j))];
+#pragma unroll
+    for (int st = 2; st >= 0; --st) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int j = 0; j < XR; ++j) {
+                if (j & (1 << b)) continue;
+                const double u = v[j], w = v[j | (1 << b)];
+                v[j] = u + w;
+                v[j | (1 << b)] = u - w;
+            }
+        if (st == 2) {
+#pragma unroll
+            for (int j = 0; j < XR; ++j) c[xswz(xl<2>(tid, j))] = v[j];
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < XR; ++j) v[j] = c[xswz(xl<1>(tid, j))];
+        } else if (st == 1) {
+#pragma unroll
+            for (int j = 0; j < XR; ++j) c[xswz(xl<1>(tid, j))] = v[j];
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < XR; ++j) v[j] = c[xswz(xl<0>(tid, j))];
+        } else {
+#pragma unroll
+            for (int j = 0; j < XR; ++j) c[xswz(xl<0>(tid, j))] = v[j];
+        }
+    }
+    __syncthreads();
+}
+
+// v[j] *= scale * exp(i theta E(l_j)) for the thread's 16 elements in stage S
+template <int S, typename T>
+__device__ __forceinline__ void diag_apply(typename V2<T>::type (&v)[XR], const XDiagSmem &d, const XDiag &D, const double *resid,
+                                           double theta, T scale, int tid) {
+    using T2 = typename V2<T>::type;
+#pragma unroll
+    for (int j = 0; j < XR; ++j) {
+        const int l = xl<S>(tid, j);
+        double E = d.A + d.SL[l & 63] + d.SH[l >> 6] + __ldg(D.R + l);
+        if (resid) E += resid[xswz(l)];
+        const T2 f = gen_phase(theta * E, T(0));
+        const T2 x = v[j];
+        v[j].x = (x.x * f.x - x.y * f.y) * scale;
+        v[j].y = (x.x * f.y + x.y * f.x) * scale;
+    }
+}
+
 // One pass (step t of the proposal) for every (tile instance, chain).  Chains whose proposal has fewer steps exit.
+// Steps: 0 = FIRST on G1; then blocks of 2 K steps, block b = 1..r:  [H on G2..GK]  (b < r ? HOST P : FINAL) on G0
+// [H on G2..GK]  HOST Dx on G1   -- the second half only for b < r.
 template <typename T>
-__global__ void __launch_bounds__(GTH) gen_pass_kernel(const GenArgs a, const int t) {
+__global__ void __launch_bounds__(XTH, sizeof(T) == 4 ? 3 : 2) gen_pass_kernel(const GenArgs a, const int t) {
     using T2 = typename V2<T>::type;
     extern __shared__ __align__(16) unsigned char smraw[];
-    T2 *st = reinterpret_cast<T2 *>(smraw);           // [GN]
-    T2 *cs = st + GN;                                 // [terms of this pass]
-    int *tm = reinterpret_cast<int *>(cs + a.max_terms);  // their tile-local masks
-    __shared__ unsigned long long hoff[GN >> GFORCED];  // index offset of the local bits 4..11
+    T2 *st = reinterpret_cast<T2 *>(smraw);  // [XN]
+    __shared__ unsigned long long hoff[XN >> XFORCED];  // index offset of the local bits 4..11
     __shared__ GenChain ch_s;
+    __shared__ XDiagSmem dg;
+    __shared__ XGroup G;
     const int tid = threadIdx.x;
-    const int n = a.n;
+    const int n = a.n, K = a.K;
     const int64_t c = blockIdx.y;
     if (tid == 0) ch_s = a.chains[c];
     __syncthreads();
-    const int r = ch_s.r, g = ch_s.grp;
-    const int p0 = a.group_pass_off[g], m = a.group_pass_off[g + 1] - p0;
-    const int T_steps = m == 1 ? 1 : r * (m - 1) + 1;
-    if (t >= T_steps) return;
-    int tile, reps;
-    if (m == 1) {
-        tile = 0;
-        reps = r;
+    const int r = ch_s.r;
+    int role, gi;
+    bool host_x = false;
+    if (t == 0) {
+        role = X_FIRST;
+        gi = 1;
+        host_x = true;
     } else {
-        const int L = t / (m - 1), o = t - L * (m - 1);
-        tile = (L & 1) ? m - 1 - o : o;
-        reps = (o == 0 && L >= 1 && L < r) ? 2 : 1;
+        const int b = 1 + (t - 1) / (2 * K), pos = (t - 1) % (2 * K);
+        if (b > r || (b == r && pos >= K)) return;
+        if (pos < K - 1) { role = X_HONLY; gi = 2 + pos; }
+        else if (pos == K - 1) { role = b == r ? X_FINAL : X_HOST; gi = 0; }
+        else if (pos < 2 * K - 1) { role = X_HONLY; gi = 2 + pos - K; }
+        else { role = X_HOST; gi = 1; host_x = true; }
     }
-    const GenPass &P = a.passes[p0 + tile];
+    if (tid < (int)(sizeof(XGroup) / 4)) reinterpret_cast<int *>(&G)[tid] = reinterpret_cast<const int *>(&a.groups[gi])[tid];
+    __syncthreads();
     // tile instance: the n - 12 bits of blockIdx.x go to the positions outside the tile
-    unsigned long long tmask = 0ULL;
-#pragma unroll
-    for (int k = 0; k < GT; ++k) tmask |= 1ULL << P.tpos[k];
     unsigned long long base = 0ULL;
     {
         unsigned long long b = blockIdx.x;
         for (int q = 0; q < n; ++q)
-            if (!((tmask >> q) & 1ULL)) {
+            if (!((G.tmask >> q) & 1ULL)) {
                 base |= (b & 1ULL) << q;
                 b >>= 1;
             }
@@ -185,129 +338,102 @@ __global__ void __launch_bounds__(GTH) gen_pass_kernel(const GenArgs a, const in
     {   // local bits 4..11 -> index offset (tid = the 8-bit pattern)
         unsigned long long o = 0ULL;
 #pragma unroll
-        for (int k = GFORCED; k < GT; ++k)
-            if ((tid >> (k - GFORCED)) & 1) o |= 1ULL << P.tpos[k];
+        for (int k = XFORCED; k < XT; ++k)
+            if ((tid >> (k - XFORCED)) & 1) o |= 1ULL << G.tpos[k];
         hoff[tid] = o;
     }
-    const int nterms = P.term1 - P.term0;
-    for (int k = tid; k < nterms; k += GTH) {  // exp(-i gamma w dt X_S) -> (cos, sin)
-        double s, cc;
-        sincos(ch_s.gamma * a.weight[P.term0 + k] * a.dt, &s, &cc);
-        T2 v;
-        v.x = (T)cc;
-        v.y = (T)s;
-        cs[k] = v;
-        tm[k] = a.lmask[P.term0 + k];
-    }
     __syncthreads();
-    T2 *state = reinterpret_cast<T2 *>(a.state) + ((size_t)c << n);
-    if (t == 0) {  // |s>
-        const unsigned long long cur = ch_s.cur;
-#pragma unroll 4
-        for (int j = tid; j < GN; j += GTH) {
-            const unsigned long long gi = base | hoff[j >> GFORCED] | (unsigned long long)(j & 15);
-            T2 z;
-            z.x = gi == cur ? T(1) : T(0);
-            z.y = T(0);
-            st[j] = z;
+    T2 *state = reinterpret_cast<T2 *>(a.state) + ((size_t)c << n) + base;
+    const int m2 = (G.active >> 8) & 15, m1 = (G.active >> 4) & 15, m0 = G.active & 15;
+    const bool use1 = (m1 | m0) != 0, use0 = m0 != 0;
+    const T hscale = (T)exp2(-0.5 * (double)G.n_active);  // normalisation of one Walsh-Hadamard transform over the group
+    T2 v[XR];
+    // stage-2 element (tid, j): local index tid | j << 8 -> offset (tid & 15) + hoff[(tid >> 4) | j << 4]
+    if (role == X_FIRST) {  // <x| H^(x)n |s> = 2^(-n/2) (-1)^popcount(s & x)
+        const T mag = (T)exp2(-0.5 * (double)n);
+#pragma unroll
+        for (int j = 0; j < XR; ++j) {
+            const unsigned long long x = base | hoff[(tid >> 4) | (j << 4)] | (unsigned long long)(tid & 15);
+            v[j].x = (__popcll(x & ch_s.cur) & 1) ? -mag : mag;
+            v[j].y = T(0);
         }
     } else {
-#pragma unroll 4
-        for (int j = tid; j < GN; j += GTH) st[j] = state[base | hoff[j >> GFORCED] | (unsigned long long)(j & 15)];
-    }
-    __syncthreads();
-    const double cphase = (1.0 - ch_s.gamma) * a.alpha * a.dt;
-    for (int rep = 0; rep < reps; ++rep) {
-        if (rep > 0 && a.phase_active) {
-#pragma unroll 2
-            for (int j = tid; j < GN; j += GTH) {
-                const unsigned long long gi = base | hoff[j >> GFORCED] | (unsigned long long)(j & 15);
-                const T2 f = gen_phase(cphase * a.D[gi], T(0));
-                const T2 x = st[j];
-                T2 o;
-                o.x = x.x * f.x - x.y * f.y;
-                o.y = x.x * f.y + x.y * f.x;
-                st[j] = o;
-            }
-            __syncthreads();
-        }
-        // Terms two at a time on orbits {i, i^S1, i^S2, i^S1^S2} held in registers (as in small_n.cu): half the
-        // shared-memory traffic and half the barriers, same arithmetic per amplitude in the same order.
-        int k = 0;
-        while (k < nterms) {
-            const int m1 = tm[k];
-            const int m2 = (k + 1 < nterms) ? tm[k + 1] : m1;
-            if (m2 != m1) {
-                const int p1 = 31 - __clz(m1);
-                const int m2r = ((m2 >> p1) & 1) ? (m2 ^ m1) : m2;
-                const int p2 = 31 - __clz(m2r);
-                const int lo_b = p1 < p2 ? p1 : p2, hi_b = p1 < p2 ? p2 : p1;
-                const int lo_m = (1 << lo_b) - 1, hi_m = (1 << hi_b) - 1;
-                const T c1 = cs[k].x, s1 = cs[k].y, c2 = cs[k + 1].x, s2 = cs[k + 1].y;
-#pragma unroll 2
-                for (int q = tid; q < (GN >> 2); q += GTH) {
-                    int i = ((q >> lo_b) << (lo_b + 1)) | (q & lo_m);  // orbit representative: bits p1, p2 clear
-                    i = ((i >> hi_b) << (hi_b + 1)) | (i & hi_m);
-                    const int i1 = i ^ m1, i2 = i ^ m2, i3 = i1 ^ m2;
-                    T2 a0 = st[i], a1 = st[i1], a2 = st[i2], a3 = st[i3];
-                    T2 u0, u1;
-                    u0.x = c1 * a0.x + s1 * a1.y; u0.y = c1 * a0.y - s1 * a1.x;
-                    u1.x = c1 * a1.x + s1 * a0.y; u1.y = c1 * a1.y - s1 * a0.x;
-                    a0 = u0; a1 = u1;
-                    u0.x = c1 * a2.x + s1 * a3.y; u0.y = c1 * a2.y - s1 * a3.x;
-                    u1.x = c1 * a3.x + s1 * a2.y; u1.y = c1 * a3.y - s1 * a2.x;
-                    a2 = u0; a3 = u1;
-                    u0.x = c2 * a0.x + s2 * a2.y; u0.y = c2 * a0.y - s2 * a2.x;
-                    u1.x = c2 * a2.x + s2 * a0.y; u1.y = c2 * a2.y - s2 * a0.x;
-                    a0 = u0; a2 = u1;
-                    u0.x = c2 * a1.x + s2 * a3.y; u0.y = c2 * a1.y - s2 * a3.x;
-                    u1.x = c2 * a3.x + s2 * a1.y; u1.y = c2 * a3.y - s2 * a1.x;
-                    a1 = u0; a3 = u1;
-                    st[i] = a0; st[i1] = a1; st[i2] = a2; st[i3] = a3;
-                }
-                __syncthreads();
-                k += 2;
-                continue;
-            }
-            const int tb = 31 - __clz(m1);
-            const int lowmask = (1 << tb) - 1;
-            const T cc = cs[k].x, s = cs[k].y;
-#pragma unroll 4
-            for (int q = tid; q < (GN >> 1); q += GTH) {
-                const int i = ((q >> tb) << (tb + 1)) | (q & lowmask);
-                const int j = i ^ m1;
-                const T2 x = st[i], y = st[j];
-                T2 ox, oy;
-                ox.x = cc * x.x + s * y.y;
-                ox.y = cc * x.y - s * y.x;
-                oy.x = cc * y.x + s * x.y;
-                oy.y = cc * y.y - s * x.x;
-                st[i] = ox;
-                st[j] = oy;
-            }
-            __syncthreads();
-            k += 1;
-        }
-    }
-#pragma unroll 4
-    for (int j = tid; j < GN; j += GTH) state[base | hoff[j >> GFORCED] | (unsigned long long)(j & 15)] = st[j];
-}
-
-// |a|^2 over 64-amplitude segments, fp64
-template <typename T>
-__global__ void __launch_bounds__(256) gen_segsum_kernel(const GenArgs a) {
-    using T2 = typename V2<T>::type;
-    const int n = a.n;
-    const int64_t c = blockIdx.y;
-    const int64_t nseg = 1LL << (n - 6);
-    const T2 *state = reinterpret_cast<const T2 *>(a.state) + ((size_t)c << n);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t seg = blockIdx.x * 8 + warp; seg < nseg; seg += (int64_t)gridDim.x * 8) {
-        const T2 x = state[seg * 64 + lane], y = state[seg * 64 + 32 + lane];
-        double s = (double)x.x * (double)x.x + (double)x.y * (double)x.y + (double)y.x * (double)y.x + (double)y.y * (double)y.y;
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (lane == 0) a.segsum[c * nseg + seg] = s;
+        for (int j = 0; j < XR; ++j) v[j] = state[hoff[(tid >> 4) | (j << 4)] | (unsigned long long)(tid & 15)];
+    }
+    const bool host = role == X_FIRST || role == X_HOST;
+    const bool pre = role != X_FIRST;  // FIRST starts in the basis of its diagonal: no transform before it
+    const XDiag &D = host_x ? a.diag_x[ch_s.grp] : *a.diag_p;
+    double theta = 0.0;
+    double *resid = nullptr;
+    if (host) {
+        theta = host_x ? -ch_s.gamma * a.dt : (a.phase_active ? (1.0 - ch_s.gamma) * a.alpha * a.dt : 0.0);
+        diag_prepare(dg, D, G, n, base, tid);
+        if (D.n_mu > 0) {
+            resid = reinterpret_cast<double *>(st + XN);
+            diag_residual(resid, D, base, tid);
+        }
+    }
+    const T dscale = pre ? hscale : T(1);  // the transform before the diagonal is normalised inside the diagonal factor
+    if (pre) wht4(v, m2);
+    if (!use1) {
+        if (host) {
+            diag_apply<2, T>(v, dg, D, resid, theta, dscale, tid);
+            wht4(v, m2);
+        }
+    } else {
+        x_to_smem<2>(v, st, tid);
+        __syncthreads();
+        x_from_smem<1>(v, st, tid);
+        if (pre) wht4(v, m1);
+        if (!use0) {
+            if (host) {
+                diag_apply<1, T>(v, dg, D, resid, theta, dscale, tid);
+                wht4(v, m1);
+            }
+        } else {
+            x_to_smem<1>(v, st, tid);  // each thread rewrites exactly the slots it read
+            __syncthreads();
+            x_from_smem<0>(v, st, tid);
+            if (pre) wht4(v, m0);
+            if (host) {
+                diag_apply<0, T>(v, dg, D, resid, theta, dscale, tid);
+                wht4(v, m0);
+            }
+            if (role == X_FINAL) {  // computational basis: 16 consecutive amplitudes per thread, 64 per segment = 4 lanes
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j < XR; ++j) {
+                    v[j].x *= hscale;
+                    v[j].y *= hscale;
+                    s += (double)v[j].x * (double)v[j].x + (double)v[j].y * (double)v[j].y;
+                }
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                if ((tid & 3) == 0) a.segsum[c * ((int64_t)1 << (n - 6)) + (int64_t)(base >> 6) + (tid >> 2)] = s;
+                x_to_smem<0>(v, st, tid);
+                __syncthreads();
+#pragma unroll 4
+                for (int j = tid; j < XN; j += XTH) state[j] = st[xswz(j)];  // G0's tile is 4096 consecutive amplitudes
+                return;
+            }
+            x_to_smem<0>(v, st, tid);
+            __syncthreads();
+            x_from_smem<1>(v, st, tid);
+            if (host) wht4(v, m1);
+        }
+        x_to_smem<1>(v, st, tid);
+        __syncthreads();
+        x_from_smem<2>(v, st, tid);
+        if (host) wht4(v, m2);
+    }
+    // normalisation of the transform after the diagonal (host pass) or of the only one (H pass)
+#pragma unroll
+    for (int j = 0; j < XR; ++j) {
+        T2 o;
+        o.x = v[j].x * hscale;
+        o.y = v[j].y * hscale;
+        state[hoff[(tid >> 4) | (j << 4)] | (unsigned long long)(tid & 15)] = o;
     }
 }
 
@@ -443,21 +569,34 @@ __global__ void __launch_bounds__(256) gen_probs_kernel(const GenArgs a) {
 
 }  // namespace
 
+// Static-analysis hook (tests/test_smem_layouts.py, CPU): local index and swizzled shared-memory slot of (tid, j) in
+// register stage 0 / 1 / 2 of the general path's tile.
+extern "C" int qmc_debug_general_slot(int stage, int tid, int j, int *local_out) {
+    if (tid < 0 || tid >= XTH || j < 0 || j >= XR || stage < 0 || stage > 2) return -1;
+    const int l = stage == 2 ? xl<2>(tid, j) : (stage == 1 ? xl<1>(tid, j) : xl<0>(tid, j));
+    if (local_out) *local_out = l;
+    return xswz(l);
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+struct DiagDev {  // device allocations behind one XDiag
+    double *lin = nullptr, *quad = nullptr, *R = nullptr, *w = nullptr;
+    int *mu_off = nullptr;
+    unsigned short *mu = nullptr;
+    unsigned long long *omask = nullptr;
+};
+
 struct GeneralWorkspace {
     int mixer_epoch = -1;
-    std::vector<GenPass> passes;
-    std::vector<int> group_pass_off;
-    std::vector<unsigned short> lmask;
-    std::vector<double> weight;
-    int max_terms_per_pass = 0, max_passes = 0;
-    GenPass *d_passes = nullptr;
-    int *d_group_pass_off = nullptr;
-    unsigned short *d_lmask = nullptr;
-    double *d_weight = nullptr;
-    double *dD = nullptr;
+    bool geometry_ready = false;
+    int K = 0;
+    XGroup groups[XMAXG];
+    std::vector<DiagDev> dev;      // [0] = P, [1 + g] = Dx of mixer group g
+    std::vector<XDiag> host_diag;  // same order
+    XDiag *d_diags = nullptr;      // device copy: [1 + n_groups]
+    bool any_residual = false;
     // per call
     int64_t cap_chains = 0;
     size_t cap_esz = 0;
@@ -466,117 +605,164 @@ struct GeneralWorkspace {
     GenChain *chains = nullptr;
 };
 
+static void free_diag(DiagDev &d) {
+    cudaFree(d.lin); cudaFree(d.quad); cudaFree(d.R); cudaFree(d.w); cudaFree(d.mu_off); cudaFree(d.mu); cudaFree(d.omask);
+    d = DiagDev();
+}
+
 void qmc_general_free(qmc_model *m) {
     GeneralWorkspace *w = m->general;
     if (!w) return;
-    cudaFree(w->d_passes); cudaFree(w->d_group_pass_off); cudaFree(w->d_lmask); cudaFree(w->d_weight);
-    cudaFree(w->dD); cudaFree(w->state); cudaFree(w->segsum); cudaFree(w->chains);
+    for (auto &d : w->dev) free_diag(d);
+    cudaFree(w->d_diags);
+    cudaFree(w->state); cudaFree(w->segsum); cudaFree(w->chains);
     delete w;
     m->general = nullptr;
 }
 
-// Greedy partition of one group's terms into tiles of GT qubits containing qubits 0..GFORCED-1.
-static int plan_group(int n, const uint64_t *masks, const double *weights, int nterms, std::vector<GenPass> &passes,
-                      std::vector<unsigned short> &lmask, std::vector<double> &weight) {
-    const uint64_t forced = (1ULL << GFORCED) - 1ULL;
-    std::vector<char> done(nterms, 0);
-    int left = nterms;
-    while (left > 0) {
-        uint64_t tile = forced;
-        for (;;) {  // grow: the undone term that adds the fewest new qubits (ties: lowest new qubit)
-            int best = -1, best_cost = 99;
-            uint64_t best_new = ~0ULL;
-            for (int k = 0; k < nterms; ++k) {
-                if (done[k]) continue;
-                const uint64_t add = masks[k] & ~tile;
-                if (!add) continue;  // already inside
-                const int cost = __builtin_popcountll(add);
-                if (__builtin_popcountll(tile) + cost > GT) continue;
-                const uint64_t low = add & (~add + 1ULL);
-                if (cost < best_cost || (cost == best_cost && low < best_new)) {
-                    best = k;
-                    best_cost = cost;
-                    best_new = low;
-                }
-            }
-            if (best < 0) break;
-            tile |= masks[best];
-        }
-        for (int q = 0; q < n && __builtin_popcountll(tile) < GT; ++q) tile |= 1ULL << q;  // fill with low qubits
-        GenPass P;
-        int k2 = 0;
+// Qubit groups: G0 = positions 0..11; then groups of 8 from the top, the last one takes what is left (1..8 positions).
+// Tile of an HI group = positions 0..3, its qubits, and the lowest free positions to make 12.
+static int plan_geometry(int n, GeneralWorkspace *w) {
+    std::vector<std::vector<int>> qs;
+    std::vector<int> g0;
+    for (int q = 0; q < XT; ++q) g0.push_back(q);
+    qs.push_back(g0);
+    for (int top = n; top > XT;) {
+        const int lo = std::max(XT, top - 8);
+        std::vector<int> g;
+        for (int q = lo; q < top; ++q) g.push_back(q);
+        qs.push_back(g);
+        top = lo;
+    }
+    QMC_REQUIRE((int)qs.size() <= XMAXG, QMC_ERR_UNSUPPORTED, "general path: n=%d needs %d qubit groups (max %d)", n, (int)qs.size(), XMAXG);
+    w->K = (int)qs.size() - 1;
+    for (size_t gi = 0; gi < qs.size(); ++gi) {
+        XGroup &G = w->groups[gi];
+        memset(&G, 0, sizeof(G));
+        unsigned long long tm = 0ULL;
+        for (int q : qs[gi]) tm |= 1ULL << q;
+        for (int q = 0; q < XFORCED; ++q) tm |= 1ULL << q;
+        for (int q = 0; q < n && __builtin_popcountll(tm) < XT; ++q) tm |= 1ULL << q;
+        int k = 0;
+        unsigned short act = 0;
         for (int q = 0; q < n; ++q)
-            if ((tile >> q) & 1ULL) P.tpos[k2++] = (unsigned char)q;
-        P.term0 = (int)lmask.size();
-        int took = 0;
-        for (int k = 0; k < nterms; ++k) {
-            if (done[k] || (masks[k] & ~tile)) continue;
-            unsigned short lm = 0;
-            for (int b = 0; b < GT; ++b)
-                if ((masks[k] >> P.tpos[b]) & 1ULL) lm |= (unsigned short)(1u << b);
-            lmask.push_back(lm);
-            weight.push_back(weights[k]);
-            done[k] = 1;
-            ++took;
-        }
-        P.term1 = (int)lmask.size();
-        if (!took) {
-            qmc_set_error("mixer term with more than %d qubits outside qubits 0..%d cannot be tiled", GT - GFORCED, GFORCED - 1);
-            return QMC_ERR_UNSUPPORTED;
-        }
-        left -= took;
-        passes.push_back(P);
+            if ((tm >> q) & 1ULL) {
+                if (std::find(qs[gi].begin(), qs[gi].end(), q) != qs[gi].end()) act |= (unsigned short)(1u << k);
+                G.tpos[k++] = (unsigned char)q;
+            }
+        G.tmask = tm;
+        G.active = act;
+        G.n_active = (int)qs[gi].size();
     }
     return QMC_OK;
 }
 
-static int general_prepare(qmc_model *m, cudaStream_t st) {
+// Device form of the diagonal with terms (mask, weight) hosted on tile geometry G.
+static int build_diag(int n, const XGroup &G, const std::vector<uint64_t> &masks, const std::vector<double> &weights,
+                      DiagDev &dd, XDiag &out, bool &any_residual) {
+    std::vector<double> lin(n, 0.0), quad((size_t)n * n, 0.0);
+    std::map<unsigned short, std::vector<std::pair<unsigned long long, double>>> resid;
+    for (size_t k = 0; k < masks.size(); ++k) {
+        const int pc = __builtin_popcountll(masks[k]);
+        if (pc == 1) {
+            lin[__builtin_ctzll(masks[k])] += weights[k];
+        } else if (pc == 2) {
+            const int a = __builtin_ctzll(masks[k]), b = 63 - __builtin_clzll(masks[k]);
+            quad[(size_t)a * n + b] += weights[k];
+            quad[(size_t)b * n + a] += weights[k];
+        } else {
+            unsigned short lm = 0;
+            for (int t = 0; t < XT; ++t)
+                if ((masks[k] >> G.tpos[t]) & 1ULL) lm |= (unsigned short)(1u << t);
+            resid[lm].push_back({masks[k] & ~G.tmask, weights[k]});
+        }
+    }
+    std::vector<double> R(XN);
+    for (int l = 0; l < XN; ++l) {
+        double r = 0.0;
+        for (int t = 0; t < XT; ++t)
+            for (int t2 = t + 1; t2 < XT; ++t2) {
+                const double z = (((l >> t) ^ (l >> t2)) & 1) ? -1.0 : 1.0;
+                r += quad[(size_t)G.tpos[t] * n + G.tpos[t2]] * z;
+            }
+        R[l] = r;
+    }
+    std::vector<int> mu_off(1, 0);
+    std::vector<unsigned short> mu;
+    std::vector<unsigned long long> om;
+    std::vector<double> wv;
+    for (auto &kv : resid) {
+        mu.push_back(kv.first);
+        for (auto &tw : kv.second) {
+            om.push_back(tw.first);
+            wv.push_back(tw.second);
+        }
+        mu_off.push_back((int)om.size());
+    }
+    auto up = [](void **p, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 8));
+        if (e == cudaSuccess && bytes) e = cudaMemcpy(*p, src, bytes, cudaMemcpyHostToDevice);
+        return e;
+    };
+    QMC_CUDA_TRY(up((void **)&dd.lin, lin.data(), sizeof(double) * lin.size()));
+    QMC_CUDA_TRY(up((void **)&dd.quad, quad.data(), sizeof(double) * quad.size()));
+    QMC_CUDA_TRY(up((void **)&dd.R, R.data(), sizeof(double) * R.size()));
+    QMC_CUDA_TRY(up((void **)&dd.mu_off, mu_off.data(), sizeof(int) * mu_off.size()));
+    QMC_CUDA_TRY(up((void **)&dd.mu, mu.data(), sizeof(unsigned short) * mu.size()));
+    QMC_CUDA_TRY(up((void **)&dd.omask, om.data(), sizeof(unsigned long long) * om.size()));
+    QMC_CUDA_TRY(up((void **)&dd.w, wv.data(), sizeof(double) * wv.size()));
+    out.lin = dd.lin; out.quad = dd.quad; out.R = dd.R; out.n_mu = (int)mu.size(); out.mu_off = dd.mu_off; out.mu = dd.mu;
+    out.omask = dd.omask; out.w = dd.w;
+    if (!mu.empty()) any_residual = true;
+    return QMC_OK;
+}
+
+static int general_prepare(qmc_model *m) {
     if (!m->general) m->general = new GeneralWorkspace();
     GeneralWorkspace *w = m->general;
     const int n = m->n;
-    if (!w->dD) {
-        double *dcJ = nullptr, *dch = nullptr;
-        QMC_CUDA_TRY(cudaMalloc(&dcJ, sizeof(double) * n * n));
-        QMC_CUDA_TRY(cudaMalloc(&dch, sizeof(double) * n));
-        QMC_CUDA_TRY(cudaMemcpyAsync(dcJ, m->host_cJ.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice, st));
-        QMC_CUDA_TRY(cudaMemcpyAsync(dch, m->host_ch.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
-        QMC_CUDA_TRY(cudaMalloc(&w->dD, sizeof(double) << n));
-        gen_phase_table_kernel<<<148 * 8, 256, sizeof(double) * (n * n + n), st>>>(n, dcJ, dch, w->dD);
-        m->launches++;
-        QMC_CUDA_TRY(cudaGetLastError());
-        QMC_CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(dcJ);
-        cudaFree(dch);
+    if (!w->geometry_ready) {
+        int rc = plan_geometry(n, w);
+        if (rc != QMC_OK) return rc;
+        w->geometry_ready = true;
     }
     if (w->mixer_epoch != m->mixer_epoch) {
-        w->passes.clear(); w->group_pass_off.assign(1, 0); w->lmask.clear(); w->weight.clear();
-        w->max_terms_per_pass = 0; w->max_passes = 0;
-        for (int g = 0; g < m->n_groups; ++g) {
-            const int t0 = m->group_off[g], t1 = m->group_off[g + 1];
-            int rc = plan_group(n, m->masks.data() + t0, m->weights.data() + t0, t1 - t0, w->passes, w->lmask, w->weight);
-            if (rc != QMC_OK) return rc;
-            w->group_pass_off.push_back((int)w->passes.size());
-            w->max_passes = std::max(w->max_passes, w->group_pass_off[g + 1] - w->group_pass_off[g]);
+        for (auto &d : w->dev) free_diag(d);
+        w->dev.assign(1 + m->n_groups, DiagDev());
+        w->host_diag.assign(1 + m->n_groups, XDiag());
+        w->any_residual = false;
+        // P: D(idx) = sum_{j<k} cJ[j][k] z_j z_k + sum_j ch[j] z_j over spins j (fn_qckt_problem_half :54-91); spin j = qubit n-1-j
+        std::vector<uint64_t> pm;
+        std::vector<double> pw;
+        for (int j = 0; j < n; ++j) {
+            pm.push_back(1ULL << (n - 1 - j));
+            pw.push_back(m->host_ch[j]);
+            for (int k = j + 1; k < n; ++k) {
+                pm.push_back((1ULL << (n - 1 - j)) | (1ULL << (n - 1 - k)));
+                pw.push_back(m->host_cJ[(size_t)j * n + k]);
+            }
         }
-        for (auto &P : w->passes) w->max_terms_per_pass = std::max(w->max_terms_per_pass, P.term1 - P.term0);
-        cudaFree(w->d_passes); cudaFree(w->d_group_pass_off); cudaFree(w->d_lmask); cudaFree(w->d_weight);
-        w->d_passes = nullptr; w->d_group_pass_off = nullptr; w->d_lmask = nullptr; w->d_weight = nullptr;
-        QMC_CUDA_TRY(cudaMalloc(&w->d_passes, sizeof(GenPass) * w->passes.size()));
-        QMC_CUDA_TRY(cudaMalloc(&w->d_group_pass_off, sizeof(int) * w->group_pass_off.size()));
-        QMC_CUDA_TRY(cudaMalloc(&w->d_lmask, sizeof(unsigned short) * w->lmask.size()));
-        QMC_CUDA_TRY(cudaMalloc(&w->d_weight, sizeof(double) * w->weight.size()));
-        QMC_CUDA_TRY(cudaMemcpy(w->d_passes, w->passes.data(), sizeof(GenPass) * w->passes.size(), cudaMemcpyHostToDevice));
-        QMC_CUDA_TRY(cudaMemcpy(w->d_group_pass_off, w->group_pass_off.data(), sizeof(int) * w->group_pass_off.size(), cudaMemcpyHostToDevice));
-        QMC_CUDA_TRY(cudaMemcpy(w->d_lmask, w->lmask.data(), sizeof(unsigned short) * w->lmask.size(), cudaMemcpyHostToDevice));
-        QMC_CUDA_TRY(cudaMemcpy(w->d_weight, w->weight.data(), sizeof(double) * w->weight.size(), cudaMemcpyHostToDevice));
+        int rc = build_diag(n, w->groups[0], pm, pw, w->dev[0], w->host_diag[0], w->any_residual);
+        if (rc != QMC_OK) return rc;
+        for (int g = 0; g < m->n_groups; ++g) {
+            std::vector<uint64_t> xm(m->masks.begin() + m->group_off[g], m->masks.begin() + m->group_off[g + 1]);
+            std::vector<double> xw(m->weights.begin() + m->group_off[g], m->weights.begin() + m->group_off[g + 1]);
+            rc = build_diag(n, w->groups[1], xm, xw, w->dev[1 + g], w->host_diag[1 + g], w->any_residual);
+            if (rc != QMC_OK) return rc;
+        }
+        cudaFree(w->d_diags);
+        w->d_diags = nullptr;
+        QMC_CUDA_TRY(cudaMalloc(&w->d_diags, sizeof(XDiag) * w->host_diag.size()));
+        QMC_CUDA_TRY(cudaMemcpy(w->d_diags, w->host_diag.data(), sizeof(XDiag) * w->host_diag.size(), cudaMemcpyHostToDevice));
         w->mixer_epoch = m->mixer_epoch;
     }
     return QMC_OK;
 }
 
-int qmc_general_num_passes(qmc_model *m, int group) {  // test / benchmark hook: tiles of a mixer group
-    if (!m || !m->general || group < 0 || group + 1 >= (int)m->general->group_pass_off.size()) return -1;
-    return m->general->group_pass_off[group + 1] - m->general->group_pass_off[group];
+int qmc_general_num_passes(qmc_model *m, int group) {  // test / benchmark hook: passes per Trotter layer
+    (void)group;
+    if (!m || !m->general || !m->general->geometry_ready) return -1;
+    return 2 * m->general->K;
 }
 
 template <typename T>
@@ -585,16 +771,20 @@ static int general_run_t(qmc_model *m, GeneralWorkspace *w, GenArgs a, int64_t n
     using T2 = typename V2<T>::type;
     const int n = m->n;
     const int64_t N = 1LL << n;
-    const size_t smem = sizeof(T2) * (size_t)(GN + w->max_terms_per_pass) + sizeof(int) * (size_t)w->max_terms_per_pass;
-    QMC_REQUIRE(smem <= 200 * 1024, QMC_ERR_UNSUPPORTED, "general path: %d mixer terms in one tile", w->max_terms_per_pass);
-    QMC_CUDA_TRY(cudaFuncSetAttribute(gen_pass_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    size_t free_b = 0, total_b = 0;
-    QMC_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    const size_t per_chain = sizeof(T2) * (size_t)N + sizeof(double) * (size_t)(N >> 6) + sizeof(GenChain);
-    const size_t have = (size_t)w->cap_chains * (w->cap_esz * (size_t)N + sizeof(double) * (size_t)(N >> 6) + sizeof(GenChain));
-    int64_t cap = (int64_t)(((double)(free_b + have) * 0.85) / (double)per_chain);
-    if (cap > 65535) cap = 65535;
-    QMC_REQUIRE(cap >= 1, QMC_ERR_CUDA, "not enough device memory for one 2^%d statevector", n);
+    const size_t smem = sizeof(T2) * (size_t)XN + (w->any_residual ? sizeof(double) * (size_t)XN : 0);
+    QMC_CUDA_TRY(cudaFuncSetAttribute(gen_pass_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device: set every call
+    int64_t cap;
+    if (w->cap_chains >= n_chains && sizeof(T2) == w->cap_esz) {
+        cap = w->cap_chains;  // steady state: no allocator / memory query
+    } else {
+        size_t free_b = 0, total_b = 0;
+        QMC_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_chain = sizeof(T2) * (size_t)N + sizeof(double) * (size_t)(N >> 6) + sizeof(GenChain);
+        const size_t have = (size_t)w->cap_chains * (w->cap_esz * (size_t)N + sizeof(double) * (size_t)(N >> 6) + sizeof(GenChain));
+        cap = (int64_t)(((double)(free_b + have) * 0.85) / (double)per_chain);
+        if (cap > 65535) cap = 65535;
+        QMC_REQUIRE(cap >= 1, QMC_ERR_CUDA, "not enough device memory for one 2^%d statevector", n);
+    }
     const int64_t batch = std::min<int64_t>(cap, n_chains);
     if (batch > w->cap_chains || sizeof(T2) != w->cap_esz) {
         QMC_CUDA_TRY(cudaStreamSynchronize(st));
@@ -609,8 +799,9 @@ static int general_run_t(qmc_model *m, GeneralWorkspace *w, GenArgs a, int64_t n
     a.state = w->state;
     a.segsum = w->segsum;
     a.chains = w->chains;
-    const int max_steps = w->max_passes == 1 ? 1 : r_cap * (w->max_passes - 1) + 1;
-    const int64_t tiles = N >> GT;
+    const int K = w->K;
+    const int max_steps = 1 + 2 * K * (r_cap - 1) + K;  // FIRST, r - 1 full blocks, the first half of block r
+    const int64_t tiles = N >> XT;
     const int64_t hops = a.mode == QMC_MODE_CHAIN ? n_hops : 1;
     for (int64_t c0 = 0; c0 < n_chains; c0 += batch) {
         const int64_t nc = std::min<int64_t>(batch, n_chains - c0);
@@ -620,10 +811,8 @@ static int general_run_t(qmc_model *m, GeneralWorkspace *w, GenArgs a, int64_t n
             a.hop_index = hop;
             gen_prepare_kernel<<<(unsigned)((nc + 127) / 128), 128, 0, st>>>(a, nc, hop == 0);
             for (int t = 0; t < max_steps; ++t)
-                gen_pass_kernel<T><<<dim3((unsigned)tiles, (unsigned)nc), GTH, smem, st>>>(a, t);
-            const unsigned sb = (unsigned)std::min<int64_t>((N >> 6) / 8, 148 * 16);
-            gen_segsum_kernel<T><<<dim3(sb < 1 ? 1 : sb, (unsigned)nc), 256, 0, st>>>(a);
-            m->launches += 2 + max_steps;
+                gen_pass_kernel<T><<<dim3((unsigned)tiles, (unsigned)nc), XTH, smem, st>>>(a, t);
+            m->launches += 1 + max_steps;
             if (a.mode == QMC_MODE_PROBS) {
                 gen_probs_kernel<T><<<148 * 4, 256, 0, st>>>(a);
             } else {
@@ -647,12 +836,12 @@ int qmc_general_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, co
                     uint64_t *proposals, uint8_t *accepted, uint64_t *final_state, int64_t *acc_count,
                     int64_t *hamming_hist, void *probs_out, void *amps_out, cudaStream_t st) {
     const int n = m->n;
-    QMC_REQUIRE(n > GT && n <= QMC_GENERAL_MAX_SPINS, QMC_ERR_UNSUPPORTED,
-                "general statevector path (k-body / custom mixers, complex128) covers %d <= n <= %d (n=%d)", GT + 1,
+    QMC_REQUIRE(n > XT && n <= QMC_GENERAL_MAX_SPINS, QMC_ERR_UNSUPPORTED,
+                "general statevector path (k-body / custom mixers, complex128) covers %d <= n <= %d (n=%d)", XT + 1,
                 QMC_GENERAL_MAX_SPINS, n);
     QMC_REQUIRE(m->n_groups >= 1, QMC_ERR_BADARG, "no mixer set (qmc_mixer_set)");
     if (n_chains == 0) return QMC_OK;
-    int rc = general_prepare(m, st);
+    int rc = general_prepare(m);
     if (rc != QMC_OK) return rc;
     GeneralWorkspace *w = m->general;
     int r_cap = qmc_trotter_steps(11, dt);
@@ -665,10 +854,12 @@ int qmc_general_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, co
     }
     GenArgs a;
     memset(&a, 0, sizeof(a));
-    a.n = n; a.n_groups = m->n_groups; a.phase_active = m->phase_active; a.mode = mode; a.max_terms = w->max_terms_per_pass;
+    a.n = n; a.n_groups = m->n_groups; a.phase_active = m->phase_active; a.mode = mode; a.K = w->K;
     a.alpha = m->alpha; a.dt = dt; a.temperature = temperature; a.g_lo = g_lo; a.g_hi = g_hi;
-    a.passes = w->d_passes; a.group_pass_off = w->d_group_pass_off; a.lmask = w->d_lmask; a.weight = w->d_weight;
-    a.D = w->dD; a.J = m->dJ; a.h = m->dh; a.group_cum = m->d_group_cum;
+    for (int g = 0; g <= w->K; ++g) a.groups[g] = w->groups[g];
+    a.diag_p = w->d_diags;
+    a.diag_x = w->d_diags + 1;
+    a.J = m->dJ; a.h = m->dh; a.group_cum = m->d_group_cum;
     a.seed = seed; a.chain_id0 = chain_id0; a.n_hops = n_hops;
     a.s_in = s_in; a.gamma_arr = gamma_arr; a.u_arr = u_arr; a.r_arr = r_arr; a.group_arr = group_arr;
     a.proposals = proposals; a.accepted = accepted; a.final_state = final_state; a.acc_count = acc_count;

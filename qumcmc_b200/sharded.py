@@ -193,7 +193,7 @@ def pick_owner(totals: np.ndarray, u: float) -> Tuple[int, float]:
 
 # Schedule defaults of ShardedProposer (measured on 8 B200, n = 36: see DESIGN.md section 5 and profiles/)
 DEFAULT_MODE = "fused"
-DEFAULT_XCHG_CTAS = 64
+DEFAULT_XCHG_CTAS = 148
 DEFAULT_OVERLAP_CHUNK_BITS = 5
 
 
@@ -257,10 +257,22 @@ class ShardedProposer:
         if mode == "overlap":
             self.handle.set_exchange_ctas(int(xchg_ctas))
         self.xchg_ctas = int(xchg_ctas) if mode == "overlap" else 0
-        self._xstream = torch.cuda.Stream(device=dev) if self.chunk_bits else None            # exchange passes
-        self._cstream = torch.cuda.Stream(device=dev, priority=-1) if self.chunk_bits else None  # local passes: SM slots first
+        self._make_streams()
         if self.fused:
             self._map_peer_buffers(device)
+
+    def _make_streams(self) -> None:
+        """Side streams of the chunked schedules.  The exchange stream has the HIGHER priority: its kernels are small
+        (overlap mode: a bounded number of persistent CTAs) and must get their CTA slots as soon as a chunk's local
+        passes are done; the local passes (thousands of CTAs, queued chunk after chunk) fill every other slot.  With the
+        priorities the other way round the block scheduler serves the queued local-pass CTAs first and the exchange only
+        starts when all of them have drained -- a serial schedule (measured: 2 GPUs, n = 34, no gain)."""
+        torch = self._torch
+        if self.chunk_bits and getattr(self, "_xstream", None) is None:
+            self._xstream = torch.cuda.Stream(device=self.dev, priority=-1)   # exchange passes
+            self._cstream = torch.cuda.Stream(device=self.dev)                # local passes
+        elif not self.chunk_bits and not hasattr(self, "_xstream"):
+            self._xstream = self._cstream = None
 
     def reconfigure(self, mode: str, chunk_bits: Optional[int] = None, xchg_ctas: Optional[int] = None) -> None:
         """Switch the exchange schedule of an existing proposer (same buffers and peer mappings): A/B runs."""
@@ -275,9 +287,7 @@ class ShardedProposer:
         self.chunk_bits = want if (self.fused and want >= g) else 0
         self.xchg_ctas = int(xchg_ctas if xchg_ctas is not None else DEFAULT_XCHG_CTAS) if mode == "overlap" else 0
         self.handle.set_exchange_ctas(self.xchg_ctas)
-        if self.chunk_bits and self._xstream is None:
-            self._xstream = torch.cuda.Stream(device=self.dev)
-            self._cstream = torch.cuda.Stream(device=self.dev, priority=-1)
+        self._make_streams()
 
     def _map_peer_buffers(self, device: int) -> None:
         """all-gather CUDA IPC handles of both state buffers, map the peers' buffers into this device's context

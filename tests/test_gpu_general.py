@@ -115,3 +115,62 @@ def test_general_path_chains_follow_the_oracle(dtype):
         assert int(b.final_state[c]) == cur and int(b.acc_count[c]) == nacc
         assert np.array_equal(b.hamming_hist[c], hist)
     assert mismatched <= 2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# n > 20: three and more qubit groups (plain Walsh-Hadamard passes between the host passes); VERDICT r1 item 6
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,kind,dtype,rs", [(21, "two", "fp32", (1, 2, 3)), (22, "two", "fp64", (2, 3)), (23, "coh", "fp32", (2,)),
+                                              (24, "three", "fp32", (2,)), (21, "one", "fp64", (1, 4))])
+def test_general_path_three_groups(n, kind, dtype, rs):
+    """21 <= n <= 24: G0 + two groups above it (K = 2: four passes per Trotter layer), two-body / coherent-sum /
+    three-body (residual Walsh terms) mixers and complex128 one-body."""
+    import qumcmc_b200 as q
+    mixer = {"one": lambda: q.GenericMixer.OneBodyMixer(n), "two": lambda: q.GenericMixer.TwoBodyMixer(n),
+             "coh": lambda: q.CoherentMixerSum([q.GenericMixer.OneBodyMixer(n), q.CustomMixer(n, [[0, 1, 2], [n - 3, n - 2, n - 1], [3, 11, 17]])],
+                                               [0.75, 0.25]),
+             "three": lambda: q.CustomMixer(n, [[a, a + 1, a + 2] for a in range(0, n - 2, 2)] + [[0, 12, n - 1], [5, 13, 20]])}[kind]()
+    _check(q, n, mixer, dtype, rs)
+
+
+def test_general_path_incoherent_groups_n21():
+    import qumcmc_b200 as q
+    n = 21
+    inc = q.IncoherentMixerSum([q.GenericMixer.OneBodyMixer(n), q.GenericMixer.TwoBodyMixer(n)], [0.5, 0.5])
+    _check(q, n, inc, "fp32", (2,), group=0)
+    _check(q, n, inc, "fp32", (3,), group=1)
+
+
+@pytest.mark.slow
+def test_two_body_mixer_n26():
+    """TwoBodyMixer at n = 26 in complex64 (K = 2 groups above G0; 325 mixer terms per layer, two host passes + two H passes
+    per layer here, 325 + 351 gate passes in the reference) against the oracle."""
+    import qumcmc_b200 as q
+    _check(q, 26, q.GenericMixer.TwoBodyMixer(26), "fp32", (2,))
+
+
+def test_general_path_chains_and_visit_histogram_n21():
+    """Chains on the multi-group general path: accept flags follow bit-exactly from the device's proposals, the visit
+    histogram equals the recorded Markov chains."""
+    import qumcmc_b200 as q
+    from oracle import np_oracle as npo
+    n, C_, H, seed = 21, 3, 3, 5
+    J, h = models.packaged_random_model(n, 4)
+    m = q.IsingEnergyFunction(J, h)
+    b = q.quantum_enhanced_mcmc(H, m, q.GenericMixer.TwoBodyMixer(n), (0.25, 0.6), temperature=1.0, n_chains=C_, seed=seed,
+                                dtype="fp32", visit_histogram=True)
+    want = np.zeros(1 << n, dtype=np.int64)
+    for c in range(C_):
+        cur = oracle.initial_state(seed, c, n)
+        e_cur = oracle.energy(J, h, cur)
+        for hop in range(H):
+            _, _, _, _, ua = oracle.hop_draws(seed, c, hop)
+            sp = int(b.proposals[c, hop])
+            e_sp = oracle.energy(J, h, sp)
+            acc = oracle.test_accept(e_cur, e_sp, 1.0, ua)
+            assert bool(b.accepted[c, hop]) == acc
+            if acc:
+                cur, e_cur = sp, e_sp
+        assert int(b.final_state[c]) == cur
+        want += np.bincount(npo.markov_chain_from(int(b.initial[c]), b.proposals[c], b.accepted[c]).astype(np.int64), minlength=1 << n)
+    assert np.array_equal(b.visit_hist, want)

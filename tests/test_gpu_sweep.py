@@ -157,15 +157,15 @@ def test_sweep_full_size_properties_n20():
 
 
 def test_unsupported_configurations_fail_loudly():
-    """Above the general path's limit (n = 24) k-body mixers and complex128 have no kernel -- and no CPU fallback."""
+    """Above the general path's limit (n = 30) k-body mixers and complex128 have no kernel -- and no CPU fallback."""
     q = _api()
     from qumcmc_b200 import _lib
-    J, h = models.packaged_random_model(25, 2)
+    J, h = models.packaged_random_model(31, 2)
     m = q.IsingEnergyFunction(J, h)
     with pytest.raises(_lib.QmcUnsupported):
-        q.transition_probabilities(m, q.GenericMixer.TwoBodyMixer(25), 0, 0.3, 2, dtype="fp32")
+        q.transition_probabilities(m, q.GenericMixer.TwoBodyMixer(31), 0, 0.3, 2, dtype="fp32")
     with pytest.raises(_lib.QmcUnsupported):
-        q.transition_probabilities(m, q.GenericMixer.OneBodyMixer(25), 0, 0.3, 2, dtype="fp64")
+        q.transition_probabilities(m, q.GenericMixer.OneBodyMixer(31), 0, 0.3, 2, dtype="fp64")
 
 
 @pytest.mark.parametrize("n,rs", [(21, (1, 2, 3, 6)), (22, (2, 5)), (23, (3, 4)), (24, (2, 7)), (25, (3,)), (26, (4,))])

@@ -84,3 +84,37 @@ def test_c128_tile_geometries(geometry):
                 assert d > 0 and d & (d - 1) == 0
                 seen.append(d.bit_length() - 1)
     assert sorted(seen) == sorted(group), (geometry, seen)
+
+
+@pytest.mark.parametrize("width", [8, 16])
+def test_general_path_register_stages(width):
+    """general.cu: the three register stages of the 4096-amplitude tile (256 threads x 16 registers) are bijections onto
+    the tile, share one slot set, and are conflict-free for 64-bit (complex64, fp64 residual table) and 128-bit
+    (complex128) elements."""
+    L = _lib()
+    loc = C.c_int()
+    lanes_per_phase = 128 // width
+    seen = None
+    for stage in (0, 1, 2):
+        slots = np.zeros((256, 16), dtype=np.int64)
+        locs = np.zeros((256, 16), dtype=np.int64)
+        for t in range(256):
+            for j in range(16):
+                slots[t, j] = L.qmc_debug_general_slot(stage, t, j, C.byref(loc))
+                locs[t, j] = loc.value
+        assert sorted(slots.ravel().tolist()) == list(range(4096)) and sorted(locs.ravel().tolist()) == list(range(4096))
+        pairs = set(zip(locs.ravel().tolist(), slots.ravel().tolist()))
+        assert seen is None or pairs == seen          # the same local index lives in the same slot in every stage
+        seen = pairs
+        for j in range(16):
+            for w in range(8):
+                for ph in range(32 // lanes_per_phase):
+                    lanes = slots[32 * w + ph * lanes_per_phase: 32 * w + (ph + 1) * lanes_per_phase, j]
+                    assert len(set((lanes % lanes_per_phase).tolist())) == lanes_per_phase, (stage, j, w, ph)
+    # stage 2 is the HBM-facing stage: lanes 0..15 of a warp sit on local bits 0..3 (runs of 16 amplitudes)
+    got = []
+    for t in range(16):
+        L.qmc_debug_general_slot(2, t, 0, C.byref(loc))
+        got.append(loc.value)
+    assert got == list(range(16))
+    assert L.qmc_debug_general_slot(3, 0, 0, None) == -1
