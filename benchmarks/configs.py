@@ -75,22 +75,38 @@ def c4():
     ts = [2 + ((int(philox4x32(4, np.array([0], dtype=np.uint64), hop, 0)[0, 2]) * 10) >> 32) for hop in range(H)]
     rs = [max(1, int(np.floor(t / 0.8))) for t in ts]
     alg = sum(2 * (1 << n) * 8 * r for r in rs)
+    # bytes the passes actually move: K = 2 register groups above the LO qubits => 2 passes per layer, the first pass of a
+    # proposal write-only and the last read-only: 16 B * 2^n * K * (r - 1) (qmc_profile_read_moved uses the same formula)
+    moved = sum(16.0 * (1 << n) * 2 * (r - 1) for r in rs)
     print(json.dumps({"config": "C4 n=28 single chain x %d hops (2 GiB complex64 statevector)" % H, "seconds": dt,
                       "proposals_per_s": H / dt, "layers": rs, "algorithmic_GB": alg / 1e9,
                       "algorithmic_GBps": alg / 1e9 / dt, "frac_of_measured_hbm": alg / 1e9 / dt / 6547.8,
-                      "path": "generic sweeps: LO(12) + HI8 + HI8 qubit groups, 2 passes per layer (B_alg counts 1)"}))
+                      "passes_per_layer": 2, "moved_GB": moved / 1e9, "moved_GBps": moved / 1e9 / dt,
+                      "per_pass_frac_of_measured_hbm": moved / 1e9 / dt / 6547.8,
+                      "path": "generic sweeps: LO(12) + HI8 + HI8 qubit groups, 2 passes per layer; SURVEY 8d's B_alg counts one "
+                              "pass per layer (k = 14 tile qubits), which strided 2^13-amplitude tiles cannot reach: "
+                              "frac_of_measured_hbm is capped at 0.5 by construction, per_pass_frac is the kernels' own rate"}))
 
 
 def general():
     """General path (tiled passes, any X-string mixer / complex128): proposals/s and the pass count."""
-    for n, mixer_name, dtype, chains, H in [(16, "two", "fp32", 512, 8), (16, "two", "fp64", 512, 8), (20, "one", "fp64", 256, 8),
-                                            (20, "two", "fp32", 256, 4)]:
+    for n, mixer_name, dtype, chains, H in [(16, "two", "fp32", 512, 8), (16, "two", "fp64", 512, 8), (20, "two", "fp32", 1024, 6),
+                                            (20, "two", "fp64", 512, 6), (24, "two", "fp32", 32, 4), (26, "two", "fp32", 8, 4)]:
         m = q.random_ising_model(n, 1)
         mx = q.GenericMixer.OneBodyMixer(n) if mixer_name == "one" else q.GenericMixer.TwoBodyMixer(n)
         q.quantum_enhanced_mcmc(1, m, mx, (0.25, 0.6), temperature=1.0, n_chains=chains, seed=3, dtype=dtype)  # warm + alloc
         dt, b = timed(lambda: q.quantum_enhanced_mcmc(H, m, mx, (0.25, 0.6), temperature=1.0, n_chains=chains, seed=4, dtype=dtype))
+        from qumcmc_b200.rng import philox4x32
+        sum_r = 0
+        for hop in range(H):
+            w2 = philox4x32(4, np.arange(chains, dtype=np.uint64), hop, 0)[:, 2].astype(np.uint64)
+            sum_r += int(np.maximum(1, np.floor((2 + ((w2 * np.uint64(10)) >> np.uint64(32))).astype(np.float64) / 0.8)).sum())
+        K = max(1, -(-(n - 12) // 8))                        # groups above qubits 0..11
+        esz = 8 if dtype == "fp32" else 16
+        moved = 2.0 * esz * (1 << n) * (2 * K * sum_r - K * chains * H)   # FIRST write-only, 2K(r-1)+K-... passes read+write
         print(json.dumps({"config": "general path n=%d, %s-body mixer, %s, %d chains x %d hops" % (n, mixer_name, dtype, chains, H),
                           "seconds": dt, "proposals_per_s": chains * H / dt, "acceptance": b.acceptance_rate(),
+                          "passes_per_layer": 2 * K, "approx_moved_GBps": moved / 1e9 / dt,
                           "reference_cost": "one statevector pass per gate: %d passes per layer" % (n * (n - 1) // 2 + n + (n if mixer_name == "one" else n * (n - 1) // 2))}))
 
 
