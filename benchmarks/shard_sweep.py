@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--chunk-bits", type=int, nargs="+", default=[3, 5])
     ap.add_argument("--ctas", type=int, nargs="+", default=[32, 64, 128])
+    ap.add_argument("--dma-chunk-bits", type=int, nargs="*", default=[3, 5], help="copy-engine exchange: chunk counts 2^k")
     ap.add_argument("--reference", action="store_true")
     args = ap.parse_args()
     import torch
@@ -38,7 +39,8 @@ def main():
     model = q.random_ising_model(n, 1)
     prop = ShardedProposer(model, q.GenericMixer.OneBodyMixer(n), device=local, fused=True, mode="fused")
     s = 0x5EED5EED5 & ((1 << n) - 1)
-    configs = [("fused", None, None)] + [("overlap", cb, c) for cb in args.chunk_bits for c in args.ctas]
+    configs = ([("fused", None, None)] + [("overlap", cb, c) for cb in args.chunk_bits for c in args.ctas]
+               + [("dma", cb, None) for cb in args.dma_chunk_bits])
     base_idx = {}
     for mode, cb, ctas in configs:
         prop.reconfigure(mode, cb, ctas)

@@ -192,11 +192,14 @@ int qmc_state_moments(qmc_model *m, int64_t count, const uint64_t *states_dev, c
  * The proposal U = M (P M)^(r-1) is a sequence of local passes (qmc_shard_op, one kernel each) and all-to-all
  * exchanges on equal chunks, which swap the top g local index bits with the rank bits; the CALLER performs the
  * exchange (torch.distributed / NCCL all_to_all_single between two state buffers) and passes the layout parity
- * (0 = no / even number of exchanges so far, 1 = odd) to every op.  The library tracks which logical qubit sits at
- * which position for each layout and never swaps back.  Op sequence for r >= 2 (K = qmc_shard_num_groups):
+ * (0 = identity, 1 = top g local positions swapped with the rank bits) to every op.  The library tracks which logical
+ * qubit sits at which position for each layout and never swaps back.  A proposal with r layers has r - 1 exchanges and
+ * STARTS in layout (r - 1) & 1 (the first pass builds the analytic product state directly in that layout), so that it
+ * ends in the identity layout and the measurement CDF runs in index order.  Op sequence for r >= 2
+ * (K = qmc_shard_num_groups):
  *   FIRST(top) ; then per layer j = 2..r:  [LO_SINGLE unless j == r] SINGLE(k = 1..K-1) <exchange>
  *                                          MID(top, pre = g) if j < r   else   SINGLE(top, pre = g) LO_FINAL
- * and LO_FINAL alone for r == 1.  qumcmc_b200/distributed.py (sharded_plan) generates exactly this list.
+ * and LO_FINAL alone for r == 1.  qumcmc_b200/sharded.py (sharded_plan, initial_layout) generates exactly this list.
  * After LO_FINAL: qmc_shard_norm -> local sum |a|^2; ranks all-gather the W sums, the owner of u * total calls
  * qmc_shard_select and broadcasts the measured index. */
 typedef struct qmc_shard qmc_shard;
@@ -233,6 +236,10 @@ int qmc_shard_op_chunk(qmc_shard *sh, int op, int k, int pre, int layout, void *
  * another stream) run beside the NVLink-bound stores instead of queueing behind them.  Same arithmetic, same results.
  * qmc_shard_exchange_can_persist: 1 when this shard's pre-exchange pass has such a variant. */
 int qmc_shard_set_exchange_ctas(qmc_shard *sh, int ctas);
+/* Exchange of one chunk by the copy engines (no SM): after the local passes of a chunk (qmc_shard_op_chunk with
+ * dst_which = -1) its 2^(nl - chunk_bits) contiguous amplitudes are copied into buffer dst_which of the owning rank
+ * (cudaMemcpyAsync into the peer mapping over NVLink).  Needs qmc_shard_set_peers and chunk_bits >= log2(world). */
+int qmc_shard_copy_chunk(qmc_shard *sh, const void *state_dev, int dst_which, int chunk_bits, int64_t chunk, void *stream);
 int qmc_shard_exchange_can_persist(const qmc_shard *sh);
 int qmc_shard_norm(qmc_shard *sh, double *total_dev, void *stream);
 int qmc_shard_select(qmc_shard *sh, void *state_dev, double target, int layout, uint64_t *index_dev, void *stream);

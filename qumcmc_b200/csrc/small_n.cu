@@ -298,6 +298,260 @@ __global__ void __launch_bounds__(SMALL_NT) smem_chain_kernel(const SmallParams 
         for (int i = tid; i < n + 1; i += NT) p.hamming_hist[chain * (n + 1) + i] = s_hist[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-per-chain kernel: 8 <= n <= 10, one-body X mixers.  One WARP owns a chain for all its hops: the 2^n amplitudes
+// sit in registers (R = n - 5 register qubits, 2^R amplitudes per lane; index = lane << R | j in layout 1), so a hop needs
+// no __syncthreads at all -- the CTA-per-chain kernel above spends most of a hop in ~60 block barriers.
+//   * storage basis S(idx) = (-i)^popcount(idx) a(idx) (sweep.cu): exp(-i theta X_q) is a real rotation, tan form
+//     S_lo' = S_lo + t S_hi, S_hi' = S_hi - t S_lo (2 FMA per amplitude per qubit), (prod cos)^r folded into |s>;
+//   * register qubits: butterflies inside the lane; then one transposition through a warp-private shared-memory tile
+//     (XOR-swizzled, __syncwarp only) makes the top R qubits register qubits (layout 2: index = j << 5 | lane); the 5 - R
+//     qubits that are lane bits in both layouts go through __shfl_xor.  Layers alternate the layout they start in;
+//   * phase factors exp(+i c D(idx)) of the proposal: computed once per hop into a second warp-private tile, read in
+//     either layout;
+//   * K3: per-lane sums in index order (layout 1: 2^R consecutive indices per lane) -> warp scan -> owner lane -> index;
+//     K4: energy table + Metropolis; the Hamming histogram lives in lane k = distance k.
+// Several chains per CTA (one per warp), no interaction between the warps.
+// ---------------------------------------------------------------------------------------------
+struct WarpParams {
+    SmallParams p;
+    const double *qweight;  // [n_groups][n] summed one-body weights
+    int64_t n_chains;
+};
+
+template <int R>
+__device__ __forceinline__ int wswz(int idx) { return idx ^ ((idx >> R) & 31); }
+
+template <typename T, int R>
+__global__ void __launch_bounds__(128) warp_chain_kernel(const WarpParams wp) {
+    using T2 = typename Vec2<T>::type;
+    constexpr int NR = 1 << R;       // amplitudes per lane
+    constexpr int n = R + 5;
+    constexpr int N = 1 << n;
+    constexpr int LEFT = 5 - R;      // qubits R .. 4 are lane bits in both layouts
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const SmallParams &p = wp.p;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (chain >= wp.n_chains) return;  // whole warp
+    T2 *tile = reinterpret_cast<T2 *>(smraw) + (size_t)warp * 2 * N;  // transposition tile
+    T2 *ph = tile + N;                                                 // phase factors of the current proposal
+    const uint64_t gchain = p.chain_id0 + (uint64_t)chain;
+    const unsigned FULL = 0xffffffffu;
+
+    uint64_t cur;
+    if (p.mode == QMC_MODE_CHAIN) cur = p.s_in ? p.s_in[chain] : qmc_initial_state(p.seed, gchain, n);
+    else cur = p.s_in[chain];
+    double e_cur = (p.mode == QMC_MODE_CHAIN) ? p.E[cur] : 0.0;
+    long long n_acc = 0;
+    int my_hist = 0;  // lane k: proposals at Hamming distance k
+    if (p.mode == QMC_MODE_CHAIN && p.hop0 == 0 && lane == 0) qmc_visit(p.visit, cur);
+
+    const int64_t hops = (p.mode == QMC_MODE_CHAIN) ? p.n_hops : 1;
+    for (int64_t hop = 0; hop < hops; ++hop) {
+        double gamma, u_meas, u_acc = 0.0;
+        int r, grp;
+        if (p.mode == QMC_MODE_CHAIN) {
+            const HopDraws d = qmc_hop_draws(p.seed, gchain, p.hop0 + (uint32_t)hop);
+            gamma = p.g_lo + (p.g_hi - p.g_lo) * d.u_gamma;
+            r = qmc_trotter_steps(d.t, p.dt);
+            grp = qmc_pick_group(p.n_groups, p.group_cum, d.u_group);
+            u_meas = d.u_meas;
+            u_acc = d.u_acc;
+        } else {
+            gamma = p.gamma_arr[chain];
+            r = p.r_arr[chain] < 1 ? 1 : p.r_arr[chain];
+            grp = p.group_arr ? p.group_arr[chain] : 0;
+            u_meas = p.u_arr ? p.u_arr[chain] : 0.0;
+        }
+        // per-qubit rotation: lane q holds tan(theta_q), theta_q = gamma w_q dt; scale = prod cos
+        double my_t = 0.0, my_c = 1.0;
+        if (lane < n) {
+            const double wq = wp.qweight[grp * n + lane];
+            if (wq != 0.0) {
+                double sn, cs;
+                sincos(gamma * wq * p.dt, &sn, &cs);
+                my_t = sn / cs;
+                my_c = cs;
+            }
+        }
+        double scale = my_c;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) scale *= __shfl_xor_sync(FULL, scale, off);
+        scale = pow(scale, (double)r);
+        T tq[n];
+#pragma unroll
+        for (int q = 0; q < n; ++q) tq[q] = (T)__shfl_sync(FULL, my_t, q);
+        // phase factors of this proposal (same c for all r - 1 layers), layout-independent slots
+        const bool phase = p.phase_active && r > 1;
+        if (phase) {
+            const double c = (1.0 - gamma) * p.alpha * p.dt;
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                const int idx = (lane << R) | j;
+                ph[wswz<R>(idx)] = phase_factor(c * p.D[idx], T(0));
+            }
+        }
+        // |s> in the storage basis: (prod cos)^r (-i)^popcount(s) at idx = s
+        T2 v[NR];
+        {
+            const int pc = __popcll(cur) & 3;
+            const T mag = (T)scale;
+            T2 s0;
+            s0.x = pc == 0 ? mag : (pc == 2 ? -mag : T(0));
+            s0.y = pc == 3 ? mag : (pc == 1 ? -mag : T(0));  // (-i)^1 = -i, (-i)^3 = +i
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                const bool hit = (int)cur == ((lane << R) | j);
+                v[j].x = hit ? s0.x : T(0);
+                v[j].y = hit ? s0.y : T(0);
+            }
+        }
+        __syncwarp();
+        bool in_l1 = true;  // layout 1: registers = qubits 0..R-1; layout 2: registers = qubits 5..n-1
+        for (int layer = 0; layer < r; ++layer) {
+            if (layer > 0 && phase) {
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    const int idx = in_l1 ? ((lane << R) | j) : ((j << 5) | lane);
+                    const T2 f = ph[wswz<R>(idx)], a = v[j];
+                    v[j].x = a.x * f.x - a.y * f.y;
+                    v[j].y = a.x * f.y + a.y * f.x;
+                }
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                // register qubits of the current layout
+#pragma unroll
+                for (int b = 0; b < R; ++b) {
+                    const T t = in_l1 ? tq[b] : tq[5 + b];
+#pragma unroll
+                    for (int j = 0; j < NR; ++j) {
+                        if (j & (1 << b)) continue;
+                        const T2 lo = v[j], hi = v[j | (1 << b)];
+                        v[j].x = lo.x + t * hi.x;
+                        v[j].y = lo.y + t * hi.y;
+                        v[j | (1 << b)].x = hi.x - t * lo.x;
+                        v[j | (1 << b)].y = hi.y - t * lo.y;
+                    }
+                }
+                if (half == 0) {
+                    // qubits R..4: lane bits in both layouts (layout 1: lane bit q - R; layout 2: lane bit q)
+#pragma unroll
+                    for (int k = 0; k < LEFT; ++k) {
+                        const int q = R + k;
+                        const int lb = in_l1 ? k : q;
+                        const T t = ((lane >> lb) & 1) ? -tq[q] : tq[q];
+#pragma unroll
+                        for (int j = 0; j < NR; ++j) {
+                            const T px = __shfl_xor_sync(FULL, v[j].x, 1 << lb), py = __shfl_xor_sync(FULL, v[j].y, 1 << lb);
+                            v[j].x += t * px;
+                            v[j].y += t * py;
+                        }
+                    }
+                    // transposition to the other layout through the warp's tile
+#pragma unroll
+                    for (int j = 0; j < NR; ++j) tile[wswz<R>(in_l1 ? ((lane << R) | j) : ((j << 5) | lane))] = v[j];
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < NR; ++j) v[j] = tile[wswz<R>(in_l1 ? ((j << 5) | lane) : ((lane << R) | j))];
+                    __syncwarp();
+                    in_l1 = !in_l1;
+                }
+            }
+        }
+        if (!in_l1) {  // measure in layout 1: 2^R consecutive indices per lane
+#pragma unroll
+            for (int j = 0; j < NR; ++j) tile[wswz<R>((j << 5) | lane)] = v[j];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < NR; ++j) v[j] = tile[wswz<R>((lane << R) | j)];
+            __syncwarp();
+        }
+        // ---- K3
+        double local = 0.0;
+#pragma unroll
+        for (int j = 0; j < NR; ++j) local += (double)(v[j].x * v[j].x + v[j].y * v[j].y);
+        double incl = local;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double x = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl += x;
+        }
+        const double total = __shfl_sync(FULL, incl, 31);
+        if (p.mode == QMC_MODE_PROBS) {
+            T *po = reinterpret_cast<T *>(p.probs_out);
+            T2 *ao = reinterpret_cast<T2 *>(p.amps_out);
+            const T inv = (T)(1.0 / total), inva = (T)(1.0 / sqrt(total));
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                const int idx = (lane << R) | j;
+                if (po) po[idx] = (v[j].x * v[j].x + v[j].y * v[j].y) * inv;
+                if (ao) {  // a = i^popcount(idx) S
+                    const int k = __popc(idx) & 3;
+                    T2 o;
+                    o.x = (k == 0 ? v[j].x : k == 1 ? -v[j].y : k == 2 ? -v[j].x : v[j].y) * inva;
+                    o.y = (k == 0 ? v[j].y : k == 1 ? v[j].x : k == 2 ? -v[j].y : -v[j].x) * inva;
+                    ao[idx] = o;
+                }
+            }
+            return;
+        }
+        const double target = u_meas * total;
+        const double lo = incl - local;
+        const unsigned owners = __ballot_sync(FULL, target < incl);
+        const int owner = owners ? (__ffs(owners) - 1) : 31;
+        int sel = NR - 1;
+        {
+            double c = lo;
+            bool found = false;
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                c += (double)(v[j].x * v[j].x + v[j].y * v[j].y);
+                if (!found && target < c) {
+                    sel = j;
+                    found = true;
+                }
+            }
+        }
+        const uint64_t sp = (uint64_t)((owner << R) | __shfl_sync(FULL, sel, owner));
+        if (p.mode == QMC_MODE_PROPOSE) {
+            if (lane == 0) p.proposals[chain] = sp;
+            return;
+        }
+        // ---- K4 (every lane evaluates identically)
+        const double e_sp = p.E[sp];
+        const bool acc = qmc_accept_dev(e_cur, e_sp, p.temperature, u_acc);
+        if (lane == 0) {
+            if (p.proposals) p.proposals[chain * p.n_hops + hop] = sp;
+            if (p.accepted) p.accepted[chain * p.n_hops + hop] = (uint8_t)acc;
+        }
+        if (lane == __popcll(cur ^ sp)) ++my_hist;
+        if (acc) {
+            cur = sp;
+            e_cur = e_sp;
+            ++n_acc;
+        }
+        if (lane == 0) qmc_visit(p.visit, cur);
+    }
+    if (lane == 0) {
+        if (p.final_state) p.final_state[chain] = cur;
+        if (p.acc_count) p.acc_count[chain] = n_acc;
+    }
+    if (p.hamming_hist && lane <= n) p.hamming_hist[chain * (n + 1) + lane] = my_hist;
+}
+
+template <typename T, int R>
+static int launch_warp_kernel(const WarpParams &wp, int64_t n_chains, cudaStream_t st) {
+    const size_t per_warp = 2 * ((size_t)1 << (R + 5)) * sizeof(typename Vec2<T>::type);
+    int warps = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
+    if (n_chains < warps) warps = (int)n_chains;
+    const size_t smem = per_warp * warps;
+    QMC_CUDA_TRY(cudaFuncSetAttribute(warp_chain_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * 4)));
+    warp_chain_kernel<T, R><<<(unsigned)((n_chains + warps - 1) / warps), warps * 32, smem, st>>>(wp);
+    return QMC_OK;
+}
+
 int qmc_small_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, const uint64_t *s_in,
                   uint64_t chain_id0, uint32_t hop0, double temperature, double g_lo, double g_hi, double dt,
                   uint64_t seed, int dtype, const double *gamma_arr, const int *r_arr, const double *u_arr,
@@ -346,6 +600,25 @@ int qmc_small_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                 m->max_terms_in_group, smem);
     QMC_REQUIRE(n_chains <= 0x7fffffffLL, QMC_ERR_BADARG, "too many chains for one launch");
     if (n_chains == 0) return QMC_OK;
+    // one-body mixers at 8 <= n <= 10: one warp per chain, state in registers, no block barriers (QUMCMC_NO_WARP_KERNEL=1
+    // keeps the CTA-per-chain kernel for A/B runs)
+    if (m->all_one_body && m->n >= 8 && m->n <= 10 && m->dD && m->dE && !getenv("QUMCMC_NO_WARP_KERNEL")) {
+        WarpParams wp;
+        wp.p = p;
+        wp.qweight = m->d_qweight;
+        wp.n_chains = n_chains;
+        int rcw = QMC_OK;
+        const bool f64 = dtype == QMC_DTYPE_F64;
+        switch (m->n) {
+            case 8: rcw = f64 ? launch_warp_kernel<double, 3>(wp, n_chains, st) : launch_warp_kernel<float, 3>(wp, n_chains, st); break;
+            case 9: rcw = f64 ? launch_warp_kernel<double, 4>(wp, n_chains, st) : launch_warp_kernel<float, 4>(wp, n_chains, st); break;
+            default: rcw = f64 ? launch_warp_kernel<double, 5>(wp, n_chains, st) : launch_warp_kernel<float, 5>(wp, n_chains, st); break;
+        }
+        if (rcw != QMC_OK) return rcw;
+        m->launches++;
+        QMC_CUDA_TRY(cudaGetLastError());
+        return QMC_OK;
+    }
     // threads per chain: one 4-amplitude orbit per thread keeps every lane busy in the term loop (2^n / 4), within
     // [64, 256]; QUMCMC_SMALL_NT overrides for A/B runs
     int threads = (int)std::min<size_t>(SMALL_NT, std::max<size_t>(64, N >> 2));

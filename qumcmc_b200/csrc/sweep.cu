@@ -2235,6 +2235,7 @@ struct qmc_shard {
     int k_fx = 0;
     ChainParams host_cp[2];         // physical-coordinate parameters of the current proposal, per layout
     float2 **d_peers[2] = {nullptr, nullptr};  // device tables: pointer to buffer `which` of every rank
+    std::vector<void *> h_peers[2];            // the same addresses on the host (copy-engine exchange)
     int xchg_ctas = 0;              // > 0: exchange passes of HI6 groups run as a persistent kernel on this many CTAs
     int r = 0;
 };
@@ -2608,6 +2609,29 @@ extern "C" int qmc_shard_set_peers(qmc_shard *sh, int which, void *const *ptrs_h
     const size_t bytes = sizeof(void *) * ((size_t)1 << sh->g);
     if (!sh->d_peers[which]) QMC_CUDA_TRY(cudaMalloc(&sh->d_peers[which], bytes));
     QMC_CUDA_TRY(cudaMemcpy(sh->d_peers[which], ptrs_host, bytes, cudaMemcpyHostToDevice));
+    sh->h_peers[which].assign(ptrs_host, ptrs_host + ((size_t)1 << sh->g));
+    return QMC_OK;
+}
+
+// Exchange of one chunk by the COPY ENGINES: the 2^(nl - chunk_bits) contiguous amplitudes of chunk `chunk` of this rank's
+// shard go to buffer `dst_which` of the rank that owns them after the qubit swap -- one cudaMemcpyAsync into the peer
+// mapping (NVLink P2P), no SM involved, so the HBM-bound local passes of the following chunks run beside it at full
+// occupancy.  chunk_bits >= log2(world): one destination rank per chunk (its top log2(world) bits).
+extern "C" int qmc_shard_copy_chunk(qmc_shard *sh, const void *state_dev, int dst_which, int chunk_bits, int64_t chunk,
+                                    void *stream) {
+    QMC_REQUIRE(sh && state_dev && (dst_which == 0 || dst_which == 1), QMC_ERR_BADARG, "qmc_shard_copy_chunk: bad argument");
+    QMC_REQUIRE(!sh->h_peers[dst_which].empty(), QMC_ERR_BADARG, "qmc_shard_copy_chunk: peer table %d not set (qmc_shard_set_peers)", dst_which);
+    QMC_REQUIRE(chunk_bits >= sh->g && chunk_bits <= sh->nl - TILE_BITS, QMC_ERR_BADARG, "qmc_shard_copy_chunk: chunk_bits %d", chunk_bits);
+    QMC_REQUIRE(chunk >= 0 && chunk < ((int64_t)1 << chunk_bits), QMC_ERR_BADARG, "chunk %lld of 2^%d", (long long)chunk, chunk_bits);
+    QMC_CUDA_TRY(cudaSetDevice(sh->m->device));
+    const int64_t len = (int64_t)1 << (sh->nl - chunk_bits);
+    const int64_t src0 = chunk << (sh->nl - chunk_bits);
+    const int dest = (int)(chunk >> (chunk_bits - sh->g));
+    const int64_t low = src0 & (((int64_t)1 << (sh->nl - sh->g)) - 1);
+    const int64_t dst0 = low | ((int64_t)sh->rank << (sh->nl - sh->g));
+    const float2 *src = reinterpret_cast<const float2 *>(state_dev) + src0;
+    float2 *dst = reinterpret_cast<float2 *>(sh->h_peers[dst_which][dest]) + dst0;
+    QMC_CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(float2) * (size_t)len, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return QMC_OK;
 }
 

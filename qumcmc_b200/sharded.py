@@ -28,6 +28,7 @@ _OPCODE = {FIRST: _lib.SHARD_OP_FIRST, MID: _lib.SHARD_OP_MID, SINGLE: _lib.SHAR
 def sharded_plan(r: int, n_groups: int, log2_world: int) -> List[Tuple[str, int, int]]:
     """Op list ``(kind, group, pre)`` of one proposal with ``r`` mixer layers.
 
+    The proposal starts in layout ``initial_layout(r)`` and ends in the identity layout.
     Positions 0..11 are the LO group; ``n_groups`` register groups of up to 8 cover the remaining local positions, group 0
     on top (it contains the ``g`` positions an exchange swaps with the rank bits).  Layer 1 is analytic (FIRST builds
     M|s> over all n qubits).  Every later layer j: the top group was mixed by the preceding FIRST/MID pass (after
@@ -46,12 +47,18 @@ def sharded_plan(r: int, n_groups: int, log2_world: int) -> List[Tuple[str, int,
         ops.append((EXCHANGE, 0, 0))
         if last:
             ops.append((SINGLE, 0, log2_world))
-            if (r - 1) % 2 == 1:  # end in the identity layout: the measurement CDF then runs in index order, like the
-                ops.append((EXCHANGE, 0, 0))  # reference's sequential sampler, and every proposal starts from layout 0
             ops.append((LO_FINAL, 0, 0))
         else:
             ops.append((MID, 0, log2_world))
     return ops
+
+
+def initial_layout(r: int) -> int:
+    """Layout parity a proposal with ``r`` mixer layers starts in.  There is one exchange per layer after the first and
+    the layout is never swapped back, so starting in layout ``(r - 1) & 1`` (FIRST builds the analytic product state
+    directly in it) ends every proposal in the identity layout: the measurement CDF runs in index order, like the
+    reference's sequential sampler, without a trailing exchange."""
+    return (r - 1) & 1 if r >= 2 else 0
 
 
 def shard_geometry(n_local: int) -> List[Tuple[int, int]]:
@@ -153,6 +160,11 @@ class ShardHandle:
                                                     state.data_ptr(), int(dst_which),
                                                     _device.current_stream_ptr(self.device)))
 
+    def copy_chunk(self, state, dst_which: int, chunk_bits: int, chunk: int) -> None:
+        """Copy-engine exchange of one chunk into buffer ``dst_which`` of the owning rank (no SM involved)."""
+        _lib.check(_lib.lib().qmc_shard_copy_chunk(self.handle, state.data_ptr(), int(dst_which), int(chunk_bits), int(chunk),
+                                                   _device.current_stream_ptr(self.device)))
+
     def op_chunk(self, kind: str, k: int, pre: int, layout: int, state, dst_which: int, chunk_bits: int, chunk: int) -> None:
         """One chunk of a SINGLE / LO_SINGLE pass; ``dst_which`` -1 = local, 0 / 1 = fused with the exchange."""
         _lib.check(_lib.lib().qmc_shard_op_chunk(self.handle, _OPCODE[kind], int(k), int(pre), int(layout),
@@ -208,14 +220,16 @@ class ShardedProposer:
         pass local and calls NCCL ``all_to_all_single``.
 
         ``mode``: ``"fused"`` -- one kernel per pass over the whole shard, the exchange pass serial after the local ones;
-        ``"overlap"`` -- the passes before each exchange run chunk by chunk (``chunk_bits``), the local ones on a
-        high-priority stream and the NVLink-bound exchange pass as a persistent kernel on ``xchg_ctas`` CTAs on a second
-        stream, so that HBM-bound and NVLink-bound work proceed side by side; ``None`` = the measured default
+        ``"overlap"`` -- the passes before each exchange run chunk by chunk (``chunk_bits``), the local ones on one
+        stream and the NVLink-bound exchange pass as a persistent kernel on ``xchg_ctas`` CTAs on a second (higher
+        priority) stream, so that HBM-bound and NVLink-bound work proceed side by side; ``"dma"`` -- every pass stays local
+        and each finished chunk is sent by the copy engines (``cudaMemcpyAsync`` into the peer mapping) while the following
+        chunks are computed: no SM is spent on the exchange; ``None`` = the measured default
         (environment override QUMCMC_SHARD_MODE / QUMCMC_SHARD_CTAS / QUMCMC_SHARD_CHUNK_BITS for A/B runs)."""
         import os
         if mode is None:
             mode = os.environ.get("QUMCMC_SHARD_MODE") or DEFAULT_MODE
-        if mode not in ("fused", "overlap"):
+        if mode not in ("fused", "overlap", "dma"):
             raise ValueError(f"unknown sharded mode {mode!r}")
         if xchg_ctas is None:
             xchg_ctas = int(os.environ.get("QUMCMC_SHARD_CTAS", DEFAULT_XCHG_CTAS))
@@ -249,7 +263,9 @@ class ShardedProposer:
         # HBM traffic floor (98 ms) sits too close to the NVLink floor (87 ms + the MID pass) for the overlap to pay
         if mode == "overlap" and (not self.fused or not self.handle.exchange_can_persist() or cmax < g):
             mode = "fused"   # no persistent variant of this shard's exchange pass (or nothing to chunk): serial schedule
-        if mode == "overlap" and chunk_bits is None:
+        if mode == "dma" and (not self.fused or cmax < g):
+            mode = "fused"
+        if mode in ("overlap", "dma") and chunk_bits is None:
             chunk_bits = max(g, min(DEFAULT_OVERLAP_CHUNK_BITS, cmax))
         self.mode = mode
         want = 0 if chunk_bits is None else min(int(chunk_bits), cmax)
@@ -280,7 +296,9 @@ class ShardedProposer:
         cmax = max_chunk_bits(self.handle.n_local)
         if mode == "overlap" and (not self.fused or not self.handle.exchange_can_persist() or cmax < g):
             mode = "fused"
-        if mode == "overlap" and chunk_bits is None:
+        if mode == "dma" and (not self.fused or cmax < g):
+            mode = "fused"
+        if mode in ("overlap", "dma") and chunk_bits is None:
             chunk_bits = max(g, min(DEFAULT_OVERLAP_CHUNK_BITS, cmax))
         want = 0 if chunk_bits is None else min(int(chunk_bits), cmax)
         self.mode = mode
@@ -345,11 +363,13 @@ class ShardedProposer:
         src, dst = self.buf[self.cur], 1 - self.cur
         self._xstream.wait_stream(main)
         self._cstream.wait_stream(main)
+        dma = self.mode == "dma"
         for c in chunk_order(self.chunk_bits, h.g, self.rank):
             ev = None
-            if len(run) > 1:
+            local = run if dma else run[:-1]
+            if local:
                 with torch.cuda.stream(self._cstream):
-                    for kind, k, pre in run[:-1]:
+                    for kind, k, pre in local:
                         h.op_chunk(kind, k, pre, self.layout, src, -1, self.chunk_bits, c)
                     ev = torch.cuda.Event()
                     ev.record(self._cstream)
@@ -357,7 +377,10 @@ class ShardedProposer:
             with torch.cuda.stream(self._xstream):
                 if ev is not None:
                     self._xstream.wait_event(ev)
-                h.op_chunk(kind, k, pre, self.layout, src, dst, self.chunk_bits, c)
+                if dma:   # copy engines: the chunk's amplitudes go to the owning rank's other buffer
+                    h.copy_chunk(src, dst, self.chunk_bits, c)
+                else:
+                    h.op_chunk(kind, k, pre, self.layout, src, dst, self.chunk_bits, c)
         main.wait_stream(self._cstream)
         main.wait_stream(self._xstream)
         self.dist.all_reduce(self._flag, group=self.group)   # barrier in stream order: every rank's stores have landed
@@ -366,6 +389,7 @@ class ShardedProposer:
         torch, dist, h = _device._torch(), self.dist, self.handle
         h.begin(s, gamma, r, delta_time, group_id)
         ops = sharded_plan(r, h.n_groups, h.g)
+        self.layout = initial_layout(r)
         i = 0
         while i < len(ops):
             kind, k, pre = ops[i]

@@ -15,10 +15,10 @@ from tests.shard_sim import logical_indices
 pytestmark = pytest.mark.gpu
 
 
-def _emulated_proposal(n, g, r, s, gamma, seed=11, us=(), fused=False, chunk_bits=0, on_device=False, xchg_ctas=0):
+def _emulated_proposal(n, g, r, s, gamma, seed=11, us=(), fused=False, chunk_bits=0, on_device=False, xchg_ctas=0, dma=False):
     import torch
     import qumcmc_b200 as q
-    from qumcmc_b200.sharded import EXCHANGE, ShardHandle, pick_owner, sharded_plan
+    from qumcmc_b200.sharded import EXCHANGE, ShardHandle, initial_layout, pick_owner, sharded_plan
     J, h = models.packaged_random_model(n, seed)
     model = q.IsingEnergyFunction(J, h)
     mixer = q.GenericMixer.OneBodyMixer(n)
@@ -31,7 +31,7 @@ def _emulated_proposal(n, g, r, s, gamma, seed=11, us=(), fused=False, chunk_bit
         if xchg_ctas:
             assert hd.exchange_can_persist()
             hd.set_exchange_ctas(xchg_ctas)
-    layout = 0
+    layout = initial_layout(r)
     ops = sharded_plan(r, hs[0].n_groups, g)
     if fused:   # the pass before every exchange stores straight into the owning "rank"'s other buffer (same device here)
         both = [bufs, [torch.zeros(1 << nl, dtype=torch.complex64, device=dev) for _ in range(W)]]
@@ -48,10 +48,13 @@ def _emulated_proposal(n, g, r, s, gamma, seed=11, us=(), fused=False, chunk_bit
             if chunk_bits and j > i and j < len(ops) and ops[j][0] == EXCHANGE:   # pipelined run, chunk by chunk
                 for R, hd in enumerate(hs):
                     for c in chunk_order(chunk_bits, g, R):
-                        for kind2, k2, pre2 in ops[i:j - 1]:
+                        for kind2, k2, pre2 in ops[i:j - (0 if dma else 1)]:
                             hd.op_chunk(kind2, k2, pre2, layout, both[cur][R], -1, chunk_bits, c)
-                        kind2, k2, pre2 = ops[j - 1]
-                        hd.op_chunk(kind2, k2, pre2, layout, both[cur][R], 1 - cur, chunk_bits, c)
+                        if dma:   # copy-engine exchange of the finished chunk
+                            hd.copy_chunk(both[cur][R], 1 - cur, chunk_bits, c)
+                        else:
+                            kind2, k2, pre2 = ops[j - 1]
+                            hd.op_chunk(kind2, k2, pre2, layout, both[cur][R], 1 - cur, chunk_bits, c)
                 cur ^= 1
                 layout ^= 1
                 i = j + 1
@@ -184,6 +187,23 @@ def test_shard_persistent_exchange_kernel_matches_staged(monkeypatch, n, g, r, c
     assert np.allclose(t0, t1, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("n,g,r,cb", [(22, 1, 3, 2), (24, 3, 4, 3), (25, 2, 5, 4), (25, 2, 2, 2), (26, 3, 6, 5)])
+def test_shard_copy_engine_exchange_matches_staged(n, g, r, cb):
+    """"dma" mode: every pass local, each finished chunk sent with qmc_shard_copy_chunk (cudaMemcpyAsync into the owning
+    rank's buffer) -- bit-identical amplitudes to pass-then-exchange."""
+    from qumcmc_b200.sharded import max_chunk_bits
+    assert g <= cb <= max_chunk_bits(n - g)
+    rng = np.random.default_rng(17 * n + g + r)
+    s = int(rng.integers(0, 1 << n))
+    gamma = float(rng.uniform(0.25, 0.6))
+    us = [0.33, 0.9]
+    _, _, p0, t0, l0, k0 = _emulated_proposal(n, g, r, s, gamma, us=us)
+    _, _, p1, t1, l1, k1 = _emulated_proposal(n, g, r, s, gamma, us=us, fused=True, chunk_bits=cb, dma=True)
+    assert l0 == l1 == 0
+    assert np.array_equal(p0, p1) and k0 == k1
+    assert np.allclose(t0, t1, rtol=1e-12, atol=0)
+
+
 def test_shard_rejects_bad_configurations():
     import qumcmc_b200 as q
     from qumcmc_b200 import _lib
@@ -199,6 +219,7 @@ def test_shard_rejects_bad_configurations():
 def _nccl_worker(rank, world, port, n, cases, q, fused):
     if fused == "overlap":
         os.environ["QUMCMC_SHARD_CTAS"] = "9"
+    mode = fused if fused in ("overlap", "dma") else "fused"
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -209,16 +230,15 @@ def _nccl_worker(rank, world, port, n, cases, q, fused):
         from qumcmc_b200.sharded import ShardedProposer
         J, h = models.packaged_random_model(n, 11)
         prop = ShardedProposer(qq.IsingEnergyFunction(J, h), qq.GenericMixer.OneBodyMixer(n), device=rank, fused=bool(fused),
-                               chunk_bits=(2 if fused in ("chunked", "overlap") else 0),
-                               mode=("overlap" if fused == "overlap" else "fused"))
-        assert prop.mode == ("overlap" if fused == "overlap" else "fused")
+                               chunk_bits=(2 if fused in ("chunked", "overlap", "dma") else 0), mode=mode)
+        assert prop.mode == mode
         out = [prop.propose(s, gamma, r, u) for (s, gamma, r, u) in cases]
         q.put((rank, out, prop.exchanges))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("fused", [False, True, "chunked", "overlap"])
+@pytest.mark.parametrize("fused", [False, True, "chunked", "overlap", "dma"])
 def test_shard_nccl_world2_matches_emulation(fused):
     import torch
     if torch.cuda.device_count() < 2:

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle
-from qumcmc_b200.sharded import EXCHANGE, pick_owner, plan_traffic_bytes, shard_geometry, sharded_plan
+from qumcmc_b200.sharded import EXCHANGE, initial_layout, pick_owner, plan_traffic_bytes, shard_geometry, sharded_plan
 from tests import models
 from tests.shard_sim import ShardSim, logical_indices
 
@@ -21,7 +21,7 @@ def _run_single_process(J, h, s, gamma, r, g, dt=0.8):
     sims = [ShardSim(J, h, al, R, g) for R in range(W)]
     for sm in sims:
         sm.begin(s, gamma, r, dt)
-    layout = 0
+    layout = initial_layout(r)
     for kind, k, pre in sharded_plan(r, len(shard_geometry(nl)), g):
         if kind == EXCHANGE:
             chunks = np.stack([sm.state.reshape(W, -1) for sm in sims])          # [rank][chunk][...]
@@ -45,8 +45,8 @@ def test_plan_shape_and_final_layout():
                 ops = sharded_plan(r, K, g)
                 kinds = [o[0] for o in ops]
                 assert kinds[0] == "first" and kinds[-1] == "lo_final"
-                assert kinds.count("exchange") % 2 == 0                     # ends in the identity layout
-                assert kinds.count("exchange") in (r - 1, r)
+                assert kinds.count("exchange") == r - 1                     # one exchange per layer after the first ...
+                assert (initial_layout(r) + kinds.count("exchange")) % 2 == 0  # ... and the identity layout at the end
                 assert kinds.count("first") + kinds.count("mid") == r - 1   # one phase layer per pass with P
                 assert kinds.count("lo_single") == r - 2
     hbm, nv = plan_traffic_bytes(sharded_plan(5, 4, 3), 33, 8)
@@ -72,7 +72,7 @@ def test_pick_owner_is_the_sequential_cdf():
     assert pick_owner(totals, 1.0)[0] == 3
 
 
-@pytest.mark.parametrize("n,g,r", [(19, 1, 1), (19, 1, 2), (19, 1, 3), (20, 2, 4), (21, 1, 5), (21, 3, 2)])
+@pytest.mark.parametrize("n,g,r", [(19, 1, 1), (19, 1, 2), (19, 1, 3), (20, 2, 4), (21, 1, 5), (21, 3, 2), (20, 2, 6)])
 def test_sharded_schedule_reproduces_oracle(n, g, r):
     J, h = models.packaged_random_model(n, 11)
     masks, w = models.one_body(n)
@@ -98,7 +98,7 @@ def _gloo_worker(rank, world, port, n, r, q):
         s, gamma = 123457 % (1 << n), 0.41
         sim = ShardSim(J, h, oracle.alpha(J, h), rank, g)
         sim.begin(s, gamma, r, 0.8)
-        layout = 0
+        layout = initial_layout(r)
         for kind, k, pre in sharded_plan(r, len(shard_geometry(nl)), g):
             if kind == EXCHANGE:
                 src = torch.from_numpy(np.ascontiguousarray(sim.state).view(np.float64))
