@@ -53,6 +53,7 @@ struct ProbeArgs {
 
 extern "C" int qmc_transition_probs(qmc_model *m, uint64_t s, double gamma, int r, double delta_time, int group,
                                     int dtype, void *probs_dev, void *amps_dev, void *stream) {
+    QMC_NVTX("qmc_transition_probs");
     QMC_REQUIRE(m && (probs_dev || amps_dev), QMC_ERR_BADARG, "qmc_transition_probs: null argument");
     QMC_REQUIRE(m->n >= 64 || s < (1ULL << m->n), QMC_ERR_BADARG, "qmc_transition_probs: state out of range");
     QMC_REQUIRE(group >= 0 && group < m->n_groups, QMC_ERR_BADARG, "qmc_transition_probs: group %d of %d", group, m->n_groups);
@@ -73,6 +74,7 @@ extern "C" int qmc_transition_probs(qmc_model *m, uint64_t s, double gamma, int 
 extern "C" int qmc_propose(qmc_model *m, int64_t n_chains, const uint64_t *s_in_dev, const double *gamma_dev,
                            const int *r_dev, const double *u_dev, const int *group_dev, double delta_time, int dtype,
                            uint64_t *s_out_dev, void *stream) {
+    QMC_NVTX("qmc_propose");
     QMC_REQUIRE(m && (n_chains == 0 || (s_in_dev && gamma_dev && r_dev && u_dev && s_out_dev)), QMC_ERR_BADARG,
                 "qmc_propose: null argument");
     return dispatch(m, QMC_MODE_PROPOSE, n_chains, 1, s_in_dev, 0, 0, 1.0, 0.0, 0.0, delta_time, 0, dtype, gamma_dev,
@@ -84,6 +86,7 @@ extern "C" int qmc_run_chains(qmc_model *m, int64_t n_chains, int64_t n_hops, co
                               double delta_time, uint64_t seed, int dtype, uint64_t *proposals_dev,
                               uint8_t *accepted_dev, uint64_t *final_state_dev, int64_t *acc_count_dev,
                               int64_t *hamming_hist_dev, void *stream) {
+    QMC_NVTX("qmc_run_chains");
     QMC_REQUIRE(m && final_state_dev, QMC_ERR_BADARG, "qmc_run_chains: final_state_dev is required");
     QMC_REQUIRE(temperature > 0.0, QMC_ERR_BADARG, "qmc_run_chains: temperature must be positive");
     return dispatch(m, QMC_MODE_CHAIN, n_chains, n_hops, s0_dev, chain_id0, hop0, temperature, gamma_lo, gamma_hi,
@@ -99,6 +102,7 @@ extern "C" int qmc_run_chains_host(qmc_model *m, int64_t n_chains, int64_t n_hop
                                    double gamma_hi, double delta_time, uint64_t seed, int dtype,
                                    uint64_t *proposals_host, uint8_t *accepted_host, uint64_t *final_state_host,
                                    int64_t *acc_count_host, int64_t *hamming_hist_host) {
+    QMC_NVTX("qmc_run_chains_host");
     QMC_REQUIRE(m && final_state_host, QMC_ERR_BADARG, "qmc_run_chains_host: final_state_host is required");
     QMC_REQUIRE(n_chains >= 0 && n_hops >= 0, QMC_ERR_BADARG, "negative chain or hop count");
     if (n_chains == 0) return QMC_OK;

@@ -105,6 +105,7 @@ extern "C" int qmc_classical_chains(qmc_model *m, int64_t n_chains, int64_t n_ho
                                     const int *kinds, const uint64_t *params, const double *probs, uint64_t seed,
                                     uint64_t *proposals_dev, uint8_t *accepted_dev, uint64_t *final_state_dev,
                                     int64_t *acc_count_dev, int64_t *hamming_hist_dev, void *stream) {
+    QMC_NVTX("qmc_classical_chains");
     QMC_REQUIRE(m && final_state_dev && kinds && params, QMC_ERR_BADARG, "qmc_classical_chains: null argument");
     QMC_REQUIRE(n_chains >= 0 && n_hops >= 0, QMC_ERR_BADARG, "negative chain or hop count");
     QMC_REQUIRE(n_methods >= 1 && n_methods <= QMC_MAX_CLASSICAL_METHODS, QMC_ERR_BADARG,

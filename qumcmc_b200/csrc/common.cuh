@@ -6,7 +6,21 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only (NVTX v3): ranges cost nothing unless a profiler is attached
+
 #include "../../include/qumcmc_b200.h"
+
+// NVTX range over a scope (SURVEY section 5 "tracing"): every C-ABI entry point and every hop of the chain drivers is a
+// named range, so an nsys / ncu timeline reads in the vocabulary of the path (proposal, hop, pass, sample).
+struct QmcNvtxRange {
+    explicit QmcNvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~QmcNvtxRange() { nvtxRangePop(); }
+    QmcNvtxRange(const QmcNvtxRange &) = delete;
+    QmcNvtxRange &operator=(const QmcNvtxRange &) = delete;
+};
+#define QMC_NVTX_CAT2(a, b) a##b
+#define QMC_NVTX_CAT(a, b) QMC_NVTX_CAT2(a, b)
+#define QMC_NVTX(name) QmcNvtxRange QMC_NVTX_CAT(qmc_nvtx_, __LINE__)(name)
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing: no exceptions cross the ABI; message kept thread-local

@@ -807,6 +807,7 @@ static int general_run_t(qmc_model *m, GeneralWorkspace *w, GenArgs a, int64_t n
         const int64_t nc = std::min<int64_t>(batch, n_chains - c0);
         a.chain0 = c0;
         for (int64_t hop = 0; hop < hops; ++hop) {
+            QMC_NVTX("general hop: prepare, Hadamard-basis passes, sample+accept");
             a.hop = hop0 + (uint32_t)hop;
             a.hop_index = hop;
             gen_prepare_kernel<<<(unsigned)((nc + 127) / 128), 128, 0, st>>>(a, nc, hop == 0);

@@ -544,6 +544,7 @@ extern "C" int qmc_energies_host(qmc_model *m, const uint64_t *idx_host, int64_t
 
 extern "C" int qmc_exact_sampling(qmc_model *m, double beta, double *logZ_dev, double *energies_dev,
                                   double *probs_dev, void *stream) {
+    QMC_NVTX("qmc_exact_sampling");
     QMC_REQUIRE(m && logZ_dev, QMC_ERR_BADARG, "qmc_exact_sampling: null argument");
     QMC_CUDA_TRY(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;

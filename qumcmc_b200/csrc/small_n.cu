@@ -322,6 +322,66 @@ struct WarpParams {
 template <int R>
 __device__ __forceinline__ int wswz(int idx) { return idx ^ ((idx >> R) & 31); }
 
+// One mixer layer (preceded by the phase layer when `apply_phase`) that starts in layout 1 (L1 = true: registers = qubits
+// 0..R-1, index = lane << R | j) or layout 2 (registers = qubits 5..n-1, index = j << 5 | lane) and ends in the other one.
+// The layout is a template parameter, so every shared-memory slot is a compile-time function of j plus one lane term.
+template <typename T, int R, bool L1>
+__device__ __forceinline__ void warp_layer(typename Vec2<T>::type (&v)[1 << R], const T my_t,
+                                           typename Vec2<T>::type *tile, const typename Vec2<T>::type *ph, bool apply_phase,
+                                           int lane) {  // my_t: lane q holds tan(theta_q), fetched by shuffle where it is used
+    using T2 = typename Vec2<T>::type;
+    constexpr int NR = 1 << R;
+    constexpr int LEFT = 5 - R;
+    const unsigned FULL = 0xffffffffu;
+    auto idx_of = [&](bool l1, int j) { return l1 ? ((lane << R) | j) : ((j << 5) | lane); };
+    if (apply_phase) {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            const T2 f = ph[wswz<R>(idx_of(L1, j))], a = v[j];
+            v[j].x = a.x * f.x - a.y * f.y;
+            v[j].y = a.x * f.y + a.y * f.x;
+        }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const bool l1 = half == 0 ? L1 : !L1;
+#pragma unroll
+        for (int b = 0; b < R; ++b) {  // register qubits of the current layout
+            const T t = __shfl_sync(FULL, my_t, l1 ? b : 5 + b);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                if (j & (1 << b)) continue;
+                const T2 lo = v[j], hi = v[j | (1 << b)];
+                v[j].x = lo.x + t * hi.x;
+                v[j].y = lo.y + t * hi.y;
+                v[j | (1 << b)].x = hi.x - t * lo.x;
+                v[j | (1 << b)].y = hi.y - t * lo.y;
+            }
+        }
+        if (half == 0) {
+#pragma unroll
+            for (int k = 0; k < LEFT; ++k) {  // qubits R..4: lane bits in both layouts (layout 1: lane bit q - R; layout 2: q)
+                const int q = R + k;
+                const int lb = l1 ? k : q;
+                const T tq_ = __shfl_sync(FULL, my_t, q);
+                const T t = ((lane >> lb) & 1) ? -tq_ : tq_;
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    const T px = __shfl_xor_sync(FULL, v[j].x, 1 << lb), py = __shfl_xor_sync(FULL, v[j].y, 1 << lb);
+                    v[j].x += t * px;
+                    v[j].y += t * py;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NR; ++j) tile[wswz<R>(idx_of(l1, j))] = v[j];  // transposition through the warp's tile
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < NR; ++j) v[j] = tile[wswz<R>(idx_of(!l1, j))];
+            __syncwarp();
+        }
+    }
+}
+
 template <typename T, int R>
 __global__ void __launch_bounds__(128) warp_chain_kernel(const WarpParams wp) {
     using T2 = typename Vec2<T>::type;
@@ -379,15 +439,13 @@ __global__ void __launch_bounds__(128) warp_chain_kernel(const WarpParams wp) {
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) scale *= __shfl_xor_sync(FULL, scale, off);
         scale = pow(scale, (double)r);
-        T tq[n];
-#pragma unroll
-        for (int q = 0; q < n; ++q) tq[q] = (T)__shfl_sync(FULL, my_t, q);
+        const T tq = (T)my_t;  // lane q: tan(theta_q)
         // phase factors of this proposal (same c for all r - 1 layers), layout-independent slots
         const bool phase = p.phase_active && r > 1;
         if (phase) {
             const double c = (1.0 - gamma) * p.alpha * p.dt;
-#pragma unroll
-            for (int j = 0; j < NR; ++j) {
+#pragma unroll 4
+            for (int j = 0; j < NR; ++j) {  // four in flight (a single warp has nothing else to hide the sincos latency), not 2^R copies
                 const int idx = (lane << R) | j;
                 ph[wswz<R>(idx)] = phase_factor(c * p.D[idx], T(0));
             }
@@ -408,59 +466,14 @@ __global__ void __launch_bounds__(128) warp_chain_kernel(const WarpParams wp) {
             }
         }
         __syncwarp();
-        bool in_l1 = true;  // layout 1: registers = qubits 0..R-1; layout 2: registers = qubits 5..n-1
+        // layers alternate the layout they start in (two instantiations of the layer body: the code must stay inside the
+        // instruction cache when hundreds of warps run different hops)
+#pragma unroll 1
         for (int layer = 0; layer < r; ++layer) {
-            if (layer > 0 && phase) {
-#pragma unroll
-                for (int j = 0; j < NR; ++j) {
-                    const int idx = in_l1 ? ((lane << R) | j) : ((j << 5) | lane);
-                    const T2 f = ph[wswz<R>(idx)], a = v[j];
-                    v[j].x = a.x * f.x - a.y * f.y;
-                    v[j].y = a.x * f.y + a.y * f.x;
-                }
-            }
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                // register qubits of the current layout
-#pragma unroll
-                for (int b = 0; b < R; ++b) {
-                    const T t = in_l1 ? tq[b] : tq[5 + b];
-#pragma unroll
-                    for (int j = 0; j < NR; ++j) {
-                        if (j & (1 << b)) continue;
-                        const T2 lo = v[j], hi = v[j | (1 << b)];
-                        v[j].x = lo.x + t * hi.x;
-                        v[j].y = lo.y + t * hi.y;
-                        v[j | (1 << b)].x = hi.x - t * lo.x;
-                        v[j | (1 << b)].y = hi.y - t * lo.y;
-                    }
-                }
-                if (half == 0) {
-                    // qubits R..4: lane bits in both layouts (layout 1: lane bit q - R; layout 2: lane bit q)
-#pragma unroll
-                    for (int k = 0; k < LEFT; ++k) {
-                        const int q = R + k;
-                        const int lb = in_l1 ? k : q;
-                        const T t = ((lane >> lb) & 1) ? -tq[q] : tq[q];
-#pragma unroll
-                        for (int j = 0; j < NR; ++j) {
-                            const T px = __shfl_xor_sync(FULL, v[j].x, 1 << lb), py = __shfl_xor_sync(FULL, v[j].y, 1 << lb);
-                            v[j].x += t * px;
-                            v[j].y += t * py;
-                        }
-                    }
-                    // transposition to the other layout through the warp's tile
-#pragma unroll
-                    for (int j = 0; j < NR; ++j) tile[wswz<R>(in_l1 ? ((lane << R) | j) : ((j << 5) | lane))] = v[j];
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < NR; ++j) v[j] = tile[wswz<R>(in_l1 ? ((j << 5) | lane) : ((lane << R) | j))];
-                    __syncwarp();
-                    in_l1 = !in_l1;
-                }
-            }
+            if (layer & 1) warp_layer<T, R, false>(v, tq, tile, ph, phase, lane);
+            else warp_layer<T, R, true>(v, tq, tile, ph, phase && layer > 0, lane);
         }
-        if (!in_l1) {  // measure in layout 1: 2^R consecutive indices per lane
+        if (r & 1) {  // odd r ends in layout 2: back to layout 1 (2^R consecutive indices per lane) for the measurement
 #pragma unroll
             for (int j = 0; j < NR; ++j) tile[wswz<R>((j << 5) | lane)] = v[j];
             __syncwarp();

@@ -2094,6 +2094,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         m->launches++;
         const int64_t hops = mode == QMC_MODE_CHAIN ? n_hops : 1;
         for (int64_t hop = 0; hop < hops; ++hop) {
+            QMC_NVTX("sweep hop: prepare, schedule, sweeps, sample+accept");
             h.hop = hop;
             hop_prepare_kernel<<<gb, 128, 0, st>>>(h, w->params);
             schedule_kernel<<<1, 1024, 0, st>>>(w->params, nc, r_max, w->order, generic ? 0 : 1,
@@ -2509,6 +2510,7 @@ extern "C" int qmc_shard_begin(qmc_shard *sh, uint64_t s, double gamma, int r, d
 // swapped-in qubits) | 3 LO_SINGLE | 4 LO_FINAL (segment sums; r == 1: of the analytic product state).
 static int shard_op_impl(qmc_shard *sh, int op, int k, int pre, int layout, void *state_dev, int dst_which, void *stream,
                          int chunk_bits = 0, int64_t chunk = 0) {
+    QMC_NVTX(dst_which >= 0 ? "shard pass + exchange" : "shard pass");
     QMC_REQUIRE(sh && state_dev, QMC_ERR_BADARG, "qmc_shard_op: null argument");
     QMC_REQUIRE(dst_which < 0 || (dst_which < 2 && sh->d_peers[dst_which]), QMC_ERR_BADARG,
                 "qmc_shard_op_exchange: peer table %d not set (qmc_shard_set_peers)", dst_which);

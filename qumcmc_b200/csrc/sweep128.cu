@@ -871,6 +871,7 @@ int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, c
         m->launches++;
         const int64_t hops = mode == QMC_MODE_CHAIN ? n_hops : 1;
         for (int64_t hop = 0; hop < hops; ++hop) {
+            QMC_NVTX("sweep128 hop: prepare, schedule, sweeps, sample+accept");
             h.hop = hop;
             hop_prepare128_kernel<<<gb, 128, 0, st>>>(h, w->params);
             schedule128_kernel<<<1, 1024, 0, st>>>(w->params, nc, r_max, w->order);

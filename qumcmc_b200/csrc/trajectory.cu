@@ -150,6 +150,7 @@ extern "C" int qmc_trajectory_stats(qmc_model *m, int64_t n_chains, int64_t n_ho
                                     const double *boltz_probs_dev, uint64_t *markov_chain_dev, double *energy_diff_dev,
                                     double *running_mag_dev, int64_t *hamming_acc_rej_dev, double *running_kl_dev,
                                     void *stream) {
+    QMC_NVTX("qmc_trajectory_stats");
     QMC_REQUIRE(m && s0_dev && (n_hops == 0 || (proposals_dev && accepted_dev)), QMC_ERR_BADARG,
                 "qmc_trajectory_stats: null argument");
     QMC_REQUIRE(n_chains >= 0 && n_hops >= 0, QMC_ERR_BADARG, "negative chain or hop count");
