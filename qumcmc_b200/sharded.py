@@ -203,9 +203,11 @@ def pick_owner(totals: np.ndarray, u: float) -> Tuple[int, float]:
     return owner, target - cum[owner]
 
 
-# Schedule defaults of ShardedProposer (measured on 8 B200, n = 36: see DESIGN.md section 5 and profiles/)
-DEFAULT_MODE = "fused"
-DEFAULT_XCHG_CTAS = 148
+# Schedule defaults of ShardedProposer, measured on 8 B200 at n = 36 (profiles/r2j_shard_sweep_8gpu.jsonl), 5-layer proposal:
+# fused 0.645 s, overlap (8-16 chunks, 222 persistent exchange CTAs) 0.552 s, dma (32 chunks) 0.513 s; 2-layer proposal:
+# 0.168 / 0.156 / 0.148 s.  On 2 B200 (n = 34) the three are within 4 % (0.513 / 0.492 / 0.508 s).
+DEFAULT_MODE = "dma"
+DEFAULT_XCHG_CTAS = 222
 DEFAULT_OVERLAP_CHUNK_BITS = 5
 
 
@@ -259,8 +261,8 @@ class ShardedProposer:
         # pipelined exchange: the passes of a layer that precede the exchange run chunk by chunk, the last of them storing
         # into the peers' buffers on a second stream while the next chunk's local passes run (chunk_bits=0 disables)
         cmax = max_chunk_bits(self.handle.n_local)
-        # default off: measured on 8 B200 (n=36, 5 layers) 0.653 s with 8 chunks vs 0.647 s unchunked -- per layer the
-        # HBM traffic floor (98 ms) sits too close to the NVLink floor (87 ms + the MID pass) for the overlap to pay
+        # (round 1's chunked pipeline with a FULL-grid exchange kernel gained nothing: 0.653 s vs 0.647 s unchunked -- the
+        # NVLink-bound CTAs took every slot; the persistent-kernel and copy-engine schedules below are what overlaps)
         if mode == "overlap" and (not self.fused or not self.handle.exchange_can_persist() or cmax < g):
             mode = "fused"   # no persistent variant of this shard's exchange pass (or nothing to chunk): serial schedule
         if mode == "dma" and (not self.fused or cmax < g):
