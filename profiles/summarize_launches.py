@@ -10,4 +10,4 @@ for (id_,k),d in per.items():
     a=agg[re.sub(r'\(.*','',k)]; a[0]+=1; a[1]+=t_us; a[2]+=B('dram__bytes_read.sum')+B('dram__bytes_write.sum')
 tot=sum(a[1] for a in agg.values())
 for k,a in sorted(agg.items(), key=lambda x:-x[1][1]):
-    print(f"{a[1]:10.0f} us {100*a[1]/tot:5.1f}% n={a[0]:4d} avg {a[1]/a[0]:8.1f} us  {a[2]/a[1]/1e3:7.1f} GB/s  {k[:80]}")
+    print(f"{a[1]:10.0f} us {100*a[1]/tot:5.1f}% n={a[0]:4d} avg {a[1]/a[0]:8.1f} us  {a[2]/a[1]/1e3:7.1f} GB/s  dram {a[2]/1e9:8.3f} GB  {k[:80]}")

@@ -27,8 +27,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 
 #include "common.cuh"
+#include "group_sched.cuh"
 
 namespace {
 
@@ -1557,10 +1560,7 @@ struct SweepWorkspace {
     int k_fx = 0;
     std::vector<HiGroup> groups;  // n > 20: register groups above the LO qubits, with their phase tables
     std::vector<cudaEvent_t> ev;
-    // L2-resident group schedule (n <= 20): side streams + fork / join events, created on first use
-    std::vector<cudaStream_t> aux;
-    std::vector<cudaEvent_t> ev_join;
-    cudaEvent_t ev_fork = nullptr;
+    QmcGroupSched gsched;  // L2-resident group schedule (n <= 20): side streams + fork / join events
 };
 
 void qmc_sweep_free(qmc_model *m) {
@@ -1581,9 +1581,7 @@ void qmc_sweep_free(qmc_model *m) {
     cudaFree(w->dhq);
     for (auto &G : w->groups) free_group_tables(G);
     for (auto e : w->ev) cudaEventDestroy(e);
-    for (auto e : w->ev_join) cudaEventDestroy(e);
-    if (w->ev_fork) cudaEventDestroy(w->ev_fork);
-    for (auto q : w->aux) cudaStreamDestroy(q);
+    w->gsched.destroy();
     delete w;
     m->sweep = nullptr;
 }
@@ -1718,19 +1716,6 @@ static int set_smem_once(K kernel, DevMask &done, int bytes = TILE * 8) {
     return QMC_OK;
 }
 
-static int ensure_aux_streams(SweepWorkspace *w, int count) {
-    if (!w->ev_fork) QMC_CUDA_TRY(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
-    while ((int)w->aux.size() < count) {
-        cudaStream_t q = nullptr;
-        cudaEvent_t e = nullptr;
-        QMC_CUDA_TRY(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
-        w->aux.push_back(q);
-        QMC_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        w->ev_join.push_back(e);
-    }
-    return QMC_OK;
-}
-
 // Launch-time variant: fast = normalisation folded into the initial product state (phase factors of unit modulus)
 // and one mixer multiplier per chain served from the constant bank (c_tan[], position-indexed).
 struct SweepTune {
@@ -1749,8 +1734,8 @@ static int launch_lo_v(const SweepArgs &a, const int *order, int off, int64_t ti
             int rc64 = set_smem_once(lo_sweep_kernel<LO_MID, 64, true>, done64, TILE * 4);
             if (rc64 != QMC_OK) return rc64;
             SweepArgs a64 = a;
-            static const int pf64 = getenv("QUMCMC_LO_PF") ? atoi(getenv("QUMCMC_LO_PF")) : 2 * a.pf_dist;
-            a64.pf_dist = pf64;
+            static const int pf64_env = getenv("QUMCMC_LO_PF") ? atoi(getenv("QUMCMC_LO_PF")) : -1;
+            a64.pf_dist = pf64_env >= 0 && a.pf_dist > 0 ? pf64_env : 2 * a.pf_dist;
             lo_sweep_kernel<LO_MID, 64, true><<<dim3((unsigned)(2 * tiles), (unsigned)count), 64, TILE * 4, st>>>(a64, order, off, off);
             return QMC_OK;
         }
@@ -2074,17 +2059,9 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     }
 
     QMC_REQUIRE(r_max <= SCHED_RMAX, QMC_ERR_UNSUPPORTED, "delta_time=%g gives up to %d Trotter layers (> %d)", dt, r_max, SCHED_RMAX);
-    std::vector<int> rhist(r_max + 2, 0), rpos;
-    // L2-resident group schedule (two-group path): chains per group = L2 budget / statevector bytes
-    int l2_group = 0, l2_streams = 1;
-    if (!generic) {
-        // read per call (not cached): the parity tests switch schedules inside one process
-        const int l2_mib = getenv("QUMCMC_L2_GROUP_MIB") ? atoi(getenv("QUMCMC_L2_GROUP_MIB")) : 48;
-        const int l2_str = getenv("QUMCMC_L2_STREAMS") ? atoi(getenv("QUMCMC_L2_STREAMS")) : 2;
-        l2_streams = std::min(8, std::max(1, l2_str));
-        if (l2_mib > 0)
-            l2_group = (int)std::max<int64_t>(1, std::min<int64_t>(4096, ((int64_t)l2_mib << 20) / ((int64_t)sizeof(float2) << n)));
-    }
+    std::vector<int> rhist(r_max + 2, 0);
+    QmcGroupKnobs l2k;  // L2-resident group schedule (two-group path only), see group_sched.cuh
+    if (!generic) l2k = qmc_group_knobs((int64_t)sizeof(float2) << n, 4);
     for (int64_t c0 = 0; c0 < n_chains; c0 += batch) {
         const int64_t nc = std::min<int64_t>(batch, n_chains - c0);
         HopArgs h;
@@ -2154,6 +2131,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                 sum_r += r;
             }
             int launched = 0;
+            const auto host_t0 = std::chrono::steady_clock::now();
             if (generic) {
                 // order[] is sorted by r descending: one schedule per distinct r over its contiguous range
                 int off = 0;
@@ -2166,62 +2144,23 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
             } else {
                 int base[2] = {0, 0};  // start of the odd-r / even-r class in order[]
                 for (int r = 1; r <= r_max; r += 2) base[1] += rhist[r];  // even class starts after all odd-r chains
-                if (l2_group > 0 && nc > l2_group) {
-                    // L2-resident schedule: `l2_group` chains whose statevectors fit the L2 together run ALL their sweeps
-                    // back to back (order[] is sorted by r inside a parity class, so a group is one or two r values), then
-                    // the next group starts.  A sweep rewrites the lines the previous one left dirty in the L2: HBM sees one
-                    // write-back per chain and proposal instead of r - 1 read + write passes.  Groups alternate over a few
-                    // streams so that the tail of one group's launch is filled by the head of another's.
-                    rc = ensure_aux_streams(w, l2_streams);
-                    if (rc != QMC_OK) return rc;
-                    QMC_CUDA_TRY(cudaEventRecord(w->ev_fork, st));
-                    for (int i = 0; i < l2_streams; ++i) QMC_CUDA_TRY(cudaStreamWaitEvent(w->aux[i], w->ev_fork, 0));
-                    rpos.resize((size_t)nc);
-                    {
-                        int k = 0;
-                        for (int cls = 1; cls >= 0; --cls)  // odd class first
-                            for (int r = r_max; r >= 1; --r)
-                                if ((r & 1) == cls)
-                                    for (int i = 0; i < rhist[r]; ++i) rpos[k++] = r;
-                    }
-                    int gi = 0;
-                    for (int cls = 0; cls < 2; ++cls) {  // cls 0: r odd (LO at odd steps), cls 1: r even
-                        const int end = cls == 0 ? base[1] : (int)nc;
-                        for (int g0 = base[cls]; g0 < end; g0 += l2_group, ++gi) {
-                            const int cnt = std::min(l2_group, end - g0);
-                            cudaStream_t sg = w->aux[gi % l2_streams];
-                            const int rg = rpos[g0];
-                            int gt = cnt;  // chains of the group with r > step (a prefix: r descends)
-                            for (int step = 1; step <= rg; ++step) {
-                                int eq = 0;
-                                while (gt > 0 && rpos[g0 + gt - 1] <= step) { --gt; ++eq; }  // r == step: class parity
-                                const bool lo_step = ((step & 1) == 1) == (cls == 0);
-                                if (lo_step) {
-                                    if (gt > 0) {
-                                        rc = step == 1 ? launch_lo<LO_FIRST>(tune, a, w->order, g0, tiles, gt, sg)
-                                                        : launch_lo<LO_MID>(tune, a, w->order, g0, tiles, gt, sg);
-                                        if (rc != QMC_OK) return rc;
-                                        ++launched;
-                                    }
-                                    if (eq > 0) {
-                                        rc = step == 1 ? launch_lo<LO_FINAL1>(tune, a, w->order, g0 + gt, tiles, eq, sg)
-                                                       : launch_lo<LO_FINAL>(tune, a, w->order, g0 + gt, tiles, eq, sg);
-                                        if (rc != QMC_OK) return rc;
-                                        ++launched;
-                                    }
-                                } else if (gt > 0) {
-                                    rc = step == 1 ? launch_hi<true>(tune, n, a, w->order, g0, tiles, gt, sg)
-                                                    : launch_hi<false>(tune, n, a, w->order, g0, tiles, gt, sg);
-                                    if (rc != QMC_OK) return rc;
-                                    ++launched;
-                                }
-                            }
+                if (l2k.group > 0 && nc > l2k.group) {
+                    SweepArgs ag = a;
+                    if (!l2k.prefetch) ag.pf_dist = 0;  // the tiles are L2 hits already: no prefetch instructions
+                    auto lo = [&](int kind, int off, int count, cudaStream_t sg) {
+                        switch (kind) {
+                            case QMC_GS_FIRST: return launch_lo<LO_FIRST>(tune, ag, w->order, off, tiles, count, sg);
+                            case QMC_GS_MID: return launch_lo<LO_MID>(tune, ag, w->order, off, tiles, count, sg);
+                            case QMC_GS_FINAL: return launch_lo<LO_FINAL>(tune, ag, w->order, off, tiles, count, sg);
+                            default: return launch_lo<LO_FINAL1>(tune, ag, w->order, off, tiles, count, sg);
                         }
-                    }
-                    for (int i = 0; i < l2_streams; ++i) {
-                        QMC_CUDA_TRY(cudaEventRecord(w->ev_join[i], w->aux[i]));
-                        QMC_CUDA_TRY(cudaStreamWaitEvent(st, w->ev_join[i], 0));
-                    }
+                    };
+                    auto hi = [&](bool first, int off, int count, cudaStream_t sg) {
+                        return first ? launch_hi<true>(tune, n, ag, w->order, off, tiles, count, sg)
+                                     : launch_hi<false>(tune, n, ag, w->order, off, tiles, count, sg);
+                    };
+                    rc = qmc_group_schedule(w->gsched, l2k, st, (int)nc, r_max, rhist, lo, hi, launched);
+                    if (rc != QMC_OK) return rc;
                 } else
                 for (int step = 1; step <= r_max; ++step) {
                     const int p = step & 1;                 // chains with r == step (mod 2) sweep LO at this step
@@ -2252,6 +2191,11 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                 }
             }
             m->launches += launched;
+            if (l2k.debug)
+                fprintf(stderr, "[qumcmc] hop %lld: %d sweep launches enqueued in %.3f ms (group %d chains x %d streams)\n",
+                        (long long)hop, launched,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(),
+                        l2k.group, l2k.streams);
             if (m->profile) {
                 QMC_CUDA_TRY(cudaEventRecord(e1, st));
                 w->ev.push_back(e0);

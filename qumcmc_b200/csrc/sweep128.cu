@@ -21,6 +21,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "group_sched.cuh"
 
 namespace {
 
@@ -674,6 +675,7 @@ struct Sweep128Workspace {
     double R_lo[APT], R_hi[APT];
     double *dJq = nullptr, *dhq = nullptr;
     bool tables_ready = false;
+    QmcGroupSched gsched;  // L2-resident group schedule: side streams + fork / join events
 };
 
 void qmc_sweep128_free(qmc_model *m) {
@@ -681,6 +683,7 @@ void qmc_sweep128_free(qmc_model *m) {
     if (!w) return;
     cudaFree(w->state); cudaFree(w->params); cudaFree(w->segsum); cudaFree(w->hist); cudaFree(w->order);
     cudaFree(w->af_lo); cudaFree(w->af_hi); cudaFree(w->dJq); cudaFree(w->dhq);
+    w->gsched.destroy();
     delete w;
     m->sweep128 = nullptr;
 }
@@ -837,6 +840,7 @@ int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, c
     }
     QMC_REQUIRE(r_max <= SCHED_RMAX, QMC_ERR_UNSUPPORTED, "delta_time=%g gives up to %d Trotter layers (> %d)", dt, r_max, SCHED_RMAX);
     std::vector<int> rhist(r_max + 2, 0);
+    const QmcGroupKnobs l2k = qmc_group_knobs((int64_t)sizeof(double2) << n, 3);
     for (int64_t c0 = 0; c0 < n_chains; c0 += batch) {
         const int64_t nc = std::min<int64_t>(batch, n_chains - c0);
         Hop128Args h;
@@ -890,6 +894,22 @@ int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, c
             int launched = 0;
             int base[2] = {0, 0};  // start of the odd-r / even-r class in order[]
             for (int r = 1; r <= r_max; r += 2) base[1] += rhist[r];
+            if (l2k.group > 0 && nc > l2k.group) {  // L2-resident group schedule, see group_sched.cuh
+                auto lo = [&](int kind, int off, int count, cudaStream_t sg) {
+                    switch (kind) {
+                        case QMC_GS_FIRST: return launch128<LoGeo, R_FIRST>(a, w->order, off, tiles, count, sg);
+                        case QMC_GS_MID: return launch128<LoGeo, R_MID>(a, w->order, off, tiles, count, sg);
+                        case QMC_GS_FINAL: return launch128<LoGeo, R_FINAL>(a, w->order, off, tiles, count, sg);
+                        default: return launch128<LoGeo, R_FINAL1>(a, w->order, off, tiles, count, sg);
+                    }
+                };
+                auto hi = [&](bool first, int off, int count, cudaStream_t sg) {
+                    return first ? launch128_hi<R_FIRST>(n, a, w->order, off, tiles, count, sg)
+                                 : launch128_hi<R_MID>(n, a, w->order, off, tiles, count, sg);
+                };
+                rc = qmc_group_schedule(w->gsched, l2k, st, (int)nc, r_max, rhist, lo, hi, launched);
+                if (rc != QMC_OK) return rc;
+            } else
             for (int step = 1; step <= r_max; ++step) {
                 const int p = step & 1;  // chains with r == step (mod 2) sweep LO at this step
                 const int lo_base = p ? base[0] : base[1];

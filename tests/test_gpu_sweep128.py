@@ -141,3 +141,18 @@ def test_sweep128_full_size_properties_n20():
     inc = q.IncoherentMixerSum([q.GenericMixer.OneBodyMixer(20), q.CustomMixer(20, [[b] for b in range(0, 20, 2)])], [0.5, 0.5])
     b = q.quantum_enhanced_mcmc(2, m, inc, (0.25, 0.6), temperature=1.0, n_chains=6, seed=2, dtype="fp64")
     assert b.proposals.shape == (6, 2)
+
+
+@pytest.mark.parametrize("n,C,mib,streams", [(13, 150, 1, 3), (16, 48, 3, 2), (20, 9, 16, 4), (20, 7, 40, 1)])
+def test_sweep128_l2_resident_group_schedule_is_bit_identical(monkeypatch, n, C, mib, streams):
+    """complex128 chains under the L2-resident group schedule (group_sched.cuh) equal the step-major schedule bit for
+    bit: same kernels on the same data, only the launch order and the streams differ."""
+    q, J, h, m, mx, masks, w = _setup(n, seed=8)
+    kw = dict(temperature=1.0, n_chains=C, seed=13, dtype="fp64", chain_id0=1)
+    monkeypatch.setenv("QUMCMC_L2_GROUP_MIB", "0")
+    ref = q.quantum_enhanced_mcmc(3, m, mx, (0.25, 0.6), **kw)
+    monkeypatch.setenv("QUMCMC_L2_GROUP_MIB", str(mib))
+    monkeypatch.setenv("QUMCMC_L2_STREAMS", str(streams))
+    got = q.quantum_enhanced_mcmc(3, m, mx, (0.25, 0.6), **kw)
+    for f in ("proposals", "accepted", "final_state", "acc_count", "hamming_hist"):
+        assert np.array_equal(getattr(ref, f), getattr(got, f)), f
