@@ -41,7 +41,9 @@ def workload_config(chains_per_gpu, n_gpus, extra=None):
         "workload": "C3: random_ising_model(20, seed=1), OneBodyMixer, gamma~U(0.25,0.6), dt=0.8, t~U{2..11}, beta=1.0",
         "n_spins": N_SPINS, "chains_per_gpu": chains_per_gpu, "chains_total": chains_per_gpu * n_gpus,
         "step": "one hop of every chain", "statevector": "complex64, 8 MiB per chain",
-        "l2_policy": "working set (chains x 8 MiB = %.1f GiB per GPU) >> 126 MB L2; no flush needed"
+        "l2_policy": "inputs larger than the L2: every step rewrites chains x 8 MiB = %.1f GiB of statevectors per GPU "
+                     "(>> 126 MB), nothing survives from one timed step to the next; inside a step the L2-resident group "
+                     "schedule keeps the statevectors of the 8 chains in flight in the L2 between their own sweeps"
                      % (chains_per_gpu * 8 / 1024),
         "parallelism": "chain-sharded x%d, no collective in the hop loop" % n_gpus,
     }
@@ -392,23 +394,38 @@ def build_line(args, world, C, K, W, ms, value, acc_rate, clocks, launches, swee
     c_ms, c_ln, c_by = _V(), _V(), _V()
     c_ms.value, c_ln.value, c_by.value = sweep_ms, sweep_launches, alg_bytes
     achieved = (c_by.value / 1e9) / (c_ms.value * 1e-3) if c_ms.value > 0 else None
-    traffic = None
+    traffic = traffic_alg = dram_ratio = None
+    grouped = os.environ.get("QUMCMC_L2_GROUP_MIB", "16") != "0"
     tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and grouped:   # the committed capture is of the default (L2-resident) schedule
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic, traffic_alg = tj.get("dram_bytes_per_launch"), tj.get("algorithmic_bytes_per_launch")
+            dram_ratio = tj.get("all_sweep_kernels", {}).get("dram_over_loadstore")
         except Exception:
             traffic = None
     moved = (moved_bytes / 1e9) / (c_ms.value * 1e-3) if c_ms.value > 0 else None
+    if not grouped:
+        dram_ratio = 1.0   # step-major schedule: every load / store of a sweep is HBM traffic (ncu: 0.99)
+    dram = None if moved is None or dram_ratio is None else moved * dram_ratio
     roofline = {
         "bound": "hbm",
         "kernel": "lo_sweep_kernel<MID> + hiq_sweep_kernel (HI MID) + their FIRST / FINAL roles: all sweep launches of the step "
                   "(fused phase + butterfly sweeps)",
         "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": None if achieved is None else achieved / peak, "traffic": traffic,
-        "dram_achieved": moved, "dram_frac": None if moved is None else moved / peak,
-        "dram_definition": "bytes the sweep launches actually move: 16 B * 2^n * (r - 1) per proposal (first sweep write-only, "
-                           "last read-only) / the same device time",
+        "traffic_algorithmic_bytes_per_launch": traffic_alg,
+        "schedule": ("L2-resident groups (group_sched.cuh): the chains of a group run all their sweeps back to back, a sweep "
+                     "rewrites the lines its predecessor left in the L2; HBM sees the write-backs only, so `frac` can exceed "
+                     "what an HBM-streaming schedule reaches and the kernels are bound by FP32 issue, not by HBM")
+                    if grouped else "step-major (QUMCMC_L2_GROUP_MIB=0): every sweep streams all statevectors through HBM",
+        "loadstore_achieved": moved, "loadstore_frac": None if moved is None else moved / peak,
+        "loadstore_definition": "bytes the sweep launches load + store: 16 B * 2^n * (r - 1) per proposal (first sweep "
+                                "write-only, last read-only) / the same device time; equals the DRAM traffic under the "
+                                "step-major schedule",
+        "dram_achieved": dram, "dram_frac": None if dram is None else dram / peak,
+        "dram_definition": "loadstore_achieved x (DRAM bytes / loaded + stored bytes of the sweep kernels in the committed ncu "
+                           "capture, profiles/sweep_traffic.json); DRAM counters cannot be read outside a profiler",
         "peak_source": peak_src, "sweep_ms_per_step": c_ms.value / max(1, K),
         "algorithmic_bytes_per_step": c_by.value / max(1, K), "launches_per_step": c_ln.value / max(1, K),
         "share_of_step": c_ms.value / ms if ms > 0 else None,
