@@ -100,17 +100,59 @@ template <typename T> struct V2;
 template <> struct V2<float> { using type = float2; };
 template <> struct V2<double> { using type = double2; };
 
-// exp(i x): argument formed and range-reduced in fp64, evaluated in T
-__device__ __forceinline__ float2 gen_phase(double x, float) {
-    double t = x * 0.31830988618379067154;  // x / pi
+// Register representation of one amplitude.  complex64 amplitudes stay packed in one 64-bit register pair so that the
+// Walsh-Hadamard butterflies are the packed FP32 adds of sm_100 (add/sub.rn.f32x2 -> SASS FADD2: one instruction per
+// complex add instead of two); complex128 amplitudes are plain double2.
+typedef unsigned long long A64;
+template <typename T> struct Reg;
+template <> struct Reg<float> { using type = A64; };
+template <> struct Reg<double> { using type = double2; };
+__device__ __forceinline__ A64 r_make(float x, float y) {
+    A64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ double2 r_make(double x, double y) { return make_double2(x, y); }
+__device__ __forceinline__ float2 r_get(A64 r) {
+    float2 o;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+    return o;
+}
+__device__ __forceinline__ double2 r_get(double2 r) { return r; }
+__device__ __forceinline__ void r_addsub(A64 &a, A64 &b) {  // (a, b) <- (a + b, a - b)
+    A64 s, d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(s) : "l"(a), "l"(b));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    a = s;
+    b = d;
+}
+__device__ __forceinline__ void r_addsub(double2 &a, double2 &b) {
+    const double2 u = a, w = b;
+    a = make_double2(u.x + w.x, u.y + w.y);
+    b = make_double2(u.x - w.x, u.y - w.y);
+}
+__device__ __forceinline__ A64 r_scale(A64 a, float s) {
+    A64 d;
+    const A64 s2 = r_make(s, s);
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(s2));
+    return d;
+}
+__device__ __forceinline__ double2 r_scale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
+
+// exp(i pi t) for a phase given in half-turns.  complex64: t is range-reduced to [-1, 1] in fp64, the sine / cosine
+// come from the special-function unit (sin/cos.approx: absolute error < 5e-7 on [-pi, pi], the same unit and error the
+// complex64 sweep kernels use for their phase layer); complex128: sincospi in fp64.
+__device__ __forceinline__ float2 gen_phase_pi(double t, float) {
     t -= 2.0 * rint(0.5 * t);
+    const float x = (float)t * 3.14159265358979323846f;
     float s, c;
-    sincospif((float)t, &s, &c);
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(x));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(x));
     return make_float2(c, s);
 }
-__device__ __forceinline__ double2 gen_phase(double x, double) {
+__device__ __forceinline__ double2 gen_phase_pi(double t, double) {
     double s, c;
-    sincos(x, &s, &c);
+    sincospi(t, &s, &c);
     return make_double2(c, s);
 }
 
@@ -158,19 +200,15 @@ __host__ __device__ __forceinline__ int xl(int tid, int j) {
 }
 __host__ __device__ __forceinline__ int xswz(int l) { return l ^ ((l >> 4) & 15); }
 
-template <typename T2>
-__device__ __forceinline__ void wht4(T2 (&v)[XR], int mask) {  // Walsh-Hadamard butterflies on the register bits in `mask`
+template <typename R>
+__device__ __forceinline__ void wht4(R (&v)[XR], int mask) {  // Walsh-Hadamard butterflies on the register bits in `mask`
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
         if (!((mask >> b) & 1)) continue;  // uniform over the CTA
 #pragma unroll
         for (int j = 0; j < XR; ++j) {
             if (j & (1 << b)) continue;
-            const T2 u = v[j], w = v[j | (1 << b)];
-            v[j].x = u.x + w.x;
-            v[j].y = u.y + w.y;
-            v[j | (1 << b)].x = u.x - w.x;
-            v[j | (1 << b)].y = u.y - w.y;
+            r_addsub(v[j], v[j | (1 << b)]);
         }
     }
 }
@@ -190,8 +228,9 @@ struct XDiagSmem {
     double F[XT];
     double rows[64];
     double A;
-    double SL[64], SH[64];
+    double SL[68], SH[64];  // SL padded by one entry per 16: stage 0 reads SL[(tid & 3) << 4 | j], a 4-way bank conflict otherwise
 };
+__host__ __device__ __forceinline__ int sl_slot(int x) { return x + (x >> 4); }
 
 // E(l) tables for the tile with outside bits `full` (index of the tile's element l = 0): A, F_t -> SL / SH.
 __device__ __forceinline__ void diag_prepare(XDiagSmem &d, const XDiag &D, const XGroup &G, int n, unsigned long long full,
@@ -224,7 +263,8 @@ __device__ __forceinline__ void diag_prepare(XDiagSmem &d, const XDiag &D, const
         double s = 0.0;
 #pragma unroll
         for (int t = 0; t < 6; ++t) s += ((x >> t) & 1) ? -d.F[6 * hi + t] : d.F[6 * hi + t];
-        (hi ? d.SH : d.SL)[x] = s;
+        if (hi) d.SH[x] = s;
+        else d.SL[sl_slot(x)] = s;
     }
     __syncthreads();
 }
@@ -275,19 +315,20 @@ __device__ __forceinline__ void diag_residual(double *c, const XDiag &D, unsigne
 }
 
 // v[j] *= scale * exp(i theta E(l_j)) for the thread's 16 elements in stage S
+// theta_pi = theta / pi: the phase of element l is pi * theta_pi * E(l) (half-turns: the range reduction is one rint)
 template <int S, typename T>
-__device__ __forceinline__ void diag_apply(typename V2<T>::type (&v)[XR], const XDiagSmem &d, const XDiag &D, const double *resid,
-                                           double theta, T scale, int tid) {
+__device__ __forceinline__ void diag_apply(typename Reg<T>::type (&v)[XR], const XDiagSmem &d, const XDiag &D, const double *resid,
+                                           double theta_pi, T scale, int tid) {
     using T2 = typename V2<T>::type;
 #pragma unroll
     for (int j = 0; j < XR; ++j) {
         const int l = xl<S>(tid, j);
-        double E = d.A + d.SL[l & 63] + d.SH[l >> 6] + __ldg(D.R + l);
+        double E = (d.A + d.SH[l >> 6]) + d.SL[sl_slot(l & 63)] + __ldg(D.R + l);  // first sum: the same for 4 (S = 1) or all j
         if (resid) E += resid[xswz(l)];
-        const T2 f = gen_phase(theta * E, T(0));
-        const T2 x = v[j];
-        v[j].x = (x.x * f.x - x.y * f.y) * scale;
-        v[j].y = (x.x * f.y + x.y * f.x) * scale;
+        const T2 f = gen_phase_pi(theta_pi * E, T(0));
+        const T2 x = r_get(v[j]);
+        const T fx = f.x * scale, fy = f.y * scale;
+        v[j] = r_make(x.x * fx - x.y * fy, x.x * fy + x.y * fx);
     }
 }
 
@@ -296,9 +337,9 @@ __device__ __forceinline__ void diag_apply(typename V2<T>::type (&v)[XR], const 
 // [H on G2..GK]  HOST Dx on G1   -- the second half only for b < r.
 template <typename T>
 __global__ void __launch_bounds__(XTH, sizeof(T) == 4 ? 3 : 2) gen_pass_kernel(const GenArgs a, const int t) {
-    using T2 = typename V2<T>::type;
+    using R = typename Reg<T>::type;  // register / memory representation of one amplitude (same bytes as V2<T>)
     extern __shared__ __align__(16) unsigned char smraw[];
-    T2 *st = reinterpret_cast<T2 *>(smraw);  // [XN]
+    R *st = reinterpret_cast<R *>(smraw);  // [XN]
     __shared__ unsigned long long hoff[XN >> XFORCED];  // index offset of the local bits 4..11
     __shared__ GenChain ch_s;
     __shared__ XDiagSmem dg;
@@ -343,19 +384,18 @@ __global__ void __launch_bounds__(XTH, sizeof(T) == 4 ? 3 : 2) gen_pass_kernel(c
         hoff[tid] = o;
     }
     __syncthreads();
-    T2 *state = reinterpret_cast<T2 *>(a.state) + ((size_t)c << n) + base;
+    R *state = reinterpret_cast<R *>(a.state) + ((size_t)c << n) + base;
     const int m2 = (G.active >> 8) & 15, m1 = (G.active >> 4) & 15, m0 = G.active & 15;
     const bool use1 = (m1 | m0) != 0, use0 = m0 != 0;
     const T hscale = (T)exp2(-0.5 * (double)G.n_active);  // normalisation of one Walsh-Hadamard transform over the group
-    T2 v[XR];
+    R v[XR];
     // stage-2 element (tid, j): local index tid | j << 8 -> offset (tid & 15) + hoff[(tid >> 4) | j << 4]
     if (role == X_FIRST) {  // <x| H^(x)n |s> = 2^(-n/2) (-1)^popcount(s & x)
         const T mag = (T)exp2(-0.5 * (double)n);
 #pragma unroll
         for (int j = 0; j < XR; ++j) {
             const unsigned long long x = base | hoff[(tid >> 4) | (j << 4)] | (unsigned long long)(tid & 15);
-            v[j].x = (__popcll(x & ch_s.cur) & 1) ? -mag : mag;
-            v[j].y = T(0);
+            v[j] = r_make((__popcll(x & ch_s.cur) & 1) ? -mag : mag, T(0));
         }
     } else {
 #pragma unroll
@@ -368,6 +408,7 @@ __global__ void __launch_bounds__(XTH, sizeof(T) == 4 ? 3 : 2) gen_pass_kernel(c
     double *resid = nullptr;
     if (host) {
         theta = host_x ? -ch_s.gamma * a.dt : (a.phase_active ? (1.0 - ch_s.gamma) * a.alpha * a.dt : 0.0);
+        theta *= 0.31830988618379067154;  // in half-turns: diag_apply forms exp(i pi theta E)
         diag_prepare(dg, D, G, n, base, tid);
         if (D.n_mu > 0) {
             resid = reinterpret_cast<double *>(st + XN);
@@ -404,9 +445,9 @@ __global__ void __launch_bounds__(XTH, sizeof(T) == 4 ? 3 : 2) gen_pass_kernel(c
                 double s = 0.0;
 #pragma unroll
                 for (int j = 0; j < XR; ++j) {
-                    v[j].x *= hscale;
-                    v[j].y *= hscale;
-                    s += (double)v[j].x * (double)v[j].x + (double)v[j].y * (double)v[j].y;
+                    v[j] = r_scale(v[j], hscale);
+                    const typename V2<T>::type o = r_get(v[j]);
+                    s += (double)o.x * (double)o.x + (double)o.y * (double)o.y;
                 }
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -430,10 +471,7 @@ __global__ void __launch_bounds__(XTH, sizeof(T) == 4 ? 3 : 2) gen_pass_kernel(c
     // normalisation of the transform after the diagonal (host pass) or of the only one (H pass)
 #pragma unroll
     for (int j = 0; j < XR; ++j) {
-        T2 o;
-        o.x = v[j].x * hscale;
-        o.y = v[j].y * hscale;
-        state[hoff[(tid >> 4) | (j << 4)] | (unsigned long long)(tid & 15)] = o;
+        state[hoff[(tid >> 4) | (j << 4)] | (unsigned long long)(tid & 15)] = r_scale(v[j], hscale);
     }
 }
 
