@@ -147,6 +147,20 @@ def run_reference(args, rank):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def pin_rank_to_cores(local_rank):
+    """torchrun leaves every rank on the full CPU mask.  The L2-resident schedule keeps one host thread per rank busy
+    launching kernels (about 10 k launches per hop), so each rank gets its own block of logical CPUs: two ranks'
+    launch threads never share a core."""
+    try:
+        lws = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+        cpus = sorted(os.sched_getaffinity(0))
+        per = len(cpus) // max(1, lws)
+        if lws > 1 and per >= 2:
+            os.sched_setaffinity(0, cpus[local_rank * per:(local_rank + 1) * per])
+    except (AttributeError, OSError, ValueError):
+        pass
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
 
@@ -156,6 +170,7 @@ def run_ours(args, rank, local_rank, world):
     from qumcmc_b200.mixers import GenericMixer
 
     torch.cuda.set_device(local_rank)
+    pin_rank_to_cores(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -215,6 +230,8 @@ def run_ours(args, rank, local_rank, world):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     run_dev(K, s0, W)
+    ev_mid = torch.cuda.Event(enable_timing=True)
+    ev_mid.record()
     g_acc = g_hist = None
     if dist is not None:  # the one exchange of the chain-parallel path: statistics gather
         g_acc, g_hist = gather_statistics(cnt.cpu().numpy(), hist.cpu().numpy(), C * world)
@@ -222,6 +239,12 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.synchronize()
     barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
+    per_rank = None   # diagnostics: every rank's own device time of the K hops and of the gather that follows
+    if dist is not None:
+        mine = torch.tensor([ev0.elapsed_time(ev_mid), ev_mid.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"hops_ms": [round(float(t[0]), 2) for t in allr], "gather_ms": [round(float(t[1]), 2) for t in allr]}
     clocks = sampler.stop() if sampler else None
     launches = dm.launch_count() - launches0
     sweep_ms, sweep_launches, alg_bytes = (torch.zeros(1, dtype=torch.float64).numpy(), np.zeros(1, dtype=np.int64),
@@ -279,6 +302,8 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0:
         state["line"] = build_line(args, world, C, K, W, ms, value, acc_rate, clocks, launches, c_ms.value, c_ln.value,
                                    c_by.value, c_mv.value, e2e_value, Ke, bi, bo, e2e_consistent, g_acc, secondary)
+        if per_rank is not None:
+            state["line"]["per_rank"] = per_rank
     if world >= 2 and (world & (world - 1)) == 0 and not args.no_secondary and not args.no_c5:
         try:   # C5: statevector sharded by global qubits, 33 local qubits per GPU (n = 36 on 8 GPUs)
             del props_buf, acc_buf
@@ -395,7 +420,7 @@ def build_line(args, world, C, K, W, ms, value, acc_rate, clocks, launches, swee
     c_ms.value, c_ln.value, c_by.value = sweep_ms, sweep_launches, alg_bytes
     achieved = (c_by.value / 1e9) / (c_ms.value * 1e-3) if c_ms.value > 0 else None
     traffic = traffic_alg = dram_ratio = None
-    grouped = os.environ.get("QUMCMC_L2_GROUP_MIB", "16") != "0"
+    grouped = os.environ.get("QUMCMC_L2_GROUP_MIB", "24") != "0"
     tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tpath) and grouped:   # the committed capture is of the default (L2-resident) schedule
         try:

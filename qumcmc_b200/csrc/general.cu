@@ -139,20 +139,22 @@ __device__ __forceinline__ A64 r_scale(A64 a, float s) {
 }
 __device__ __forceinline__ double2 r_scale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
 
-// exp(i pi t) for a phase given in half-turns.  complex64: t is range-reduced to [-1, 1] in fp64, the sine / cosine
-// come from the special-function unit (sin/cos.approx: absolute error < 5e-7 on [-pi, pi], the same unit and error the
-// complex64 sweep kernels use for their phase layer); complex128: sincospi in fp64.
-__device__ __forceinline__ float2 gen_phase_pi(double t, float) {
-    t -= 2.0 * rint(0.5 * t);
-    const float x = (float)t * 3.14159265358979323846f;
+// exp(2 pi i theta E) for a phase in full turns (theta = angle per unit of E / 2 pi).
+// complex64: the product and the range reduction are ONE fp64 FMA -- theta * E + 1.5 * 2^20 has an ulp of 2^-32, so the
+// low mantissa word of the sum is frac(theta E) * 2^32 as a two's-complement integer (|theta E| < 2^19 turns); sine and
+// cosine of that angle come from the special-function unit (sin/cos.approx: absolute error < 5e-7 on [-pi, pi], the
+// unit and error the complex64 sweep kernels use for their phase layer).  complex128: sincospi in fp64.
+__device__ __forceinline__ float2 gen_phase_turns(double theta, double E, float) {
+    const int fx = __double2loint(fma(theta, E, 1572864.0));
+    const float x = (float)fx * 1.4629180792671596e-9f;  // 2 pi / 2^32
     float s, c;
     asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(x));
     asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(x));
     return make_float2(c, s);
 }
-__device__ __forceinline__ double2 gen_phase_pi(double t, double) {
+__device__ __forceinline__ double2 gen_phase_turns(double theta, double E, double) {
     double s, c;
-    sincospi(t, &s, &c);
+    sincospi(2.0 * theta * E, &s, &c);
     return make_double2(c, s);
 }
 
@@ -315,17 +317,17 @@ __device__ __forceinline__ void diag_residual(double *c, const XDiag &D, unsigne
 }
 
 // v[j] *= scale * exp(i theta E(l_j)) for the thread's 16 elements in stage S
-// theta_pi = theta / pi: the phase of element l is pi * theta_pi * E(l) (half-turns: the range reduction is one rint)
+// theta in turns per unit of E: the phase of element l is 2 pi theta E(l)
 template <int S, typename T>
 __device__ __forceinline__ void diag_apply(typename Reg<T>::type (&v)[XR], const XDiagSmem &d, const XDiag &D, const double *resid,
-                                           double theta_pi, T scale, int tid) {
+                                           double theta, T scale, int tid) {
     using T2 = typename V2<T>::type;
 #pragma unroll
     for (int j = 0; j < XR; ++j) {
         const int l = xl<S>(tid, j);
         double E = (d.A + d.SH[l >> 6]) + d.SL[sl_slot(l & 63)] + __ldg(D.R + l);  // first sum: the same for 4 (S = 1) or all j
         if (resid) E += resid[xswz(l)];
-        const T2 f = gen_phase_pi(theta_pi * E, T(0));
+        const T2 f = gen_phase_turns(theta, E, T(0));
         const T2 x = r_get(v[j]);
         const T fx = f.x * scale, fy = f.y * scale;
         v[j] = r_make(x.x * fx - x.y * fy, x.x * fy + x.y * fx);
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(XTH, sizeof(T) == 4 ? 3 : 2) gen_pass_kernel(c
     double *resid = nullptr;
     if (host) {
         theta = host_x ? -ch_s.gamma * a.dt : (a.phase_active ? (1.0 - ch_s.gamma) * a.alpha * a.dt : 0.0);
-        theta *= 0.31830988618379067154;  // in half-turns: diag_apply forms exp(i pi theta E)
+        theta *= 0.15915494309189533577;  // in turns: diag_apply forms exp(2 pi i theta E)
         diag_prepare(dg, D, G, n, base, tid);
         if (D.n_mu > 0) {
             resid = reinterpret_cast<double *>(st + XN);

@@ -46,17 +46,20 @@ struct QmcGroupSched {
 
 // Knobs (read per call: the parity tests switch schedules inside one process).  QUMCMC_L2_GROUP_MIB = statevector bytes
 // per group (0 = step-major schedule), QUMCMC_L2_STREAMS = side streams.  Defaults measured on B200
-// (profiles/r2_l2_group_sweep.txt): about 64 MiB of statevectors in flight is what stays resident -- 16 MiB x 4 streams
-// for complex64 (C3: 46.7 k proposals/s; 80 MiB in flight: 42.4 k), 16 MiB x 3 streams for complex128 (18.2 k vs 15.0 k).
+// (profiles/r2_l2_group_sweep.txt): about 64 MiB of statevectors in flight is what stays resident (C3, complex64: 16 MiB x 4
+// streams 46.7 k proposals/s, 24 MiB x 3 streams 46.4 k, 16 MiB x 5 = 80 MiB in flight 42.4 k).  The schedule costs one
+// kernel launch per group and sweep -- 10.6 k launches per hop of 4096 chains at 24 MiB x 3 (15.9 k at 16 MiB x 4), about
+// 3 us of one host core each -- so the default takes the larger group: 24 MiB x 3 streams for complex64, 16 MiB x 3 for
+// complex128 (one 2^20 statevector per group: 18.2 k proposals/s vs 15.0 k step-major).
 struct QmcGroupKnobs {
     int group = 0;    // chains per group (0: off)
     int streams = 1;
     bool prefetch = false;
     bool debug = false;
 };
-inline QmcGroupKnobs qmc_group_knobs(int64_t state_bytes, int default_streams) {
+inline QmcGroupKnobs qmc_group_knobs(int64_t state_bytes, int default_mib, int default_streams) {
     QmcGroupKnobs k;
-    const int mib = getenv("QUMCMC_L2_GROUP_MIB") ? atoi(getenv("QUMCMC_L2_GROUP_MIB")) : 16;
+    const int mib = getenv("QUMCMC_L2_GROUP_MIB") ? atoi(getenv("QUMCMC_L2_GROUP_MIB")) : default_mib;
     const int str = getenv("QUMCMC_L2_STREAMS") ? atoi(getenv("QUMCMC_L2_STREAMS")) : default_streams;
     k.streams = std::min(8, std::max(1, str));
     if (mib > 0) k.group = (int)std::max<int64_t>(1, std::min<int64_t>(4096, ((int64_t)mib << 20) / state_bytes));

@@ -2061,7 +2061,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     QMC_REQUIRE(r_max <= SCHED_RMAX, QMC_ERR_UNSUPPORTED, "delta_time=%g gives up to %d Trotter layers (> %d)", dt, r_max, SCHED_RMAX);
     std::vector<int> rhist(r_max + 2, 0);
     QmcGroupKnobs l2k;  // L2-resident group schedule (two-group path only), see group_sched.cuh
-    if (!generic) l2k = qmc_group_knobs((int64_t)sizeof(float2) << n, 4);
+    if (!generic) l2k = qmc_group_knobs((int64_t)sizeof(float2) << n, 24, 3);
     for (int64_t c0 = 0; c0 < n_chains; c0 += batch) {
         const int64_t nc = std::min<int64_t>(batch, n_chains - c0);
         HopArgs h;

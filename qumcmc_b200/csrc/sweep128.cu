@@ -840,7 +840,7 @@ int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, c
     }
     QMC_REQUIRE(r_max <= SCHED_RMAX, QMC_ERR_UNSUPPORTED, "delta_time=%g gives up to %d Trotter layers (> %d)", dt, r_max, SCHED_RMAX);
     std::vector<int> rhist(r_max + 2, 0);
-    const QmcGroupKnobs l2k = qmc_group_knobs((int64_t)sizeof(double2) << n, 3);
+    const QmcGroupKnobs l2k = qmc_group_knobs((int64_t)sizeof(double2) << n, 16, 3);
     for (int64_t c0 = 0; c0 < n_chains; c0 += batch) {
         const int64_t nc = std::min<int64_t>(batch, n_chains - c0);
         Hop128Args h;
