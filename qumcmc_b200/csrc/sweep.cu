@@ -107,6 +107,11 @@ __device__ __forceinline__ A64 fma2(A64 a, A64 b, A64 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+__device__ __forceinline__ A64 mul2(A64 a, A64 b) {
+    A64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ float norm2(A64 a) {
     const float2 f = upk(a);
     return f.x * f.x + f.y * f.y;
@@ -325,23 +330,22 @@ __device__ __forceinline__ void init_product(A64 (&v)[64], uint64_t base_idx, in
     for (int q = 0; q < n; ++q)
         if ((diff >> q) & 1ULL) mag0 *= cp.tq[q];
     const float2 g = times_i_pow(make_float2(1.f, 0.f), -(int)__popcll(cp.cur));  // (-i)^popcount(s0)
-    float f[6];
-    int sbit[6];
+    // Register qubit b contributes e_b(j_b): it differs from s0 -> factor t_q, and a minus sign when the bit is set in idx
+    // but not in s0.  The 64 products are built by doubling: level b turns every v[j], j < 2^b, into the pair
+    // (v[j] e_b(0), v[j] e_b(1)) -- 126 packed multiplies instead of 6 selects + multiplies per amplitude.
+    v[0] = pk(mag0 * g.x, mag0 * g.y);
 #pragma unroll
     for (int b = 0; b < 6; ++b) {
-        f[b] = cp.tq[qpos(b)];
-        sbit[b] = (int)((cp.cur >> qpos(b)) & 1ULL);
-    }
+        const float t = cp.tq[qpos(b)];
+        const bool sb = (cp.cur >> qpos(b)) & 1ULL;
+        const float e0 = sb ? t : 1.0f, e1 = sb ? 1.0f : -t;
+        const A64 p0 = pk(e0, e0), p1 = pk(e1, e1);
 #pragma unroll
-    for (int j = 0; j < 64; ++j) {
-        float mag = mag0;
-#pragma unroll
-        for (int b = 0; b < 6; ++b) {
-            const int jb = (j >> b) & 1;
-            mag *= (jb ^ sbit[b]) ? f[b] : 1.0f;      // qubit differs from s0: factor t_q
-            mag = (jb & (sbit[b] ^ 1)) ? -mag : mag;  // bit set in idx but not in s0: sign
+        for (int j = 0; j < (1 << b); ++j) {
+            const A64 x = v[j];
+            v[j | (1 << b)] = mul2(x, p1);
+            v[j] = mul2(x, p0);
         }
-        v[j] = pk(mag * g.x, mag * g.y);
     }
 }
 
