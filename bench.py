@@ -151,6 +151,8 @@ def pin_rank_to_cores(local_rank):
     """torchrun leaves every rank on the full CPU mask.  The L2-resident schedule keeps one host thread per rank busy
     launching kernels (about 10 k launches per hop), so each rank gets its own block of logical CPUs: two ranks'
     launch threads never share a core."""
+    if os.environ.get("QUMCMC_BENCH_NO_PIN"):   # A/B switch
+        return
     try:
         lws = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
         cpus = sorted(os.sched_getaffinity(0))
