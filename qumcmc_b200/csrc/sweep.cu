@@ -2065,7 +2065,14 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     QMC_REQUIRE(r_max <= SCHED_RMAX, QMC_ERR_UNSUPPORTED, "delta_time=%g gives up to %d Trotter layers (> %d)", dt, r_max, SCHED_RMAX);
     std::vector<int> rhist(r_max + 2, 0);
     QmcGroupKnobs l2k;  // L2-resident group schedule (two-group path only), see group_sched.cuh
-    if (!generic) l2k = qmc_group_knobs((int64_t)sizeof(float2) << n, 24, 3);
+    if (!generic) {
+        l2k = qmc_group_knobs((int64_t)sizeof(float2) << n, 24, 3);
+    } else if (n <= 22) {
+        // one chain per group, 64 MiB of statevectors in flight (benchmarks/l2_generic_sweep.py: n = 21 12.0 -> 13.7 k
+        // proposals/s, n = 22 6.1 -> 6.9 k; n = 23, a single chain in flight: 2.96 -> 2.86 k, left on the r-major schedule)
+        l2k = qmc_group_knobs((int64_t)sizeof(float2) << n, 1, n == 21 ? 4 : 2);
+        if (getenv("QUMCMC_L2_GENERIC") && atoi(getenv("QUMCMC_L2_GENERIC")) == 0) l2k.group = 0;
+    }
     for (int64_t c0 = 0; c0 < n_chains; c0 += batch) {
         const int64_t nc = std::min<int64_t>(batch, n_chains - c0);
         HopArgs h;
@@ -2139,6 +2146,30 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
             if (generic) {
                 // order[] is sorted by r descending: one schedule per distinct r over its contiguous range
                 int off = 0;
+                if (l2k.group > 0 && nc > l2k.group) {
+                    // n = 21, 22: a few statevectors (16 / 32 MiB) still fit the L2 together -- every chain runs all its
+                    // passes back to back on one of the side streams (group_sched.cuh), 4 / 2 chains in flight
+                    QmcGroupSched &gs = w->gsched;
+                    rc = gs.ensure(l2k.streams);
+                    if (rc != QMC_OK) return rc;
+                    QMC_CUDA_TRY(cudaEventRecord(gs.ev_fork, st));
+                    for (int i = 0; i < l2k.streams; ++i) QMC_CUDA_TRY(cudaStreamWaitEvent(gs.aux[i], gs.ev_fork, 0));
+                    SweepArgs ag = a;
+                    if (!l2k.prefetch) ag.pf_dist = 0;
+                    int gi = 0;
+                    for (int r = r_max; r >= 1; --r) {
+                        for (int g0 = 0; g0 < rhist[r]; g0 += l2k.group, ++gi) {
+                            rc = run_generic_schedule(n, r, ag, groups, w->order, off + g0, std::min(l2k.group, rhist[r] - g0), tiles,
+                                                      gs.aux[gi % l2k.streams], launched);
+                            if (rc != QMC_OK) return rc;
+                        }
+                        off += rhist[r];
+                    }
+                    for (int i = 0; i < l2k.streams; ++i) {
+                        QMC_CUDA_TRY(cudaEventRecord(gs.ev_join[i], gs.aux[i]));
+                        QMC_CUDA_TRY(cudaStreamWaitEvent(st, gs.ev_join[i], 0));
+                    }
+                } else
                 for (int r = r_max; r >= 1; --r) {
                     if (rhist[r] == 0) continue;
                     rc = run_generic_schedule(n, r, a, groups, w->order, off, rhist[r], tiles, st, launched);

@@ -371,3 +371,17 @@ def test_l2_resident_group_schedule_vs_oracle_sampler(monkeypatch):
         props, _ = oracle.run_chain(J, h, masks, w, s0, 1, 1.0, (0.25, 0.6), 0.8, seed, chain_id=c)
         bad += int(props[0]) != int(b.proposals[c, 0])
     assert bad <= 1, bad  # fp32 vs fp64 CDF: a draw within 1e-6 of a boundary may differ
+
+
+@pytest.mark.parametrize("n,C", [(21, 9), (22, 5)])
+def test_l2_resident_schedule_on_the_generic_path_is_bit_identical(monkeypatch, n, C):
+    """n = 21, 22: a few statevectors still fit the L2, every chain runs all its passes back to back on a side stream
+    (4 / 2 chains in flight).  Same kernels, same data: chains equal the r-major schedule bit for bit."""
+    q, J, h, m, mx, masks, w = _setup(n, seed=5)
+    kw = dict(temperature=1.0, n_chains=C, seed=23, dtype="fp32")
+    monkeypatch.setenv("QUMCMC_L2_GENERIC", "0")
+    ref = q.quantum_enhanced_mcmc(2, m, mx, (0.25, 0.6), **kw)
+    monkeypatch.delenv("QUMCMC_L2_GENERIC")
+    got = q.quantum_enhanced_mcmc(2, m, mx, (0.25, 0.6), **kw)
+    for f in ("proposals", "accepted", "final_state", "acc_count", "hamming_hist"):
+        assert np.array_equal(getattr(ref, f), getattr(got, f)), f
