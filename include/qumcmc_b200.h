@@ -264,6 +264,11 @@ int qmc_profile_read_moved(qmc_model *m, double *moved_bytes);
  * They back the barrier-free "a thread rewrites exactly the slots it read" steps and the conflict-free swizzles with an
  * exhaustive check (compute-sanitizer is not available on the GPU pool). */
 int qmc_debug_smem_slot(int layout, int tid, int j);
+/* Launch list of one hop under the L2-resident group schedule (csrc/group_sched.cuh; pure host logic, no GPU needed):
+ * rhist[r], r = 0..r_max = chains with r mixer layers (rhist[0] = 0, sum = n_chains); out receives 4 ints per launch --
+ * kind (0 LO first, 1 LO mid, 2 LO final, 3 LO final of an r = 1 proposal, 4 HI first, 5 HI mid), first position in the
+ * r-sorted chain order, number of chains, side stream.  Returns the number of launches, or -1 on bad arguments. */
+int qmc_debug_group_plan(int n_chains, int r_max, const int *rhist, int group, int streams, int *out, int cap);
 int qmc_debug_layout128(int geometry, int layout, int tid, int j, long long *out4);
 int qmc_debug_general_slot(int stage, int tid, int j, int *local_out);
 

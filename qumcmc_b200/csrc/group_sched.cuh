@@ -16,11 +16,21 @@
 
 #include "common.cuh"
 
+enum { QMC_GS_FIRST = 0, QMC_GS_MID = 1, QMC_GS_FINAL = 2, QMC_GS_FINAL1 = 3, QMC_GS_HI_FIRST = 4, QMC_GS_HI_MID = 5 };
+
+struct QmcGroupLaunch {
+    int kind;    // QMC_GS_*: role of the sweep
+    int off;     // first position in order[]
+    int count;   // chains
+    int stream;  // side stream index
+};
+
 struct QmcGroupSched {
     std::vector<cudaStream_t> aux;
     std::vector<cudaEvent_t> ev_join;
     cudaEvent_t ev_fork = nullptr;
     std::vector<int> rpos;  // r of the chain at position i of order[]
+    std::vector<QmcGroupLaunch> plan;  // launch list of the current hop
 
     int ensure(int count) {
         if (!ev_fork) QMC_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
@@ -68,9 +78,47 @@ inline QmcGroupKnobs qmc_group_knobs(int64_t state_bytes, int default_mib, int d
     return k;
 }
 
-enum { QMC_GS_FIRST = 0, QMC_GS_MID = 1, QMC_GS_FINAL = 2, QMC_GS_FINAL1 = 3 };
+// The launch list of one hop (pure host logic: qmc_debug_group_plan exposes it to the CPU tests).
+// rhist[r] = chains with r layers; order[] = odd-r chains (r descending), then even-r chains (r descending).  A chain with
+// r layers takes r sweeps, alternately on the LO and the HI group, the last one always LO: odd r starts with LO.
+// Launches of one stream execute in list order; a group lives on one stream, so every chain sees its sweeps in order.
+inline void qmc_group_plan(int nc, int r_max, const std::vector<int> &rhist, int group, int streams, std::vector<int> &rpos,
+                           std::vector<QmcGroupLaunch> &out) {
+    out.clear();
+    rpos.resize((size_t)nc);
+    int base[2] = {0, 0};
+    {
+        int k = 0;
+        for (int parity = 1; parity >= 0; --parity) {
+            if (parity == 0) base[1] = k;
+            for (int r = r_max; r >= 1; --r)
+                if ((r & 1) == parity)
+                    for (int i = 0; i < rhist[r]; ++i) rpos[k++] = r;
+        }
+    }
+    int gi = 0;
+    for (int cls = 0; cls < 2; ++cls) {  // cls 0: r odd (LO sweeps at odd steps), cls 1: r even (LO sweeps at even steps)
+        const int end = cls == 0 ? base[1] : nc;
+        for (int g0 = base[cls]; g0 < end; g0 += group, ++gi) {
+            const int cnt = std::min(group, end - g0);
+            const int sg = gi % streams;
+            const int rg = rpos[g0];
+            int gt = cnt;  // chains of the group with r > step: a prefix, r descends
+            for (int step = 1; step <= rg; ++step) {
+                int eq = 0;
+                while (gt > 0 && rpos[g0 + gt - 1] <= step) { --gt; ++eq; }
+                const bool lo_step = ((step & 1) == 1) == (cls == 0);
+                if (lo_step) {
+                    if (gt > 0) out.push_back({step == 1 ? QMC_GS_FIRST : QMC_GS_MID, g0, gt, sg});
+                    if (eq > 0) out.push_back({step == 1 ? QMC_GS_FINAL1 : QMC_GS_FINAL, g0 + gt, eq, sg});
+                } else if (gt > 0) {
+                    out.push_back({step == 1 ? QMC_GS_HI_FIRST : QMC_GS_HI_MID, g0, gt, sg});
+                }
+            }
+        }
+    }
+}
 
-// rhist[r] = chains with r layers; order[] = odd-r chains (r descending), then even-r chains (r descending).
 // lo(kind, off, count, stream) / hi(first, off, count, stream) launch one sweep over order[off .. off + count).
 template <typename LaunchLo, typename LaunchHi>
 int qmc_group_schedule(QmcGroupSched &gs, const QmcGroupKnobs &kn, cudaStream_t st, int nc, int r_max,
@@ -79,47 +127,12 @@ int qmc_group_schedule(QmcGroupSched &gs, const QmcGroupKnobs &kn, cudaStream_t 
     if (rc != QMC_OK) return rc;
     QMC_CUDA_TRY(cudaEventRecord(gs.ev_fork, st));
     for (int i = 0; i < kn.streams; ++i) QMC_CUDA_TRY(cudaStreamWaitEvent(gs.aux[i], gs.ev_fork, 0));
-    gs.rpos.resize((size_t)nc);
-    int base[2] = {0, 0};
-    {
-        int k = 0;
-        for (int parity = 1; parity >= 0; --parity) {
-            if (parity == 0) base[1] = k;
-            for (int r = r_max; r >= 1; --r)
-                if ((r & 1) == parity)
-                    for (int i = 0; i < rhist[r]; ++i) gs.rpos[k++] = r;
-        }
-    }
-    int gi = 0;
-    for (int cls = 0; cls < 2; ++cls) {  // cls 0: r odd (LO sweeps at odd steps), cls 1: r even (LO sweeps at even steps)
-        const int end = cls == 0 ? base[1] : nc;
-        for (int g0 = base[cls]; g0 < end; g0 += kn.group, ++gi) {
-            const int cnt = std::min(kn.group, end - g0);
-            cudaStream_t sg = gs.aux[gi % kn.streams];
-            const int rg = gs.rpos[g0];
-            int gt = cnt;  // chains of the group with r > step: a prefix, r descends
-            for (int step = 1; step <= rg; ++step) {
-                int eq = 0;
-                while (gt > 0 && gs.rpos[g0 + gt - 1] <= step) { --gt; ++eq; }
-                const bool lo_step = ((step & 1) == 1) == (cls == 0);
-                if (lo_step) {
-                    if (gt > 0) {
-                        rc = lo(step == 1 ? QMC_GS_FIRST : QMC_GS_MID, g0, gt, sg);
-                        if (rc != QMC_OK) return rc;
-                        ++launched;
-                    }
-                    if (eq > 0) {
-                        rc = lo(step == 1 ? QMC_GS_FINAL1 : QMC_GS_FINAL, g0 + gt, eq, sg);
-                        if (rc != QMC_OK) return rc;
-                        ++launched;
-                    }
-                } else if (gt > 0) {
-                    rc = hi(step == 1, g0, gt, sg);
-                    if (rc != QMC_OK) return rc;
-                    ++launched;
-                }
-            }
-        }
+    qmc_group_plan(nc, r_max, rhist, kn.group, kn.streams, gs.rpos, gs.plan);
+    for (const QmcGroupLaunch &L : gs.plan) {
+        rc = L.kind >= QMC_GS_HI_FIRST ? hi(L.kind == QMC_GS_HI_FIRST, L.off, L.count, gs.aux[L.stream])
+                                       : lo(L.kind, L.off, L.count, gs.aux[L.stream]);
+        if (rc != QMC_OK) return rc;
+        ++launched;
     }
     for (int i = 0; i < kn.streams; ++i) {
         QMC_CUDA_TRY(cudaEventRecord(gs.ev_join[i], gs.aux[i]));

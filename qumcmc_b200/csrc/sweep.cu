@@ -1442,6 +1442,26 @@ __global__ void af_table_kernel(int n, const double *__restrict__ Jq, const doub
 // thread `tid` touches for register `j` in one of the transposition layouts of the sweep kernels, evaluated by the very
 // functions the kernels call.  layout: 0 LO A, 1 LO B (64-bit slots, j < 64); 2 HI A', 3 HI B' (64-bit, j < 64);
 // 4 HIQ A'', 5 HIQ B'' (128-bit slots, j < 32).  Returns -1 for an unknown layout.
+// Static-analysis hook (tests/test_group_sched.py, CPU): the launch list of one hop under the L2-resident group schedule.
+// out = 4 ints per launch (kind, first position in order[], chains, side stream); returns the number of launches.
+extern "C" int qmc_debug_group_plan(int n_chains, int r_max, const int *rhist, int group, int streams, int *out, int cap) {
+    if (n_chains < 0 || r_max < 1 || !rhist || group < 1 || streams < 1) return -1;
+    std::vector<int> rh(rhist, rhist + r_max + 1), rpos;
+    rh.push_back(0);
+    int total = 0;
+    for (int r = 1; r <= r_max; ++r) total += rh[r];
+    if (total != n_chains || rh[0] != 0) return -1;
+    std::vector<QmcGroupLaunch> plan;
+    qmc_group_plan(n_chains, r_max, rh, group, streams, rpos, plan);
+    for (size_t i = 0; i < plan.size() && (int)i < cap; ++i) {
+        out[4 * i] = plan[i].kind;
+        out[4 * i + 1] = plan[i].off;
+        out[4 * i + 2] = plan[i].count;
+        out[4 * i + 3] = plan[i].stream;
+    }
+    return (int)plan.size();
+}
+
 extern "C" int qmc_debug_smem_slot(int layout, int tid, int j) {
     switch (layout) {
         case 0: return (lo_base_a(tid) ^ (j & 15)) + (j << 6);                                  // lo_a_to_smem / lo_smem_to_a
