@@ -489,6 +489,30 @@ extern "C" int qmc_mixer_set(qmc_model *m, int n_groups, const int *group_offset
     }
     m->max_terms_in_group = max_terms;
     m->all_one_body = one_body;
+    m->quad_mixer = false;
+    m->xJ.clear();
+    m->xh.clear();
+    if (!one_body && n_groups == 1) {  // one coherent group of one- and two-qubit X strings: a quadratic form in the x basis
+        bool quad = true;
+        for (int k = 0; k < nt; ++k) quad = quad && __builtin_popcountll(masks[k]) <= 2;
+        if (quad) {
+            const int n = m->n;
+            m->xJ.assign((size_t)n * n, 0.0);
+            m->xh.assign((size_t)n, 0.0);
+            for (int k = 0; k < nt; ++k) {
+                const int q1 = __builtin_ffsll((long long)masks[k]) - 1;
+                const uint64_t rest = masks[k] & (masks[k] - 1);
+                if (!rest) {
+                    m->xh[q1] += weights[k];
+                } else {
+                    const int q2 = __builtin_ffsll((long long)rest) - 1;
+                    m->xJ[(size_t)q1 * n + q2] += weights[k];
+                    m->xJ[(size_t)q2 * n + q1] += weights[k];
+                }
+            }
+            m->quad_mixer = true;
+        }
+    }
     m->qweight.clear();
     cudaFree(m->d_qweight);
     m->d_qweight = nullptr;

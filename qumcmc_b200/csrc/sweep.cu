@@ -52,6 +52,8 @@ struct ChainParams {
     int shift;   // k_fx + m - 32
     float scale; // prod_q cos(theta_q)
     int active;  // phase layer present
+    int cfx_x;   // XQ mode: rate of the mixer diagonal, round(-gamma dt / (2 pi) * 2^m')
+    int shift_x; // k_fx_x + m' - 32
     float tq[QMC_MAX_SPINS];  // tan(theta_q), theta_q = gamma w_q dt
 };
 
@@ -77,6 +79,7 @@ struct SweepArgs {
     float2 *amps_out;
     int pf_dist;              // > 0: each CTA L2-prefetches the tile of the CTA launched pf_dist later (in launch order)
     int pf_lines;             // strided tiles: 1 = per-thread prefetch.global.L2 of 128-byte lines, 0 = bulk prefetch per row
+    float gen_scale;          // XQ mode: normalisation of the Walsh-Hadamard transforms of this launch (applied with the phase)
     // Fused exchange (sharded statevector): when xchg_peers != null the pass stores amplitude L of this rank to
     // xchg_peers[L >> xchg_shift][(L & low) | (xchg_rank << xchg_shift)] -- the all-to-all that swaps the top local
     // index bits with the rank bits, done by the sweep's own stores over NVLink peer mappings (no staging copy).
@@ -267,8 +270,9 @@ __device__ __forceinline__ PhaseAF load_af(const int4 *__restrict__ af, int64_t 
 __device__ __forceinline__ int turns32(int dfx, int cfx, int shift) {
     return (int)(unsigned int)(((long long)dfx * (long long)cfx) >> shift);
 }
+template <bool XQ_X = false>
 __device__ __forceinline__ void build_hs(int *hs, const int (&dr)[64], const ChainParams *cpg, int tid) {
-    if (tid < 64) hs[tid] = turns32(dr[tid], cpg->cfx, cpg->shift);
+    if (tid < 64) hs[tid] = XQ_X ? turns32(dr[tid], cpg->cfx_x, cpg->shift_x) : turns32(dr[tid], cpg->cfx, cpg->shift);
 }
 
 // K1 for the thread's 64 amplitudes.  The phase angle is accumulated directly in 32-bit integer turns along the
@@ -279,16 +283,22 @@ __device__ __forceinline__ void build_hs(int *hs, const int (&dr)[64], const Cha
 // No branch on cp.active: an absent phase layer has cfx = 0, i.e. every factor is exactly (1, 0).  (A branch here
 // forces the register allocator to re-home all 64 amplitudes at the join: ~450 MOV / XOR-swap instructions.)
 template <bool FOLD>
+__device__ __forceinline__ void phase_gray(A64 (&v)[64], const PhaseAF af, const int *hs_all, const int dr0, const int cfx,
+                                           const int shift, const float sc);
+template <bool FOLD>
 __device__ __forceinline__ void phase_gray(A64 (&v)[64], const PhaseAF af, const int *hs_all, const int dr0,
                                            const ChainParams &cp) {
-    const int cfx = cp.cfx, shift = cp.shift;
+    phase_gray<FOLD>(v, af, hs_all, dr0, cp.cfx, cp.shift, cp.scale);
+}
+template <bool FOLD>
+__device__ __forceinline__ void phase_gray(A64 (&v)[64], const PhaseAF af, const int *hs_all, const int dr0, const int cfx,
+                                           const int shift, const float sc) {
     const int F[6] = {af.a0.y, af.a0.z, af.a0.w, af.a1.x, af.a1.y, af.a1.z};
     int G[6];
 #pragma unroll
     for (int b = 0; b < 6; ++b) G[b] = turns32(2 * F[b], cfx, shift);
     int t = turns32(af.a0.x + F[0] + F[1] + F[2] + F[3] + F[4] + F[5] + dr0, cfx, shift);
     const int4 *hs = reinterpret_cast<const int4 *>(hs_all);
-    const float sc = cp.scale;
     int4 hn = hs[0];
 #pragma unroll
     for (int i4 = 0; i4 < 16; ++i4) {
@@ -347,6 +357,23 @@ __device__ __forceinline__ void init_product(A64 (&v)[64], uint64_t base_idx, in
             v[j] = mul2(x, p0);
         }
     }
+}
+
+// XQ mode: the x-basis image of |s0> restricted to this thread's 64 amplitudes: mag * (-1)^popcount(idx & ~s0), real.
+template <typename QP>
+__device__ __forceinline__ void init_hadamard(A64 (&v)[64], uint64_t base_idx, const ChainParams &cp, QP qpos, float mag) {
+    // The transform into the x basis is the butterfly with multiplier +1, B = [[1, 1], [-1, 1]] per qubit (= Z H sqrt 2), so
+    // the start state is B^(x)n |s0>: component x carries (-1)^popcount(x & ~s0) (the convention of init_product).
+    uint64_t regmask = 0;
+    int sreg = 0;  // bits of ~s0 at the six register positions
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        regmask |= 1ULL << qpos(b);
+        sreg |= (int)((~cp.cur >> qpos(b)) & 1ULL) << b;
+    }
+    const int p0 = __popcll(base_idx & ~cp.cur & ~regmask) & 1;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = pk(((p0 ^ __popc(j & sreg)) & 1) ? -mag : mag, 0.f);
 }
 
 struct LoQ0 { __device__ __forceinline__ int operator()(int b) const { return b; } };       // B layout: bits 0..5
@@ -487,7 +514,10 @@ __device__ __forceinline__ void stage_params(ChainParams &dst_s, const ChainPara
 enum { LO_FIRST = 0, LO_MID = 1, LO_FINAL = 2, LO_SINGLE = 3, LO_FINAL1 = 4 };  // SINGLE: M_lo only (3+ qubit groups); FINAL1: r == 1
 
 // FAST = normalisation folded into the initial product state + one mixer multiplier per chain from c_tan[]
-template <int ROLE, int NTH, bool FAST>
+// XQ (general two-body path, roles MID / FINAL only): the butterflies are Walsh-Hadamard transforms -- the same FFMA2 with
+// multiplier -1 (back from the x basis: lo - hi, hi + lo) before the phase layer and +1 (into the x basis) after it -- and
+// the amplitudes are plain (no (-i)^popcount storage basis); the phase factor carries the normalisation a.gen_scale.
+template <int ROLE, int NTH, bool FAST, bool XQ = false>
 __global__ void __launch_bounds__(NTH, 384 / NTH) lo_sweep_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off, const int ct_off) {
     constexpr int TB = NTH == 128 ? 13 : 12;  // tile bits
     extern __shared__ __align__(16) float2 sm[];
@@ -497,7 +527,8 @@ __global__ void __launch_bounds__(NTH, 384 / NTH) lo_sweep_kernel(const SweepArg
     const int64_t tile = sweep_tile(a, blockIdx.x);
     const int64_t chain = order[list_off + blockIdx.y];
     // ct_off == list_off: passed separately so that this index stays pure uniform-datapath arithmetic (LDCU -> UR)
-    const float tu = FAST ? c_tan[ct_off + blockIdx.y] : 0.f;
+    const float tu = XQ ? -1.f : (FAST ? c_tan[ct_off + blockIdx.y] : 0.f);
+    const float tu2 = XQ ? 1.f : tu;  // multiplier of the butterflies after the phase layer
     const int n = a.n;
     float2 *state = a.state + (chain << n);
     A64 v[64];
@@ -524,7 +555,7 @@ __global__ void __launch_bounds__(NTH, 384 / NTH) lo_sweep_kernel(const SweepArg
             float2 *ao = a.amps_out + (chain << n) + (tile << TB) + (tid << 6);
 #pragma unroll
             const int kb = __popcll(a.gbits | ((unsigned long long)tile << TB) | ((unsigned)tid << 6));
-            for (int j = 0; j < 64; ++j) ao[j] = times_i_pow(upk(v[j]), kb + __builtin_popcount(j));  // a = i^popcount S
+            for (int j = 0; j < 64; ++j) ao[j] = XQ ? upk(v[j]) : times_i_pow(upk(v[j]), kb + __builtin_popcount(j));  // a = i^popcount S
         }
         return;
     }
@@ -557,12 +588,13 @@ __global__ void __launch_bounds__(NTH, 384 / NTH) lo_sweep_kernel(const SweepArg
         lo_smem_to_b(v, sm, tid);
         bfly6<63, FAST>(v, cp, LoQ0(), tu);
     }
-    phase_gray<FAST>(v, af, hs_s, a.dr_lo[0], cp);
-    bfly6<63, FAST>(v, cp, LoQ0(), tu);
+    if (XQ) phase_gray<false>(v, af, hs_s, a.dr_lo[0], cp.cfx, cp.shift, a.gen_scale);
+    else phase_gray<FAST>(v, af, hs_s, a.dr_lo[0], cp);
+    bfly6<63, FAST>(v, cp, LoQ0(), tu2);
     lo_b_to_smem(v, sm, tid);  // each thread rewrites exactly the slots it read: no barrier needed before
     __syncthreads();
     lo_smem_to_a(v, sm, tid);
-    bfly6<63, FAST>(v, cp, LoQ6(), tu);
+    bfly6<63, FAST>(v, cp, LoQ6(), tu2);
     lo_store_a(v, state + (tile << TB), tid);
 }
 
@@ -625,7 +657,9 @@ __global__ void __launch_bounds__(NT, MINB) lo_probe_kernel(const SweepArgs a, c
 }
 #endif
 
-template <int W, bool FIRST, bool FAST>
+// XQ: the phase layer of an HI sweep is the MIXER diagonal exp(-i gamma dt E_x(x)) (tables a.af_hi* / a.dr_hi* built from
+// the mixer's pair weights, rate cfx_x), between a transform into the x basis (+1) and back (-1); FIRST starts from H|s0>.
+template <int W, bool FIRST, bool FAST, bool XQ = false>
 __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off, const int ct_off) {
     using G = HiGeom<W>;
     extern __shared__ __align__(16) float2 sm[];
@@ -635,7 +669,8 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
     const int64_t tile = blockIdx.x;
     const int64_t chain = order[list_off + blockIdx.y];
     // ct_off == list_off: passed separately so that this index stays pure uniform-datapath arithmetic (LDCU -> UR)
-    const float tu = FAST ? c_tan[ct_off + blockIdx.y] : 0.f;
+    const float tu = XQ ? 1.f : (FAST ? c_tan[ct_off + blockIdx.y] : 0.f);
+    const float tu2 = XQ ? -1.f : tu;
     const int n = a.n;
     float2 *state = a.state + (chain << n);
     A64 v[64];
@@ -652,14 +687,16 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
             else for (int r = tid; r < ROWS; r += NT) l2_prefetch_bulk(src + ((int64_t)r << 12), ROW_BYTES);
         }
     }
-    build_hs(hs_s, G::two_rounds ? a.dr_hib : a.dr_hia, a.params + chain, tid);
+    build_hs<XQ>(hs_s, G::two_rounds ? a.dr_hib : a.dr_hia, a.params + chain, tid);
     stage_params(cp_s, a.params + chain, tid);
     const ChainParams &cp = cp_s;
     const PhaseAF af = load_af(G::two_rounds ? a.af_hib : a.af_hia, tile * NT + tid);
+    const float mag0 = XQ ? exp2f(-0.5f * (float)n) : 0.f;
     if (G::two_rounds) {
         const int64_t base_b = hi_base_b<W>(tid, tile);
         if (FIRST) {
-            init_product(v, (uint64_t)base_b, n, cp, HiQB<W>());
+            if (XQ) init_hadamard(v, (uint64_t)base_b, cp, HiQB<W>(), mag0);
+            else init_product(v, (uint64_t)base_b, n, cp, HiQB<W>());
         } else {
             bfly6<G::active_a, FAST>(v, cp, HiQA<W>(), tu);
 #pragma unroll
@@ -670,24 +707,27 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
             bfly6<G::active_b, FAST>(v, cp, HiQB<W>(), tu);
             __syncthreads();
         }
-        phase_gray<FAST>(v, af, hs_s, a.dr_hib[0], cp);
-        bfly6<G::active_b, FAST>(v, cp, HiQB<W>(), tu);
+        if (XQ) phase_gray<false>(v, af, hs_s, a.dr_hib[0], cp.cfx_x, cp.shift_x, a.gen_scale);
+        else phase_gray<FAST>(v, af, hs_s, a.dr_hib[0], cp);
+        bfly6<G::active_b, FAST>(v, cp, HiQB<W>(), tu2);
 #pragma unroll
         for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(sm)[hi_loc_b(tid, j)] = v[j];
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < 64; ++j) v[j] = reinterpret_cast<const A64 *>(sm)[hi_loc_a(tid, j)];
-        bfly6<G::active_a, FAST>(v, cp, HiQA<W>(), tu);
+        bfly6<G::active_a, FAST>(v, cp, HiQA<W>(), tu2);
 #pragma unroll
         for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(state)[base_a + G::off_a(j)] = v[j];
     } else {
         if (FIRST) {
-            init_product(v, (uint64_t)base_a, n, cp, HiQA<W>());
+            if (XQ) init_hadamard(v, (uint64_t)base_a, cp, HiQA<W>(), mag0);
+            else init_product(v, (uint64_t)base_a, n, cp, HiQA<W>());
         } else {
             bfly6<G::active_a, FAST>(v, cp, HiQA<W>(), tu);
         }
-        phase_gray<FAST>(v, af, hs_s, a.dr_hia[0], cp);
-        bfly6<G::active_a, FAST>(v, cp, HiQA<W>(), tu);
+        if (XQ) phase_gray<false>(v, af, hs_s, a.dr_hia[0], cp.cfx_x, cp.shift_x, a.gen_scale);
+        else phase_gray<FAST>(v, af, hs_s, a.dr_hia[0], cp);
+        bfly6<G::active_a, FAST>(v, cp, HiQA<W>(), tu2);
 #pragma unroll
         for (int j = 0; j < 64; ++j) reinterpret_cast<A64 *>(state)[base_a + G::off_a(j)] = v[j];
     }
@@ -722,7 +762,7 @@ __host__ __device__ __forceinline__ int hiq_loc_b(int tid, int jp) {
     return (tid & 15) | ((jp & 7) << 4) | ((jp >> 3) << 7) | (((tid >> 4) & 1) << 9) | ((tid >> 5) << 10);
 }
 
-template <bool FAST>
+template <bool FAST, bool XQ = false>
 __global__ void __launch_bounds__(NT, 3) hiq_sweep_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off,
                                                           const int ct_off) {
     extern __shared__ __align__(16) float2 sm[];
@@ -731,7 +771,8 @@ __global__ void __launch_bounds__(NT, 3) hiq_sweep_kernel(const SweepArgs a, con
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t chain = order[list_off + blockIdx.y];
-    const float tu = FAST ? c_tan[ct_off + blockIdx.y] : 0.f;
+    const float tu = XQ ? 1.f : (FAST ? c_tan[ct_off + blockIdx.y] : 0.f);
+    const float tu2 = XQ ? -1.f : tu;
     const int n = a.n;
     A64 *state = reinterpret_cast<A64 *>(a.state + (chain << n)) + hiq_base_a(tid, tile);
     P128 *smq = reinterpret_cast<P128 *>(sm);
@@ -747,7 +788,7 @@ __global__ void __launch_bounds__(NT, 3) hiq_sweep_kernel(const SweepArgs a, con
         if (pf_target(a, order, list_off, pc, pt))
             l2_prefetch_rows(reinterpret_cast<const char *>(a.state + (pc << n) + (pt << 5)), (int64_t)8 << 12, 256, tid);
     }
-    build_hs(hs_s, a.dr_hic, a.params + chain, tid);
+    build_hs<XQ>(hs_s, a.dr_hic, a.params + chain, tid);
     stage_params(cp_s, a.params + chain, tid);
     const ChainParams &cp = cp_s;
     const PhaseAF af = load_af(a.af_hic, tile * NT + tid);
@@ -762,8 +803,9 @@ __global__ void __launch_bounds__(NT, 3) hiq_sweep_kernel(const SweepArgs a, con
         v[2 * jp + 1] = x.y;
     }
     bfly6<14, FAST>(v, cp, HiqQB(), tu);
-    phase_gray<FAST>(v, af, hs_s, a.dr_hic[0], cp);
-    bfly6<14, FAST>(v, cp, HiqQB(), tu);
+    if (XQ) phase_gray<false>(v, af, hs_s, a.dr_hic[0], cp.cfx_x, cp.shift_x, a.gen_scale);
+    else phase_gray<FAST>(v, af, hs_s, a.dr_hic[0], cp);
+    bfly6<14, FAST>(v, cp, HiqQB(), tu2);
 #pragma unroll
     for (int jp = 0; jp < 32; ++jp) smq[hiq_loc_b(tid, jp)] = make_ulonglong2(v[2 * jp], v[2 * jp + 1]);  // own slots
     __syncthreads();
@@ -773,7 +815,7 @@ __global__ void __launch_bounds__(NT, 3) hiq_sweep_kernel(const SweepArgs a, con
         v[2 * jp] = x.x;
         v[2 * jp + 1] = x.y;
     }
-    bfly6<62, FAST>(v, cp, HiqQA(), tu);
+    bfly6<62, FAST>(v, cp, HiqQA(), tu2);
 #pragma unroll
     for (int jp = 0; jp < 32; ++jp)
         *reinterpret_cast<P128 *>(state + ((int64_t)jp << 15)) = make_ulonglong2(v[2 * jp], v[2 * jp + 1]);
@@ -1137,6 +1179,8 @@ __global__ void __launch_bounds__(1024) schedule_kernel(const ChainParams *__res
 struct HopArgs {
     int n, mode, n_groups, phase_active, k_fx;
     int fold;  // 1: cp.scale = (prod cos)^r, applied once in the initial product state
+    int xq;    // XQ mode: quadratic X mixer hosted by the sweep kernels; cp.r counts half-layers (2 r)
+    int k_fx_x;
     int64_t n_chains, n_hops, hop;
     uint64_t chain_id0, seed;
     uint32_t hop0;
@@ -1162,7 +1206,35 @@ struct HopArgs {
 __device__ void fill_proposal_params(ChainParams &cp, const HopArgs &h, double gamma, int r, int grp) {
     cp.r = r < 1 ? 1 : r;
     cp.group = grp;
+    cp.cfx_x = 0;
+    cp.shift_x = 0;
     for (int q = 0; q < QMC_MAX_SPINS; ++q) cp.tq[q] = 0.f;
+    if (h.xq) {
+        // U = H Dx H (P H Dx H)^(r-1): 2 r passes -- HI FIRST, (LO MID, HI MID) x (r - 1), LO FINAL -- scheduled as a
+        // proposal of 2 r sweeps.  tq = -1 is the multiplier of the last transform (x basis -> computational basis on the LO
+        // qubits), which the sampler repeats for the selected tile.
+        const int real_r = cp.r;
+        cp.r = 2 * real_r;
+        for (int q = 0; q < h.n; ++q) cp.tq[q] = -1.f;
+        cp.scale = 1.f;
+        const double cp_ = (1.0 - gamma) * h.alpha * h.dt * 0.15915494309189533577;  // c / (2 pi)
+        cp.active = h.phase_active && real_r > 1 && cp_ != 0.0;
+        int m = 0;
+        if (cp.active) {
+            m = (int)floor(log2(2147483647.0 / fabs(cp_)));
+            m = m > 40 ? 40 : (m < 0 ? 0 : m);
+        }
+        cp.cfx = cp.active ? (int)rint(ldexp(cp_, m)) : 0;
+        cp.shift = cp.active ? h.k_fx + m - 32 : 0;
+        const double cx = -gamma * h.dt * 0.15915494309189533577;  // mixer diagonal: exp(-i gamma dt E_x)
+        if (cx != 0.0) {
+            int mx = (int)floor(log2(2147483647.0 / fabs(cx)));
+            mx = mx > 40 ? 40 : (mx < 0 ? 0 : mx);
+            cp.cfx_x = (int)rint(ldexp(cx, mx));
+            cp.shift_x = h.k_fx_x + mx - 32;
+        }
+        return;
+    }
     double scale = 1.0;
     for (int q = 0; q < h.n; ++q) {  // theta_q = gamma * (summed weight of the group's terms on qubit q) * dt
         const double wq = h.qweight[grp * h.n + q];
@@ -1585,6 +1657,13 @@ struct SweepWorkspace {
     std::vector<HiGroup> groups;  // n > 20: register groups above the LO qubits, with their phase tables
     std::vector<cudaEvent_t> ev;
     QmcGroupSched gsched;  // L2-resident group schedule (n <= 20): side streams + fork / join events
+    // XQ mode (one- and two-qubit X strings, 14 <= n <= 20): phase tables of the MIXER diagonal in the HI layouts
+    int xq_epoch = -1;            // mixer epoch the tables were built for
+    int4 *afx_lo = nullptr, *afx_hia = nullptr, *afx_hib = nullptr, *afx_hic = nullptr;
+    int drx_hia[64], drx_hib[64], drx_hic[64];
+    double *dxJ = nullptr, *dxh = nullptr;
+    double fx_scale_x = 1.0;
+    int k_fx_x = 0;
 };
 
 void qmc_sweep_free(qmc_model *m) {
@@ -1606,6 +1685,7 @@ void qmc_sweep_free(qmc_model *m) {
     for (auto &G : w->groups) free_group_tables(G);
     for (auto e : w->ev) cudaEventDestroy(e);
     w->gsched.destroy();
+    cudaFree(w->afx_lo); cudaFree(w->afx_hia); cudaFree(w->afx_hib); cudaFree(w->afx_hic); cudaFree(w->dxJ); cudaFree(w->dxh);
     delete w;
     m->sweep = nullptr;
 }
@@ -1725,6 +1805,54 @@ static int ensure_workspace(qmc_model *m, int64_t chains, cudaStream_t st) {
     return QMC_OK;
 }
 
+// XQ mode: A / F_b tables and Gray increments of the mixer diagonal E_x(x) = sum_q xh[q] z_q + sum_{q<q'} xJ[q][q'] z_q z_q'
+// for the HI register layouts -- the phase-layer machinery fed with the mixer's weights (rebuilt when the mixer changes).
+static int ensure_xq_tables(qmc_model *m, cudaStream_t st) {
+    SweepWorkspace *w = m->sweep;
+    if (w->xq_epoch == m->mixer_epoch) return QMC_OK;
+    const int n = m->n;
+    const int64_t N = 1LL << n;
+    QMC_REQUIRE(m->quad_mixer && n >= 14 && n <= 20 && (int)m->xh.size() == n, QMC_ERR_UNSUPPORTED,
+                "sweep path: the mixer is not a single group of one- and two-qubit X strings (n=%d)", n);
+    QMC_CUDA_TRY(cudaStreamSynchronize(st));  // tables of an earlier mixer may still be in use
+    double dmax = 0.0;
+    for (int a = 0; a < n; ++a) {
+        dmax += fabs(m->xh[a]);
+        for (int b = a + 1; b < n; ++b) dmax += fabs(m->xJ[(size_t)a * n + b]);
+    }
+    if (dmax < 1e-300) dmax = 1.0;
+    w->k_fx_x = (int)floor(log2(2147483647.0 / (dmax * 1.0000001))) - 1;
+    if (w->k_fx_x > 30) w->k_fx_x = 30;
+    w->fx_scale_x = ldexp(1.0, w->k_fx_x);
+    const size_t af_bytes = sizeof(int4) * 2 * (size_t)(N >> 6);
+    if (!w->dxJ) {
+        QMC_CUDA_TRY(cudaMalloc(&w->dxJ, sizeof(double) * (size_t)n * n));
+        QMC_CUDA_TRY(cudaMalloc(&w->dxh, sizeof(double) * (size_t)n));
+        QMC_CUDA_TRY(cudaMalloc(&w->afx_lo, af_bytes));
+        QMC_CUDA_TRY(cudaMalloc(&w->afx_hia, af_bytes));
+        QMC_CUDA_TRY(cudaMalloc(&w->afx_hib, af_bytes));
+        if (n == 20) QMC_CUDA_TRY(cudaMalloc(&w->afx_hic, af_bytes));
+    }
+    QMC_CUDA_TRY(cudaMemcpy(w->dxJ, m->xJ.data(), sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
+    QMC_CUDA_TRY(cudaMemcpy(w->dxh, m->xh.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    int pos[3][6];
+    if (n == 20) {
+        const int grid = (int)std::min<int64_t>(148 * 8, (((int64_t)1 << (n - 6)) + 127) / 128);
+        af_table_kernel<8, 3><<<grid, 128, 0, st>>>(n, w->dxJ, w->dxh, w->fx_scale_x, w->afx_hic);
+        m->launches++;
+        const int pc[6] = {hiq_pos_b(0), hiq_pos_b(1), hiq_pos_b(2), hiq_pos_b(3), hiq_pos_b(4), hiq_pos_b(5)};
+        gray_increments(m->xJ, n, w->fx_scale_x, pc, w->drx_hic);
+    }
+    int rc = build_af_tables(n, w->dxJ, w->dxh, w->fx_scale_x, w->afx_lo, w->afx_hia, w->afx_hib, pos, st);
+    if (rc != QMC_OK) return rc;
+    m->launches += 3;
+    QMC_CUDA_TRY(cudaGetLastError());
+    gray_increments(m->xJ, n, w->fx_scale_x, pos[1], w->drx_hia);
+    gray_increments(m->xJ, n, w->fx_scale_x, pos[2], w->drx_hib);
+    w->xq_epoch = m->mixer_epoch;
+    return QMC_OK;
+}
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: `done` is a bit mask indexed by
 // the current device, so a process that drives several GPUs opts in on each of them.
 typedef unsigned long long DevMask;
@@ -1770,6 +1898,55 @@ static int launch_lo_v(const SweepArgs &a, const int *order, int off, int64_t ti
     lo_sweep_kernel<ROLE, NT, FAST><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off, off);
     return QMC_OK;
 }
+// XQ mode (general two-body path): MID on 64-thread CTAs, FINAL on 128-thread CTAs; multipliers are the constants +-1
+template <int ROLE>
+static int launch_lo_xq(const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
+    static_assert(ROLE == LO_MID || ROLE == LO_FINAL, "XQ mode has LO MID and LO FINAL sweeps only");
+    if (ROLE == LO_MID) {
+        static DevMask done64 = 0;
+        int rc64 = set_smem_once(lo_sweep_kernel<LO_MID, 64, true, true>, done64, TILE * 4);
+        if (rc64 != QMC_OK) return rc64;
+        SweepArgs a64 = a;
+        a64.pf_dist = 2 * a.pf_dist;
+        lo_sweep_kernel<LO_MID, 64, true, true><<<dim3((unsigned)(2 * tiles), (unsigned)count), 64, TILE * 4, st>>>(a64, order, off, off);
+        return QMC_OK;
+    }
+    static DevMask done = 0;
+    int rc = set_smem_once(lo_sweep_kernel<ROLE, NT, true, true>, done);
+    if (rc != QMC_OK) return rc;
+    lo_sweep_kernel<ROLE, NT, true, true><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off, off);
+    return QMC_OK;
+}
+template <int W, bool FIRST>
+static int launch_hi_xq_w(const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
+    if (W == 8 && !FIRST && a.hiq) {
+        static DevMask doneq = 0;
+        int rcq = set_smem_once(hiq_sweep_kernel<true, true>, doneq);
+        if (rcq != QMC_OK) return rcq;
+        hiq_sweep_kernel<true, true><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off, off);
+        return QMC_OK;
+    }
+    static DevMask done = 0;
+    int rc = set_smem_once(hi_sweep_kernel<W, FIRST, true, true>, done);
+    if (rc != QMC_OK) return rc;
+    hi_sweep_kernel<W, FIRST, true, true><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off, off);
+    return QMC_OK;
+}
+template <bool FIRST>
+static int launch_hi_xq(int n, const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
+    switch (n - LO_BITS) {
+        case 2: return launch_hi_xq_w<2, FIRST>(a, order, off, tiles, count, st);
+        case 3: return launch_hi_xq_w<3, FIRST>(a, order, off, tiles, count, st);
+        case 4: return launch_hi_xq_w<4, FIRST>(a, order, off, tiles, count, st);
+        case 5: return launch_hi_xq_w<5, FIRST>(a, order, off, tiles, count, st);
+        case 6: return launch_hi_xq_w<6, FIRST>(a, order, off, tiles, count, st);
+        case 7: return launch_hi_xq_w<7, FIRST>(a, order, off, tiles, count, st);
+        case 8: return launch_hi_xq_w<8, FIRST>(a, order, off, tiles, count, st);
+    }
+    qmc_set_error("sweep path: n=%d outside [14, 20]", n);
+    return QMC_ERR_UNSUPPORTED;
+}
+
 template <int ROLE>
 static int launch_lo(const SweepTune &tu, const SweepArgs &a, const int *order, int off, int64_t tiles, int count,
                      cudaStream_t st) {
@@ -1970,9 +2147,11 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                 QMC_SMEM_MAX_SPINS_F64, n);
     QMC_REQUIRE(n >= 14 && n <= QMC_MAX_SPINS, QMC_ERR_UNSUPPORTED, "HBM sweep path covers 14 <= n <= %d (n=%d)", QMC_MAX_SPINS, n);
     const bool generic = n > 20;  // three or more qubit groups
-    QMC_REQUIRE(m->all_one_body, QMC_ERR_UNSUPPORTED,
-                "n=%d > %d: only one-body X mixers have an HBM sweep path (k-body/custom mixers: shared-memory path)", n,
-                QMC_SMEM_MAX_SPINS_F32);
+    // XQ mode: one coherent group of one- and two-qubit X strings (abi.cu routes it here for 14 <= n <= 20)
+    const bool xq = !m->all_one_body && m->quad_mixer && n <= 20;
+    QMC_REQUIRE(m->all_one_body || xq, QMC_ERR_UNSUPPORTED,
+                "n=%d: the HBM sweep path hosts one-body X mixers (n <= %d) and single groups of one- and two-qubit X "
+                "strings (n <= 20); other mixers take the general path", n, QMC_MAX_SPINS);
     if (n_chains == 0) return QMC_OK;
     {
         static DevMask smem_attr = 0;
@@ -2000,6 +2179,10 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     int rc = ensure_workspace(m, batch, st);
     if (rc != QMC_OK) return rc;
     SweepWorkspace *w = m->sweep;
+    if (xq) {
+        rc = ensure_xq_tables(m, st);
+        if (rc != QMC_OK) return rc;
+    }
     if (generic && w->groups.empty()) {  // register groups above the LO qubits, built once per model
         std::vector<int> kind, pos, act;
         rc = hi_group_geometry(n, kind, pos, act);
@@ -2046,7 +2229,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     // Folding the normalisation (prod_q cos theta_q)^r into the initial product state is exact as long as that
     // factor stays far inside the fp32 range: bound it from below over every (gamma, r) this call can draw.
     SweepTune tune;
-    {
+    if (!xq) {
         double log_min = 0.0;  // min over proposals of r * sum_q log|cos(gamma w_q dt)|
         auto log_scale = [&](double gamma, int grp) {
             double ls = 0.0;
@@ -2082,6 +2265,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         if (fast_env) tune.fast = tune.fast && fast_env[0] == '1';
     }
 
+    if (xq) r_max *= 2;  // XQ mode schedules half-layers: 2 r sweeps per proposal (HI first, LO last)
     QMC_REQUIRE(r_max <= SCHED_RMAX, QMC_ERR_UNSUPPORTED, "delta_time=%g gives up to %d Trotter layers (> %d)", dt, r_max, SCHED_RMAX);
     std::vector<int> rhist(r_max + 2, 0);
     QmcGroupKnobs l2k;  // L2-resident group schedule (two-group path only), see group_sched.cuh
@@ -2097,6 +2281,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         const int64_t nc = std::min<int64_t>(batch, n_chains - c0);
         HopArgs h;
         h.n = n; h.mode = mode; h.n_groups = m->n_groups; h.phase_active = m->phase_active; h.k_fx = w->k_fx; h.fold = tune.fast ? 1 : 0;
+        h.xq = xq ? 1 : 0; h.k_fx_x = w->k_fx_x;
         h.n_chains = nc; h.n_hops = n_hops; h.hop = 0;
         h.chain_id0 = chain_id0 + (uint64_t)c0; h.seed = seed; h.hop0 = hop0;
         h.temperature = temperature; h.g_lo = g_lo; h.g_hi = g_hi; h.dt = dt; h.alpha = m->alpha;
@@ -2122,6 +2307,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         a.segsum = w->segsum;
         a.pf_dist = pf_dist;
         a.pf_lines = pf_lines;
+        a.gen_scale = 1.f;
         a.xchg_peers = nullptr; a.xchg_shift = 0; a.xchg_rank = 0; a.xchg_g = 0; a.xchg_tile_bits = 0; a.xchg_idx0 = 0;
         a.probs_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float *>(probs_out) : nullptr;
         a.amps_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float2 *>(amps_out) : nullptr;
@@ -2135,7 +2321,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
             QMC_NVTX("sweep hop: prepare, schedule, sweeps, sample+accept");
             h.hop = hop;
             hop_prepare_kernel<<<gb, 128, 0, st>>>(h, w->params);
-            schedule_kernel<<<1, 1024, 0, st>>>(w->params, nc, r_max, w->order, generic ? 0 : 1,
+            schedule_kernel<<<1, 1024, 0, st>>>(w->params, nc, r_max, w->order, (generic || xq) ? 0 : 1,
                                                 tune.fast ? w->tan_sorted : nullptr);
             if (tune.fast)
                 QMC_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tan, w->tan_sorted, sizeof(float) * (size_t)nc, 0,
@@ -2158,6 +2344,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                 } else {
                     r = std::max(1, r_host[c0 + c]);
                 }
+                if (xq) r *= 2;
                 rhist[r]++;
                 sum_r += r;
             }
@@ -2199,21 +2386,46 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
             } else {
                 int base[2] = {0, 0};  // start of the odd-r / even-r class in order[]
                 for (int r = 1; r <= r_max; r += 2) base[1] += rhist[r];  // even class starts after all odd-r chains
-                if (l2k.group > 0 && nc > l2k.group) {
-                    SweepArgs ag = a;
-                    if (!l2k.prefetch) ag.pf_dist = 0;  // the tiles are L2 hits already: no prefetch instructions
-                    auto lo = [&](int kind, int off, int count, cudaStream_t sg) {
-                        switch (kind) {
-                            case QMC_GS_FIRST: return launch_lo<LO_FIRST>(tune, ag, w->order, off, tiles, count, sg);
-                            case QMC_GS_MID: return launch_lo<LO_MID>(tune, ag, w->order, off, tiles, count, sg);
-                            case QMC_GS_FINAL: return launch_lo<LO_FINAL>(tune, ag, w->order, off, tiles, count, sg);
-                            default: return launch_lo<LO_FINAL1>(tune, ag, w->order, off, tiles, count, sg);
-                        }
-                    };
-                    auto hi = [&](bool first, int off, int count, cudaStream_t sg) {
-                        return first ? launch_hi<true>(tune, n, ag, w->order, off, tiles, count, sg)
-                                     : launch_hi<false>(tune, n, ag, w->order, off, tiles, count, sg);
-                    };
+                const bool grouped = l2k.group > 0 && nc > l2k.group;
+                SweepArgs ag = a;
+                if (grouped && !l2k.prefetch) ag.pf_dist = 0;  // the tiles are L2 hits already: no prefetch instructions
+                // XQ mode: LO sweeps host the phase layer (model tables), HI sweeps the mixer diagonal (mixer tables); the
+                // phase factor of every sweep carries the normalisation of the transforms of that sweep and of the FINAL one
+                SweepArgs ax_lo = ag, ax_hif = ag, ax_him = ag;
+                if (xq) {
+                    const int nh = n - LO_BITS;
+                    ax_lo.gen_scale = ldexpf(1.f, -LO_BITS);
+                    ax_him.af_hia = ax_hif.af_hia = w->afx_hia;
+                    ax_him.af_hib = ax_hif.af_hib = w->afx_hib;
+                    ax_him.af_hic = ax_hif.af_hic = w->afx_hic;
+                    memcpy(ax_him.dr_hia, w->drx_hia, sizeof(a.dr_hia)); memcpy(ax_hif.dr_hia, w->drx_hia, sizeof(a.dr_hia));
+                    memcpy(ax_him.dr_hib, w->drx_hib, sizeof(a.dr_hib)); memcpy(ax_hif.dr_hib, w->drx_hib, sizeof(a.dr_hib));
+                    if (w->afx_hic) { memcpy(ax_him.dr_hic, w->drx_hic, sizeof(a.dr_hic)); memcpy(ax_hif.dr_hic, w->drx_hic, sizeof(a.dr_hic)); }
+                    ax_him.gen_scale = ldexpf(1.f, -nh);
+                    ax_hif.gen_scale = (float)exp2(-0.5 * nh - 0.5 * LO_BITS);  // its own back-transform + the FINAL sweep's
+                }
+                auto lo = [&](int kind, int off, int count, cudaStream_t sg) {
+                    if (xq) {
+                        if (kind == QMC_GS_MID) return launch_lo_xq<LO_MID>(ax_lo, w->order, off, tiles, count, sg);
+                        if (kind == QMC_GS_FINAL) return launch_lo_xq<LO_FINAL>(ax_lo, w->order, off, tiles, count, sg);
+                        qmc_set_error("XQ schedule: LO role %d cannot occur (every proposal has an even number of sweeps)", kind);
+                        return (int)QMC_ERR_CUDA;
+                    }
+                    switch (kind) {
+                        case QMC_GS_FIRST: return launch_lo<LO_FIRST>(tune, ag, w->order, off, tiles, count, sg);
+                        case QMC_GS_MID: return launch_lo<LO_MID>(tune, ag, w->order, off, tiles, count, sg);
+                        case QMC_GS_FINAL: return launch_lo<LO_FINAL>(tune, ag, w->order, off, tiles, count, sg);
+                        default: return launch_lo<LO_FINAL1>(tune, ag, w->order, off, tiles, count, sg);
+                    }
+                };
+                auto hi = [&](bool first, int off, int count, cudaStream_t sg) {
+                    if (xq)
+                        return first ? launch_hi_xq<true>(n, ax_hif, w->order, off, tiles, count, sg)
+                                     : launch_hi_xq<false>(n, ax_him, w->order, off, tiles, count, sg);
+                    return first ? launch_hi<true>(tune, n, ag, w->order, off, tiles, count, sg)
+                                 : launch_hi<false>(tune, n, ag, w->order, off, tiles, count, sg);
+                };
+                if (grouped) {
                     rc = qmc_group_schedule(w->gsched, l2k, st, (int)nc, r_max, rhist, lo, hi, launched);
                     if (rc != QMC_OK) return rc;
                 } else
@@ -2226,20 +2438,17 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                     for (int r = step + 1; r <= r_max; r += 2) hi_gt += rhist[r];
                     const int lo_eq = rhist[step];
                     if (lo_gt > 0) {
-                        rc = step == 1 ? launch_lo<LO_FIRST>(tune, a, w->order, lo_base, tiles, lo_gt, st)
-                                        : launch_lo<LO_MID>(tune, a, w->order, lo_base, tiles, lo_gt, st);
+                        rc = lo(step == 1 ? QMC_GS_FIRST : QMC_GS_MID, lo_base, lo_gt, st);
                         if (rc != QMC_OK) return rc;
                         ++launched;
                     }
                     if (lo_eq > 0) {
-                        rc = step == 1 ? launch_lo<LO_FINAL1>(tune, a, w->order, lo_base + lo_gt, tiles, lo_eq, st)
-                                       : launch_lo<LO_FINAL>(tune, a, w->order, lo_base + lo_gt, tiles, lo_eq, st);
+                        rc = lo(step == 1 ? QMC_GS_FINAL1 : QMC_GS_FINAL, lo_base + lo_gt, lo_eq, st);
                         if (rc != QMC_OK) return rc;
                         ++launched;
                     }
                     if (hi_gt > 0) {
-                        rc = step == 1 ? launch_hi<true>(tune, n, a, w->order, hi_base, tiles, hi_gt, st)
-                                        : launch_hi<false>(tune, n, a, w->order, hi_base, tiles, hi_gt, st);
+                        rc = hi(step == 1, hi_base, hi_gt, st);
                         if (rc != QMC_OK) return rc;
                         ++launched;
                     }

@@ -9,6 +9,13 @@ from tests import models
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _general_path_only(monkeypatch):
+    """Single groups of one- and two-qubit X strings at 14 <= n <= 20 in complex64 are hosted by the sweep kernels
+    (tests/test_gpu_xq.py); this file keeps every mixer on general.cu."""
+    monkeypatch.setenv("QUMCMC_NO_XQ", "1")
+
+
 def _lowered(mixer):
     offs, masks, w, probs = mixer.lower()
     return offs, masks, w, probs

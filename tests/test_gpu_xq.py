@@ -1,0 +1,151 @@
+"""Quadratic X mixers on the sweep kernels (sweep.cu, XQ mode): one coherent group of one- and two-qubit X strings
+(GenericMixer.TwoBodyMixer, pair CustomMixer, CoherentMixerSum of them; qumcmc/mixers.py:21-130) at 14 <= n <= 20 in
+complex64.  U = H Dx H (P H Dx H)^(r-1) with the mixer a quadratic diagonal in the x basis: 2 r sweeps per proposal.
+Against the oracle's fused complex128 simulator (<= 1e-6 on probabilities) and against the Hadamard-basis general path."""
+import numpy as np
+import pytest
+
+import oracle
+from tests import models
+
+pytestmark = pytest.mark.gpu
+
+
+def _mixer(q, n, kind):
+    if kind == "two":
+        return q.GenericMixer.TwoBodyMixer(n)
+    if kind == "pairs":   # pairs across and inside the qubit groups + a few singles, repeated qubits
+        return q.CustomMixer(n, [[0, n - 1], [3, 7], [1], [12, 13], [5, n - 2], [11, 12], [n - 1], [2, 9], [0, 1], [6]])
+    if kind == "coh":
+        return q.CoherentMixerSum([q.GenericMixer.OneBodyMixer(n), q.GenericMixer.TwoBodyMixer(n)], [0.7, 0.3])
+    raise ValueError(kind)
+
+
+def _check(q, n, mixer, rs, seed=3, tol_p=1e-6, tol_a=5e-5):
+    J, h = models.packaged_random_model(n, seed)
+    m = q.IsingEnergyFunction(J, h)
+    offs, masks, w, _ = mixer.lower()
+    al = oracle.alpha(J, h)
+    rng = np.random.default_rng(7 * n + len(masks))
+    for r in rs:
+        s = int(rng.integers(0, 1 << n))
+        gamma = float(rng.uniform(0.25, 0.6))
+        p, a = q.transition_probabilities(m, mixer, s, gamma, r, dtype="fp32", return_amplitudes=True)
+        ref = oracle.evolve(J, h, al, gamma, 0.8, r, masks, w, s, gatewise=False)
+        assert abs(p.sum() - 1.0) < 1e-5
+        assert np.abs(p - np.abs(ref) ** 2).max() < tol_p, (n, r, np.abs(p - np.abs(ref) ** 2).max())
+        assert np.linalg.norm(a - ref) < tol_a, (n, r, np.linalg.norm(a - ref))
+
+
+@pytest.mark.parametrize("n", [14, 15, 16, 17, 18, 19, 20])
+def test_xq_two_body_vs_oracle(n):
+    """Every HI geometry (W = n - 12 = 2..8, odd and even: the transform normalisation 2^(-W/2) is irrational for odd W),
+    r = 1 (HI FIRST + LO FINAL only), even and odd r."""
+    import qumcmc_b200 as q
+    _check(q, n, _mixer(q, n, "two"), (1, 2, 3, 6) if n < 19 else (1, 4))
+
+
+@pytest.mark.parametrize("n,kind", [(14, "pairs"), (17, "pairs"), (20, "pairs"), (15, "coh"), (18, "coh")])
+def test_xq_custom_pairs_and_coherent_sums_vs_oracle(n, kind):
+    import qumcmc_b200 as q
+    _check(q, n, _mixer(q, n, kind), (1, 2, 5))
+
+
+def test_xq_gamma_extremes_and_absent_phase_layer():
+    """gamma = 1 (no phase layer: c = 0), gamma = 0 (identity mixer) and a model below the skip threshold of
+    fn_qckt_problem_half (quantum_mcmc_routines.py:64-67)."""
+    import qumcmc_b200 as q
+    n = 16
+    J, h = models.packaged_random_model(n, 5)
+    mixer = _mixer(q, n, "two")
+    offs, masks, w, _ = mixer.lower()
+    for Jm, hm in ((J, h), (J * 1e-4, h * 1e-4)):
+        m = q.IsingEnergyFunction(Jm, hm)
+        al = oracle.alpha(Jm, hm)
+        for gamma in (1.0, 0.0, 0.37):
+            p = q.transition_probabilities(m, mixer, 12345, gamma, 3, dtype="fp32")
+            ref = oracle.evolve(Jm, hm, al, gamma, 0.8, 3, masks, w, 12345, gatewise=False)   # skip rule inside the oracle
+            assert np.abs(p - np.abs(ref) ** 2).max() < 1e-6, gamma
+
+
+@pytest.mark.parametrize("n", [14, 20])
+def test_xq_matches_the_general_path(monkeypatch, n):
+    import qumcmc_b200 as q
+    J, h = models.packaged_random_model(n, 2)
+    m = q.IsingEnergyFunction(J, h)
+    mixer = _mixer(q, n, "coh")
+    p_xq = q.transition_probabilities(m, mixer, 4321, 0.41, 4, dtype="fp32")
+    monkeypatch.setenv("QUMCMC_NO_XQ", "1")
+    p_gen = q.transition_probabilities(m, mixer, 4321, 0.41, 4, dtype="fp32")
+    assert np.abs(p_xq - p_gen).max() < 2e-6
+
+
+def test_xq_chains_follow_the_oracle():
+    """quantum_enhanced_mcmc with a two-body mixer at n = 14: proposals equal the oracle's sequential inverse CDF (up to
+    CDF-boundary ties in fp32); accept flags / counts / final states / Hamming histograms follow bit-exactly."""
+    import qumcmc_b200 as q
+    n, C, H, seed = 14, 8, 5, 19
+    J, h = models.packaged_random_model(n, 8)
+    m = q.IsingEnergyFunction(J, h)
+    mixer = q.GenericMixer.TwoBodyMixer(n)
+    offs, masks, w, _ = mixer.lower()
+    b = q.quantum_enhanced_mcmc(H, m, mixer, (0.25, 0.6), temperature=1.0, n_chains=C, seed=seed, dtype="fp32")
+    al = oracle.alpha(J, h)
+    mismatched = 0
+    for c in range(C):
+        cur = oracle.initial_state(seed, c, n)
+        assert int(b.initial[c]) == cur
+        e_cur = oracle.energy(J, h, cur)
+        hist = np.zeros(n + 1, dtype=np.int64)
+        nacc = 0
+        for hop in range(H):
+            ug, t, _, um, ua = oracle.hop_draws(seed, c, hop)
+            gamma = 0.25 + (0.6 - 0.25) * ug
+            r = oracle.trotter_steps(t, 0.8)
+            st = oracle.evolve(J, h, al, gamma, 0.8, r, masks, w, cur, gatewise=False)
+            want = oracle.sample_index(st, um)
+            sp = int(b.proposals[c, hop])
+            if sp != want:
+                cdf = np.cumsum(np.abs(st) ** 2)
+                lo = cdf[sp - 1] if sp > 0 else 0.0
+                assert lo - 5e-6 <= um <= cdf[sp] + 5e-6, (c, hop, sp, want)
+                mismatched += 1
+            e_sp = oracle.energy(J, h, sp)
+            acc = oracle.test_accept(e_cur, e_sp, 1.0, ua)
+            assert bool(b.accepted[c, hop]) == acc
+            hist[bin(cur ^ sp).count("1")] += 1
+            if acc:
+                cur, e_cur, nacc = sp, e_sp, nacc + 1
+        assert int(b.final_state[c]) == cur and int(b.acc_count[c]) == nacc
+        assert np.array_equal(b.hamming_hist[c], hist)
+    assert mismatched <= 2
+
+
+@pytest.mark.parametrize("n,C,mib", [(14, 150, 1), (18, 30, 4), (20, 11, 24)])
+def test_xq_group_schedule_is_bit_identical(monkeypatch, n, C, mib):
+    """The L2-resident group schedule with 2 r sweeps per proposal (all chains in the even class: HI first, LO last)."""
+    import qumcmc_b200 as q
+    J, h = models.packaged_random_model(n, 6)
+    m = q.IsingEnergyFunction(J, h)
+    mixer = _mixer(q, n, "two")
+    kw = dict(temperature=1.0, n_chains=C, seed=31, dtype="fp32")
+    monkeypatch.setenv("QUMCMC_L2_GROUP_MIB", "0")
+    ref = q.quantum_enhanced_mcmc(2, m, mixer, (0.25, 0.6), **kw)
+    monkeypatch.setenv("QUMCMC_L2_GROUP_MIB", str(mib))
+    got = q.quantum_enhanced_mcmc(2, m, mixer, (0.25, 0.6), **kw)
+    for f in ("proposals", "accepted", "final_state", "acc_count", "hamming_hist"):
+        assert np.array_equal(getattr(ref, f), getattr(got, f)), f
+
+
+def test_mixers_outside_xq_keep_their_paths():
+    """Three-body terms, incoherent sums and complex128 do not qualify: they still run (general path) and agree with the oracle."""
+    import qumcmc_b200 as q
+    n = 14
+    J, h = models.packaged_random_model(n, 3)
+    m = q.IsingEnergyFunction(J, h)
+    al = oracle.alpha(J, h)
+    for mixer, dtype in ((q.CustomMixer(n, [[0, 1, 2], [3, 4], [5]]), "fp32"), (q.GenericMixer.TwoBodyMixer(n), "fp64")):
+        offs, masks, w, _ = mixer.lower()
+        p = q.transition_probabilities(m, mixer, 77, 0.4, 3, dtype=dtype)
+        ref = oracle.evolve(J, h, al, 0.4, 0.8, 3, masks, w, 77, gatewise=False)
+        assert np.abs(p - np.abs(ref) ** 2).max() < (1e-6 if dtype == "fp32" else 1e-10)
