@@ -40,6 +40,7 @@ struct ChainParams128 {
     long long n_acc;
     int r, group, active, pad;
     double cphase;      // (1 - gamma) alpha dt, 0 when the phase layer is skipped
+    double cphase_x;    // XQ mode: -gamma dt, the rate of the mixer diagonal exp(-i gamma dt E_x)
     double scale;       // (prod_q cos theta_q)^r, folded into the initial product state
     double tq[NMAX];    // tan(theta_q)
 };
@@ -124,6 +125,7 @@ struct Sweep128Args {
     const double *af_lo, *af_hi;  // [2^(n-5)][6]: A, F0..F4 of the phase layout of the LO / HI tiles
     double R_lo[APT], R_hi[APT];  // R(j): couplings among the register qubits of the phase layout
     double *segsum;            // [chains][2^(n-5)]
+    double gen_scale;          // XQ mode: normalisation of the Walsh-Hadamard transforms of this launch
     double *probs_out;         // PROBS mode (unnormalised) or null
     double2 *amps_out;
 };
@@ -137,6 +139,20 @@ __device__ __forceinline__ void bfly5(double2 (&v)[APT], const ChainParams128 &c
     for (int b = 0; b < RB; ++b) {
         if (!((ACTIVE >> b) & 1)) continue;
         const double t = cp.tq[qpos(b)];
+#pragma unroll
+        for (int j = 0; j < APT; ++j) {
+            if (j & (1 << b)) continue;
+            const double2 u = v[j], w = v[j | (1 << b)];
+            v[j] = make_double2(fma(t, w.x, u.x), fma(t, w.y, u.y));
+            v[j | (1 << b)] = make_double2(fma(-t, u.x, w.x), fma(-t, u.y, w.y));
+        }
+    }
+}
+template <int ACTIVE>
+__device__ __forceinline__ void bfly5t(double2 (&v)[APT], const double t) {  // one multiplier for every qubit (XQ: +-1)
+#pragma unroll
+    for (int b = 0; b < RB; ++b) {
+        if (!((ACTIVE >> b) & 1)) continue;
 #pragma unroll
         for (int j = 0; j < APT; ++j) {
             if (j & (1 << b)) continue;
@@ -169,7 +185,8 @@ template <typename G> struct Q2 { __device__ __forceinline__ int operator()(int 
 // Phase layer on the thread's 32 amplitudes (register layout with qubits qp(0..4)): factor(j) = exp(i c (A + sum_b z_b F_b
 // + R(j))), z_b = +1 / -1 for register bit b clear / set.  er[j] = exp(i c R(j)) comes from shared memory; the thread part
 // is a running product along the Gray-code order: one complex multiplication per step by exp(-/+ 2 i c F_b).
-__device__ __forceinline__ void phase32(double2 (&v)[APT], const double *__restrict__ af, const double2 *er, double c) {
+__device__ __forceinline__ void phase32(double2 (&v)[APT], const double *__restrict__ af, const double2 *er, double c,
+                                        double sc = 1.0) {
     double F[RB];
     double a = af[0];
 #pragma unroll
@@ -178,6 +195,8 @@ __device__ __forceinline__ void phase32(double2 (&v)[APT], const double *__restr
         a += F[b];
     }
     double2 f = cis(c * a);  // j = 0: every z_b = +1
+    f.x *= sc;               // XQ mode: the running product carries the normalisation of the sweep's transforms
+    f.y *= sc;
     double2 g[RB];           // exp(-2 i c F_b): register bit b goes 0 -> 1
 #pragma unroll
     for (int b = 0; b < RB; ++b) g[b] = cis(-2.0 * c * F[b]);
@@ -226,6 +245,21 @@ __device__ __forceinline__ void init_product32(double2 (&v)[APT], uint64_t base_
     }
 }
 
+// XQ mode: the x-basis image of |s0> (see sweep.cu: init_hadamard): mag * (-1)^popcount(idx & ~s0), real.
+template <typename QP>
+__device__ __forceinline__ void init_hadamard32(double2 (&v)[APT], uint64_t base_idx, const ChainParams128 &cp, QP qpos, double mag) {
+    uint64_t regmask = 0;
+    int sreg = 0;
+#pragma unroll
+    for (int b = 0; b < RB; ++b) {
+        regmask |= 1ULL << qpos(b);
+        sreg |= (int)((~cp.cur >> qpos(b)) & 1ULL) << b;
+    }
+    const int p0 = __popcll(base_idx & ~cp.cur & ~regmask) & 1;
+#pragma unroll
+    for (int j = 0; j < APT; ++j) v[j] = make_double2(((p0 ^ __popc(j & sreg)) & 1) ? -mag : mag, 0.0);
+}
+
 template <typename G>
 __device__ __forceinline__ void to_smem1(const double2 (&v)[APT], double2 *sm, int tid) {
     const int base = local1<G>(tid, 0);
@@ -270,7 +304,10 @@ __device__ __forceinline__ void stage_params128(ChainParams128 &dst_s, const Cha
 enum { R_FIRST = 0, R_MID = 1, R_FINAL = 2, R_FINAL1 = 3 };
 
 // One sweep over (tile, chain).  G = LoGeo: roles FIRST / MID / FINAL / FINAL1; G = HiGeo<LC>: FIRST / MID.
-template <typename G, int ROLE>
+// XQ (one coherent group of one- and two-qubit X strings, see sweep.cu): the butterflies are Walsh-Hadamard transforms
+// (multiplier +1 into the x basis, -1 back), HI sweeps host the mixer diagonal (tables a.af_hi / a.R_hi built from the mixer's
+// weights, rate cphase_x), LO sweeps the phase layer; plain amplitudes, normalisation a.gen_scale with the phase factor.
+template <typename G, int ROLE, bool XQ = false>
 __global__ void __launch_bounds__(NT, 3) sweep128_kernel(const Sweep128Args a, const int *__restrict__ order, const int list_off) {
     extern __shared__ __align__(16) unsigned char smraw[];
     double2 *sm = reinterpret_cast<double2 *>(smraw);
@@ -289,7 +326,7 @@ __global__ void __launch_bounds__(NT, 3) sweep128_kernel(const Sweep128Args a, c
     if (ROLE == R_FIRST || ROLE == R_MID) {
         if (tid < APT) {
             const ChainParams128 *cg = a.params + chain;
-            er_s[tid] = cis(cg->cphase * (LO ? a.R_lo[tid] : a.R_hi[tid]));
+            er_s[tid] = cis((XQ && !LO ? cg->cphase_x : cg->cphase) * (LO ? a.R_lo[tid] : a.R_hi[tid]));
         }
     }
     __syncthreads();
@@ -299,15 +336,20 @@ __global__ void __launch_bounds__(NT, 3) sweep128_kernel(const Sweep128Args a, c
     // phase layout = L2 when the tile has two layouts, else L1
     const int64_t base_phase = (int64_t)G::tile_base(tile) + (G::two ? gmap<G>(local2<G>(tid, 0)) : off1);
     const double *af = (LO ? a.af_lo : a.af_hi) + (tile * NT + tid) * 6;
+    const double t1 = LO ? -1.0 : 1.0, t2 = -t1;  // XQ multipliers before / after the diagonal of the sweep
+    const double cdiag = XQ && !LO ? cp.cphase_x : cp.cphase;
+    const double sdiag = XQ ? a.gen_scale : 1.0;
     if (ROLE == R_FINAL || ROLE == R_FINAL1) {  // LO only
         if (ROLE == R_FINAL1) {
             init_product32(v, (uint64_t)base_phase, n, cp, q2);
         } else {
-            bfly5<G::act1>(v, cp, q1);
+            if (XQ) bfly5t<G::act1>(v, t1);
+            else bfly5<G::act1>(v, cp, q1);
             to_smem1<G>(v, sm, tid);
             __syncthreads();
             from_smem2<G>(v, sm, tid);
-            bfly5<G::act2>(v, cp, q2);
+            if (XQ) bfly5t<G::act2>(v, t1);
+            else bfly5<G::act2>(v, cp, q2);
         }
         double s = 0.0;
 #pragma unroll
@@ -322,32 +364,44 @@ __global__ void __launch_bounds__(NT, 3) sweep128_kernel(const Sweep128Args a, c
             double2 *ao = a.amps_out + (chain << n) + base_phase;
             const int kb = __popcll((unsigned long long)base_phase);
 #pragma unroll
-            for (int j = 0; j < APT; ++j) ao[j] = times_i_pow(v[j], kb + __builtin_popcount(j));  // a = i^popcount S
+            for (int j = 0; j < APT; ++j) ao[j] = XQ ? v[j] : times_i_pow(v[j], kb + __builtin_popcount(j));  // a = i^popcount S
         }
         return;
     }
+    const double mag0 = XQ ? exp2(-0.5 * (double)n) : 0.0;
     if (G::two) {
         if (ROLE == R_FIRST) {
-            init_product32(v, (uint64_t)base_phase, n, cp, q2);
+            if (XQ) init_hadamard32(v, (uint64_t)base_phase, cp, q2, mag0);
+            else init_product32(v, (uint64_t)base_phase, n, cp, q2);
         } else {
-            bfly5<G::act1>(v, cp, q1);
+            if (XQ) bfly5t<G::act1>(v, t1);
+            else bfly5<G::act1>(v, cp, q1);
             to_smem1<G>(v, sm, tid);
             __syncthreads();
             from_smem2<G>(v, sm, tid);
-            bfly5<G::act2>(v, cp, q2);
+            if (XQ) bfly5t<G::act2>(v, t1);
+            else bfly5<G::act2>(v, cp, q2);
         }
-        phase32(v, af, er_s, cp.cphase);
-        bfly5<G::act2>(v, cp, q2);
+        phase32(v, af, er_s, cdiag, sdiag);
+        if (XQ) bfly5t<G::act2>(v, t2);
+        else bfly5<G::act2>(v, cp, q2);
         if (ROLE != R_FIRST) __syncthreads();  // every thread has read its layout-2 slots
         to_smem2<G>(v, sm, tid);
         __syncthreads();
         from_smem1<G>(v, sm, tid);
-        bfly5<G::act1>(v, cp, q1);
-    } else {
-        if (ROLE == R_FIRST) init_product32(v, (uint64_t)base_phase, n, cp, q1);
+        if (XQ) bfly5t<G::act1>(v, t2);
         else bfly5<G::act1>(v, cp, q1);
-        phase32(v, af, er_s, cp.cphase);
-        bfly5<G::act1>(v, cp, q1);
+    } else {
+        if (ROLE == R_FIRST) {
+            if (XQ) init_hadamard32(v, (uint64_t)base_phase, cp, q1, mag0);
+            else init_product32(v, (uint64_t)base_phase, n, cp, q1);
+        } else {
+            if (XQ) bfly5t<G::act1>(v, t1);
+            else bfly5<G::act1>(v, cp, q1);
+        }
+        phase32(v, af, er_s, cdiag, sdiag);
+        if (XQ) bfly5t<G::act1>(v, t2);
+        else bfly5<G::act1>(v, cp, q1);
     }
     store1<G>(v, state + off1);
 }
@@ -392,6 +446,7 @@ __global__ void af128_kernel(int n, const double *__restrict__ Jq, const double 
 // ---------------------------------------------------------------------------------------------
 struct Hop128Args {
     int n, mode, n_groups, phase_active;
+    int xq;  // XQ mode: cp.r counts half-layers (2 r sweeps per proposal)
     int64_t n_chains, n_hops, hop;
     uint64_t chain_id0, seed;
     uint32_t hop0;
@@ -413,8 +468,20 @@ struct Hop128Args {
 __device__ void fill_params128(ChainParams128 &cp, const Hop128Args &h, double gamma, int r, int grp) {
     cp.r = r < 1 ? 1 : r;
     cp.group = grp;
+    cp.cphase_x = 0.0;
     double scale = 1.0;
     for (int q = 0; q < NMAX; ++q) cp.tq[q] = 0.0;
+    if (h.xq) {  // see sweep.cu: fill_proposal_params
+        const int real_r = cp.r;
+        cp.r = 2 * real_r;
+        for (int q = 0; q < h.n; ++q) cp.tq[q] = -1.0;  // the sampler repeats the last transform (back on the LO qubits)
+        cp.scale = 1.0;
+        const double c = (1.0 - gamma) * h.alpha * h.dt;
+        cp.active = h.phase_active && real_r > 1 && c != 0.0;
+        cp.cphase = cp.active ? c : 0.0;
+        cp.cphase_x = -gamma * h.dt;
+        return;
+    }
     for (int q = 0; q < h.n; ++q) {
         const double wq = h.qweight[grp * h.n + q];
         if (wq == 0.0) continue;
@@ -676,6 +743,10 @@ struct Sweep128Workspace {
     double *dJq = nullptr, *dhq = nullptr;
     bool tables_ready = false;
     QmcGroupSched gsched;  // L2-resident group schedule: side streams + fork / join events
+    // XQ mode: tables of the mixer diagonal in the HI phase layout
+    int xq_epoch = -1;
+    double *afx_hi = nullptr, *dxJ = nullptr, *dxh = nullptr;
+    double Rx_hi[APT];
 };
 
 void qmc_sweep128_free(qmc_model *m) {
@@ -684,6 +755,7 @@ void qmc_sweep128_free(qmc_model *m) {
     cudaFree(w->state); cudaFree(w->params); cudaFree(w->segsum); cudaFree(w->hist); cudaFree(w->order);
     cudaFree(w->af_lo); cudaFree(w->af_hi); cudaFree(w->dJq); cudaFree(w->dhq);
     w->gsched.destroy();
+    cudaFree(w->afx_hi); cudaFree(w->dxJ); cudaFree(w->dxh);
     delete w;
     m->sweep128 = nullptr;
 }
@@ -701,25 +773,25 @@ static int smem_optin(K kernel, DevMask128 &done) {
     return QMC_OK;
 }
 
-template <typename G, int ROLE>
+template <typename G, int ROLE, bool XQ = false>
 static int launch128(const Sweep128Args &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
     static DevMask128 done = 0;
-    int rc = smem_optin(sweep128_kernel<G, ROLE>, done);
+    int rc = smem_optin(sweep128_kernel<G, ROLE, XQ>, done);
     if (rc != QMC_OK) return rc;
-    sweep128_kernel<G, ROLE><<<dim3((unsigned)tiles, (unsigned)count), NT, SMEM_BYTES, st>>>(a, order, off);
+    sweep128_kernel<G, ROLE, XQ><<<dim3((unsigned)tiles, (unsigned)count), NT, SMEM_BYTES, st>>>(a, order, off);
     return QMC_OK;
 }
-template <int ROLE>
+template <int ROLE, bool XQ = false>
 static int launch128_hi(int n, const Sweep128Args &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
     switch (22 - n) {  // LC
-        case 2: return launch128<HiGeo<2>, ROLE>(a, order, off, tiles, count, st);
-        case 3: return launch128<HiGeo<3>, ROLE>(a, order, off, tiles, count, st);
-        case 4: return launch128<HiGeo<4>, ROLE>(a, order, off, tiles, count, st);
-        case 5: return launch128<HiGeo<5>, ROLE>(a, order, off, tiles, count, st);
-        case 6: return launch128<HiGeo<6>, ROLE>(a, order, off, tiles, count, st);
-        case 7: return launch128<HiGeo<7>, ROLE>(a, order, off, tiles, count, st);
-        case 8: return launch128<HiGeo<8>, ROLE>(a, order, off, tiles, count, st);
-        case 9: return launch128<HiGeo<9>, ROLE>(a, order, off, tiles, count, st);
+        case 2: return launch128<HiGeo<2>, ROLE, XQ>(a, order, off, tiles, count, st);
+        case 3: return launch128<HiGeo<3>, ROLE, XQ>(a, order, off, tiles, count, st);
+        case 4: return launch128<HiGeo<4>, ROLE, XQ>(a, order, off, tiles, count, st);
+        case 5: return launch128<HiGeo<5>, ROLE, XQ>(a, order, off, tiles, count, st);
+        case 6: return launch128<HiGeo<6>, ROLE, XQ>(a, order, off, tiles, count, st);
+        case 7: return launch128<HiGeo<7>, ROLE, XQ>(a, order, off, tiles, count, st);
+        case 8: return launch128<HiGeo<8>, ROLE, XQ>(a, order, off, tiles, count, st);
+        case 9: return launch128<HiGeo<9>, ROLE, XQ>(a, order, off, tiles, count, st);
     }
     qmc_set_error("complex128 sweep path: n=%d outside [13, 20]", n);
     return QMC_ERR_UNSUPPORTED;
@@ -796,6 +868,38 @@ static int ensure_workspace128(qmc_model *m, int64_t chains, cudaStream_t st) {
     return QMC_OK;
 }
 
+static int ensure_xq_tables128(qmc_model *m, cudaStream_t st) {
+    Sweep128Workspace *w = m->sweep128;
+    if (w->xq_epoch == m->mixer_epoch) return QMC_OK;
+    const int n = m->n;
+    const int64_t N = 1LL << n;
+    QMC_REQUIRE(m->quad_mixer && (int)m->xh.size() == n, QMC_ERR_UNSUPPORTED,
+                "complex128 sweep path: the mixer is not a single group of one- and two-qubit X strings");
+    QMC_CUDA_TRY(cudaStreamSynchronize(st));
+    if (!w->dxJ) {
+        QMC_CUDA_TRY(cudaMalloc(&w->dxJ, sizeof(double) * (size_t)n * n));
+        QMC_CUDA_TRY(cudaMalloc(&w->dxh, sizeof(double) * (size_t)n));
+        QMC_CUDA_TRY(cudaMalloc(&w->afx_hi, sizeof(double) * 6 * (size_t)(N >> RB)));
+    }
+    QMC_CUDA_TRY(cudaMemcpy(w->dxJ, m->xJ.data(), sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
+    QMC_CUDA_TRY(cudaMemcpy(w->dxh, m->xh.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    switch (22 - n) {
+        case 2: build_af128<HiGeo<2>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<2>>(m->xJ, n, w->Rx_hi); break;
+        case 3: build_af128<HiGeo<3>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<3>>(m->xJ, n, w->Rx_hi); break;
+        case 4: build_af128<HiGeo<4>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<4>>(m->xJ, n, w->Rx_hi); break;
+        case 5: build_af128<HiGeo<5>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<5>>(m->xJ, n, w->Rx_hi); break;
+        case 6: build_af128<HiGeo<6>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<6>>(m->xJ, n, w->Rx_hi); break;
+        case 7: build_af128<HiGeo<7>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<7>>(m->xJ, n, w->Rx_hi); break;
+        case 8: build_af128<HiGeo<8>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<8>>(m->xJ, n, w->Rx_hi); break;
+        case 9: build_af128<HiGeo<9>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<9>>(m->xJ, n, w->Rx_hi); break;
+        default: qmc_set_error("complex128 sweep path: n=%d outside [13, 20]", n); return QMC_ERR_UNSUPPORTED;
+    }
+    m->launches++;
+    QMC_CUDA_TRY(cudaGetLastError());
+    w->xq_epoch = m->mixer_epoch;
+    return QMC_OK;
+}
+
 int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, const uint64_t *s_in, uint64_t chain_id0,
                      uint32_t hop0, double temperature, double g_lo, double g_hi, double dt, uint64_t seed,
                      const double *gamma_arr, const int *r_arr, const double *u_arr, const int *group_arr,
@@ -803,7 +907,9 @@ int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, c
                      int64_t *hamming_hist, void *probs_out, void *amps_out, cudaStream_t st) {
     const int n = m->n;
     QMC_REQUIRE(n >= 13 && n <= NMAX, QMC_ERR_UNSUPPORTED, "complex128 sweep path covers 13 <= n <= %d (n=%d)", NMAX, n);
-    QMC_REQUIRE(m->all_one_body, QMC_ERR_UNSUPPORTED, "complex128 sweep path: one-body X mixers only");
+    const bool xq = !m->all_one_body && m->quad_mixer;  // one coherent group of one- and two-qubit X strings
+    QMC_REQUIRE(m->all_one_body || xq, QMC_ERR_UNSUPPORTED,
+                "complex128 sweep path: one-body X mixers and single groups of one- and two-qubit X strings only");
     if (n_chains == 0) return QMC_OK;
     {
         static DevMask128 attr = 0;
@@ -829,6 +935,10 @@ int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, c
     int rc = ensure_workspace128(m, batch, st);
     if (rc != QMC_OK) return rc;
     Sweep128Workspace *w = m->sweep128;
+    if (xq) {
+        rc = ensure_xq_tables128(m, st);
+        if (rc != QMC_OK) return rc;
+    }
     int r_max = qmc_trotter_steps(11, dt);
     std::vector<int> r_host;
     if (mode != QMC_MODE_CHAIN) {
@@ -838,6 +948,7 @@ int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, c
         r_max = 1;
         for (int64_t c = 0; c < n_chains; ++c) r_max = std::max(r_max, r_host[c]);
     }
+    if (xq) r_max *= 2;  // XQ mode: 2 r sweeps per proposal (HI first, LO last)
     QMC_REQUIRE(r_max <= SCHED_RMAX, QMC_ERR_UNSUPPORTED, "delta_time=%g gives up to %d Trotter layers (> %d)", dt, r_max, SCHED_RMAX);
     std::vector<int> rhist(r_max + 2, 0);
     const QmcGroupKnobs l2k = qmc_group_knobs((int64_t)sizeof(double2) << n, 16, 3);
@@ -846,6 +957,7 @@ int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, c
         Hop128Args h;
         memset(&h, 0, sizeof(h));
         h.n = n; h.mode = mode; h.n_groups = m->n_groups; h.phase_active = m->phase_active;
+        h.xq = xq ? 1 : 0;
         h.n_chains = nc; h.n_hops = n_hops; h.hop = 0;
         h.chain_id0 = chain_id0 + (uint64_t)c0; h.seed = seed; h.hop0 = hop0;
         h.temperature = temperature; h.g_lo = g_lo; h.g_hi = g_hi; h.dt = dt; h.alpha = m->alpha;
@@ -889,24 +1001,46 @@ int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, c
                 } else {
                     r = std::max(1, r_host[c0 + c]);
                 }
+                if (xq) r *= 2;
                 rhist[r]++;
             }
             int launched = 0;
             int base[2] = {0, 0};  // start of the odd-r / even-r class in order[]
             for (int r = 1; r <= r_max; r += 2) base[1] += rhist[r];
+            // XQ mode: LO sweeps host the phase layer, HI sweeps the mixer diagonal (its tables); every sweep's phase factor
+            // carries the normalisation of its own transforms, the HI FIRST sweep also that of the FINAL sweep
+            Sweep128Args ax_lo = a, ax_hif = a, ax_him = a;
+            if (xq) {
+                const int nh = n - LOQ;
+                ax_lo.gen_scale = ldexp(1.0, -LOQ);
+                ax_hif.af_hi = ax_him.af_hi = w->afx_hi;
+                memcpy(ax_hif.R_hi, w->Rx_hi, sizeof(a.R_hi));
+                memcpy(ax_him.R_hi, w->Rx_hi, sizeof(a.R_hi));
+                ax_him.gen_scale = ldexp(1.0, -nh);
+                ax_hif.gen_scale = exp2(-0.5 * nh - 0.5 * LOQ);
+            }
+            auto lo = [&](int kind, int off, int count, cudaStream_t sg) {
+                if (xq) {
+                    if (kind == QMC_GS_MID) return launch128<LoGeo, R_MID, true>(ax_lo, w->order, off, tiles, count, sg);
+                    if (kind == QMC_GS_FINAL) return launch128<LoGeo, R_FINAL, true>(ax_lo, w->order, off, tiles, count, sg);
+                    qmc_set_error("XQ schedule: LO role %d cannot occur (every proposal has an even number of sweeps)", kind);
+                    return (int)QMC_ERR_CUDA;
+                }
+                switch (kind) {
+                    case QMC_GS_FIRST: return launch128<LoGeo, R_FIRST>(a, w->order, off, tiles, count, sg);
+                    case QMC_GS_MID: return launch128<LoGeo, R_MID>(a, w->order, off, tiles, count, sg);
+                    case QMC_GS_FINAL: return launch128<LoGeo, R_FINAL>(a, w->order, off, tiles, count, sg);
+                    default: return launch128<LoGeo, R_FINAL1>(a, w->order, off, tiles, count, sg);
+                }
+            };
+            auto hi = [&](bool first, int off, int count, cudaStream_t sg) {
+                if (xq)
+                    return first ? launch128_hi<R_FIRST, true>(n, ax_hif, w->order, off, tiles, count, sg)
+                                 : launch128_hi<R_MID, true>(n, ax_him, w->order, off, tiles, count, sg);
+                return first ? launch128_hi<R_FIRST>(n, a, w->order, off, tiles, count, sg)
+                             : launch128_hi<R_MID>(n, a, w->order, off, tiles, count, sg);
+            };
             if (l2k.group > 0 && nc > l2k.group) {  // L2-resident group schedule, see group_sched.cuh
-                auto lo = [&](int kind, int off, int count, cudaStream_t sg) {
-                    switch (kind) {
-                        case QMC_GS_FIRST: return launch128<LoGeo, R_FIRST>(a, w->order, off, tiles, count, sg);
-                        case QMC_GS_MID: return launch128<LoGeo, R_MID>(a, w->order, off, tiles, count, sg);
-                        case QMC_GS_FINAL: return launch128<LoGeo, R_FINAL>(a, w->order, off, tiles, count, sg);
-                        default: return launch128<LoGeo, R_FINAL1>(a, w->order, off, tiles, count, sg);
-                    }
-                };
-                auto hi = [&](bool first, int off, int count, cudaStream_t sg) {
-                    return first ? launch128_hi<R_FIRST>(n, a, w->order, off, tiles, count, sg)
-                                 : launch128_hi<R_MID>(n, a, w->order, off, tiles, count, sg);
-                };
                 rc = qmc_group_schedule(w->gsched, l2k, st, (int)nc, r_max, rhist, lo, hi, launched);
                 if (rc != QMC_OK) return rc;
             } else
@@ -919,20 +1053,17 @@ int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, c
                 for (int r = step + 1; r <= r_max; r += 2) hi_gt += rhist[r];
                 const int lo_eq = rhist[step];
                 if (lo_gt > 0) {
-                    rc = step == 1 ? launch128<LoGeo, R_FIRST>(a, w->order, lo_base, tiles, lo_gt, st)
-                                   : launch128<LoGeo, R_MID>(a, w->order, lo_base, tiles, lo_gt, st);
+                    rc = lo(step == 1 ? QMC_GS_FIRST : QMC_GS_MID, lo_base, lo_gt, st);
                     if (rc != QMC_OK) return rc;
                     ++launched;
                 }
                 if (lo_eq > 0) {
-                    rc = step == 1 ? launch128<LoGeo, R_FINAL1>(a, w->order, lo_base + lo_gt, tiles, lo_eq, st)
-                                   : launch128<LoGeo, R_FINAL>(a, w->order, lo_base + lo_gt, tiles, lo_eq, st);
+                    rc = lo(step == 1 ? QMC_GS_FINAL1 : QMC_GS_FINAL, lo_base + lo_gt, lo_eq, st);
                     if (rc != QMC_OK) return rc;
                     ++launched;
                 }
                 if (hi_gt > 0) {
-                    rc = step == 1 ? launch128_hi<R_FIRST>(n, a, w->order, hi_base, tiles, hi_gt, st)
-                                   : launch128_hi<R_MID>(n, a, w->order, hi_base, tiles, hi_gt, st);
+                    rc = hi(step == 1, hi_base, hi_gt, st);
                     if (rc != QMC_OK) return rc;
                     ++launched;
                 }

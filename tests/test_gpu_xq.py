@@ -21,7 +21,8 @@ def _mixer(q, n, kind):
     raise ValueError(kind)
 
 
-def _check(q, n, mixer, rs, seed=3, tol_p=1e-6, tol_a=5e-5):
+def _check(q, n, mixer, rs, seed=3, dtype="fp32"):
+    tol_p, tol_a = (1e-6, 5e-5) if dtype == "fp32" else (1e-10, 1e-9)
     J, h = models.packaged_random_model(n, seed)
     m = q.IsingEnergyFunction(J, h)
     offs, masks, w, _ = mixer.lower()
@@ -30,7 +31,7 @@ def _check(q, n, mixer, rs, seed=3, tol_p=1e-6, tol_a=5e-5):
     for r in rs:
         s = int(rng.integers(0, 1 << n))
         gamma = float(rng.uniform(0.25, 0.6))
-        p, a = q.transition_probabilities(m, mixer, s, gamma, r, dtype="fp32", return_amplitudes=True)
+        p, a = q.transition_probabilities(m, mixer, s, gamma, r, dtype=dtype, return_amplitudes=True)
         ref = oracle.evolve(J, h, al, gamma, 0.8, r, masks, w, s, gatewise=False)
         assert abs(p.sum() - 1.0) < 1e-5
         assert np.abs(p - np.abs(ref) ** 2).max() < tol_p, (n, r, np.abs(p - np.abs(ref) ** 2).max())
@@ -49,6 +50,31 @@ def test_xq_two_body_vs_oracle(n):
 def test_xq_custom_pairs_and_coherent_sums_vs_oracle(n, kind):
     import qumcmc_b200 as q
     _check(q, n, _mixer(q, n, kind), (1, 2, 5))
+
+
+@pytest.mark.parametrize("n,kind", [(13, "two"), (14, "two"), (15, "coh"), (16, "two"), (17, "pairs"), (18, "two"), (19, "coh"), (20, "two")])
+def test_xq_complex128_vs_oracle(n, kind):
+    """The same in the reference's own precision (sweep128.cu, XQ mode): every HI geometry of the complex128 tiles
+    (LC = 22 - n = 9..2), tolerance 1e-10 on the probabilities."""
+    import qumcmc_b200 as q
+    _check(q, n, _mixer(q, n, kind), (1, 2, 5) if n < 19 else (1, 3), dtype="fp64")
+
+
+def test_xq_complex128_chains_equal_the_oracle_chain():
+    """complex128 chains with a two-body mixer at n = 13: proposals, accept flags and final states equal oracle.run_chain
+    hop for hop."""
+    import qumcmc_b200 as q
+    n, C, H, seed = 13, 6, 6, 41
+    J, h = models.packaged_random_model(n, 7)
+    m = q.IsingEnergyFunction(J, h)
+    mixer = q.GenericMixer.TwoBodyMixer(n)
+    offs, masks, w, _ = mixer.lower()
+    b = q.quantum_enhanced_mcmc(H, m, mixer, (0.25, 0.6), temperature=1.0, n_chains=C, seed=seed, dtype="fp64")
+    for c in range(C):
+        s0 = oracle.initial_state(seed, c, n)
+        props, acc = oracle.run_chain(J, h, masks, w, s0, H, 1.0, (0.25, 0.6), 0.8, seed, chain_id=c)
+        assert np.array_equal(np.asarray(props, dtype=np.int64), b.proposals[c].astype(np.int64)), c
+        assert np.array_equal(np.asarray(acc, dtype=np.uint8), b.accepted[c].astype(np.uint8)), c
 
 
 def test_xq_gamma_extremes_and_absent_phase_layer():
@@ -138,14 +164,16 @@ def test_xq_group_schedule_is_bit_identical(monkeypatch, n, C, mib):
 
 
 def test_mixers_outside_xq_keep_their_paths():
-    """Three-body terms, incoherent sums and complex128 do not qualify: they still run (general path) and agree with the oracle."""
+    """Three-body terms and incoherent sums do not qualify: they still run (general path) and agree with the oracle."""
     import qumcmc_b200 as q
     n = 14
     J, h = models.packaged_random_model(n, 3)
     m = q.IsingEnergyFunction(J, h)
     al = oracle.alpha(J, h)
-    for mixer, dtype in ((q.CustomMixer(n, [[0, 1, 2], [3, 4], [5]]), "fp32"), (q.GenericMixer.TwoBodyMixer(n), "fp64")):
+    inc = q.IncoherentMixerSum([q.GenericMixer.OneBodyMixer(n), q.GenericMixer.TwoBodyMixer(n)], [0.5, 0.5])
+    for mixer, dtype, group in ((q.CustomMixer(n, [[0, 1, 2], [3, 4], [5]]), "fp32", 0), (inc, "fp32", 1), (inc, "fp64", 1)):
         offs, masks, w, _ = mixer.lower()
-        p = q.transition_probabilities(m, mixer, 77, 0.4, 3, dtype=dtype)
-        ref = oracle.evolve(J, h, al, 0.4, 0.8, 3, masks, w, 77, gatewise=False)
+        gm, gw = masks[offs[group]:offs[group + 1]], w[offs[group]:offs[group + 1]]
+        p = q.transition_probabilities(m, mixer, 77, 0.4, 3, dtype=dtype, group=group)
+        ref = oracle.evolve(J, h, al, 0.4, 0.8, 3, gm, gw, 77, gatewise=False)
         assert np.abs(p - np.abs(ref) ** 2).max() < (1e-6 if dtype == "fp32" else 1e-10)
