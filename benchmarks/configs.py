@@ -89,11 +89,15 @@ def c4():
 
 
 def general():
-    """General path (tiled passes, any X-string mixer / complex128): proposals/s and the pass count."""
+    """Mixers beyond one-body: two-body (n <= 20: XQ mode of the sweep kernels, 2 sweeps per layer; n > 20: Hadamard-basis
+    general path) and three-body (general path at every n): proposals/s and the pass count."""
+    import os
     for n, mixer_name, dtype, chains, H in [(16, "two", "fp32", 512, 8), (16, "two", "fp64", 512, 8), (20, "two", "fp32", 1024, 6),
-                                            (20, "two", "fp64", 512, 6), (24, "two", "fp32", 32, 4), (26, "two", "fp32", 8, 4)]:
+                                            (20, "two", "fp64", 512, 6), (16, "three", "fp32", 512, 8), (20, "three", "fp32", 512, 6),
+                                            (24, "two", "fp32", 32, 4), (26, "two", "fp32", 8, 4)]:
         m = q.random_ising_model(n, 1)
-        mx = q.GenericMixer.OneBodyMixer(n) if mixer_name == "one" else q.GenericMixer.TwoBodyMixer(n)
+        mx = {"one": q.GenericMixer.OneBodyMixer, "two": q.GenericMixer.TwoBodyMixer, "three": q.GenericMixer.ThreeBodyMixer}[mixer_name](n)
+        xq = mixer_name == "two" and n <= 20 and not os.environ.get("QUMCMC_NO_XQ")
         q.quantum_enhanced_mcmc(1, m, mx, (0.25, 0.6), temperature=1.0, n_chains=chains, seed=3, dtype=dtype)  # warm + alloc
         dt, b = timed(lambda: q.quantum_enhanced_mcmc(H, m, mx, (0.25, 0.6), temperature=1.0, n_chains=chains, seed=4, dtype=dtype))
         from qumcmc_b200.rng import philox4x32
@@ -104,10 +108,12 @@ def general():
         K = max(1, -(-(n - 12) // 8))                        # groups above qubits 0..11
         esz = 8 if dtype == "fp32" else 16
         moved = 2.0 * esz * (1 << n) * (2 * K * sum_r - K * chains * H)   # FIRST write-only, 2K(r-1)+K-... passes read+write
-        print(json.dumps({"config": "general path n=%d, %s-body mixer, %s, %d chains x %d hops" % (n, mixer_name, dtype, chains, H),
+        print(json.dumps({"config": "%s n=%d, %s-body mixer, %s, %d chains x %d hops" % (
+                              "sweep kernels (XQ mode)" if xq else "general path", n, mixer_name, dtype, chains, H),
                           "seconds": dt, "proposals_per_s": chains * H / dt, "acceptance": b.acceptance_rate(),
                           "passes_per_layer": 2 * K, "approx_moved_GBps": moved / 1e9 / dt,
-                          "reference_cost": "one statevector pass per gate: %d passes per layer" % (n * (n - 1) // 2 + n + (n if mixer_name == "one" else n * (n - 1) // 2))}))
+                          "reference_cost": "one statevector pass per gate: %d passes per layer" % (
+                              n * (n - 1) // 2 + n + {"one": n, "two": n * (n - 1) // 2, "three": n * (n - 1) * (n - 2) // 6}[mixer_name])}))
 
 
 def c128():

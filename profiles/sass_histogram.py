@@ -9,9 +9,10 @@ import re
 import subprocess
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "qumcmc_b200", "csrc")
-WANT = [("sweep.o", r"lo_sweep_kernelILi1ELi64ELb1"), ("sweep.o", r"hiq_sweep_kernelILb1"), ("sweep.o", r"lo_sweep_kernelILi0ELi128ELb1"),
-        ("sweep.o", r"lo_sweep_kernelILi2ELi128ELb1"), ("sweep.o", r"hi8_sweep_kernelILi1ELi8ELi8"), ("sweep128.o", r"sweep128_kernelINS_5LoGeoELi1"),
-        ("sweep128.o", r"sweep128_kernelINS_5HiGeoILi2EEELi1"), ("general.o", r"gen_pass_kernelIfE"), ("general.o", r"gen_pass_kernelIdE"),
+WANT = [("sweep.o", r"lo_sweep_kernelILi1ELi64ELb1ELb0"), ("sweep.o", r"hiq_sweep_kernelILb1ELb0"), ("sweep.o", r"lo_sweep_kernelILi0ELi128ELb1ELb0"),
+        ("sweep.o", r"lo_sweep_kernelILi2ELi128ELb1ELb0"), ("sweep.o", r"lo_sweep_kernelILi1ELi64ELb1ELb1"), ("sweep.o", r"hiq_sweep_kernelILb1ELb1"),
+        ("sweep.o", r"hi8_sweep_kernelILi1ELi8ELi8"), ("sweep128.o", r"sweep128_kernelINS_5LoGeoELi1ELb0"),
+        ("sweep128.o", r"sweep128_kernelINS_5HiGeoILi2EEELi1ELb0"), ("general.o", r"gen_pass_kernelIfE"), ("general.o", r"gen_pass_kernelIdE"),
         ("small_n.o", r"warp_chain_kernelIfLi4E"), ("small_n.o", r"warp_chain_kernelIdLi5E")]
 KEYS = ["FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "DFMA", "DADD", "DMUL", "MUFU", "I2FP", "I2F", "IADD3", "LOP3", "LDG", "STG",
         "LDS", "STS", "LDC", "LDCU", "BAR", "CCTL", "UBLKPF", "SHFL", "BRA", "MOV", "LDL", "STL"]
