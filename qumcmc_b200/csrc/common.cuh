@@ -150,10 +150,10 @@ struct qmc_model {
                                       // exp(-i a X) exp(-i b X) = exp(-i (a + b) X), their weights add up)
     std::vector<double> qweight;      // all_one_body: summed weight per (group, qubit), [n_groups][n]
     double *d_qweight = nullptr;
-    // one coherent group whose terms have weight <= 2 (and not all 1): E_x(x) = sum_q xh[q] z_q + sum_{q<q'} xJ[q][q'] z_q z_q'
+    // every term of every group has weight <= 2 (and not all 1): per group E_x(x) = sum_q xh[q] z_q + sum_{q<q'} xJ[q][q'] z_q z_q'
     // is the same kind of quadratic form as the phase layer, so the sweep kernels can host it (sweep.cu, XQ mode)
     bool quad_mixer = false;
-    std::vector<double> xJ, xh;       // [n][n] symmetric with zero diagonal, [n]; index = qubit = index bit
+    std::vector<double> xJ, xh;       // [n_groups][n][n] symmetric with zero diagonal, [n_groups][n]; index = qubit = index bit
     std::vector<double> host_J, host_h, host_cJ, host_ch;
     // fast exact enumerator: symmetrised couplings / fields in qubit order, constant 0.5 * trace(J)
     double *dJp = nullptr, *dhq_e = nullptr;

@@ -492,24 +492,25 @@ extern "C" int qmc_mixer_set(qmc_model *m, int n_groups, const int *group_offset
     m->quad_mixer = false;
     m->xJ.clear();
     m->xh.clear();
-    if (!one_body && n_groups == 1) {  // one coherent group of one- and two-qubit X strings: a quadratic form in the x basis
+    if (!one_body) {  // every group made of one- and two-qubit X strings: quadratic forms in the x basis, one per group
         bool quad = true;
         for (int k = 0; k < nt; ++k) quad = quad && __builtin_popcountll(masks[k]) <= 2;
         if (quad) {
             const int n = m->n;
-            m->xJ.assign((size_t)n * n, 0.0);
-            m->xh.assign((size_t)n, 0.0);
-            for (int k = 0; k < nt; ++k) {
-                const int q1 = __builtin_ffsll((long long)masks[k]) - 1;
-                const uint64_t rest = masks[k] & (masks[k] - 1);
-                if (!rest) {
-                    m->xh[q1] += weights[k];
-                } else {
-                    const int q2 = __builtin_ffsll((long long)rest) - 1;
-                    m->xJ[(size_t)q1 * n + q2] += weights[k];
-                    m->xJ[(size_t)q2 * n + q1] += weights[k];
+            m->xJ.assign((size_t)n_groups * n * n, 0.0);
+            m->xh.assign((size_t)n_groups * n, 0.0);
+            for (int g = 0; g < n_groups; ++g)
+                for (int k = group_offsets[g]; k < group_offsets[g + 1]; ++k) {
+                    const int q1 = __builtin_ffsll((long long)masks[k]) - 1;
+                    const uint64_t rest = masks[k] & (masks[k] - 1);
+                    if (!rest) {
+                        m->xh[(size_t)g * n + q1] += weights[k];
+                    } else {
+                        const int q2 = __builtin_ffsll((long long)rest) - 1;
+                        m->xJ[((size_t)g * n + q1) * n + q2] += weights[k];
+                        m->xJ[((size_t)g * n + q2) * n + q1] += weights[k];
+                    }
                 }
-            }
             m->quad_mixer = true;
         }
     }

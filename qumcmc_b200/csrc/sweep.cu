@@ -80,6 +80,8 @@ struct SweepArgs {
     int pf_dist;              // > 0: each CTA L2-prefetches the tile of the CTA launched pf_dist later (in launch order)
     int pf_lines;             // strided tiles: 1 = per-thread prefetch.global.L2 of 128-byte lines, 0 = bulk prefetch per row
     float gen_scale;          // XQ mode: normalisation of the Walsh-Hadamard transforms of this launch (applied with the phase)
+    const int *xq_dr;         // XQ mode: Gray increments of the mixer diagonal, [mixer group][layout: hia, hib, hic][64]
+    int64_t xq_af_stride;     // XQ mode: int4 entries between the af_hi* tables of consecutive mixer groups
     // Fused exchange (sharded statevector): when xchg_peers != null the pass stores amplitude L of this rank to
     // xchg_peers[L >> xchg_shift][(L & low) | (xchg_rank << xchg_shift)] -- the all-to-all that swaps the top local
     // index bits with the rank bits, done by the sweep's own stores over NVLink peer mappings (no staging copy).
@@ -270,9 +272,12 @@ __device__ __forceinline__ PhaseAF load_af(const int4 *__restrict__ af, int64_t 
 __device__ __forceinline__ int turns32(int dfx, int cfx, int shift) {
     return (int)(unsigned int)(((long long)dfx * (long long)cfx) >> shift);
 }
-template <bool XQ_X = false>
 __device__ __forceinline__ void build_hs(int *hs, const int (&dr)[64], const ChainParams *cpg, int tid) {
-    if (tid < 64) hs[tid] = XQ_X ? turns32(dr[tid], cpg->cfx_x, cpg->shift_x) : turns32(dr[tid], cpg->cfx, cpg->shift);
+    if (tid < 64) hs[tid] = turns32(dr[tid], cpg->cfx, cpg->shift);
+}
+// XQ mode, HI sweeps: increments of the mixer diagonal of the chain's mixer group (global memory), rate cfx_x
+__device__ __forceinline__ void build_hs_x(int *hs, const int *__restrict__ drx, const ChainParams *cpg, int tid) {
+    if (tid < 64) hs[tid] = turns32(__ldg(drx + tid), cpg->cfx_x, cpg->shift_x);
 }
 
 // K1 for the thread's 64 amplitudes.  The phase angle is accumulated directly in 32-bit integer turns along the
@@ -687,10 +692,14 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
             else for (int r = tid; r < ROWS; r += NT) l2_prefetch_bulk(src + ((int64_t)r << 12), ROW_BYTES);
         }
     }
-    build_hs<XQ>(hs_s, G::two_rounds ? a.dr_hib : a.dr_hia, a.params + chain, tid);
+    // XQ: tables of the chain's mixer group (IncoherentMixerSum picks one sub-mixer per proposal)
+    const int grp = XQ ? a.params[chain].group : 0;
+    const int *drx = XQ ? a.xq_dr + ((int64_t)grp * 3 + (G::two_rounds ? 1 : 0)) * 64 : nullptr;
+    if (XQ) build_hs_x(hs_s, drx, a.params + chain, tid);
+    else build_hs(hs_s, G::two_rounds ? a.dr_hib : a.dr_hia, a.params + chain, tid);
     stage_params(cp_s, a.params + chain, tid);
     const ChainParams &cp = cp_s;
-    const PhaseAF af = load_af(G::two_rounds ? a.af_hib : a.af_hia, tile * NT + tid);
+    const PhaseAF af = load_af((G::two_rounds ? a.af_hib : a.af_hia) + (XQ ? grp * a.xq_af_stride : 0), tile * NT + tid);
     const float mag0 = XQ ? exp2f(-0.5f * (float)n) : 0.f;
     if (G::two_rounds) {
         const int64_t base_b = hi_base_b<W>(tid, tile);
@@ -707,7 +716,7 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
             bfly6<G::active_b, FAST>(v, cp, HiQB<W>(), tu);
             __syncthreads();
         }
-        if (XQ) phase_gray<false>(v, af, hs_s, a.dr_hib[0], cp.cfx_x, cp.shift_x, a.gen_scale);
+        if (XQ) phase_gray<false>(v, af, hs_s, __ldg(drx), cp.cfx_x, cp.shift_x, a.gen_scale);
         else phase_gray<FAST>(v, af, hs_s, a.dr_hib[0], cp);
         bfly6<G::active_b, FAST>(v, cp, HiQB<W>(), tu2);
 #pragma unroll
@@ -725,7 +734,7 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
         } else {
             bfly6<G::active_a, FAST>(v, cp, HiQA<W>(), tu);
         }
-        if (XQ) phase_gray<false>(v, af, hs_s, a.dr_hia[0], cp.cfx_x, cp.shift_x, a.gen_scale);
+        if (XQ) phase_gray<false>(v, af, hs_s, __ldg(drx), cp.cfx_x, cp.shift_x, a.gen_scale);
         else phase_gray<FAST>(v, af, hs_s, a.dr_hia[0], cp);
         bfly6<G::active_a, FAST>(v, cp, HiQA<W>(), tu2);
 #pragma unroll
@@ -788,10 +797,13 @@ __global__ void __launch_bounds__(NT, 3) hiq_sweep_kernel(const SweepArgs a, con
         if (pf_target(a, order, list_off, pc, pt))
             l2_prefetch_rows(reinterpret_cast<const char *>(a.state + (pc << n) + (pt << 5)), (int64_t)8 << 12, 256, tid);
     }
-    build_hs<XQ>(hs_s, a.dr_hic, a.params + chain, tid);
+    const int grp = XQ ? a.params[chain].group : 0;
+    const int *drx = XQ ? a.xq_dr + ((int64_t)grp * 3 + 2) * 64 : nullptr;
+    if (XQ) build_hs_x(hs_s, drx, a.params + chain, tid);
+    else build_hs(hs_s, a.dr_hic, a.params + chain, tid);
     stage_params(cp_s, a.params + chain, tid);
     const ChainParams &cp = cp_s;
-    const PhaseAF af = load_af(a.af_hic, tile * NT + tid);
+    const PhaseAF af = load_af(a.af_hic + (XQ ? grp * a.xq_af_stride : 0), tile * NT + tid);
     bfly6<62, FAST>(v, cp, HiqQA(), tu);
 #pragma unroll
     for (int jp = 0; jp < 32; ++jp) smq[hiq_loc_a(tid, jp)] = make_ulonglong2(v[2 * jp], v[2 * jp + 1]);
@@ -803,7 +815,7 @@ __global__ void __launch_bounds__(NT, 3) hiq_sweep_kernel(const SweepArgs a, con
         v[2 * jp + 1] = x.y;
     }
     bfly6<14, FAST>(v, cp, HiqQB(), tu);
-    if (XQ) phase_gray<false>(v, af, hs_s, a.dr_hic[0], cp.cfx_x, cp.shift_x, a.gen_scale);
+    if (XQ) phase_gray<false>(v, af, hs_s, __ldg(drx), cp.cfx_x, cp.shift_x, a.gen_scale);
     else phase_gray<FAST>(v, af, hs_s, a.dr_hic[0], cp);
     bfly6<14, FAST>(v, cp, HiqQB(), tu2);
 #pragma unroll
@@ -1660,7 +1672,8 @@ struct SweepWorkspace {
     // XQ mode (one- and two-qubit X strings, 14 <= n <= 20): phase tables of the MIXER diagonal in the HI layouts
     int xq_epoch = -1;            // mixer epoch the tables were built for
     int4 *afx_lo = nullptr, *afx_hia = nullptr, *afx_hib = nullptr, *afx_hic = nullptr;
-    int drx_hia[64], drx_hib[64], drx_hic[64];
+    int *d_drx = nullptr;         // [mixer groups][hia, hib, hic][64] Gray increments of the mixer diagonals
+    int xq_groups = 0;
     double *dxJ = nullptr, *dxh = nullptr;
     double fx_scale_x = 1.0;
     int k_fx_x = 0;
@@ -1686,6 +1699,7 @@ void qmc_sweep_free(qmc_model *m) {
     for (auto e : w->ev) cudaEventDestroy(e);
     w->gsched.destroy();
     cudaFree(w->afx_lo); cudaFree(w->afx_hia); cudaFree(w->afx_hib); cudaFree(w->afx_hic); cudaFree(w->dxJ); cudaFree(w->dxh);
+    cudaFree(w->d_drx);
     delete w;
     m->sweep = nullptr;
 }
@@ -1810,45 +1824,65 @@ static int ensure_workspace(qmc_model *m, int64_t chains, cudaStream_t st) {
 static int ensure_xq_tables(qmc_model *m, cudaStream_t st) {
     SweepWorkspace *w = m->sweep;
     if (w->xq_epoch == m->mixer_epoch) return QMC_OK;
-    const int n = m->n;
+    const int n = m->n, ng = m->n_groups;
     const int64_t N = 1LL << n;
-    QMC_REQUIRE(m->quad_mixer && n >= 14 && n <= 20 && (int)m->xh.size() == n, QMC_ERR_UNSUPPORTED,
-                "sweep path: the mixer is not a single group of one- and two-qubit X strings (n=%d)", n);
+    QMC_REQUIRE(m->quad_mixer && n >= 14 && n <= 20 && (int)m->xh.size() == ng * n, QMC_ERR_UNSUPPORTED,
+                "sweep path: the mixer groups are not made of one- and two-qubit X strings (n=%d)", n);
     QMC_CUDA_TRY(cudaStreamSynchronize(st));  // tables of an earlier mixer may still be in use
-    double dmax = 0.0;
-    for (int a = 0; a < n; ++a) {
-        dmax += fabs(m->xh[a]);
-        for (int b = a + 1; b < n; ++b) dmax += fabs(m->xJ[(size_t)a * n + b]);
+    double dmax = 0.0;  // one fixed-point scale for every group
+    for (int g = 0; g < ng; ++g) {
+        double d = 0.0;
+        for (int a = 0; a < n; ++a) {
+            d += fabs(m->xh[(size_t)g * n + a]);
+            for (int b = a + 1; b < n; ++b) d += fabs(m->xJ[((size_t)g * n + a) * n + b]);
+        }
+        dmax = std::max(dmax, d);
     }
     if (dmax < 1e-300) dmax = 1.0;
     w->k_fx_x = (int)floor(log2(2147483647.0 / (dmax * 1.0000001))) - 1;
     if (w->k_fx_x > 30) w->k_fx_x = 30;
     w->fx_scale_x = ldexp(1.0, w->k_fx_x);
-    const size_t af_bytes = sizeof(int4) * 2 * (size_t)(N >> 6);
-    if (!w->dxJ) {
-        QMC_CUDA_TRY(cudaMalloc(&w->dxJ, sizeof(double) * (size_t)n * n));
-        QMC_CUDA_TRY(cudaMalloc(&w->dxh, sizeof(double) * (size_t)n));
-        QMC_CUDA_TRY(cudaMalloc(&w->afx_lo, af_bytes));
-        QMC_CUDA_TRY(cudaMalloc(&w->afx_hia, af_bytes));
-        QMC_CUDA_TRY(cudaMalloc(&w->afx_hib, af_bytes));
-        if (n == 20) QMC_CUDA_TRY(cudaMalloc(&w->afx_hic, af_bytes));
+    const size_t af_entries = 2 * (size_t)(N >> 6);
+    const size_t af_bytes = sizeof(int4) * af_entries;
+    if (w->xq_groups != ng) {
+        cudaFree(w->dxJ); cudaFree(w->dxh); cudaFree(w->afx_lo); cudaFree(w->afx_hia); cudaFree(w->afx_hib); cudaFree(w->afx_hic);
+        cudaFree(w->d_drx);
+        w->dxJ = w->dxh = nullptr; w->afx_lo = w->afx_hia = w->afx_hib = w->afx_hic = nullptr; w->d_drx = nullptr;
+        QMC_CUDA_TRY(cudaMalloc(&w->dxJ, sizeof(double) * (size_t)ng * n * n));
+        QMC_CUDA_TRY(cudaMalloc(&w->dxh, sizeof(double) * (size_t)ng * n));
+        QMC_CUDA_TRY(cudaMalloc(&w->afx_lo, af_bytes));  // scratch: build_af_tables also writes the LO layout
+        QMC_CUDA_TRY(cudaMalloc(&w->afx_hia, af_bytes * ng));
+        QMC_CUDA_TRY(cudaMalloc(&w->afx_hib, af_bytes * ng));
+        if (n == 20) QMC_CUDA_TRY(cudaMalloc(&w->afx_hic, af_bytes * ng));
+        QMC_CUDA_TRY(cudaMalloc(&w->d_drx, sizeof(int) * (size_t)ng * 3 * 64));
+        w->xq_groups = ng;
     }
-    QMC_CUDA_TRY(cudaMemcpy(w->dxJ, m->xJ.data(), sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
-    QMC_CUDA_TRY(cudaMemcpy(w->dxh, m->xh.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
-    int pos[3][6];
-    if (n == 20) {
-        const int grid = (int)std::min<int64_t>(148 * 8, (((int64_t)1 << (n - 6)) + 127) / 128);
-        af_table_kernel<8, 3><<<grid, 128, 0, st>>>(n, w->dxJ, w->dxh, w->fx_scale_x, w->afx_hic);
-        m->launches++;
-        const int pc[6] = {hiq_pos_b(0), hiq_pos_b(1), hiq_pos_b(2), hiq_pos_b(3), hiq_pos_b(4), hiq_pos_b(5)};
-        gray_increments(m->xJ, n, w->fx_scale_x, pc, w->drx_hic);
+    QMC_CUDA_TRY(cudaMemcpy(w->dxJ, m->xJ.data(), sizeof(double) * (size_t)ng * n * n, cudaMemcpyHostToDevice));
+    QMC_CUDA_TRY(cudaMemcpy(w->dxh, m->xh.data(), sizeof(double) * (size_t)ng * n, cudaMemcpyHostToDevice));
+    std::vector<int> drx((size_t)ng * 3 * 64, 0);
+    for (int g = 0; g < ng; ++g) {
+        const double *dJ = w->dxJ + (size_t)g * n * n, *dh = w->dxh + (size_t)g * n;
+        const std::vector<double> xJg(m->xJ.begin() + (size_t)g * n * n, m->xJ.begin() + (size_t)(g + 1) * n * n);
+        int pos[3][6];
+        int tmp[64];
+        if (n == 20) {
+            const int grid = (int)std::min<int64_t>(148 * 8, (((int64_t)1 << (n - 6)) + 127) / 128);
+            af_table_kernel<8, 3><<<grid, 128, 0, st>>>(n, dJ, dh, w->fx_scale_x, w->afx_hic + g * af_entries);
+            m->launches++;
+            const int pc[6] = {hiq_pos_b(0), hiq_pos_b(1), hiq_pos_b(2), hiq_pos_b(3), hiq_pos_b(4), hiq_pos_b(5)};
+            gray_increments(xJg, n, w->fx_scale_x, pc, tmp);
+            memcpy(&drx[((size_t)g * 3 + 2) * 64], tmp, sizeof(tmp));
+        }
+        int rc = build_af_tables(n, dJ, dh, w->fx_scale_x, w->afx_lo, w->afx_hia + g * af_entries, w->afx_hib + g * af_entries, pos, st);
+        if (rc != QMC_OK) return rc;
+        m->launches += 3;
+        gray_increments(xJg, n, w->fx_scale_x, pos[1], tmp);
+        memcpy(&drx[((size_t)g * 3 + 0) * 64], tmp, sizeof(tmp));
+        gray_increments(xJg, n, w->fx_scale_x, pos[2], tmp);
+        memcpy(&drx[((size_t)g * 3 + 1) * 64], tmp, sizeof(tmp));
     }
-    int rc = build_af_tables(n, w->dxJ, w->dxh, w->fx_scale_x, w->afx_lo, w->afx_hia, w->afx_hib, pos, st);
-    if (rc != QMC_OK) return rc;
-    m->launches += 3;
     QMC_CUDA_TRY(cudaGetLastError());
-    gray_increments(m->xJ, n, w->fx_scale_x, pos[1], w->drx_hia);
-    gray_increments(m->xJ, n, w->fx_scale_x, pos[2], w->drx_hib);
+    QMC_CUDA_TRY(cudaMemcpy(w->d_drx, drx.data(), sizeof(int) * drx.size(), cudaMemcpyHostToDevice));
     w->xq_epoch = m->mixer_epoch;
     return QMC_OK;
 }
@@ -2308,6 +2342,8 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         a.pf_dist = pf_dist;
         a.pf_lines = pf_lines;
         a.gen_scale = 1.f;
+        a.xq_dr = nullptr;
+        a.xq_af_stride = 0;
         a.xchg_peers = nullptr; a.xchg_shift = 0; a.xchg_rank = 0; a.xchg_g = 0; a.xchg_tile_bits = 0; a.xchg_idx0 = 0;
         a.probs_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float *>(probs_out) : nullptr;
         a.amps_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float2 *>(amps_out) : nullptr;
@@ -2398,9 +2434,8 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                     ax_him.af_hia = ax_hif.af_hia = w->afx_hia;
                     ax_him.af_hib = ax_hif.af_hib = w->afx_hib;
                     ax_him.af_hic = ax_hif.af_hic = w->afx_hic;
-                    memcpy(ax_him.dr_hia, w->drx_hia, sizeof(a.dr_hia)); memcpy(ax_hif.dr_hia, w->drx_hia, sizeof(a.dr_hia));
-                    memcpy(ax_him.dr_hib, w->drx_hib, sizeof(a.dr_hib)); memcpy(ax_hif.dr_hib, w->drx_hib, sizeof(a.dr_hib));
-                    if (w->afx_hic) { memcpy(ax_him.dr_hic, w->drx_hic, sizeof(a.dr_hic)); memcpy(ax_hif.dr_hic, w->drx_hic, sizeof(a.dr_hic)); }
+                    ax_him.xq_dr = ax_hif.xq_dr = w->d_drx;
+                    ax_him.xq_af_stride = ax_hif.xq_af_stride = 2 * (N >> 6);
                     ax_him.gen_scale = ldexpf(1.f, -nh);
                     ax_hif.gen_scale = (float)exp2(-0.5 * nh - 0.5 * LO_BITS);  // its own back-transform + the FINAL sweep's
                 }

@@ -126,6 +126,8 @@ struct Sweep128Args {
     double R_lo[APT], R_hi[APT];  // R(j): couplings among the register qubits of the phase layout
     double *segsum;            // [chains][2^(n-5)]
     double gen_scale;          // XQ mode: normalisation of the Walsh-Hadamard transforms of this launch
+    const double *xq_R;        // XQ mode, HI sweeps: R(j) of the mixer diagonal, [mixer group][32]
+    int64_t xq_af_stride;      // XQ mode: doubles between the af_hi tables of consecutive mixer groups
     double *probs_out;         // PROBS mode (unnormalised) or null
     double2 *amps_out;
 };
@@ -326,7 +328,8 @@ __global__ void __launch_bounds__(NT, 3) sweep128_kernel(const Sweep128Args a, c
     if (ROLE == R_FIRST || ROLE == R_MID) {
         if (tid < APT) {
             const ChainParams128 *cg = a.params + chain;
-            er_s[tid] = cis((XQ && !LO ? cg->cphase_x : cg->cphase) * (LO ? a.R_lo[tid] : a.R_hi[tid]));
+            if (XQ && !LO) er_s[tid] = cis(cg->cphase_x * __ldg(a.xq_R + cg->group * APT + tid));  // the chain's mixer group
+            else er_s[tid] = cis(cg->cphase * (LO ? a.R_lo[tid] : a.R_hi[tid]));
         }
     }
     __syncthreads();
@@ -335,7 +338,7 @@ __global__ void __launch_bounds__(NT, 3) sweep128_kernel(const Sweep128Args a, c
     const Q2<G> q2;
     // phase layout = L2 when the tile has two layouts, else L1
     const int64_t base_phase = (int64_t)G::tile_base(tile) + (G::two ? gmap<G>(local2<G>(tid, 0)) : off1);
-    const double *af = (LO ? a.af_lo : a.af_hi) + (tile * NT + tid) * 6;
+    const double *af = (LO ? a.af_lo : a.af_hi) + (XQ && !LO ? cp.group * a.xq_af_stride : 0) + (tile * NT + tid) * 6;
     const double t1 = LO ? -1.0 : 1.0, t2 = -t1;  // XQ multipliers before / after the diagonal of the sweep
     const double cdiag = XQ && !LO ? cp.cphase_x : cp.cphase;
     const double sdiag = XQ ? a.gen_scale : 1.0;
@@ -746,7 +749,8 @@ struct Sweep128Workspace {
     // XQ mode: tables of the mixer diagonal in the HI phase layout
     int xq_epoch = -1;
     double *afx_hi = nullptr, *dxJ = nullptr, *dxh = nullptr;
-    double Rx_hi[APT];
+    double *d_Rx = nullptr;  // [mixer groups][32]
+    int xq_groups = 0;
 };
 
 void qmc_sweep128_free(qmc_model *m) {
@@ -755,7 +759,7 @@ void qmc_sweep128_free(qmc_model *m) {
     cudaFree(w->state); cudaFree(w->params); cudaFree(w->segsum); cudaFree(w->hist); cudaFree(w->order);
     cudaFree(w->af_lo); cudaFree(w->af_hi); cudaFree(w->dJq); cudaFree(w->dhq);
     w->gsched.destroy();
-    cudaFree(w->afx_hi); cudaFree(w->dxJ); cudaFree(w->dxh);
+    cudaFree(w->afx_hi); cudaFree(w->dxJ); cudaFree(w->dxh); cudaFree(w->d_Rx);
     delete w;
     m->sweep128 = nullptr;
 }
@@ -868,34 +872,54 @@ static int ensure_workspace128(qmc_model *m, int64_t chains, cudaStream_t st) {
     return QMC_OK;
 }
 
+template <typename G>
+static void build_xq128(int n, const double *dJ, const double *dh, double *af, const std::vector<double> &xJg, double *R, cudaStream_t st) {
+    build_af128<G>(n, dJ, dh, af, st);
+    double Rg[APT];
+    host_R<G>(xJg, n, Rg);
+    memcpy(R, Rg, sizeof(Rg));
+}
+
 static int ensure_xq_tables128(qmc_model *m, cudaStream_t st) {
     Sweep128Workspace *w = m->sweep128;
     if (w->xq_epoch == m->mixer_epoch) return QMC_OK;
-    const int n = m->n;
+    const int n = m->n, ng = m->n_groups;
     const int64_t N = 1LL << n;
-    QMC_REQUIRE(m->quad_mixer && (int)m->xh.size() == n, QMC_ERR_UNSUPPORTED,
-                "complex128 sweep path: the mixer is not a single group of one- and two-qubit X strings");
+    QMC_REQUIRE(m->quad_mixer && (int)m->xh.size() == ng * n, QMC_ERR_UNSUPPORTED,
+                "complex128 sweep path: the mixer groups are not made of one- and two-qubit X strings");
     QMC_CUDA_TRY(cudaStreamSynchronize(st));
-    if (!w->dxJ) {
-        QMC_CUDA_TRY(cudaMalloc(&w->dxJ, sizeof(double) * (size_t)n * n));
-        QMC_CUDA_TRY(cudaMalloc(&w->dxh, sizeof(double) * (size_t)n));
-        QMC_CUDA_TRY(cudaMalloc(&w->afx_hi, sizeof(double) * 6 * (size_t)(N >> RB)));
+    const size_t af_doubles = 6 * (size_t)(N >> RB);
+    if (w->xq_groups != ng) {
+        cudaFree(w->dxJ); cudaFree(w->dxh); cudaFree(w->afx_hi); cudaFree(w->d_Rx);
+        w->dxJ = w->dxh = w->afx_hi = w->d_Rx = nullptr;
+        QMC_CUDA_TRY(cudaMalloc(&w->dxJ, sizeof(double) * (size_t)ng * n * n));
+        QMC_CUDA_TRY(cudaMalloc(&w->dxh, sizeof(double) * (size_t)ng * n));
+        QMC_CUDA_TRY(cudaMalloc(&w->afx_hi, sizeof(double) * af_doubles * ng));
+        QMC_CUDA_TRY(cudaMalloc(&w->d_Rx, sizeof(double) * (size_t)ng * APT));
+        w->xq_groups = ng;
     }
-    QMC_CUDA_TRY(cudaMemcpy(w->dxJ, m->xJ.data(), sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
-    QMC_CUDA_TRY(cudaMemcpy(w->dxh, m->xh.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
-    switch (22 - n) {
-        case 2: build_af128<HiGeo<2>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<2>>(m->xJ, n, w->Rx_hi); break;
-        case 3: build_af128<HiGeo<3>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<3>>(m->xJ, n, w->Rx_hi); break;
-        case 4: build_af128<HiGeo<4>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<4>>(m->xJ, n, w->Rx_hi); break;
-        case 5: build_af128<HiGeo<5>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<5>>(m->xJ, n, w->Rx_hi); break;
-        case 6: build_af128<HiGeo<6>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<6>>(m->xJ, n, w->Rx_hi); break;
-        case 7: build_af128<HiGeo<7>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<7>>(m->xJ, n, w->Rx_hi); break;
-        case 8: build_af128<HiGeo<8>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<8>>(m->xJ, n, w->Rx_hi); break;
-        case 9: build_af128<HiGeo<9>>(n, w->dxJ, w->dxh, w->afx_hi, st); host_R<HiGeo<9>>(m->xJ, n, w->Rx_hi); break;
-        default: qmc_set_error("complex128 sweep path: n=%d outside [13, 20]", n); return QMC_ERR_UNSUPPORTED;
+    QMC_CUDA_TRY(cudaMemcpy(w->dxJ, m->xJ.data(), sizeof(double) * (size_t)ng * n * n, cudaMemcpyHostToDevice));
+    QMC_CUDA_TRY(cudaMemcpy(w->dxh, m->xh.data(), sizeof(double) * (size_t)ng * n, cudaMemcpyHostToDevice));
+    std::vector<double> Rx((size_t)ng * APT, 0.0);
+    for (int g = 0; g < ng; ++g) {
+        const double *dJ = w->dxJ + (size_t)g * n * n, *dh = w->dxh + (size_t)g * n;
+        double *af = w->afx_hi + g * af_doubles, *R = &Rx[(size_t)g * APT];
+        const std::vector<double> xJg(m->xJ.begin() + (size_t)g * n * n, m->xJ.begin() + (size_t)(g + 1) * n * n);
+        switch (22 - n) {
+            case 2: build_xq128<HiGeo<2>>(n, dJ, dh, af, xJg, R, st); break;
+            case 3: build_xq128<HiGeo<3>>(n, dJ, dh, af, xJg, R, st); break;
+            case 4: build_xq128<HiGeo<4>>(n, dJ, dh, af, xJg, R, st); break;
+            case 5: build_xq128<HiGeo<5>>(n, dJ, dh, af, xJg, R, st); break;
+            case 6: build_xq128<HiGeo<6>>(n, dJ, dh, af, xJg, R, st); break;
+            case 7: build_xq128<HiGeo<7>>(n, dJ, dh, af, xJg, R, st); break;
+            case 8: build_xq128<HiGeo<8>>(n, dJ, dh, af, xJg, R, st); break;
+            case 9: build_xq128<HiGeo<9>>(n, dJ, dh, af, xJg, R, st); break;
+            default: qmc_set_error("complex128 sweep path: n=%d outside [13, 20]", n); return QMC_ERR_UNSUPPORTED;
+        }
+        m->launches++;
     }
-    m->launches++;
     QMC_CUDA_TRY(cudaGetLastError());
+    QMC_CUDA_TRY(cudaMemcpy(w->d_Rx, Rx.data(), sizeof(double) * Rx.size(), cudaMemcpyHostToDevice));
     w->xq_epoch = m->mixer_epoch;
     return QMC_OK;
 }
@@ -1014,8 +1038,8 @@ int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, c
                 const int nh = n - LOQ;
                 ax_lo.gen_scale = ldexp(1.0, -LOQ);
                 ax_hif.af_hi = ax_him.af_hi = w->afx_hi;
-                memcpy(ax_hif.R_hi, w->Rx_hi, sizeof(a.R_hi));
-                memcpy(ax_him.R_hi, w->Rx_hi, sizeof(a.R_hi));
+                ax_hif.xq_R = ax_him.xq_R = w->d_Rx;
+                ax_hif.xq_af_stride = ax_him.xq_af_stride = 6 * (N >> RB);
                 ax_him.gen_scale = ldexp(1.0, -nh);
                 ax_hif.gen_scale = exp2(-0.5 * nh - 0.5 * LOQ);
             }

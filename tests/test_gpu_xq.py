@@ -21,17 +21,18 @@ def _mixer(q, n, kind):
     raise ValueError(kind)
 
 
-def _check(q, n, mixer, rs, seed=3, dtype="fp32"):
+def _check(q, n, mixer, rs, seed=3, dtype="fp32", group=0):
     tol_p, tol_a = (1e-6, 5e-5) if dtype == "fp32" else (1e-10, 1e-9)
     J, h = models.packaged_random_model(n, seed)
     m = q.IsingEnergyFunction(J, h)
     offs, masks, w, _ = mixer.lower()
+    masks, w = masks[offs[group]:offs[group + 1]], w[offs[group]:offs[group + 1]]
     al = oracle.alpha(J, h)
     rng = np.random.default_rng(7 * n + len(masks))
     for r in rs:
         s = int(rng.integers(0, 1 << n))
         gamma = float(rng.uniform(0.25, 0.6))
-        p, a = q.transition_probabilities(m, mixer, s, gamma, r, dtype=dtype, return_amplitudes=True)
+        p, a = q.transition_probabilities(m, mixer, s, gamma, r, dtype=dtype, return_amplitudes=True, group=group)
         ref = oracle.evolve(J, h, al, gamma, 0.8, r, masks, w, s, gatewise=False)
         assert abs(p.sum() - 1.0) < 1e-5
         assert np.abs(p - np.abs(ref) ** 2).max() < tol_p, (n, r, np.abs(p - np.abs(ref) ** 2).max())
@@ -75,6 +76,32 @@ def test_xq_complex128_chains_equal_the_oracle_chain():
         props, acc = oracle.run_chain(J, h, masks, w, s0, H, 1.0, (0.25, 0.6), 0.8, seed, chain_id=c)
         assert np.array_equal(np.asarray(props, dtype=np.int64), b.proposals[c].astype(np.int64)), c
         assert np.array_equal(np.asarray(acc, dtype=np.uint8), b.accepted[c].astype(np.uint8)), c
+
+
+@pytest.mark.parametrize("n,dtype", [(14, "fp32"), (17, "fp32"), (20, "fp32"), (13, "fp64"), (18, "fp64")])
+def test_xq_incoherent_sum_uses_the_tables_of_the_chosen_group(n, dtype):
+    """IncoherentMixerSum (qumcmc/mixers.py:133-151) picks one sub-mixer per proposal: every group -- one-body, two-body,
+    pairs -- has its own mixer-diagonal tables, selected per chain inside the HI sweeps."""
+    import qumcmc_b200 as q
+    inc = q.IncoherentMixerSum([q.GenericMixer.OneBodyMixer(n), q.GenericMixer.TwoBodyMixer(n), _mixer(q, n, "pairs")], [0.3, 0.4, 0.3])
+    for group in range(3):
+        _check(q, n, inc, (1, 3) if n < 20 else (2,), dtype=dtype, group=group)
+
+
+def test_xq_incoherent_chains_equal_the_general_path(monkeypatch):
+    """Chains whose proposals draw different sub-mixers inside one launch (complex128, n = 13): proposals and accept flags
+    equal the general path's, which evolves every group with its own diagonal."""
+    import qumcmc_b200 as q
+    n = 13
+    J, h = models.packaged_random_model(n, 9)
+    m = q.IsingEnergyFunction(J, h)
+    inc = q.IncoherentMixerSum([q.GenericMixer.OneBodyMixer(n), q.GenericMixer.TwoBodyMixer(n)], [0.5, 0.5])
+    kw = dict(temperature=1.0, n_chains=24, seed=77, dtype="fp64")
+    got = q.quantum_enhanced_mcmc(4, m, inc, (0.25, 0.6), **kw)
+    monkeypatch.setenv("QUMCMC_NO_XQ", "1")
+    ref = q.quantum_enhanced_mcmc(4, m, inc, (0.25, 0.6), **kw)
+    assert np.array_equal(ref.proposals, got.proposals)
+    assert np.array_equal(ref.accepted, got.accepted)
 
 
 def test_xq_gamma_extremes_and_absent_phase_layer():
@@ -164,14 +191,14 @@ def test_xq_group_schedule_is_bit_identical(monkeypatch, n, C, mib):
 
 
 def test_mixers_outside_xq_keep_their_paths():
-    """Three-body terms and incoherent sums do not qualify: they still run (general path) and agree with the oracle."""
+    """Groups with a three-body term do not qualify: they still run (general path) and agree with the oracle."""
     import qumcmc_b200 as q
     n = 14
     J, h = models.packaged_random_model(n, 3)
     m = q.IsingEnergyFunction(J, h)
     al = oracle.alpha(J, h)
-    inc = q.IncoherentMixerSum([q.GenericMixer.OneBodyMixer(n), q.GenericMixer.TwoBodyMixer(n)], [0.5, 0.5])
-    for mixer, dtype, group in ((q.CustomMixer(n, [[0, 1, 2], [3, 4], [5]]), "fp32", 0), (inc, "fp32", 1), (inc, "fp64", 1)):
+    inc = q.IncoherentMixerSum([q.GenericMixer.TwoBodyMixer(n), q.CustomMixer(n, [[0, 1, 2], [3, 4], [5]])], [0.5, 0.5])
+    for mixer, dtype, group in ((q.CustomMixer(n, [[0, 1, 2], [3, 4], [5]]), "fp32", 0), (inc, "fp32", 0), (inc, "fp64", 1)):
         offs, masks, w, _ = mixer.lower()
         gm, gw = masks[offs[group]:offs[group + 1]], w[offs[group]:offs[group + 1]]
         p = q.transition_probabilities(m, mixer, 77, 0.4, 3, dtype=dtype, group=group)
