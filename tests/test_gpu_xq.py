@@ -15,7 +15,7 @@ def _mixer(q, n, kind):
     if kind == "two":
         return q.GenericMixer.TwoBodyMixer(n)
     if kind == "pairs":   # pairs across and inside the qubit groups + a few singles, repeated qubits
-        return q.CustomMixer(n, [[0, n - 1], [3, 7], [1], [12, 13], [5, n - 2], [11, 12], [n - 1], [2, 9], [0, 1], [6]])
+        return q.CustomMixer(n, [[0, n - 1], [3, 7], [1], [n - 3, n - 2], [5, n - 2], [11, 12], [n - 1], [2, 9], [0, 1], [6]])
     if kind == "coh":
         return q.CoherentMixerSum([q.GenericMixer.OneBodyMixer(n), q.GenericMixer.TwoBodyMixer(n)], [0.7, 0.3])
     raise ValueError(kind)
