@@ -135,6 +135,9 @@ struct qmc_model {
     double *dD = nullptr;
     // energy table E(idx) for the shared-memory path (n <= QMC_SMEM_MAX_SPINS_F32)
     double *dE = nullptr;
+    // mixer exponent in the Hadamard basis, E_x(x) = sum_S w_S (-1)^popcount(x & S), per group: [n_groups][2^n] fp64
+    // (shared-memory path only: a group with many terms is applied as H . exp(-i gamma dt E_x) . H)
+    double *dEx = nullptr;
     // mixer
     int n_groups = 0;
     std::vector<int> group_off;       // n_groups+1

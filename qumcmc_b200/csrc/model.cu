@@ -396,6 +396,7 @@ extern "C" int qmc_model_destroy(qmc_model *m) {
     cudaFree(m->dJp);
     cudaFree(m->dhq_e);
     cudaFree(m->dE);
+    cudaFree(m->dEx);
     cudaFree(m->d_group_off);
     cudaFree(m->d_masks);
     cudaFree(m->d_weights);
@@ -524,6 +525,22 @@ extern "C" int qmc_mixer_set(qmc_model *m, int n_groups, const int *group_offset
                 m->qweight[(size_t)g * m->n + (__builtin_ffsll((long long)masks[k]) - 1)] += weights[k];
         QMC_CUDA_TRY(cudaMalloc(&m->d_qweight, sizeof(double) * m->qweight.size()));
         QMC_CUDA_TRY(cudaMemcpy(m->d_qweight, m->qweight.data(), sizeof(double) * m->qweight.size(), cudaMemcpyHostToDevice));
+    }
+    // shared-memory path: E_x(x) of every group (host: 2^n x terms sign flips; n <= 13)
+    cudaFree(m->dEx);
+    m->dEx = nullptr;
+    if (m->n <= QMC_SMEM_MAX_SPINS_F32 && !one_body) {
+        const size_t N = (size_t)1 << m->n;
+        std::vector<double> ex((size_t)n_groups * N, 0.0);
+        for (int g = 0; g < n_groups; ++g)
+            for (int k = group_offsets[g]; k < group_offsets[g + 1]; ++k) {
+                const uint64_t mk = masks[k];
+                const double wk = weights[k];
+                double *e = &ex[(size_t)g * N];
+                for (size_t x = 0; x < N; ++x) e[x] += (__builtin_popcountll((uint64_t)x & mk) & 1) ? -wk : wk;
+            }
+        QMC_CUDA_TRY(cudaMalloc(&m->dEx, sizeof(double) * ex.size()));
+        QMC_CUDA_TRY(cudaMemcpy(m->dEx, ex.data(), sizeof(double) * ex.size(), cudaMemcpyHostToDevice));
     }
     m->mixer_epoch++;
     cudaFree(m->d_group_off);

@@ -22,6 +22,8 @@ struct SmallParams {
     uint32_t hop0;
     double temperature, g_lo, g_hi, dt, alpha;
     const double *D, *E;
+    const double *Ex;   // [n_groups][2^n] mixer exponent in the Hadamard basis, or null
+    int hx_min_terms;   // groups with at least this many terms run as H . exp(-i gamma dt E_x) . H (0: never)
     const int *group_off;
     const uint64_t *masks;
     const double *weights, *group_cum;
@@ -58,6 +60,9 @@ __device__ __forceinline__ double2 phase_factor(double x, double) {
 
 constexpr int SMALL_NT = 256;
 
+__device__ __forceinline__ float2 cmul_t(const float2 a, const float2 f) { return make_float2(a.x * f.x - a.y * f.y, a.x * f.y + a.y * f.x); }
+__device__ __forceinline__ double2 cmul_t(const double2 a, const double2 f) { return make_double2(a.x * f.x - a.y * f.y, a.x * f.y + a.y * f.x); }
+
 template <typename T>
 __global__ void __launch_bounds__(SMALL_NT) smem_chain_kernel(const SmallParams p) {
     using T2 = typename Vec2<T>::type;
@@ -66,7 +71,8 @@ __global__ void __launch_bounds__(SMALL_NT) smem_chain_kernel(const SmallParams 
     const int N = 1 << n;
     T2 *st = reinterpret_cast<T2 *>(smraw);
     T2 *ph = st + N;
-    T2 *cs = ph + N;
+    T2 *xph = ph + N;                                     // Hadamard-basis mode: 2^-n exp(-i gamma dt E_x(x)) of the proposal
+    T2 *cs = p.hx_min_terms > 0 ? xph + N : xph;
     int *tm = reinterpret_cast<int *>(cs + p.max_terms);  // term masks of the current group
     __shared__ double s_incl[SMALL_NT];
     __shared__ double s_warp[SMALL_NT / 32];
@@ -108,9 +114,23 @@ __global__ void __launch_bounds__(SMALL_NT) smem_chain_kernel(const SmallParams 
         }
         const int t0 = p.group_off[grp], t1 = p.group_off[grp + 1];
         const int nterms = t1 - t0;
+        // Hadamard-basis mode: all X strings commute and are diagonal in the x basis, M = H exp(-i gamma dt E_x) H, so a
+        // group with many terms costs 2 ceil(n / 2) butterfly passes per layer instead of one pass per two terms
+        const bool hx = p.hx_min_terms > 0 && nterms >= p.hx_min_terms;
+        if (hx) {
+            const double cx = -gamma * p.dt;
+            const T norm = (T)ldexp(1.0, -n);  // of the two unnormalised transforms around the diagonal
+            const double *ex = p.Ex + (size_t)grp * N;
+            for (int i = tid; i < N; i += NT) {
+                T2 f = phase_factor(cx * ex[i], T(0));
+                f.x *= norm;
+                f.y *= norm;
+                xph[i] = f;
+            }
+        }
 
         // ---- per-term rotation constants: exp(-i gamma w dt X_S) -> (cos, sin); masks staged next to them
-        for (int k = tid; k < nterms; k += NT) {
+        for (int k = tid; k < (hx ? 0 : nterms); k += NT) {
             double s, c;
             sincos(gamma * p.weights[t0 + k] * p.dt, &s, &c);
             T2 v;
@@ -136,6 +156,47 @@ __global__ void __launch_bounds__(SMALL_NT) smem_chain_kernel(const SmallParams 
 
         // ---- K2: M (P M)^{r-1}
         for (int layer = 0; layer < r; ++layer) {
+            if (hx) {
+                // [P] H Dx H with the diagonals fused into the butterfly passes: P on the loads of the first pass, Dx on the
+                // stores of the last pass of the first transform.  Two qubits per pass (4-amplitude orbits in registers).
+                const int passes = (n + 1) >> 1;
+                for (int half = 0; half < 2; ++half)
+                    for (int ps = 0; ps < passes; ++ps) {
+                        const T2 *pre = (half == 0 && ps == 0 && layer > 0 && phase) ? ph : nullptr;
+                        const T2 *post = (half == 0 && ps == passes - 1) ? xph : nullptr;
+                        const int b1 = 2 * ps, b2 = 2 * ps + 1;
+                        if (b2 < n) {
+                            const int lo_m = (1 << b1) - 1, hi_m = (1 << b2) - 1;
+                            for (int q = tid; q < (N >> 2); q += NT) {
+                                int i = ((q >> b1) << (b1 + 1)) | (q & lo_m);
+                                i = ((i >> b2) << (b2 + 1)) | (i & hi_m);
+                                const int i1 = i | (1 << b1), i2 = i | (1 << b2), i3 = i1 | (1 << b2);
+                                T2 a0 = st[i], a1 = st[i1], a2 = st[i2], a3 = st[i3];
+                                if (pre) { a0 = cmul_t(a0, pre[i]); a1 = cmul_t(a1, pre[i1]); a2 = cmul_t(a2, pre[i2]); a3 = cmul_t(a3, pre[i3]); }
+                                T2 s0, s1, d0, d1;
+                                s0.x = a0.x + a1.x; s0.y = a0.y + a1.y; d0.x = a0.x - a1.x; d0.y = a0.y - a1.y;
+                                s1.x = a2.x + a3.x; s1.y = a2.y + a3.y; d1.x = a2.x - a3.x; d1.y = a2.y - a3.y;
+                                a0.x = s0.x + s1.x; a0.y = s0.y + s1.y; a2.x = s0.x - s1.x; a2.y = s0.y - s1.y;
+                                a1.x = d0.x + d1.x; a1.y = d0.y + d1.y; a3.x = d0.x - d1.x; a3.y = d0.y - d1.y;
+                                if (post) { a0 = cmul_t(a0, post[i]); a1 = cmul_t(a1, post[i1]); a2 = cmul_t(a2, post[i2]); a3 = cmul_t(a3, post[i3]); }
+                                st[i] = a0; st[i1] = a1; st[i2] = a2; st[i3] = a3;
+                            }
+                        } else {  // odd n: the last qubit alone
+                            const int lowmask = (1 << b1) - 1;
+                            for (int q = tid; q < (N >> 1); q += NT) {
+                                const int i = ((q >> b1) << (b1 + 1)) | (q & lowmask), j = i | (1 << b1);
+                                T2 a = st[i], b = st[j];
+                                if (pre) { a = cmul_t(a, pre[i]); b = cmul_t(b, pre[j]); }
+                                T2 oa, ob;
+                                oa.x = a.x + b.x; oa.y = a.y + b.y; ob.x = a.x - b.x; ob.y = a.y - b.y;
+                                if (post) { oa = cmul_t(oa, post[i]); ob = cmul_t(ob, post[j]); }
+                                st[i] = oa; st[j] = ob;
+                            }
+                        }
+                        __syncthreads();
+                    }
+                continue;
+            }
             if (layer > 0 && phase) {
                 for (int i = tid; i < N; i += NT) {
                     const T2 a = st[i], f = ph[i];
@@ -587,6 +648,8 @@ int qmc_small_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     p.alpha = m->alpha;
     p.D = m->dD;
     p.E = m->dE;
+    p.Ex = m->dEx;
+    p.hx_min_terms = 0;
     p.group_off = m->d_group_off;
     p.masks = m->d_masks;
     p.weights = m->d_weights;
@@ -607,7 +670,19 @@ int qmc_small_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
 
     const size_t N = (size_t)1 << m->n;
     const size_t esz = dtype == QMC_DTYPE_F64 ? sizeof(double2) : sizeof(float2);
-    const size_t smem = (2 * N + (size_t)m->max_terms_in_group) * esz + sizeof(int) * (size_t)m->max_terms_in_group;
+    size_t smem = (2 * N + (size_t)m->max_terms_in_group) * esz + sizeof(int) * (size_t)m->max_terms_in_group;
+    // Hadamard-basis mode for groups with many terms: a layer costs 2 ceil(n / 2) butterfly passes, the term loop one pass
+    // per two terms -- worth it from 2 n + 4 terms on (two-body mixers from n = 6, three-body from n = 5); needs a third
+    // 2^n table in shared memory.  QUMCMC_SMALL_HX=0 keeps the term loop, =k sets the threshold.
+    if (m->dEx && m->max_terms_in_group >= 2 * m->n + 4) {
+        int thr = 2 * m->n + 4;
+        if (const char *e = getenv("QUMCMC_SMALL_HX")) thr = atoi(e);
+        const size_t smem_hx = smem + N * esz;
+        if (thr > 0 && smem_hx <= 227 * 1024) {
+            p.hx_min_terms = thr;
+            smem = smem_hx;
+        }
+    }
     QMC_REQUIRE(smem <= 227 * 1024, QMC_ERR_UNSUPPORTED,
                 "shared-memory path: n=%d with %d mixer terms needs %zu B of shared memory (> 227 KiB)", m->n,
                 m->max_terms_in_group, smem);

@@ -113,3 +113,66 @@ def test_warp_kernel_fp32_chains_follow_the_oracle_sampler():
                 cur, e_cur = sp, e_sp
         assert int(b.final_state[c]) == cur
     assert near <= C * H // 50
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Hadamard-basis mode of the CTA-per-chain kernel: groups with >= 2 n + 4 terms run as H . exp(-i gamma dt E_x) . H
+# ---------------------------------------------------------------------------------------------------------------
+def _kbody_mixers(q, n):
+    return {"two": q.GenericMixer.TwoBodyMixer(n), "three": q.GenericMixer.ThreeBodyMixer(n),
+            "coh": q.CoherentMixerSum([q.GenericMixer.OneBodyMixer(n), q.GenericMixer.TwoBodyMixer(n)], [0.6, 0.4]),
+            "inc": q.IncoherentMixerSum([q.GenericMixer.OneBodyMixer(n), q.GenericMixer.ThreeBodyMixer(n)], [0.5, 0.5])}
+
+
+@pytest.mark.parametrize("n", [6, 9, 10, 12, 13])
+@pytest.mark.parametrize("dtype,tol_p,tol_a", [("fp64", 1e-10, 1e-9), ("fp32", 1e-6, 2e-5)])
+def test_hadamard_basis_mode_transition_probabilities(n, dtype, tol_p, tol_a):
+    """Two-body, three-body, coherent and incoherent sums (one group below the threshold: term loop; one above) against
+    the oracle; odd and even n (the last butterfly pass of an odd n handles one qubit), r = 1 and r > 1."""
+    q = _api()
+    if n == 13 and dtype == "fp64":
+        pytest.skip("complex128 statevectors live in shared memory up to n = 12")
+    J, h = models.packaged_random_model(n, 11)
+    m = q.IsingEnergyFunction(J, h)
+    al = oracle.alpha(J, h)
+    rng = np.random.default_rng(100 + n)
+    for name, mx in _kbody_mixers(q, n).items():
+        offs, mk, wk, _ = mx.lower()
+        for group in range(len(offs) - 1):
+            masks, w = [int(x) for x in mk[offs[group]:offs[group + 1]]], [float(x) for x in wk[offs[group]:offs[group + 1]]]
+            for r in (1, 2, 5):
+                s = int(rng.integers(0, 1 << n))
+                gamma = float(rng.uniform(0.1, 0.8))
+                p, a = q.transition_probabilities(m, mx, s, gamma, r, dtype=dtype, return_amplitudes=True, group=group)
+                ref = oracle.evolve(J, h, al, gamma, 0.8, r, masks, w, s, gatewise=False)
+                assert np.abs(p - np.abs(ref) ** 2).max() < tol_p, (n, name, group, r, dtype)
+                assert np.linalg.norm(a - ref) < tol_a, (n, name, group, r, np.linalg.norm(a - ref))
+
+
+def test_hadamard_basis_mode_equals_the_term_loop(monkeypatch):
+    """Same proposals from both formulations of the mixer (complex128, BAS 3x3 with a two-body mixer)."""
+    q = _api()
+    J, h, _ = models.bas3("both")
+    m = q.IsingEnergyFunction(J, h)
+    mx = q.GenericMixer.TwoBodyMixer(9)
+    kw = dict(initial_state="111000111", temperature=1 / 1.5, n_chains=64, seed=5, dtype="fp64")
+    got = q.quantum_enhanced_mcmc(40, m, mx, (0.25, 0.6), **kw)
+    monkeypatch.setenv("QUMCMC_SMALL_HX", "0")
+    ref = q.quantum_enhanced_mcmc(40, m, mx, (0.25, 0.6), **kw)
+    assert np.array_equal(ref.proposals, got.proposals)
+    assert np.array_equal(ref.accepted, got.accepted)
+
+
+def test_hadamard_basis_mode_chains_equal_the_oracle_chain():
+    q = _api()
+    n = 8
+    J, h = models.packaged_random_model(n, 4)
+    m = q.IsingEnergyFunction(J, h)
+    mx = q.GenericMixer.ThreeBodyMixer(n)
+    _, mk, wk, _ = mx.lower()
+    b = q.quantum_enhanced_mcmc(12, m, mx, (0.25, 0.6), temperature=1.0, n_chains=5, seed=3, dtype="fp64")
+    for c in range(5):
+        s0 = oracle.initial_state(3, c, n)
+        props, acc = oracle.run_chain(J, h, mk, wk, s0, 12, 1.0, (0.25, 0.6), 0.8, 3, chain_id=c)
+        assert np.array_equal(np.asarray(props, dtype=np.int64), b.proposals[c].astype(np.int64)), c
+        assert np.array_equal(np.asarray(acc, dtype=np.uint8), b.accepted[c].astype(np.uint8)), c
