@@ -443,7 +443,11 @@ __device__ __forceinline__ void warp_layer(typename Vec2<T>::type (&v)[1 << R], 
     }
 }
 
-template <typename T, int R>
+// HX = true (any mixer; needs the E_x tables): the mixer layer is H . exp(-i gamma dt E_x) . H -- warp_layer with multiplier
+// +1 on every qubit (B = sqrt 2 Z H, into the x basis), the x-basis diagonal from a third warp-private tile, warp_layer with
+// multiplier -1 (B^T, back): two calls per Trotter layer whatever the number of terms, plain amplitudes, the 2^-n of the two
+// transforms inside the diagonal.  A layer starts and ends in layout 1.
+template <typename T, int R, bool HX = false>
 __global__ void __launch_bounds__(128) warp_chain_kernel(const WarpParams wp) {
     using T2 = typename Vec2<T>::type;
     constexpr int NR = 1 << R;       // amplitudes per lane
@@ -455,8 +459,9 @@ __global__ void __launch_bounds__(128) warp_chain_kernel(const WarpParams wp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (chain >= wp.n_chains) return;  // whole warp
-    T2 *tile = reinterpret_cast<T2 *>(smraw) + (size_t)warp * 2 * N;  // transposition tile
+    T2 *tile = reinterpret_cast<T2 *>(smraw) + (size_t)warp * (HX ? 3 : 2) * N;  // transposition tile
     T2 *ph = tile + N;                                                 // phase factors of the current proposal
+    T2 *xph = ph + N;                                                  // HX: 2^-n exp(-i gamma dt E_x(x)) of the proposal
     const uint64_t gchain = p.chain_id0 + (uint64_t)chain;
     const unsigned FULL = 0xffffffffu;
 
@@ -487,7 +492,20 @@ __global__ void __launch_bounds__(128) warp_chain_kernel(const WarpParams wp) {
         }
         // per-qubit rotation: lane q holds tan(theta_q), theta_q = gamma w_q dt; scale = prod cos
         double my_t = 0.0, my_c = 1.0;
-        if (lane < n) {
+        if (HX) {
+            my_t = lane < n ? 1.0 : 0.0;
+            const double cx = -gamma * p.dt;
+            const T norm = (T)ldexp(1.0, -n);
+            const double *ex = p.Ex + (size_t)grp * N;
+#pragma unroll 4
+            for (int j = 0; j < NR; ++j) {
+                const int idx = (lane << R) | j;
+                T2 f = phase_factor(cx * ex[idx], T(0));
+                f.x *= norm;
+                f.y *= norm;
+                xph[wswz<R>(idx)] = f;
+            }
+        } else if (lane < n) {
             const double wq = wp.qweight[grp * n + lane];
             if (wq != 0.0) {
                 double sn, cs;
@@ -499,7 +517,7 @@ __global__ void __launch_bounds__(128) warp_chain_kernel(const WarpParams wp) {
         double scale = my_c;
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) scale *= __shfl_xor_sync(FULL, scale, off);
-        scale = pow(scale, (double)r);
+        scale = HX ? 1.0 : pow(scale, (double)r);
         const T tq = (T)my_t;  // lane q: tan(theta_q)
         // phase factors of this proposal (same c for all r - 1 layers), layout-independent slots
         const bool phase = p.phase_active && r > 1;
@@ -514,7 +532,7 @@ __global__ void __launch_bounds__(128) warp_chain_kernel(const WarpParams wp) {
         // |s> in the storage basis: (prod cos)^r (-i)^popcount(s) at idx = s
         T2 v[NR];
         {
-            const int pc = __popcll(cur) & 3;
+            const int pc = HX ? 0 : (__popcll(cur) & 3);  // HX: plain amplitudes
             const T mag = (T)scale;
             T2 s0;
             s0.x = pc == 0 ? mag : (pc == 2 ? -mag : T(0));
@@ -531,10 +549,16 @@ __global__ void __launch_bounds__(128) warp_chain_kernel(const WarpParams wp) {
         // instruction cache when hundreds of warps run different hops)
 #pragma unroll 1
         for (int layer = 0; layer < r; ++layer) {
-            if (layer & 1) warp_layer<T, R, false>(v, tq, tile, ph, phase, lane);
-            else warp_layer<T, R, true>(v, tq, tile, ph, phase && layer > 0, lane);
+            if (HX) {
+                warp_layer<T, R, true>(v, tq, tile, ph, phase && layer > 0, lane);   // [P] then into the x basis
+                warp_layer<T, R, false>(v, -tq, tile, xph, true, lane);              // mixer diagonal, then back
+            } else if (layer & 1) {
+                warp_layer<T, R, false>(v, tq, tile, ph, phase, lane);
+            } else {
+                warp_layer<T, R, true>(v, tq, tile, ph, phase && layer > 0, lane);
+            }
         }
-        if (r & 1) {  // odd r ends in layout 2: back to layout 1 (2^R consecutive indices per lane) for the measurement
+        if (!HX && (r & 1)) {  // odd r ends in layout 2: back to layout 1 (2^R consecutive indices per lane) for the measurement
 #pragma unroll
             for (int j = 0; j < NR; ++j) tile[wswz<R>((j << 5) | lane)] = v[j];
             __syncwarp();
@@ -562,7 +586,7 @@ __global__ void __launch_bounds__(128) warp_chain_kernel(const WarpParams wp) {
                 const int idx = (lane << R) | j;
                 if (po) po[idx] = (v[j].x * v[j].x + v[j].y * v[j].y) * inv;
                 if (ao) {  // a = i^popcount(idx) S
-                    const int k = __popc(idx) & 3;
+                    const int k = HX ? 0 : (__popc(idx) & 3);
                     T2 o;
                     o.x = (k == 0 ? v[j].x : k == 1 ? -v[j].y : k == 2 ? -v[j].x : v[j].y) * inva;
                     o.y = (k == 0 ? v[j].y : k == 1 ? v[j].x : k == 2 ? -v[j].y : -v[j].x) * inva;
@@ -615,14 +639,14 @@ __global__ void __launch_bounds__(128) warp_chain_kernel(const WarpParams wp) {
     if (p.hamming_hist && lane <= n) p.hamming_hist[chain * (n + 1) + lane] = my_hist;
 }
 
-template <typename T, int R>
+template <typename T, int R, bool HX = false>
 static int launch_warp_kernel(const WarpParams &wp, int64_t n_chains, cudaStream_t st) {
-    const size_t per_warp = 2 * ((size_t)1 << (R + 5)) * sizeof(typename Vec2<T>::type);
+    const size_t per_warp = (HX ? 3 : 2) * ((size_t)1 << (R + 5)) * sizeof(typename Vec2<T>::type);
     int warps = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
     if (n_chains < warps) warps = (int)n_chains;
     const size_t smem = per_warp * warps;
-    QMC_CUDA_TRY(cudaFuncSetAttribute(warp_chain_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * 4)));
-    warp_chain_kernel<T, R><<<(unsigned)((n_chains + warps - 1) / warps), warps * 32, smem, st>>>(wp);
+    QMC_CUDA_TRY(cudaFuncSetAttribute(warp_chain_kernel<T, R, HX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * 4)));
+    warp_chain_kernel<T, R, HX><<<(unsigned)((n_chains + warps - 1) / warps), warps * 32, smem, st>>>(wp);
     return QMC_OK;
 }
 
@@ -701,6 +725,26 @@ int qmc_small_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
             case 8: rcw = f64 ? launch_warp_kernel<double, 3>(wp, n_chains, st) : launch_warp_kernel<float, 3>(wp, n_chains, st); break;
             case 9: rcw = f64 ? launch_warp_kernel<double, 4>(wp, n_chains, st) : launch_warp_kernel<float, 4>(wp, n_chains, st); break;
             default: rcw = f64 ? launch_warp_kernel<double, 5>(wp, n_chains, st) : launch_warp_kernel<float, 5>(wp, n_chains, st); break;
+        }
+        if (rcw != QMC_OK) return rcw;
+        m->launches++;
+        QMC_CUDA_TRY(cudaGetLastError());
+        return QMC_OK;
+    }
+    // any other mixer at 8 <= n <= 10: the same warp-per-chain kernel in Hadamard-basis mode (two warp_layer calls per Trotter
+    // layer whatever the number of terms); QUMCMC_NO_WARP_KERNEL=1 or QUMCMC_SMALL_HX=0 keep the CTA-per-chain kernel
+    if (!m->all_one_body && m->dEx && m->n >= 8 && m->n <= 10 && m->dD && m->dE && !getenv("QUMCMC_NO_WARP_KERNEL") &&
+        !(getenv("QUMCMC_SMALL_HX") && atoi(getenv("QUMCMC_SMALL_HX")) == 0)) {
+        WarpParams wp;
+        wp.p = p;
+        wp.qweight = nullptr;
+        wp.n_chains = n_chains;
+        int rcw = QMC_OK;
+        const bool f64 = dtype == QMC_DTYPE_F64;
+        switch (m->n) {
+            case 8: rcw = f64 ? launch_warp_kernel<double, 3, true>(wp, n_chains, st) : launch_warp_kernel<float, 3, true>(wp, n_chains, st); break;
+            case 9: rcw = f64 ? launch_warp_kernel<double, 4, true>(wp, n_chains, st) : launch_warp_kernel<float, 4, true>(wp, n_chains, st); break;
+            default: rcw = f64 ? launch_warp_kernel<double, 5, true>(wp, n_chains, st) : launch_warp_kernel<float, 5, true>(wp, n_chains, st); break;
         }
         if (rcw != QMC_OK) return rcw;
         m->launches++;
