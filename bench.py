@@ -306,6 +306,11 @@ def run_ours(args, rank, local_rank, world):
                                    c_by.value, c_mv.value, e2e_value, Ke, bi, bo, e2e_consistent, g_acc, secondary)
         if per_rank is not None:
             state["line"]["per_rank"] = per_rank
+    if world == 1 and not args.no_secondary:
+        try:   # mixers beyond one-body (the paper's subject) on the same model sizes: short runs, a few seconds in total
+            secondary["mixers"] = mixers_block(args)
+        except Exception as e:  # noqa: BLE001
+            secondary["mixers"] = {"error": repr(e)[:300]}
     if world >= 2 and (world & (world - 1)) == 0 and not args.no_secondary and not args.no_c5:
         try:   # C5: statevector sharded by global qubits, 33 local qubits per GPU (n = 36 on 8 GPUs)
             del props_buf, acc_buf
@@ -344,6 +349,36 @@ def start_watchdog(seconds, rank, state):
     t.daemon = True
     t.start()
     return t
+
+
+def mixers_block(args):
+    """Secondary lines for mixers of higher weight (qumcmc/mixers.py:21-151), through the public Python API: two-body mixers
+    at n = 20 run on the sweep kernels in XQ mode (2 sweeps per Trotter layer), k-body mixers at n = 9 (BAS 3x3) on the
+    warp-per-chain kernel in Hadamard-basis mode; one-body lines beside them for the ratio."""
+    import torch
+    import qumcmc_b200 as q
+    from tests import models as tmodels
+
+    out = []
+    Jb, hb, _ = tmodels.bas3("both")
+    cases = [("n=20 random Ising", q.random_ising_model(N_SPINS, MODEL_SEED), N_SPINS, None, 1.0, 1024, 4, ("two",), ("fp32", "fp64")),
+             ("BAS 3x3 (n=9)", q.IsingEnergyFunction(Jb, hb), 9, "111000111", 1 / 1.5, 1024, 400, ("one", "two", "three"), ("fp32", "fp64"))]
+    for label, model, n, init, temp, chains, hops, kinds, dtypes in cases:
+        for kind in kinds:
+            mx = {"one": q.GenericMixer.OneBodyMixer, "two": q.GenericMixer.TwoBodyMixer, "three": q.GenericMixer.ThreeBodyMixer}[kind](n)
+            for dtype in dtypes:
+                kw = dict(temperature=temp, n_chains=chains, seed=2, dtype=dtype, record=False)
+                if init:
+                    kw["initial_state"] = init
+                q.quantum_enhanced_mcmc(max(1, hops // 20), model, mx, GAMMA, **kw)   # warm: tables, workspace
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                b = q.quantum_enhanced_mcmc(hops, model, mx, GAMMA, **kw)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                out.append({"model": label, "mixer": kind + "-body", "terms": int(len(mx.lower()[1])), "dtype": dtype, "chains": chains,
+                            "hops": hops, "proposals_per_s": chains * hops / dt, "acceptance": b.acceptance_rate()})
+    return out
 
 
 def strong_scaling_block(args, L, dm, rank, world, dev, stream, barrier, max_over_ranks):
