@@ -34,7 +34,9 @@ static int dispatch(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, co
                              hamming_hist, probs_out, amps_out, st);
     // complex64 + one coherent group of one- and two-qubit X strings (TwoBodyMixer, pair CustomMixer, coherent sums of
     // them), 14 <= n <= 20: the mixer is a quadratic diagonal in the Hadamard basis, hosted by the same sweep kernels
-    if (dtype == QMC_DTYPE_F32 && m->quad_mixer && m->n >= 14 && m->n <= 20 && !getenv("QUMCMC_NO_XQ"))
+    // ... and every other X-string mixer at those sizes with the mixer exponent tabulated (XT mode; QUMCMC_NO_XT=1: general path)
+    if (dtype == QMC_DTYPE_F32 && !m->all_one_body && m->n >= 14 && m->n <= 20 && !getenv("QUMCMC_NO_XQ") &&
+        (m->quad_mixer || !getenv("QUMCMC_NO_XT")))
         return qmc_sweep_run(m, mode, n_chains, n_hops, s_in, chain_id0, hop0, temperature, g_lo, g_hi, dt, seed, dtype,
                              gamma_arr, r_arr, u_arr, group_arr, proposals, accepted, final_state, acc_count,
                              hamming_hist, probs_out, amps_out, st);

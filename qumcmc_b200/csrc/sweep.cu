@@ -82,6 +82,7 @@ struct SweepArgs {
     float gen_scale;          // XQ mode: normalisation of the Walsh-Hadamard transforms of this launch (applied with the phase)
     const int *xq_dr;         // XQ mode: Gray increments of the mixer diagonal, [mixer group][layout: hia, hib, hic][64]
     int64_t xq_af_stride;     // XQ mode: int4 entries between the af_hi* tables of consecutive mixer groups
+    const int *xt_ex;         // XT mode: tabulated mixer exponent E_x(x) in fixed point, [mixer group][2^n]
     // Fused exchange (sharded statevector): when xchg_peers != null the pass stores amplitude L of this rank to
     // xchg_peers[L >> xchg_shift][(L & low) | (xchg_rank << xchg_shift)] -- the all-to-all that swaps the top local
     // index bits with the rank bits, done by the sweep's own stores over NVLink peer mappings (no staging copy).
@@ -328,6 +329,28 @@ __device__ __forceinline__ void phase_gray(A64 (&v)[64], const PhaseAF af, const
                 const int h = (k == 0) ? h4.y : (k == 1) ? h4.z : (k == 2) ? h4.w : hn.x;
                 t = ((jn >> b) & 1) ? t - G[b] + h : t + G[b] + h;
             }
+        }
+    }
+}
+
+// XT mode: phase factor of the mixer diagonal from the tabulated exponent (any X-string mixer: E_x is not a quadratic form
+// when terms of weight >= 3 are present).  ex points at the thread's base index, off(j) is the index offset of register j.
+template <typename OFF>
+__device__ __forceinline__ void phase_lookup(A64 (&v)[64], const int *__restrict__ ex, OFF off, const int cfx, const int shift,
+                                             const float sc) {
+#pragma unroll
+    for (int j0 = 0; j0 < 64; j0 += 16) {
+        int e[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) e[k] = __ldg(ex + off(j0 + k));  // 16 loads in flight
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float sn, cs;
+            __sincosf((float)turns32(e[k], cfx, shift) * 1.4629180792671596e-09f, &sn, &cs);  // 2 pi / 2^32
+            sn *= sc;
+            cs *= sc;
+            const float2 a = upk(v[j0 + k]);
+            v[j0 + k] = pk(a.x * cs - a.y * sn, a.y * cs + a.x * sn);
         }
     }
 }
@@ -664,7 +687,9 @@ __global__ void __launch_bounds__(NT, MINB) lo_probe_kernel(const SweepArgs a, c
 
 // XQ: the phase layer of an HI sweep is the MIXER diagonal exp(-i gamma dt E_x(x)) (tables a.af_hi* / a.dr_hi* built from
 // the mixer's pair weights, rate cfx_x), between a transform into the x basis (+1) and back (-1); FIRST starts from H|s0>.
-template <int W, bool FIRST, bool FAST, bool XQ = false>
+// XT (with XQ): the same for ANY X-string mixer -- the diagonal comes from the tabulated exponent a.xt_ex (one 4-byte load per
+// amplitude, L2-resident: 4 MiB per mixer group at n = 20) instead of the quadratic-form tables.
+template <int W, bool FIRST, bool FAST, bool XQ = false, bool XT = false>
 __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, const int *__restrict__ order, const int list_off, const int ct_off) {
     using G = HiGeom<W>;
     extern __shared__ __align__(16) float2 sm[];
@@ -694,12 +719,16 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
     }
     // XQ: tables of the chain's mixer group (IncoherentMixerSum picks one sub-mixer per proposal)
     const int grp = XQ ? a.params[chain].group : 0;
-    const int *drx = XQ ? a.xq_dr + ((int64_t)grp * 3 + (G::two_rounds ? 1 : 0)) * 64 : nullptr;
-    if (XQ) build_hs_x(hs_s, drx, a.params + chain, tid);
-    else build_hs(hs_s, G::two_rounds ? a.dr_hib : a.dr_hia, a.params + chain, tid);
+    const int *drx = XQ && !XT ? a.xq_dr + ((int64_t)grp * 3 + (G::two_rounds ? 1 : 0)) * 64 : nullptr;
+    const int *ext = XT ? a.xt_ex + ((int64_t)grp << n) : nullptr;
+    if (!XT) {
+        if (XQ) build_hs_x(hs_s, drx, a.params + chain, tid);
+        else build_hs(hs_s, G::two_rounds ? a.dr_hib : a.dr_hia, a.params + chain, tid);
+    }
     stage_params(cp_s, a.params + chain, tid);
     const ChainParams &cp = cp_s;
-    const PhaseAF af = load_af((G::two_rounds ? a.af_hib : a.af_hia) + (XQ ? grp * a.xq_af_stride : 0), tile * NT + tid);
+    PhaseAF af;
+    if (!XT) af = load_af((G::two_rounds ? a.af_hib : a.af_hia) + (XQ ? grp * a.xq_af_stride : 0), tile * NT + tid);
     const float mag0 = XQ ? exp2f(-0.5f * (float)n) : 0.f;
     if (G::two_rounds) {
         const int64_t base_b = hi_base_b<W>(tid, tile);
@@ -716,7 +745,8 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
             bfly6<G::active_b, FAST>(v, cp, HiQB<W>(), tu);
             __syncthreads();
         }
-        if (XQ) phase_gray<false>(v, af, hs_s, __ldg(drx), cp.cfx_x, cp.shift_x, a.gen_scale);
+        if (XT) phase_lookup(v, ext + base_b, [](int j) { return G::off_b(j); }, cp.cfx_x, cp.shift_x, a.gen_scale);
+        else if (XQ) phase_gray<false>(v, af, hs_s, __ldg(drx), cp.cfx_x, cp.shift_x, a.gen_scale);
         else phase_gray<FAST>(v, af, hs_s, a.dr_hib[0], cp);
         bfly6<G::active_b, FAST>(v, cp, HiQB<W>(), tu2);
 #pragma unroll
@@ -734,7 +764,8 @@ __global__ void __launch_bounds__(NT, 3) hi_sweep_kernel(const SweepArgs a, cons
         } else {
             bfly6<G::active_a, FAST>(v, cp, HiQA<W>(), tu);
         }
-        if (XQ) phase_gray<false>(v, af, hs_s, __ldg(drx), cp.cfx_x, cp.shift_x, a.gen_scale);
+        if (XT) phase_lookup(v, ext + base_a, [](int j) { return G::off_a(j); }, cp.cfx_x, cp.shift_x, a.gen_scale);
+        else if (XQ) phase_gray<false>(v, af, hs_s, __ldg(drx), cp.cfx_x, cp.shift_x, a.gen_scale);
         else phase_gray<FAST>(v, af, hs_s, a.dr_hia[0], cp);
         bfly6<G::active_a, FAST>(v, cp, HiQA<W>(), tu2);
 #pragma unroll
@@ -1677,6 +1708,10 @@ struct SweepWorkspace {
     double *dxJ = nullptr, *dxh = nullptr;
     double fx_scale_x = 1.0;
     int k_fx_x = 0;
+    // XT mode (any other X-string mixer, 14 <= n <= 20): tabulated mixer exponent, int32 fixed point, [mixer groups][2^n]
+    int xt_epoch = -1;
+    int xt_groups = 0;
+    int *d_xt = nullptr;
 };
 
 void qmc_sweep_free(qmc_model *m) {
@@ -1700,6 +1735,7 @@ void qmc_sweep_free(qmc_model *m) {
     w->gsched.destroy();
     cudaFree(w->afx_lo); cudaFree(w->afx_hia); cudaFree(w->afx_hib); cudaFree(w->afx_hic); cudaFree(w->dxJ); cudaFree(w->dxh);
     cudaFree(w->d_drx);
+    cudaFree(w->d_xt);
     delete w;
     m->sweep = nullptr;
 }
@@ -1816,6 +1852,61 @@ static int ensure_workspace(qmc_model *m, int64_t chains, cudaStream_t st) {
         QMC_CUDA_TRY(cudaMalloc(&w->tan_sorted, sizeof(float) * (size_t)chains));
         w->cap_chains = chains;
     }
+    return QMC_OK;
+}
+
+// XT mode: E_x(x) = sum_S w_S (-1)^popcount(x & S) is the Walsh-Hadamard transform of the coefficient vector w[S] (indexed by
+// the term's mask): n in-place butterfly passes in fp64 on the device, then one rounding to int32 fixed point.
+__global__ void xt_wht_kernel(double *__restrict__ x, int64_t half, int bit) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < half; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = ((q >> bit) << (bit + 1)) | (q & (((int64_t)1 << bit) - 1)), j = i | ((int64_t)1 << bit);
+        const double u = x[i], v = x[j];
+        x[i] = u + v;
+        x[j] = u - v;
+    }
+}
+__global__ void xt_round_kernel(const double *__restrict__ x, int64_t N, double scale, int *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int)rint(x[i] * scale);
+}
+static int ensure_xt_tables(qmc_model *m, cudaStream_t st) {
+    SweepWorkspace *w = m->sweep;
+    if (w->xt_epoch == m->mixer_epoch) return QMC_OK;
+    const int n = m->n, ng = m->n_groups;
+    const int64_t N = 1LL << n;
+    QMC_REQUIRE(n >= 14 && n <= 20, QMC_ERR_UNSUPPORTED, "sweep path: tabulated mixer diagonals cover 14 <= n <= 20 (n=%d)", n);
+    QMC_CUDA_TRY(cudaStreamSynchronize(st));
+    double dmax = 0.0;  // one fixed-point scale for every group: |E_x| <= sum |w_S|
+    for (int g = 0; g < ng; ++g) {
+        double d = 0.0;
+        for (int k = m->group_off[g]; k < m->group_off[g + 1]; ++k) d += fabs(m->weights[k]);
+        dmax = std::max(dmax, d);
+    }
+    if (dmax < 1e-300) dmax = 1.0;
+    w->k_fx_x = (int)floor(log2(2147483647.0 / (dmax * 1.0000001))) - 1;
+    if (w->k_fx_x > 30) w->k_fx_x = 30;
+    w->fx_scale_x = ldexp(1.0, w->k_fx_x);
+    if (w->xt_groups != ng) {
+        cudaFree(w->d_xt);
+        w->d_xt = nullptr;
+        QMC_CUDA_TRY(cudaMalloc(&w->d_xt, sizeof(int) * (size_t)ng * N));
+        w->xt_groups = ng;
+    }
+    double *tmp = nullptr;
+    QMC_CUDA_TRY(cudaMalloc(&tmp, sizeof(double) * (size_t)N));
+    std::vector<double> coef((size_t)N);
+    for (int g = 0; g < ng; ++g) {
+        std::fill(coef.begin(), coef.end(), 0.0);
+        for (int k = m->group_off[g]; k < m->group_off[g + 1]; ++k) coef[(size_t)m->masks[k]] += m->weights[k];
+        QMC_CUDA_TRY(cudaMemcpyAsync(tmp, coef.data(), sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, st));
+        for (int b = 0; b < n; ++b) xt_wht_kernel<<<148 * 8, 256, 0, st>>>(tmp, N >> 1, b);
+        xt_round_kernel<<<148 * 8, 256, 0, st>>>(tmp, N, w->fx_scale_x, w->d_xt + (size_t)g * N);
+        m->launches += n + 1;
+        QMC_CUDA_TRY(cudaStreamSynchronize(st));  // coef is reused by the next group
+    }
+    QMC_CUDA_TRY(cudaGetLastError());
+    cudaFree(tmp);
+    w->xt_epoch = m->mixer_epoch;
     return QMC_OK;
 }
 
@@ -1953,6 +2044,13 @@ static int launch_lo_xq(const SweepArgs &a, const int *order, int off, int64_t t
 }
 template <int W, bool FIRST>
 static int launch_hi_xq_w(const SweepArgs &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
+    if (a.xt_ex) {  // XT mode: tabulated mixer exponent
+        static DevMask donet = 0;
+        int rct = set_smem_once(hi_sweep_kernel<W, FIRST, true, true, true>, donet);
+        if (rct != QMC_OK) return rct;
+        hi_sweep_kernel<W, FIRST, true, true, true><<<dim3((unsigned)tiles, (unsigned)count), NT, TILE * 8, st>>>(a, order, off, off);
+        return QMC_OK;
+    }
     if (W == 8 && !FIRST && a.hiq) {
         static DevMask doneq = 0;
         int rcq = set_smem_once(hiq_sweep_kernel<true, true>, doneq);
@@ -2182,10 +2280,12 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     QMC_REQUIRE(n >= 14 && n <= QMC_MAX_SPINS, QMC_ERR_UNSUPPORTED, "HBM sweep path covers 14 <= n <= %d (n=%d)", QMC_MAX_SPINS, n);
     const bool generic = n > 20;  // three or more qubit groups
     // XQ mode: one coherent group of one- and two-qubit X strings (abi.cu routes it here for 14 <= n <= 20)
-    const bool xq = !m->all_one_body && m->quad_mixer && n <= 20;
+    // XT mode: any other mixer at n <= 20 -- the same schedule and LO sweeps, HI sweeps read the tabulated mixer exponent
+    const bool xt = !m->all_one_body && !m->quad_mixer && n <= 20;
+    const bool xq = !m->all_one_body && n <= 20;  // XQ or XT: 2 r sweeps per proposal
     QMC_REQUIRE(m->all_one_body || xq, QMC_ERR_UNSUPPORTED,
-                "n=%d: the HBM sweep path hosts one-body X mixers (n <= %d) and single groups of one- and two-qubit X "
-                "strings (n <= 20); other mixers take the general path", n, QMC_MAX_SPINS);
+                "n=%d: the HBM sweep path hosts one-body X mixers (n <= %d) and every other X-string mixer at n <= 20 (XQ / XT modes: "
+                "quadratic or tabulated mixer diagonal); n > 20 with other mixers takes the general path", n, QMC_MAX_SPINS);
     if (n_chains == 0) return QMC_OK;
     {
         static DevMask smem_attr = 0;
@@ -2214,7 +2314,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
     if (rc != QMC_OK) return rc;
     SweepWorkspace *w = m->sweep;
     if (xq) {
-        rc = ensure_xq_tables(m, st);
+        rc = xt ? ensure_xt_tables(m, st) : ensure_xq_tables(m, st);
         if (rc != QMC_OK) return rc;
     }
     if (generic && w->groups.empty()) {  // register groups above the LO qubits, built once per model
@@ -2344,6 +2444,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
         a.gen_scale = 1.f;
         a.xq_dr = nullptr;
         a.xq_af_stride = 0;
+        a.xt_ex = nullptr;
         a.xchg_peers = nullptr; a.xchg_shift = 0; a.xchg_rank = 0; a.xchg_g = 0; a.xchg_tile_bits = 0; a.xchg_idx0 = 0;
         a.probs_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float *>(probs_out) : nullptr;
         a.amps_out = mode == QMC_MODE_PROBS ? reinterpret_cast<float2 *>(amps_out) : nullptr;
@@ -2436,6 +2537,7 @@ int qmc_sweep_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, cons
                     ax_him.af_hic = ax_hif.af_hic = w->afx_hic;
                     ax_him.xq_dr = ax_hif.xq_dr = w->d_drx;
                     ax_him.xq_af_stride = ax_hif.xq_af_stride = 2 * (N >> 6);
+                    if (xt) ax_him.xt_ex = ax_hif.xt_ex = w->d_xt;
                     ax_him.gen_scale = ldexpf(1.f, -nh);
                     ax_hif.gen_scale = (float)exp2(-0.5 * nh - 0.5 * LO_BITS);  // its own back-transform + the FINAL sweep's
                 }

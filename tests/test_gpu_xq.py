@@ -190,8 +190,10 @@ def test_xq_group_schedule_is_bit_identical(monkeypatch, n, C, mib):
         assert np.array_equal(getattr(ref, f), getattr(got, f)), f
 
 
-def test_mixers_outside_xq_keep_their_paths():
-    """Groups with a three-body term do not qualify: they still run (general path) and agree with the oracle."""
+def test_mixers_outside_xq_keep_their_paths(monkeypatch):
+    """Groups with a three-body term are not quadratic: with the tabulated mode switched off they run on the general path and
+    agree with the oracle."""
+    monkeypatch.setenv("QUMCMC_NO_XT", "1")
     import qumcmc_b200 as q
     n = 14
     J, h = models.packaged_random_model(n, 3)
@@ -204,3 +206,67 @@ def test_mixers_outside_xq_keep_their_paths():
         p = q.transition_probabilities(m, mixer, 77, 0.4, 3, dtype=dtype, group=group)
         ref = oracle.evolve(J, h, al, 0.4, 0.8, 3, gm, gw, 77, gatewise=False)
         assert np.abs(p - np.abs(ref) ** 2).max() < (1e-6 if dtype == "fp32" else 1e-10)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# XT mode: every other X-string mixer at 14 <= n <= 20 in complex64 -- the mixer diagonal from the tabulated exponent
+# ---------------------------------------------------------------------------------------------------------------
+def _xt_mixer(q, n, kind):
+    if kind == "three":
+        return q.GenericMixer.ThreeBodyMixer(n)
+    if kind == "custom":   # weights 1..4, terms inside and across the qubit groups
+        return q.CustomMixer(n, [[0, 5, n - 1], [1, 2, 3, 4], [n - 2], [12, 13], [6, 11, 12], [n - 3, n - 2, n - 1], [0, 1]])
+    if kind == "coh":
+        return q.CoherentMixerSum([q.GenericMixer.OneBodyMixer(n), q.GenericMixer.ThreeBodyMixer(n)], [0.8, 0.2])
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("n,kind", [(14, "three"), (15, "custom"), (16, "coh"), (17, "three"), (18, "custom"), (19, "coh"), (20, "three")])
+def test_xt_mixers_vs_oracle(n, kind):
+    import qumcmc_b200 as q
+    _check(q, n, _xt_mixer(q, n, kind), (1, 2, 5) if n < 19 else (1, 3))
+
+
+def test_xt_incoherent_sum_and_general_path_agreement(monkeypatch):
+    """Incoherent sum with a three-body member (every group reads its own table) per group against the oracle, and the
+    whole-path agreement with general.cu."""
+    import qumcmc_b200 as q
+    n = 15
+    inc = q.IncoherentMixerSum([q.GenericMixer.TwoBodyMixer(n), q.GenericMixer.ThreeBodyMixer(n)], [0.5, 0.5])
+    for group in (0, 1):
+        _check(q, n, inc, (2, 3), group=group)
+    J, h = models.packaged_random_model(n, 2)
+    m = q.IsingEnergyFunction(J, h)
+    mx = q.GenericMixer.ThreeBodyMixer(n)
+    p_xt = q.transition_probabilities(m, mx, 999, 0.33, 4, dtype="fp32")
+    monkeypatch.setenv("QUMCMC_NO_XT", "1")
+    p_gen = q.transition_probabilities(m, mx, 999, 0.33, 4, dtype="fp32")
+    assert np.abs(p_xt - p_gen).max() < 2e-6
+
+
+def test_xt_chains_and_group_schedule(monkeypatch):
+    """Three-body chains at n = 14: bit-identical between the schedules, accept bookkeeping follows the proposals."""
+    import qumcmc_b200 as q
+    n, C, H, seed = 14, 120, 3, 11
+    J, h = models.packaged_random_model(n, 6)
+    m = q.IsingEnergyFunction(J, h)
+    mx = q.GenericMixer.ThreeBodyMixer(n)
+    kw = dict(temperature=1.0, n_chains=C, seed=seed, dtype="fp32")
+    monkeypatch.setenv("QUMCMC_L2_GROUP_MIB", "0")
+    ref = q.quantum_enhanced_mcmc(H, m, mx, (0.25, 0.6), **kw)
+    monkeypatch.setenv("QUMCMC_L2_GROUP_MIB", "1")
+    got = q.quantum_enhanced_mcmc(H, m, mx, (0.25, 0.6), **kw)
+    for f in ("proposals", "accepted", "final_state", "acc_count", "hamming_hist"):
+        assert np.array_equal(getattr(ref, f), getattr(got, f)), f
+    for c in range(0, C, 17):
+        cur = oracle.initial_state(seed, c, n)
+        e_cur = oracle.energy(J, h, cur)
+        for hop in range(H):
+            _, _, _, _, ua = oracle.hop_draws(seed, c, hop)
+            sp = int(got.proposals[c, hop])
+            e_sp = oracle.energy(J, h, sp)
+            acc = oracle.test_accept(e_cur, e_sp, 1.0, ua)
+            assert bool(got.accepted[c, hop]) == acc
+            if acc:
+                cur, e_cur = sp, e_sp
+        assert int(got.final_state[c]) == cur
