@@ -97,7 +97,7 @@ def general():
                                             (24, "two", "fp32", 32, 4), (26, "two", "fp32", 8, 4)]:
         m = q.random_ising_model(n, 1)
         mx = {"one": q.GenericMixer.OneBodyMixer, "two": q.GenericMixer.TwoBodyMixer, "three": q.GenericMixer.ThreeBodyMixer}[mixer_name](n)
-        xq = mixer_name == "two" and n <= 20 and not os.environ.get("QUMCMC_NO_XQ")
+        xq = n <= 20 and not os.environ.get("QUMCMC_NO_XQ") and (mixer_name == "two" or not os.environ.get("QUMCMC_NO_XT"))
         q.quantum_enhanced_mcmc(1, m, mx, (0.25, 0.6), temperature=1.0, n_chains=chains, seed=3, dtype=dtype)  # warm + alloc
         dt, b = timed(lambda: q.quantum_enhanced_mcmc(H, m, mx, (0.25, 0.6), temperature=1.0, n_chains=chains, seed=4, dtype=dtype))
         from qumcmc_b200.rng import philox4x32
@@ -109,7 +109,7 @@ def general():
         esz = 8 if dtype == "fp32" else 16
         moved = 2.0 * esz * (1 << n) * (2 * K * sum_r - K * chains * H)   # FIRST write-only, 2K(r-1)+K-... passes read+write
         print(json.dumps({"config": "%s n=%d, %s-body mixer, %s, %d chains x %d hops" % (
-                              "sweep kernels (XQ mode)" if xq else "general path", n, mixer_name, dtype, chains, H),
+                              ("sweep kernels (XQ mode)" if mixer_name == "two" else "sweep kernels (XT mode)") if xq else "general path", n, mixer_name, dtype, chains, H),
                           "seconds": dt, "proposals_per_s": chains * H / dt, "acceptance": b.acceptance_rate(),
                           "passes_per_layer": 2 * K, "approx_moved_GBps": moved / 1e9 / dt,
                           "reference_cost": "one statevector pass per gate: %d passes per layer" % (

@@ -46,8 +46,8 @@ static int dispatch(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, co
                                 gamma_arr, r_arr, u_arr, group_arr, proposals, accepted, final_state, acc_count,
                                 hamming_hist, probs_out, amps_out, st);
     // the same in complex128, 13 <= n <= 20 (sweep128.cu, XQ mode)
-    if (dtype == QMC_DTYPE_F64 && m->quad_mixer && m->n >= 13 && m->n <= QMC_SWEEP_F64_MAX_SPINS && !getenv("QUMCMC_NO_XQ") &&
-        !getenv("QUMCMC_NO_SWEEP128"))
+    if (dtype == QMC_DTYPE_F64 && !m->all_one_body && m->n >= 13 && m->n <= QMC_SWEEP_F64_MAX_SPINS && !getenv("QUMCMC_NO_XQ") &&
+        (m->quad_mixer || !getenv("QUMCMC_NO_XT")) && !getenv("QUMCMC_NO_SWEEP128"))
         return qmc_sweep128_run(m, mode, n_chains, n_hops, s_in, chain_id0, hop0, temperature, g_lo, g_hi, dt, seed,
                                 gamma_arr, r_arr, u_arr, group_arr, proposals, accepted, final_state, acc_count,
                                 hamming_hist, probs_out, amps_out, st);

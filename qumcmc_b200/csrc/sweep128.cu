@@ -128,6 +128,7 @@ struct Sweep128Args {
     double gen_scale;          // XQ mode: normalisation of the Walsh-Hadamard transforms of this launch
     const double *xq_R;        // XQ mode, HI sweeps: R(j) of the mixer diagonal, [mixer group][32]
     int64_t xq_af_stride;      // XQ mode: doubles between the af_hi tables of consecutive mixer groups
+    const double *xt_ex;       // XT mode: tabulated mixer exponent E_x(x), fp64, [mixer group][2^n] (null: quadratic tables)
     double *probs_out;         // PROBS mode (unnormalised) or null
     double2 *amps_out;
 };
@@ -212,6 +213,19 @@ __device__ __forceinline__ void phase32(double2 (&v)[APT], const double *__restr
             const int jn = i1 ^ (i1 >> 1);
             f = ((jn >> b) & 1) ? cmul(f, g[b]) : cmul(f, make_double2(g[b].x, -g[b].y));
         }
+    }
+}
+
+// XT mode (any X-string mixer): factor(j) = sc * exp(i c E_x(idx_j)) from the tabulated exponent; ex points at the thread's
+// base index, off(j) is the index offset of register j in the phase layout.
+template <typename OFF>
+__device__ __forceinline__ void phase_lookup32(double2 (&v)[APT], const double *__restrict__ ex, OFF off, double c, double sc) {
+    const double ct = c * 0.15915494309189533577;  // turns
+#pragma unroll 8
+    for (int j = 0; j < APT; ++j) {
+        double sn, cs;
+        sincospi(2.0 * ct * __ldg(ex + off(j)), &sn, &cs);
+        v[j] = cmul(v[j], make_double2(cs * sc, sn * sc));
     }
 }
 
@@ -328,7 +342,7 @@ __global__ void __launch_bounds__(NT, 3) sweep128_kernel(const Sweep128Args a, c
     if (ROLE == R_FIRST || ROLE == R_MID) {
         if (tid < APT) {
             const ChainParams128 *cg = a.params + chain;
-            if (XQ && !LO) er_s[tid] = cis(cg->cphase_x * __ldg(a.xq_R + cg->group * APT + tid));  // the chain's mixer group
+            if (XQ && !LO) er_s[tid] = a.xt_ex ? make_double2(1.0, 0.0) : cis(cg->cphase_x * __ldg(a.xq_R + cg->group * APT + tid));  // the chain's mixer group
             else er_s[tid] = cis(cg->cphase * (LO ? a.R_lo[tid] : a.R_hi[tid]));
         }
     }
@@ -385,7 +399,9 @@ __global__ void __launch_bounds__(NT, 3) sweep128_kernel(const Sweep128Args a, c
             if (XQ) bfly5t<G::act2>(v, t1);
             else bfly5<G::act2>(v, cp, q2);
         }
-        phase32(v, af, er_s, cdiag, sdiag);
+        if (XQ && !LO && a.xt_ex)
+            phase_lookup32(v, a.xt_ex + ((int64_t)cp.group << n) + base_phase, [](int j) { return gmap<G>(local2<G>(0, j)); }, cdiag, sdiag);
+        else phase32(v, af, er_s, cdiag, sdiag);
         if (XQ) bfly5t<G::act2>(v, t2);
         else bfly5<G::act2>(v, cp, q2);
         if (ROLE != R_FIRST) __syncthreads();  // every thread has read its layout-2 slots
@@ -402,7 +418,9 @@ __global__ void __launch_bounds__(NT, 3) sweep128_kernel(const Sweep128Args a, c
             if (XQ) bfly5t<G::act1>(v, t1);
             else bfly5<G::act1>(v, cp, q1);
         }
-        phase32(v, af, er_s, cdiag, sdiag);
+        if (XQ && !LO && a.xt_ex)
+            phase_lookup32(v, a.xt_ex + ((int64_t)cp.group << n) + base_phase, [](int j) { return gmap<G>(local1<G>(0, j)); }, cdiag, sdiag);
+        else phase32(v, af, er_s, cdiag, sdiag);
         if (XQ) bfly5t<G::act1>(v, t2);
         else bfly5<G::act1>(v, cp, q1);
     }
@@ -751,6 +769,9 @@ struct Sweep128Workspace {
     double *afx_hi = nullptr, *dxJ = nullptr, *dxh = nullptr;
     double *d_Rx = nullptr;  // [mixer groups][32]
     int xq_groups = 0;
+    // XT mode: tabulated mixer exponent, fp64, [mixer groups][2^n]
+    int xt_epoch = -1, xt_groups = 0;
+    double *d_xt = nullptr;
 };
 
 void qmc_sweep128_free(qmc_model *m) {
@@ -759,7 +780,7 @@ void qmc_sweep128_free(qmc_model *m) {
     cudaFree(w->state); cudaFree(w->params); cudaFree(w->segsum); cudaFree(w->hist); cudaFree(w->order);
     cudaFree(w->af_lo); cudaFree(w->af_hi); cudaFree(w->dJq); cudaFree(w->dhq);
     w->gsched.destroy();
-    cudaFree(w->afx_hi); cudaFree(w->dxJ); cudaFree(w->dxh); cudaFree(w->d_Rx);
+    cudaFree(w->afx_hi); cudaFree(w->dxJ); cudaFree(w->dxh); cudaFree(w->d_Rx); cudaFree(w->d_xt);
     delete w;
     m->sweep128 = nullptr;
 }
@@ -880,6 +901,42 @@ static void build_xq128(int n, const double *dJ, const double *dh, double *af, c
     memcpy(R, Rg, sizeof(Rg));
 }
 
+// XT mode: E_x = Walsh-Hadamard transform of the coefficient vector (see sweep.cu: ensure_xt_tables), kept in fp64
+__global__ void xt128_wht_kernel(double *__restrict__ x, int64_t half, int bit) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < half; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = ((q >> bit) << (bit + 1)) | (q & (((int64_t)1 << bit) - 1)), j = i | ((int64_t)1 << bit);
+        const double u = x[i], v = x[j];
+        x[i] = u + v;
+        x[j] = u - v;
+    }
+}
+static int ensure_xt_tables128(qmc_model *m, cudaStream_t st) {
+    Sweep128Workspace *w = m->sweep128;
+    if (w->xt_epoch == m->mixer_epoch) return QMC_OK;
+    const int n = m->n, ng = m->n_groups;
+    const int64_t N = 1LL << n;
+    QMC_CUDA_TRY(cudaStreamSynchronize(st));
+    if (w->xt_groups != ng) {
+        cudaFree(w->d_xt);
+        w->d_xt = nullptr;
+        QMC_CUDA_TRY(cudaMalloc(&w->d_xt, sizeof(double) * (size_t)ng * N));
+        w->xt_groups = ng;
+    }
+    std::vector<double> coef((size_t)N);
+    for (int g = 0; g < ng; ++g) {
+        std::fill(coef.begin(), coef.end(), 0.0);
+        for (int k = m->group_off[g]; k < m->group_off[g + 1]; ++k) coef[(size_t)m->masks[k]] += m->weights[k];
+        double *x = w->d_xt + (size_t)g * N;
+        QMC_CUDA_TRY(cudaMemcpyAsync(x, coef.data(), sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, st));
+        for (int b = 0; b < n; ++b) xt128_wht_kernel<<<148 * 8, 256, 0, st>>>(x, N >> 1, b);
+        m->launches += n;
+        QMC_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    QMC_CUDA_TRY(cudaGetLastError());
+    w->xt_epoch = m->mixer_epoch;
+    return QMC_OK;
+}
+
 static int ensure_xq_tables128(qmc_model *m, cudaStream_t st) {
     Sweep128Workspace *w = m->sweep128;
     if (w->xq_epoch == m->mixer_epoch) return QMC_OK;
@@ -931,9 +988,8 @@ int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, c
                      int64_t *hamming_hist, void *probs_out, void *amps_out, cudaStream_t st) {
     const int n = m->n;
     QMC_REQUIRE(n >= 13 && n <= NMAX, QMC_ERR_UNSUPPORTED, "complex128 sweep path covers 13 <= n <= %d (n=%d)", NMAX, n);
-    const bool xq = !m->all_one_body && m->quad_mixer;  // one coherent group of one- and two-qubit X strings
-    QMC_REQUIRE(m->all_one_body || xq, QMC_ERR_UNSUPPORTED,
-                "complex128 sweep path: one-body X mixers and single groups of one- and two-qubit X strings only");
+    const bool xt = !m->all_one_body && !m->quad_mixer;  // XT mode: any other mixer, tabulated mixer exponent
+    const bool xq = !m->all_one_body;                    // XQ or XT: 2 r sweeps per proposal
     if (n_chains == 0) return QMC_OK;
     {
         static DevMask128 attr = 0;
@@ -960,7 +1016,7 @@ int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, c
     if (rc != QMC_OK) return rc;
     Sweep128Workspace *w = m->sweep128;
     if (xq) {
-        rc = ensure_xq_tables128(m, st);
+        rc = xt ? ensure_xt_tables128(m, st) : ensure_xq_tables128(m, st);
         if (rc != QMC_OK) return rc;
     }
     int r_max = qmc_trotter_steps(11, dt);
@@ -1040,6 +1096,11 @@ int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, c
                 ax_hif.af_hi = ax_him.af_hi = w->afx_hi;
                 ax_hif.xq_R = ax_him.xq_R = w->d_Rx;
                 ax_hif.xq_af_stride = ax_him.xq_af_stride = 6 * (N >> RB);
+                if (xt) {
+                    ax_hif.xt_ex = ax_him.xt_ex = w->d_xt;
+                    ax_hif.af_hi = ax_him.af_hi = w->af_hi;  // unused by the lookup; keeps the address arithmetic in bounds
+                    ax_hif.xq_af_stride = ax_him.xq_af_stride = 0;
+                }
                 ax_him.gen_scale = ldexp(1.0, -nh);
                 ax_hif.gen_scale = exp2(-0.5 * nh - 0.5 * LOQ);
             }

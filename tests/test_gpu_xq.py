@@ -270,3 +270,25 @@ def test_xt_chains_and_group_schedule(monkeypatch):
             if acc:
                 cur, e_cur = sp, e_sp
         assert int(got.final_state[c]) == cur
+
+
+@pytest.mark.parametrize("n,kind", [(13, "three"), (14, "custom"), (16, "coh"), (17, "three"), (20, "custom")])
+def test_xt_complex128_vs_oracle(n, kind):
+    """XT mode in the reference's precision (sweep128.cu): tabulated fp64 exponent, sincospi per amplitude; 1e-10."""
+    import qumcmc_b200 as q
+    _check(q, n, _xt_mixer(q, n, kind), (1, 2, 4) if n < 19 else (1, 3), dtype="fp64")
+
+
+def test_xt_complex128_chains_equal_the_oracle_chain():
+    import qumcmc_b200 as q
+    n, C, H, seed = 13, 5, 5, 23
+    J, h = models.packaged_random_model(n, 5)
+    m = q.IsingEnergyFunction(J, h)
+    mixer = q.GenericMixer.ThreeBodyMixer(n)
+    offs, masks, w, _ = mixer.lower()
+    b = q.quantum_enhanced_mcmc(H, m, mixer, (0.25, 0.6), temperature=1.0, n_chains=C, seed=seed, dtype="fp64")
+    for c in range(C):
+        s0 = oracle.initial_state(seed, c, n)
+        props, acc = oracle.run_chain(J, h, masks, w, s0, H, 1.0, (0.25, 0.6), 0.8, seed, chain_id=c)
+        assert np.array_equal(np.asarray(props, dtype=np.int64), b.proposals[c].astype(np.int64)), c
+        assert np.array_equal(np.asarray(acc, dtype=np.uint8), b.accepted[c].astype(np.uint8)), c
