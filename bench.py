@@ -353,15 +353,15 @@ def start_watchdog(seconds, rank, state):
 
 def mixers_block(args):
     """Secondary lines for mixers of higher weight (qumcmc/mixers.py:21-151), through the public Python API: two-body mixers
-    at n = 20 run on the sweep kernels in XQ mode (2 sweeps per Trotter layer), k-body mixers at n = 9 (BAS 3x3) on the
-    warp-per-chain kernel in Hadamard-basis mode; one-body lines beside them for the ratio."""
+    and three-body mixers at n = 20 run on the sweep kernels in XQ / XT mode (2 sweeps per Trotter layer), k-body mixers at
+    n = 9 (BAS 3x3) on the warp-per-chain kernel in Hadamard-basis mode; one-body lines beside them for the ratio."""
     import torch
     import qumcmc_b200 as q
     from tests import models as tmodels
 
     out = []
     Jb, hb, _ = tmodels.bas3("both")
-    cases = [("n=20 random Ising", q.random_ising_model(N_SPINS, MODEL_SEED), N_SPINS, None, 1.0, 1024, 4, ("two",), ("fp32", "fp64")),
+    cases = [("n=20 random Ising", q.random_ising_model(N_SPINS, MODEL_SEED), N_SPINS, None, 1.0, 1024, 4, ("two", "three"), ("fp32", "fp64")),
              ("BAS 3x3 (n=9)", q.IsingEnergyFunction(Jb, hb), 9, "111000111", 1 / 1.5, 1024, 400, ("one", "two", "three"), ("fp32", "fp64"))]
     for label, model, n, init, temp, chains, hops, kinds, dtypes in cases:
         for kind in kinds:
