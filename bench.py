@@ -361,7 +361,7 @@ def mixers_block(args):
 
     out = []
     Jb, hb, _ = tmodels.bas3("both")
-    cases = [("n=20 random Ising", q.random_ising_model(N_SPINS, MODEL_SEED), N_SPINS, None, 1.0, 1024, 4, ("two", "three"), ("fp32", "fp64")),
+    cases = [("n=20 random Ising", q.random_ising_model(N_SPINS, MODEL_SEED), N_SPINS, None, 1.0, 1024, 8, ("two", "three"), ("fp32", "fp64")),
              ("BAS 3x3 (n=9)", q.IsingEnergyFunction(Jb, hb), 9, "111000111", 1 / 1.5, 1024, 400, ("one", "two", "three"), ("fp32", "fp64"))]
     for label, model, n, init, temp, chains, hops, kinds, dtypes in cases:
         for kind in kinds:
