@@ -20,6 +20,17 @@
 //     last written state (64 KiB) to resolve the index inside the segment.
 //   * K4: energies in the oracle's fixed fp64 order + Metropolis accept with Philox uniforms.
 //
+//
+// Round 2 additions (DESIGN sections 4.2, 4.2b, 4.3):
+//   * L2-resident group schedule (group_sched.cuh): the chains of a group run all their sweeps back to back on side
+//     streams, so a sweep finds its statevectors in the L2; bit-identical to the step-major schedule.
+//   * XQ mode: mixers made of one- and two-qubit X strings are quadratic diagonals in the Hadamard basis,
+//     U = H Dx H (P H Dx H)^(r-1) -- the same kernels with butterfly multipliers +-1 (Walsh-Hadamard transforms), HI
+//     sweeps hosting Dx (phase tables built from the mixer's weights), LO sweeps hosting P: 2 r sweeps per proposal.
+//   * XT mode: any other X-string mixer, Dx from the tabulated exponent E_x(x) (device Walsh-Hadamard transform of the
+//     coefficient vector): one 4-byte lookup per amplitude in the HI sweeps.
+//   * n >= 21: generic multi-group sweeps (LO + HI8 / HI6 register groups), sharded statevectors (qmc_shard_*).
+//
 // Layout in HBM: state[chain][2^n] interleaved complex64 (8 B/amplitude), index order.
 #include <math.h>
 
