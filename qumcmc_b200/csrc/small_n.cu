@@ -389,6 +389,36 @@ struct WarpParams {
 template <int R>
 __device__ __forceinline__ int wswz(int idx) { return idx ^ ((idx >> R) & 31); }
 
+// Register form of an amplitude inside warp_layer: complex64 amplitudes are packed into one 64-bit register pair so that a
+// butterfly is two packed FMAs (fma.rn.f32x2 -> FFMA2) instead of four scalar ones; complex128 stays double2.
+typedef unsigned long long W64;
+template <typename T> struct WReg;
+template <> struct WReg<float> { using type = W64; };
+template <> struct WReg<double> { using type = double2; };
+__device__ __forceinline__ W64 w_pack(float2 a) {
+    W64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ double2 w_pack(double2 a) { return a; }
+__device__ __forceinline__ float2 w_unpack(W64 r) {
+    float2 o;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+    return o;
+}
+__device__ __forceinline__ double2 w_unpack(double2 r) { return r; }
+__device__ __forceinline__ W64 w_fma(float t, W64 b, W64 c) {  // t * b + c on both halves
+    W64 d, tt;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(tt) : "f"(t));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(tt), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ double2 w_fma(double t, double2 b, double2 c) { return make_double2(fma(t, b.x, c.x), fma(t, b.y, c.y)); }
+__device__ __forceinline__ W64 w_shfl_xor(W64 v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double2 w_shfl_xor(double2 v, int m) {
+    return make_double2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+
 // One mixer layer (preceded by the phase layer when `apply_phase`) that starts in layout 1 (L1 = true: registers = qubits
 // 0..R-1, index = lane << R | j) or layout 2 (registers = qubits 5..n-1, index = j << 5 | lane) and ends in the other one.
 // The layout is a template parameter, so every shared-memory slot is a compile-time function of j plus one lane term.
@@ -401,13 +431,21 @@ __device__ __forceinline__ void warp_layer(typename Vec2<T>::type (&v)[1 << R], 
     constexpr int LEFT = 5 - R;
     const unsigned FULL = 0xffffffffu;
     auto idx_of = [&](bool l1, int j) { return l1 ? ((lane << R) | j) : ((j << 5) | lane); };
+    using WR = typename WReg<T>::type;
+    WR *wtile = reinterpret_cast<WR *>(tile);
+    WR w[NR];
     if (apply_phase) {
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
             const T2 f = ph[wswz<R>(idx_of(L1, j))], a = v[j];
-            v[j].x = a.x * f.x - a.y * f.y;
-            v[j].y = a.x * f.y + a.y * f.x;
+            T2 o;
+            o.x = a.x * f.x - a.y * f.y;
+            o.y = a.x * f.y + a.y * f.x;
+            w[j] = w_pack(o);
         }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) w[j] = w_pack(v[j]);
     }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -418,11 +456,9 @@ __device__ __forceinline__ void warp_layer(typename Vec2<T>::type (&v)[1 << R], 
 #pragma unroll
             for (int j = 0; j < NR; ++j) {
                 if (j & (1 << b)) continue;
-                const T2 lo = v[j], hi = v[j | (1 << b)];
-                v[j].x = lo.x + t * hi.x;
-                v[j].y = lo.y + t * hi.y;
-                v[j | (1 << b)].x = hi.x - t * lo.x;
-                v[j | (1 << b)].y = hi.y - t * lo.y;
+                const WR lo = w[j], hi = w[j | (1 << b)];
+                w[j] = w_fma(t, hi, lo);
+                w[j | (1 << b)] = w_fma(-t, lo, hi);
             }
         }
         if (half == 0) {
@@ -433,26 +469,20 @@ __device__ __forceinline__ void warp_layer(typename Vec2<T>::type (&v)[1 << R], 
                 const T tq_ = __shfl_sync(FULL, my_t, q);
                 const T t = ((lane >> lb) & 1) ? -tq_ : tq_;
 #pragma unroll
-                for (int j = 0; j < NR; ++j) {
-                    const T px = __shfl_xor_sync(FULL, v[j].x, 1 << lb), py = __shfl_xor_sync(FULL, v[j].y, 1 << lb);
-                    v[j].x += t * px;
-                    v[j].y += t * py;
-                }
+                for (int j = 0; j < NR; ++j) w[j] = w_fma(t, w_shfl_xor(w[j], 1 << lb), w[j]);
             }
 #pragma unroll
-            for (int j = 0; j < NR; ++j) tile[wswz<R>(idx_of(l1, j))] = v[j];  // transposition through the warp's tile
+            for (int j = 0; j < NR; ++j) wtile[wswz<R>(idx_of(l1, j))] = w[j];  // transposition through the warp's tile
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < NR; ++j) v[j] = tile[wswz<R>(idx_of(!l1, j))];
+            for (int j = 0; j < NR; ++j) w[j] = wtile[wswz<R>(idx_of(!l1, j))];
             __syncwarp();
         }
     }
+#pragma unroll
+    for (int j = 0; j < NR; ++j) v[j] = w_unpack(w[j]);
 }
 
-// HX = true (any mixer; needs the E_x tables): the mixer layer is H . exp(-i gamma dt E_x) . H -- warp_layer with multiplier
-// +1 on every qubit (B = sqrt 2 Z H, into the x basis), the x-basis diagonal from a third warp-private tile, warp_layer with
-// multiplier -1 (B^T, back): two calls per Trotter layer whatever the number of terms, plain amplitudes, the 2^-n of the two
-// transforms inside the diagonal.  A layer starts and ends in layout 1.
 template <typename T, int R, bool HX = false>
 __global__ void __launch_bounds__(128) warp_chain_kernel(const WarpParams wp) {
     using T2 = typename Vec2<T>::type;
