@@ -1906,17 +1906,20 @@ static int ensure_xt_tables(qmc_model *m, cudaStream_t st) {
     double *tmp = nullptr;
     QMC_CUDA_TRY(cudaMalloc(&tmp, sizeof(double) * (size_t)N));
     std::vector<double> coef((size_t)N);
-    for (int g = 0; g < ng; ++g) {
+    cudaError_t err = cudaSuccess;
+    for (int g = 0; g < ng && err == cudaSuccess; ++g) {
         std::fill(coef.begin(), coef.end(), 0.0);
         for (int k = m->group_off[g]; k < m->group_off[g + 1]; ++k) coef[(size_t)m->masks[k]] += m->weights[k];
-        QMC_CUDA_TRY(cudaMemcpyAsync(tmp, coef.data(), sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, st));
+        err = cudaMemcpyAsync(tmp, coef.data(), sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, st);
+        if (err != cudaSuccess) break;
         for (int b = 0; b < n; ++b) xt_wht_kernel<<<148 * 8, 256, 0, st>>>(tmp, N >> 1, b);
         xt_round_kernel<<<148 * 8, 256, 0, st>>>(tmp, N, w->fx_scale_x, w->d_xt + (size_t)g * N);
         m->launches += n + 1;
-        QMC_CUDA_TRY(cudaStreamSynchronize(st));  // coef is reused by the next group
+        err = cudaStreamSynchronize(st);  // coef is reused by the next group
     }
-    QMC_CUDA_TRY(cudaGetLastError());
-    cudaFree(tmp);
+    if (err == cudaSuccess) err = cudaGetLastError();
+    cudaFree(tmp);  // on every path
+    QMC_CUDA_TRY(err);
     w->xt_epoch = m->mixer_epoch;
     return QMC_OK;
 }
