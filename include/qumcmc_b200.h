@@ -269,6 +269,10 @@ int qmc_debug_smem_slot(int layout, int tid, int j);
  * kind (0 LO first, 1 LO mid, 2 LO final, 3 LO final of an r = 1 proposal, 4 HI first, 5 HI mid), first position in the
  * r-sorted chain order, number of chains, side stream.  Returns the number of launches, or -1 on bad arguments. */
 int qmc_debug_group_plan(int n_chains, int r_max, const int *rhist, int group, int streams, int *out, int cap);
+/* How the dispatcher classifies a mixer given its term masks (qumcmc/mixers.py:21-151 lowered to X-string masks): 1 = one-body
+ * (rotation kernels), 2 = terms of weight <= 2 (XQ mode at 14 <= n <= 20), 3 = anything else (XT mode / on-chip Hadamard-basis
+ * mode / general path); -1 on bad arguments.  Pure host logic. */
+int qmc_debug_mixer_class(int n, int n_terms, const uint64_t *masks);
 int qmc_debug_layout128(int geometry, int layout, int tid, int j, long long *out4);
 int qmc_debug_general_slot(int stage, int tid, int j, int *local_out);
 

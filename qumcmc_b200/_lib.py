@@ -44,7 +44,7 @@ EXPORTS = [
     "qmc_enable_peer_access", "qmc_ipc_export", "qmc_ipc_open", "qmc_ipc_close_all",
     "qmc_classical_chains", "qmc_classical_chains_host", "qmc_trajectory_stats", "qmc_state_moments", "qmc_shard_op_chunk",
     "qmc_set_visit_histogram", "qmc_profile_read_moved", "qmc_shard_set_exchange_ctas", "qmc_shard_exchange_can_persist", "qmc_shard_copy_chunk",
-    "qmc_debug_smem_slot", "qmc_debug_layout128", "qmc_debug_general_slot", "qmc_debug_group_plan",
+    "qmc_debug_smem_slot", "qmc_debug_layout128", "qmc_debug_general_slot", "qmc_debug_group_plan", "qmc_debug_mixer_class",
 ]
 
 
@@ -162,6 +162,7 @@ def lib() -> C.CDLL:
     L.qmc_set_visit_histogram.argtypes = [C.c_void_p, i64p]
     L.qmc_profile_read_moved.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.qmc_debug_smem_slot.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.qmc_debug_mixer_class.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     L.qmc_debug_group_plan.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
     L.qmc_debug_general_slot.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.qmc_debug_layout128.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]

@@ -446,6 +446,22 @@ extern "C" int qmc_set_visit_histogram(qmc_model *m, int64_t *visit_hist_dev) {
     return QMC_OK;
 }
 
+// Static-analysis hook (CPU tests): how the dispatcher classifies a mixer -- 1: every term is a single-qubit X (rotation
+// kernels), 2: every term has weight <= 2 (quadratic diagonal in the Hadamard basis: XQ mode), 3: anything else (tabulated
+// diagonal: XT mode / on-chip Hadamard-basis mode / general path); -1 on bad arguments.  Same rule as qmc_mixer_set.
+extern "C" int qmc_debug_mixer_class(int n, int n_terms, const uint64_t *masks) {
+    if (n < 1 || n > 64 || n_terms < 1 || !masks) return -1;
+    const uint64_t full = n >= 64 ? ~0ULL : ((1ULL << n) - 1ULL);
+    int cls = 1;
+    for (int k = 0; k < n_terms; ++k) {
+        if (masks[k] == 0 || (masks[k] & ~full)) return -1;
+        const int wgt = __builtin_popcountll(masks[k]);
+        if (wgt > 2) cls = 3;
+        else if (wgt == 2 && cls < 2) cls = 2;
+    }
+    return cls;
+}
+
 extern "C" int qmc_mixer_set(qmc_model *m, int n_groups, const int *group_offsets, const uint64_t *masks,
                              const double *weights, const double *group_prob) {
     QMC_REQUIRE(m && group_offsets && masks && weights, QMC_ERR_BADARG, "qmc_mixer_set: null argument");
@@ -459,12 +475,11 @@ extern "C" int qmc_mixer_set(qmc_model *m, int n_groups, const int *group_offset
         if (c > max_terms) max_terms = c;
     }
     const uint64_t full = (m->n >= 64) ? ~0ULL : ((1ULL << m->n) - 1ULL);
-    bool one_body = true;
-    for (int k = 0; k < nt; ++k) {
+    for (int k = 0; k < nt; ++k)
         QMC_REQUIRE(masks[k] != 0 && (masks[k] & ~full) == 0, QMC_ERR_BADARG,
                     "qmc_mixer_set: term %d has an empty mask or a qubit >= n", k);
-        if (__builtin_popcountll(masks[k]) != 1) one_body = false;
-    }
+    const int mixer_class = qmc_debug_mixer_class(m->n, nt, masks);  // 1 one-body, 2 weight <= 2, 3 anything else
+    const bool one_body = mixer_class == 1;
     QMC_CUDA_TRY(cudaSetDevice(m->device));
     m->n_groups = n_groups;
     m->group_off.assign(group_offsets, group_offsets + n_groups + 1);
@@ -494,9 +509,7 @@ extern "C" int qmc_mixer_set(qmc_model *m, int n_groups, const int *group_offset
     m->xJ.clear();
     m->xh.clear();
     if (!one_body) {  // every group made of one- and two-qubit X strings: quadratic forms in the x basis, one per group
-        bool quad = true;
-        for (int k = 0; k < nt; ++k) quad = quad && __builtin_popcountll(masks[k]) <= 2;
-        if (quad) {
+        if (mixer_class == 2) {
             const int n = m->n;
             m->xJ.assign((size_t)n_groups * n * n, 0.0);
             m->xh.assign((size_t)n_groups * n, 0.0);

@@ -102,3 +102,27 @@ def test_bad_arguments():
     assert L.qmc_debug_group_plan(5, 2, rh, 2, 2, out, 16) == -1      # histogram does not sum to n_chains
     assert L.qmc_debug_group_plan(4, 2, rh, 0, 2, out, 16) == -1
     assert L.qmc_debug_group_plan(4, 2, rh, 2, 0, out, 16) == -1
+
+
+def test_mixer_classification_of_the_reference_mixer_classes():
+    """The dispatcher's rule (one-body -> rotation kernels, weight <= 2 -> XQ mode, anything else -> tabulated diagonal) on
+    the lowered masks of the reference's mixer classes (qumcmc/mixers.py:21-151)."""
+    import qumcmc_b200 as q
+    L = _lib.lib()
+
+    def cls(mixer, n):
+        _, masks, _, _ = mixer.lower()
+        arr = (C.c_uint64 * len(masks))(*[int(x) for x in masks])
+        return L.qmc_debug_mixer_class(n, len(masks), arr)
+
+    n = 16
+    assert cls(q.GenericMixer.OneBodyMixer(n), n) == 1
+    assert cls(q.CustomMixer(n, [[0], [3], [15]]), n) == 1
+    assert cls(q.GenericMixer.TwoBodyMixer(n), n) == 2
+    assert cls(q.CoherentMixerSum([q.GenericMixer.OneBodyMixer(n), q.GenericMixer.TwoBodyMixer(n)], [0.7, 0.3]), n) == 2
+    assert cls(q.IncoherentMixerSum([q.GenericMixer.OneBodyMixer(n), q.CustomMixer(n, [[0, 5], [2]])], [0.5, 0.5]), n) == 2
+    assert cls(q.GenericMixer.ThreeBodyMixer(n), n) == 3
+    assert cls(q.CustomMixer(n, [[0, 1], [2, 3, 4, 5]]), n) == 3
+    bad = (C.c_uint64 * 1)(1 << 20)
+    assert L.qmc_debug_mixer_class(n, 1, bad) == -1       # qubit >= n
+    assert L.qmc_debug_mixer_class(n, 0, bad) == -1
