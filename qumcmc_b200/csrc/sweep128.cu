@@ -323,7 +323,9 @@ enum { R_FIRST = 0, R_MID = 1, R_FINAL = 2, R_FINAL1 = 3 };
 // XQ (one coherent group of one- and two-qubit X strings, see sweep.cu): the butterflies are Walsh-Hadamard transforms
 // (multiplier +1 into the x basis, -1 back), HI sweeps host the mixer diagonal (tables a.af_hi / a.R_hi built from the mixer's
 // weights, rate cphase_x), LO sweeps the phase layer; plain amplitudes, normalisation a.gen_scale with the phase factor.
-template <typename G, int ROLE, bool XQ = false>
+// XT (with XQ, HI sweeps): the mixer diagonal from the tabulated exponent -- a separate instantiation, so that the XQ kernels
+// do not carry the per-amplitude sincospi code (as a run-time branch it cost the XQ HI sweep a third of its rate).
+template <typename G, int ROLE, bool XQ = false, bool XT = false>
 __global__ void __launch_bounds__(NT, 3) sweep128_kernel(const Sweep128Args a, const int *__restrict__ order, const int list_off) {
     extern __shared__ __align__(16) unsigned char smraw[];
     double2 *sm = reinterpret_cast<double2 *>(smraw);
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(NT, 3) sweep128_kernel(const Sweep128Args a, c
     if (ROLE == R_FIRST || ROLE == R_MID) {
         if (tid < APT) {
             const ChainParams128 *cg = a.params + chain;
-            if (XQ && !LO) er_s[tid] = a.xt_ex ? make_double2(1.0, 0.0) : cis(cg->cphase_x * __ldg(a.xq_R + cg->group * APT + tid));  // the chain's mixer group
+            if (XQ && !LO) er_s[tid] = XT ? make_double2(1.0, 0.0) : cis(cg->cphase_x * __ldg(a.xq_R + cg->group * APT + tid));  // the chain's mixer group
             else er_s[tid] = cis(cg->cphase * (LO ? a.R_lo[tid] : a.R_hi[tid]));
         }
     }
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(NT, 3) sweep128_kernel(const Sweep128Args a, c
             if (XQ) bfly5t<G::act2>(v, t1);
             else bfly5<G::act2>(v, cp, q2);
         }
-        if (XQ && !LO && a.xt_ex)
+        if (XT && !LO)
             phase_lookup32(v, a.xt_ex + ((int64_t)cp.group << n) + base_phase, [](int j) { return gmap<G>(local2<G>(0, j)); }, cdiag, sdiag);
         else phase32(v, af, er_s, cdiag, sdiag);
         if (XQ) bfly5t<G::act2>(v, t2);
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(NT, 3) sweep128_kernel(const Sweep128Args a, c
             if (XQ) bfly5t<G::act1>(v, t1);
             else bfly5<G::act1>(v, cp, q1);
         }
-        if (XQ && !LO && a.xt_ex)
+        if (XT && !LO)
             phase_lookup32(v, a.xt_ex + ((int64_t)cp.group << n) + base_phase, [](int j) { return gmap<G>(local1<G>(0, j)); }, cdiag, sdiag);
         else phase32(v, af, er_s, cdiag, sdiag);
         if (XQ) bfly5t<G::act1>(v, t2);
@@ -798,25 +800,25 @@ static int smem_optin(K kernel, DevMask128 &done) {
     return QMC_OK;
 }
 
-template <typename G, int ROLE, bool XQ = false>
+template <typename G, int ROLE, bool XQ = false, bool XT = false>
 static int launch128(const Sweep128Args &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
     static DevMask128 done = 0;
-    int rc = smem_optin(sweep128_kernel<G, ROLE, XQ>, done);
+    int rc = smem_optin(sweep128_kernel<G, ROLE, XQ, XT>, done);
     if (rc != QMC_OK) return rc;
-    sweep128_kernel<G, ROLE, XQ><<<dim3((unsigned)tiles, (unsigned)count), NT, SMEM_BYTES, st>>>(a, order, off);
+    sweep128_kernel<G, ROLE, XQ, XT><<<dim3((unsigned)tiles, (unsigned)count), NT, SMEM_BYTES, st>>>(a, order, off);
     return QMC_OK;
 }
-template <int ROLE, bool XQ = false>
+template <int ROLE, bool XQ = false, bool XT = false>
 static int launch128_hi(int n, const Sweep128Args &a, const int *order, int off, int64_t tiles, int count, cudaStream_t st) {
     switch (22 - n) {  // LC
-        case 2: return launch128<HiGeo<2>, ROLE, XQ>(a, order, off, tiles, count, st);
-        case 3: return launch128<HiGeo<3>, ROLE, XQ>(a, order, off, tiles, count, st);
-        case 4: return launch128<HiGeo<4>, ROLE, XQ>(a, order, off, tiles, count, st);
-        case 5: return launch128<HiGeo<5>, ROLE, XQ>(a, order, off, tiles, count, st);
-        case 6: return launch128<HiGeo<6>, ROLE, XQ>(a, order, off, tiles, count, st);
-        case 7: return launch128<HiGeo<7>, ROLE, XQ>(a, order, off, tiles, count, st);
-        case 8: return launch128<HiGeo<8>, ROLE, XQ>(a, order, off, tiles, count, st);
-        case 9: return launch128<HiGeo<9>, ROLE, XQ>(a, order, off, tiles, count, st);
+        case 2: return launch128<HiGeo<2>, ROLE, XQ, XT>(a, order, off, tiles, count, st);
+        case 3: return launch128<HiGeo<3>, ROLE, XQ, XT>(a, order, off, tiles, count, st);
+        case 4: return launch128<HiGeo<4>, ROLE, XQ, XT>(a, order, off, tiles, count, st);
+        case 5: return launch128<HiGeo<5>, ROLE, XQ, XT>(a, order, off, tiles, count, st);
+        case 6: return launch128<HiGeo<6>, ROLE, XQ, XT>(a, order, off, tiles, count, st);
+        case 7: return launch128<HiGeo<7>, ROLE, XQ, XT>(a, order, off, tiles, count, st);
+        case 8: return launch128<HiGeo<8>, ROLE, XQ, XT>(a, order, off, tiles, count, st);
+        case 9: return launch128<HiGeo<9>, ROLE, XQ, XT>(a, order, off, tiles, count, st);
     }
     qmc_set_error("complex128 sweep path: n=%d outside [13, 20]", n);
     return QMC_ERR_UNSUPPORTED;
@@ -1119,6 +1121,9 @@ int qmc_sweep128_run(qmc_model *m, int mode, int64_t n_chains, int64_t n_hops, c
                 }
             };
             auto hi = [&](bool first, int off, int count, cudaStream_t sg) {
+                if (xt)
+                    return first ? launch128_hi<R_FIRST, true, true>(n, ax_hif, w->order, off, tiles, count, sg)
+                                 : launch128_hi<R_MID, true, true>(n, ax_him, w->order, off, tiles, count, sg);
                 if (xq)
                     return first ? launch128_hi<R_FIRST, true>(n, ax_hif, w->order, off, tiles, count, sg)
                                  : launch128_hi<R_MID, true>(n, ax_him, w->order, off, tiles, count, sg);
